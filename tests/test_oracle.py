@@ -1,0 +1,90 @@
+"""CPU: pin both oracles (Python restatement, C restatement) to the golden fixtures that
+were produced by executing the reference's own source text (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, frisk_oracle, ref_exec
+from tests.helpers import Golden, SMALL_CASES, assert_rows_close, max_rel_err
+
+
+def _tables_array(maps, kmin, kmax):
+    return np.concatenate([np.fromiter(maps[k - kmin].values(), dtype=np.uint64) for k in range(kmin, kmax + 1)])
+
+
+@pytest.mark.parametrize("case", SMALL_CASES)
+def test_c_oracle_matches_reference(case):
+    g = Golden(case)
+    out = c_oracle.run(g.scaffolds(), host=g.host(), threads=4, **g.kwargs())
+    assert np.array_equal(out["tables"], g.tables), "genome tables must be bit-exact"
+    assert np.array_equal(out["meta"], g.genome_meta), "totalLen / exMax / nnTotal"
+    assert out["names"] == g.names
+    assert np.array_equal(out["coords"], g.coords)
+    ref = g.vals.copy()
+    zd = np.isinf(ref[:, 0])
+    assert np.array_equal(zd, (out["status"] & c_oracle.ERR_KLD_ZERODIV) != 0), "ZeroDivisionError rows"
+    ref[zd, 0] = 0.0
+    out["rows"][zd, 0] = 0.0
+    # same operation order as the reference -> agreement far inside the 1e-6 contract
+    assert_rows_close(out["rows"], ref, rtol_kld=1e-12, rtol_other=0.0, what=case)
+
+
+@pytest.mark.parametrize("case", ["edge_default", "edge_k2_5_w1000_i250", "edge_scaffoldsAll"])
+def test_c_oracle_window_tables(case):
+    g = Golden(case)
+    sc = g.scaffolds()
+    kw = g.kwargs()
+    seq, off = c_oracle.concat(sc)
+    _, woff, wlen, _, _ = c_oracle.crawl(seq, off, kw["w"], kw["step"], kw["scaffolds_all"])
+    for slot, idx in enumerate(g.win_pick):
+        win = seq[int(woff[idx]):int(woff[idx]) + int(wlen[idx])]
+        _, _, wt, wm = c_oracle.window_tables(win, g.tables, g.genome_meta, kw["kmin"], kw["kmax"])
+        assert np.array_equal(wt, g.win_tables[slot].astype(np.uint64))
+        assert np.array_equal(wm, g.win_meta[slot])
+
+
+@pytest.mark.parametrize("case", ["edge_default", "edge_scaffoldsAll", "edge_maskHost", "edge_k1_3_w3000_i1000",
+                                  "edge_k4_8"])
+def test_python_oracle_matches_reference(case):
+    g = Golden(case)
+    sc = [(n, s.tobytes().decode()) for n, s in g.scaffolds()]
+    kw = g.kwargs()
+    genome, rows = frisk_oracle.score_windows(sc, **kw)
+    kmin, kmax = kw["kmin"], kw["kmax"]
+    assert np.array_equal(_tables_array(genome, kmin, kmax), g.tables)
+    kr = kmax - kmin
+    assert [genome[kr + 1]["totalLen"], genome[kr + 2]["exMax"], genome[kr + 3]["nnTotal"]] == list(g.genome_meta)
+    assert [r[0] for r in rows] == g.names
+    assert np.array_equal(np.array([[r[1], r[2]] for r in rows]).reshape(-1, 2), g.coords)
+    vals = np.array([[np.inf if isinstance(v, str) else (np.nan if v is None else v) for v in r[3:]] for r in rows],
+                    dtype=float).reshape(-1, 5)
+    assert np.array_equal(np.isinf(vals[:, 0]), np.isinf(g.vals[:, 0]))
+    # identical operation order in the same language: bit-identical expected
+    fin = np.isfinite(g.vals)
+    assert np.array_equal(vals[fin], g.vals[fin])
+
+
+def test_python_and_c_oracle_agree_on_fresh_input():
+    from frisk_b200 import synth
+    sc = synth.make("C2", 0.002, seed=99)
+    out = c_oracle.run(sc, threads=2)
+    genome, rows = frisk_oracle.score_windows([(n, s.tobytes().decode()) for n, s in sc])
+    assert np.array_equal(_tables_array(genome, 1, 8), out["tables"])
+    assert len(rows) == len(out["rows"])
+    assert max_rel_err([r[3] for r in rows], out["rows"][:, 0]) < 1e-12
+
+
+@pytest.mark.skipif(not ref_exec.available(), reason="/root/reference only exists in the build container")
+def test_live_reference_text_matches_golden_and_oracle():
+    """Container-only: re-execute the reference's source text and compare (guards the fixtures)."""
+    import os, tempfile
+    from frisk_b200 import synth
+    g = Golden("edge_k1_3_w3000_i1000")
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "q.fa")
+    synth.write_fasta(g.scaffolds(), path)
+    p = g.params
+    args = ref_exec.make_args(path, querySeq=path, **p)
+    genome, rows = ref_exec.run_hot_path(args, genomepickle=os.path.join(tmp, "g.p"))
+    assert np.array_equal(_tables_array(genome, p["kmin"], p["kmax"]), g.tables)
+    assert [r[0] for r in rows] == g.names
+    assert np.array_equal(np.array([r[3] for r in rows], float), g.vals[:, 0])
