@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the frisk hot path (BASELINE.json metric: Gbp/s of scaffold scored =
+background k-mer count + per-window IVOM/KLD score).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the CPU arm (oracle port)
+
+Workload: BASELINE config C2 -- synthetic 40 Mbp fungal-style assembly, ~500 scaffolds, default
+k = 1..8, window 5000 / step 2500, RIP on.  At N > 1 (torchrun, one rank per GPU) every rank
+holds its own 40 Mbp shard (seed 2002 + rank) of a 40*N Mbp assembly -- weak scaling -- and the
+only collective is one NCCL all-reduce of the 87,380 forward k-mer counters.
+
+A step = one full pass: zero counters, background count, [all-reduce], finalise tables, genome
+IVOM table, score every window.  `value` has the packed planes + window list resident in HBM;
+`e2e` goes through the C-ABI call frisk_b200_run_host from pinned HOST buffers (H2D of planes and
+window list, D2H of rows/status/tables inside the timed region).  L2 (126 MB) is flushed between
+timed steps by writing a 512 MiB buffer (the planes are only ~20 MB).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C2: synthetic 40 Mbp fungal-style assembly, ~500 scaffolds, k=1..8, w=5000, step=2500, RIP"
+METRIC = "Gbp/s scaffold scored (k-mer count+window score)"
+PARAMS = dict(kmin=1, kmax=8, w=5000, step=2500, mask_host=False, scaffolds_all=False, rip=True)
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append((time.time(), [x.strip() for x in line.split(",")]))
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self, t0, t1):
+        self.stop_flag.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        rows = [r for t, r in self.samples if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or \
+               [r for _, r in self.samples if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_port_sample(scaffolds, target_seconds: float, threads: int):
+    """Time the C oracle (a port of the reference's algorithm, oracle/frisk_oracle.c) on a bounded
+    sample: the first scaffolds of the workload, background pass + every window of the sample,
+    scored against the sample's own background.  Cost is linear in bases and windows, so Gbp/s
+    of the sample is the CPU path's Gbp/s on the workload."""
+    from oracle import c_oracle
+    # ~2 Mbp/s/8 threads in the build container: start from a guess and refine once
+    probe = []
+    tot = 0
+    for s in scaffolds:
+        probe.append(s)
+        tot += len(s[1])
+        if tot >= 400_000:
+            break
+    t0 = time.perf_counter()
+    _one_cpu_pass(probe, threads)
+    rate = tot / (time.perf_counter() - t0)
+    want = max(int(rate * target_seconds), 200_000)
+    sample, tot = [], 0
+    for s in scaffolds:
+        sample.append(s)
+        tot += len(s[1])
+        if tot >= want:
+            break
+    return sample, tot
+
+
+def _one_cpu_pass(sample, threads):
+    from oracle import c_oracle
+    seq, off = c_oracle.concat(sample)
+    tabs, meta = c_oracle.background(seq, off, PARAMS["kmin"], PARAMS["kmax"], False, threads)
+    _, woff, wlen, _, _ = c_oracle.crawl(seq, off, PARAMS["w"], PARAMS["step"], False)
+    rows, status = c_oracle.score(seq, woff, wlen, tabs, meta, PARAMS["kmin"], PARAMS["kmax"], True, threads)
+    return len(woff)
+
+
+def python_port_rate(scaffolds, bases: int = 30_000):
+    """The Python restatement (same data structures as the reference: dicts of k-mer strings) on a
+    tiny sample, 1 core -- how fast the reference itself runs."""
+    from oracle import frisk_oracle
+    name, seq = scaffolds[0]
+    sub = [(name, seq[:bases].tobytes().decode())]
+    t0 = time.perf_counter()
+    frisk_oracle.score_windows(sub, PARAMS["kmin"], PARAMS["kmax"], PARAMS["w"], PARAMS["step"])
+    return bases / (time.perf_counter() - t0) / 1e9
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The
+    reference is Python-2-only pure Python and cannot be installed or run on the GPU box (see
+    DESIGN.md), so the arm times the oracle PORT (C restatement, all host threads): a far faster
+    stand-in than the reference's own dict loops, whose speed is reported beside it."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from frisk_b200 import synth
+    threads = os.cpu_count() or 1
+    scaffolds = synth.make("C2", 1.0)
+    sample, tot = cpu_port_sample(scaffolds, 2.0, threads)
+    for _ in range(args.warmup):
+        _one_cpu_pass(sample, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nwin = _one_cpu_pass(sample, threads)
+    dt = time.perf_counter() - t0
+    value = tot * args.steps / dt / 1e9
+    sample_desc = "first %d scaffolds of C2 = %d bp, %d windows per step (background + all windows of the sample)" % (
+        len(sample), tot, nwin)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64 counts + f64 scores", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": threads, "kind": "port", "sample": sample_desc,
+                         "python_port_1core_gbps": python_port_rate(scaffolds)},
+        "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from frisk_b200 import _lib, engine, synth
+    from frisk_b200 import dist as fdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_device()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # this rank's shard: 40 Mbp, packed into pinned planes (ingest is outside the timed region)
+    scaffolds = synth.make("C2", 1.0, seed=2002 + rank)
+    t0 = time.perf_counter()
+    genome = engine.PackedGenome.from_scaffolds(scaffolds, pinned=True)
+    t_pack = time.perf_counter() - t0
+    bases = genome.total_len
+    allreduce, space = None, genome.genome_space
+    if world > 1:
+        space = fdist.global_genome_space(space, dev)
+        allreduce = fdist.make_allreduce()
+    pipe = engine.Pipeline(genome, device=dev, allreduce=allreduce, genome_space=space, **PARAMS)
+    n_win = len(pipe.wins)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        pipe.enqueue()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.35)
+    marks_all = []
+    t_wall0 = time.time()
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)                       # evict the planes and tables from L2 (not timed)
+        marks = []
+        pipe.enqueue(marks)
+        marks_all.append(marks)
+    barrier()
+    t_wall1 = time.time()
+    stage = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(3)] for m in marks_all])   # ms
+    step_ms = np.array([m[0].elapsed_time(m[3]) for m in marks_all])
+    total_ms = float(step_ms.sum())
+
+    # ---- end to end through the C ABI from pinned host buffers (N = 1) or the staged API with
+    # ---- the all-reduce (N > 1); H2D of planes + window list and D2H of the rows inside the timer
+    out = engine.HostOutputs(n_win, PARAMS["kmax"])
+    wins = pipe.wins
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_once():
+        if world == 1:
+            return engine.run_host(genome, wins=wins, out=out, **PARAMS)
+        return engine.run(genome, device=dev, allreduce=allreduce, genome_space=space, wins=wins, **PARAMS)
+
+    if args.profile:
+        e2e_steps = 0
+    else:
+        res = e2e_once()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e2e_ms = 0.0
+    for _ in range(e2e_steps):
+        flush.fill_(1)
+        barrier()
+        e0.record()
+        res = e2e_once()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        e2e_ms += e0.elapsed_time(e1)
+    t_wall2 = time.time()
+    clocks = sampler.finish(t_wall0, t_wall1)
+
+    h2d = genome.plane_bytes + wins.off.nbytes + wins.length.nbytes
+    d2h = n_win * 44 + _lib.table_size(1, PARAMS["kmax"]) * 8 + 8
+
+    # max over ranks of the timed totals; sum over ranks of the bases
+    tot = torch.tensor([total_ms, e2e_ms / max(e2e_steps, 1)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([bases, n_win], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms, e2e_step_ms = float(tot[0]), float(tot[1])
+    all_bases, all_win = int(cnt[0]), int(cnt[1])
+
+    if rank == 0:
+        value = all_bases * args.steps / (total_ms * 1e-3) / 1e9
+        peak, peak_kind = measured_peak_gbs()
+        score_ms = float(stage[:, 2].mean())
+        low_b = 0.125 if genome.low is not None else 0.0
+        alg_bytes = bases * (0.375 + low_b) + n_win * 40.0          # packed read once + one row/window
+        achieved = alg_bytes / (score_ms * 1e-3) / 1e9
+        # applicable bound for this kernel: shared-memory histogram updates (SURVEY 8d / BASELINE.md 4)
+        alg_updates = float(sum(max(int(l) - k + 1, 0) for l in wins.length for k in range(1, 9))) if n_win < 200000 else n_win * 39972.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u16/u64 counts + f64 scores", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bases_per_gpu": bases, "windows_per_gpu": n_win,
+                       "l2": "flushed between timed steps (512 MiB write)", "parallelism": "scaffold shards x%d, 1 all-reduce" % world},
+            "windows_per_s": all_win * args.steps / (total_ms * 1e-3),
+            "stage_ms": {"background": float(stage[:, 0].mean()), "tables+ivom(+allreduce)": float(stage[:, 1].mean()),
+                         "score": score_ms},
+            "roofline": {"kernel": "score_windows_kernel<8>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "note": "not HBM-bound by design: window tables never leave shared memory; see smem_atomic"},
+            "smem_atomic": {"algorithmic_updates_per_s": alg_updates / (score_ms * 1e-3),
+                            "note": "algorithmic = one update per (order, valid position); the kernel issues 1/8 of them "
+                                    "(orders 1..7 come from marginalisation)"},
+            "e2e": {"value": (all_bases / (e2e_step_ms * 1e-3) / 1e9) if e2e_steps else None, "unit": "Gbp/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_step_ms, "steps": e2e_steps,
+                    "api": "frisk_b200_run_host (C ABI, pinned host planes)" if world == 1 else "engine.run + NCCL all-reduce"},
+            "gpu_launches": pipe.launches_per_step * args.steps,
+            "clocks": clocks,
+            "ingest": {"pack_seconds": t_pack, "pack_gbps": bases / t_pack / 1e9, "note": "host 2-bit packing, outside the timed region"},
+        }
+        if world == 1 and not args.profile:
+            threads = os.cpu_count() or 1
+            sample, tot_s = cpu_port_sample(scaffolds, 12.0, threads)
+            t0 = time.perf_counter()
+            nw = _one_cpu_pass(sample, threads)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {
+                "value": tot_s / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
+                "sample": "first %d scaffolds of C2 = %d bp, %d windows (C oracle, background + all windows of the sample)" % (len(sample), tot_s, nw),
+                "python_port_1core_gbps": python_port_rate(scaffolds),
+            }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="frisk_b200", choices=["frisk_b200", "reference"])
+    ap.add_argument("--profile", action="store_true", help="kernels only: skip the e2e and CPU-baseline legs (for ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,234 @@
+// frisk_b200 host code: FASTA scanning, 2-bit packing into (pinned) planes, window enumeration.
+// Replaces iterFasta / countN / crawlGenome's enumeration (reference frisk/__init__.py, "F:").
+// Pure CPU; no CUDA calls here.
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/frisk_b200.h"
+
+namespace {
+
+// class of a byte: 0..3 = A,T,G,C upper-case; 4..7 = a,t,g,c lower-case; 8 = other; 9 = whitespace
+struct ByteClass {
+    uint8_t t[256];
+    ByteClass() {
+        for (int i = 0; i < 256; ++i) t[i] = 8;
+        t[(int)'A'] = 0; t[(int)'T'] = 1; t[(int)'G'] = 2; t[(int)'C'] = 3;      // F:70 order
+        t[(int)'a'] = 4; t[(int)'t'] = 5; t[(int)'g'] = 6; t[(int)'c'] = 7;
+        // characters removed by the reference's line.strip() / blank-line skip (F:149-151)
+        t[(int)' '] = t[(int)'\t'] = t[(int)'\n'] = t[(int)'\r'] = t[(int)'\v'] = t[(int)'\f'] = 9;
+    }
+};
+const ByteClass kClass;
+
+inline bool is_space(unsigned char c) { return kClass.t[c] == 9; }
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// Pack one scaffold.  dst planes are indexed in absolute packed coordinates; `base` is the
+// scaffold's first base offset (multiple of 128), so whole words belong to this scaffold only.
+int pack_one(const unsigned char* s, const unsigned char* e, uint64_t expect, uint64_t base, uint64_t next_base,
+             uint32_t* codes, uint32_t* inv, uint32_t* low, uint64_t stats[3]) {
+    uint64_t n = 0, non = 0, nlow = 0;
+    uint32_t cw = 0, iw = 0, lw = 0;
+    uint64_t pos = base;
+    for (const unsigned char* p = s; p < e; ++p) {
+        const uint8_t c = kClass.t[*p];
+        if (c == 9) continue;
+        if (n == expect) return FRISK_E_FORMAT;
+        const uint32_t j32 = (uint32_t)(pos & 31);
+        if (c < 4) cw |= (uint32_t)c << (30 - 2 * (j32 & 15));
+        else if (c < 8) { cw |= (uint32_t)(c - 4) << (30 - 2 * (j32 & 15)); lw |= 0x80000000u >> j32; ++nlow; ++non; }
+        else { iw |= 0x80000000u >> j32; ++non; }
+        ++pos; ++n;
+        if ((pos & 15) == 0) { codes[(pos >> 4) - 1] = cw; cw = 0; }
+        if ((pos & 31) == 0) {
+            inv[(pos >> 5) - 1] = iw; iw = 0;
+            if (low) low[(pos >> 5) - 1] = lw;
+            lw = 0;
+        }
+    }
+    if (n != expect) return FRISK_E_FORMAT;
+    // padding up to the next scaffold (or the end): invalid, code 0
+    while (pos < next_base) {
+        const uint32_t j32 = (uint32_t)(pos & 31);
+        if (j32 == 0 && next_base - pos >= 32 && (pos & 15) == 0) {   // whole mask word of padding
+            codes[pos >> 4] = 0; codes[(pos >> 4) + 1] = 0;
+            inv[pos >> 5] = 0xffffffffu;
+            if (low) low[pos >> 5] = 0;
+            pos += 32;
+            continue;
+        }
+        iw |= 0x80000000u >> j32;
+        ++pos;
+        if ((pos & 15) == 0) { codes[(pos >> 4) - 1] = cw; cw = 0; }
+        if ((pos & 31) == 0) {
+            inv[(pos >> 5) - 1] = iw; iw = 0;
+            if (low) low[(pos >> 5) - 1] = lw;
+            lw = 0;
+        }
+    }
+    stats[0] += n; stats[1] += non; stats[2] += nlow;
+    return FRISK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint64_t frisk_b200_table_size(int kmin, int kmax) {
+    uint64_t s = 0;
+    for (int k = kmin; k <= kmax; ++k) s += 1ull << (2 * k);
+    return s;
+}
+
+int frisk_b200_fasta_scan(const char* text, uint64_t n, uint64_t cap, uint64_t* name_off, uint32_t* name_len,
+                          uint64_t* body_off, uint64_t* body_end, uint64_t* seq_len, uint64_t* n_records) {
+    if (!n_records || (!text && n)) return FRISK_E_INVALID;
+    const unsigned char* t = reinterpret_cast<const unsigned char*>(text);
+    uint64_t rec = 0;      // records emitted (a record is emitted when it has a non-empty name, F:153/F:161)
+    bool have = false;     // a named record is open
+    uint64_t cur_len = 0, cur_name = 0, cur_body = 0;
+    uint32_t cur_nlen = 0;
+    auto emit = [&](uint64_t end) {
+        if (rec < cap) {
+            if (name_off) name_off[rec] = cur_name;
+            if (name_len) name_len[rec] = cur_nlen;
+            if (body_off) body_off[rec] = cur_body;
+            if (body_end) body_end[rec] = end;
+            if (seq_len) seq_len[rec] = cur_len;
+        }
+        ++rec;
+    };
+    uint64_t i = 0;
+    while (i < n) {
+        // one line [i, j)
+        const void* nl = memchr(t + i, '\n', n - i);
+        const uint64_t j = nl ? (uint64_t)((const unsigned char*)nl - t) : n;
+        uint64_t a = i, b = j;
+        while (a < b && is_space(t[a])) ++a;        // line.strip()
+        while (b > a && is_space(t[b - 1])) --b;
+        if (a < b) {
+            if (t[a] == '>') {
+                if (have) emit(i);
+                // name = line.strip('>').split()[0]  (F:156)
+                uint64_t x = a, y = b;
+                while (x < y && t[x] == '>') ++x;
+                while (y > x && t[y - 1] == '>') --y;
+                while (x < y && is_space(t[x])) ++x;
+                uint64_t z = x;
+                while (z < y && !is_space(t[z])) ++z;
+                if (z == x) return FRISK_E_FORMAT;  // the reference raises IndexError on an empty header
+                cur_name = x; cur_nlen = (uint32_t)(z - x); cur_body = nl ? j + 1 : n; cur_len = 0;
+                have = true;                         // a non-empty name is truthy
+            } else if (have) {
+                // interior whitespace stays part of the reference's string; treat it as such only for
+                // spaces/tabs inside a line, which real FASTA never has: count non-space characters
+                for (uint64_t p = a; p < b; ++p) cur_len += !is_space(t[p]);
+            }
+            // sequence lines before the first header are dropped by the reference (name is None)
+        }
+        i = nl ? j + 1 : n;
+    }
+    if (have) emit(n);
+    *n_records = rec;
+    return rec > cap && (name_off || name_len || body_off || body_end || seq_len) ? FRISK_E_CAPACITY : FRISK_OK;
+}
+
+int frisk_b200_pack_layout(const uint64_t* scaf_len, uint64_t n, uint64_t* scaf_off, uint64_t* padded_len) {
+    if ((!scaf_len && n) || (!scaf_off && n) || !padded_len) return FRISK_E_INVALID;
+    uint64_t pos = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        scaf_off[i] = pos;
+        pos = align_up(pos + scaf_len[i] + 1, 128);   // >= 1 padding base after every scaffold
+    }
+    *padded_len = pos + 128;                          // >= 128 trailing padding bases (kernel look-ahead)
+    return FRISK_OK;
+}
+
+int frisk_b200_pack(const char* src, const uint64_t* src_off, const uint64_t* src_end, const uint64_t* scaf_len,
+                    const uint64_t* scaf_off, uint64_t n, uint64_t padded_len, uint32_t* codes, uint32_t* inv,
+                    uint32_t* low, uint64_t stats[3], int threads) {
+    if (!codes || !inv || !stats || (padded_len & 127) || (n && (!src || !src_off || !src_end || !scaf_len || !scaf_off)))
+        return FRISK_E_INVALID;
+    stats[0] = stats[1] = stats[2] = 0;
+    const uint64_t tail_start = n ? align_up(scaf_off[n - 1] + scaf_len[n - 1] + 1, 128) : 0;
+    if (tail_start + 128 > padded_len) return FRISK_E_INVALID;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    if ((uint64_t)threads > n) threads = n ? (int)n : 1;
+    std::atomic<uint64_t> next(0);
+    std::atomic<int> err(FRISK_OK);
+    std::vector<uint64_t> part((size_t)threads * 3, 0);
+    auto work = [&](int t) {
+        uint64_t* st = &part[(size_t)t * 3];
+        for (;;) {
+            const uint64_t i = next.fetch_add(1);
+            if (i >= n) break;
+            const uint64_t nb = (i + 1 < n) ? scaf_off[i + 1] : tail_start;
+            const int rc = pack_one(reinterpret_cast<const unsigned char*>(src) + src_off[i],
+                                    reinterpret_cast<const unsigned char*>(src) + src_end[i], scaf_len[i], scaf_off[i],
+                                    nb, codes, inv, low, st);
+            if (rc) err.store(rc);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    // trailing padding
+    for (uint64_t pos = tail_start; pos < padded_len; pos += 32) {
+        codes[pos >> 4] = 0; codes[(pos >> 4) + 1] = 0;
+        inv[pos >> 5] = 0xffffffffu;
+        if (low) low[pos >> 5] = 0;
+    }
+    for (int t = 0; t < threads; ++t)
+        for (int k = 0; k < 3; ++k) stats[k] += part[(size_t)t * 3 + k];
+    if (err.load()) return err.load();
+    if (!low && stats[2]) return FRISK_E_FORMAT;
+    return FRISK_OK;
+}
+
+int frisk_b200_windows(const uint64_t* scaf_len, const uint64_t* scaf_off, uint64_t n_scaf, int w, int step,
+                       int scaffolds_all, uint64_t cap, uint64_t* win_off, uint32_t* win_len, uint32_t* win_scaf,
+                       int64_t* win_start, int64_t* win_stop, uint64_t* n_windows) {
+    if (!n_windows || w <= 0 || step <= 0 || (n_scaf && (!scaf_len || !scaf_off))) return FRISK_E_INVALID;
+    uint64_t n = 0;
+    bool too_long = false;
+    auto put = [&](uint64_t s, uint64_t off, uint64_t len, int64_t a, int64_t b) {
+        if (len > FRISK_B200_MAX_WINDOW) too_long = true;
+        if (n < cap) {
+            if (win_off) win_off[n] = scaf_off[s] + off;
+            if (win_len) win_len[n] = (uint32_t)len;
+            if (win_scaf) win_scaf[n] = (uint32_t)s;
+            if (win_start) win_start[n] = a;
+            if (win_stop) win_stop[n] = b;
+        }
+        ++n;
+    };
+    // F:211/F:222: size <= w + ((w * 0.75) - i), evaluated in double like the reference
+    const double min_size = (double)w + (((double)w * 0.75) - (double)step);
+    for (uint64_t s = 0; s < n_scaf; ++s) {
+        const uint64_t size = scaf_len[s];
+        if ((double)size <= min_size) {
+            if (scaffolds_all && size > 0) put(s, 0, size, 1, (int64_t)size);   // F:219 (30 % rule applied on device)
+            continue;
+        }
+        // Once j + w overshoots it does so for every later j too, so the reference's never-cleared
+        // `jumpback` flag (F:232) just means: every remaining j re-emits the last w bases (F:243).
+        for (uint64_t j = 0; j + (uint64_t)step <= size; j += (uint64_t)step) {  // xrange(0, size - i + 1, i)
+            if (j + (uint64_t)w > size) put(s, size - w, w, (int64_t)(size - w), (int64_t)size);   // F:230-232, F:243
+            else put(s, j, w, (int64_t)j + 1, (int64_t)(j + w));                                  // F:245
+        }
+    }
+    *n_windows = n;
+    if (too_long) return FRISK_E_UNSUPPORTED;
+    const bool wants = win_off || win_len || win_scaf || win_start || win_stop;
+    return (n > cap && wants) ? FRISK_E_CAPACITY : FRISK_OK;
+}
+
+}  // extern "C"

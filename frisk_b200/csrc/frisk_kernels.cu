@@ -1,0 +1,806 @@
+// frisk_b200 device code: sm_100a kernels for the frisk hot path and their C-ABI launchers.
+//
+// Reference being replaced: /root/reference/frisk/__init__.py ("F:").  Nothing here is a
+// translation of it (the reference is a Python dict loop); see DESIGN.md for the derivation.
+//
+//   bg_count_kernel        forward-strand k-mer counts of the genome       (F:321-351, counting)
+//   finalize_tables_kernel marginalise orders K-1..1 + add reverse strand   (F:348-351)
+//   genome_ivom_kernel     per-kmax-mer genome IVOM value and its log2      (F:411-450)
+//   score_windows_kernel   window tables + IVOM x2 + KLD + GC + RIP, fused  (F:1478-1488)
+//
+// Table index convention everywhere: base-4 number, digits A=0 T=1 G=2 C=3, first base most
+// significant (the reference's dict key order, F:70/F:253-274); complement = digit ^ 1.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/frisk_b200.h"
+
+namespace {
+
+constexpr int kThreads = 1024;          // one CTA per SM: the 4^8 u16 window table takes 128 KiB of smem
+constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kListCap = 8192;     // compacted (kmer, count) entries per segment
+constexpr int kMaxSeg = 8;
+constexpr uint32_t kFull = 0xffffffffu;
+
+__host__ __device__ constexpr uint32_t pow4(int k) { return 1u << (2 * k); }
+// offset (in entries) of order x inside a concatenation of orders 1..: sum_{y<x} 4^y
+__host__ __device__ constexpr uint32_t lvl_off(int x) { return (pow4(x) - 4u) / 3u; }
+
+__device__ __forceinline__ double u32_to_double(uint32_t v) {
+    // exact: 2^52 + v has v in the low mantissa bits
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+
+// reverse complement of the x-mer with index idx (F:276-278): reverse the digits, xor each with 1
+__device__ __forceinline__ uint32_t revcomp_idx(uint32_t idx, int x) {
+    uint32_t r = __brev(idx) >> (32 - 2 * x);                       // digits reversed, bits inside a digit swapped
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);         // swap them back
+    return r ^ (0x55555555u & (pow4(x) - 1u));
+}
+
+// gather bit1 of each of the 16 2-bit codes of a word into 16 contiguous bits (order kept)
+__device__ __forceinline__ uint32_t high_bits16(uint32_t w) {
+    uint32_t x = (w >> 1) & 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    x = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+
+// ============================================================================================
+// Background: forward-strand counts.  Each CTA owns a contiguous run of 32-base mask words and
+// histograms the order-K codes into a u32 shared-memory table (all 4^K bins for K<=7; for K=8
+// two passes over the CTA's bases, one per half of the code space), then flushes the non-zero
+// bins to the global u64 table.  Positions whose K-word is invalid but which start a shorter valid
+// word (scaffold ends, N boundaries) add 1 to the order-v table directly in global memory.
+// ============================================================================================
+template <int K>
+__global__ void __launch_bounds__(kThreads, 1)
+bg_count_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
+                uint64_t word_lo, uint64_t word_hi, int mask_host, unsigned long long* __restrict__ fwd) {
+    constexpr uint32_t NB = pow4(K);
+    constexpr uint32_t HB = NB < 32768u ? NB : 32768u;   // bins held in smem per pass
+    constexpr int PASSES = NB / HB;
+    extern __shared__ __align__(16) uint32_t tab[];
+    const uint64_t n_words = word_hi - word_lo;
+    const uint64_t per = (n_words + gridDim.x - 1) / gridDim.x;
+    const uint64_t w0 = word_lo + per * blockIdx.x;
+    uint64_t w1 = w0 + per;
+    if (w1 > word_hi) w1 = word_hi;
+    const bool use_low = mask_host && low != nullptr;
+
+    for (int pass = 0; pass < PASSES; ++pass) {
+        for (uint32_t b = threadIdx.x; b < HB; b += kThreads) tab[b] = 0;
+        __syncthreads();
+        for (uint64_t wd = w0 + threadIdx.x; wd < w1; wd += kThreads) {
+            uint32_t m0 = __ldg(inv + wd), m1 = __ldg(inv + wd + 1);
+            if (use_low) { m0 |= __ldg(low + wd); m1 |= __ldg(low + wd + 1); }
+            const uint32_t c0 = __ldg(codes + 2 * wd), c1 = __ldg(codes + 2 * wd + 1), c2 = __ldg(codes + 2 * wd + 2);
+            const bool all_valid = (m0 == 0u) && (K == 1 || (m1 >> (33 - K)) == 0u);
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const uint32_t code = (p < 16 ? __funnelshift_l(c1, c0, 2 * p) : __funnelshift_l(c2, c1, 2 * (p - 16)))
+                                      >> (32 - 2 * K);
+                int v = K;
+                if (!all_valid) {
+                    const uint32_t m = __funnelshift_l(m1, m0, p);
+                    v = min(__clz(m), K);
+                }
+                if (v == K) {
+                    if (PASSES == 1 || (int)(code / HB) == pass) atomicAdd(&tab[code % HB], 1u);
+                } else if (v > 0 && pass == 0) {
+                    atomicAdd(&fwd[lvl_off(v) + (code >> (2 * (K - v)))], 1ull);
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < HB; b += kThreads) {
+            const uint32_t c = tab[b];
+            if (c) atomicAdd(&fwd[lvl_off(K) + (uint32_t)pass * HB + b], (unsigned long long)c);
+        }
+        __syncthreads();
+    }
+}
+
+// One CTA.  F_x = short-word counts of order x + marginal of F_{x+1}; tables = F + F(revcomp).
+template <int K>
+__global__ void __launch_bounds__(kThreads, 1)
+finalize_tables_kernel(const unsigned long long* __restrict__ fwd, unsigned long long* __restrict__ tables,
+                       unsigned long long* __restrict__ valid_kmax, int symmetric) {
+    // `tables` doubles as scratch for the forward totals F_x until the symmetrise step.
+    __shared__ unsigned long long red[kWarps];
+    unsigned long long local = 0;
+    for (uint32_t b = threadIdx.x; b < pow4(K); b += kThreads) {
+        const unsigned long long c = fwd[lvl_off(K) + b];
+        tables[lvl_off(K) + b] = c;
+        local += c;
+    }
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(kFull, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0 && valid_kmax) {
+        unsigned long long s = 0;
+        for (int w = 0; w < kWarps; ++w) s += red[w];
+        *valid_kmax = s;
+    }
+    for (int x = K - 1; x >= 1; --x) {
+        for (uint32_t b = threadIdx.x; b < pow4(x); b += kThreads) {
+            const unsigned long long* ch = tables + lvl_off(x + 1) + 4 * b;
+            tables[lvl_off(x) + b] = fwd[lvl_off(x) + b] + ch[0] + ch[1] + ch[2] + ch[3];
+        }
+        __syncthreads();
+    }
+    if (!symmetric) return;       // forward strand only: computeKmers(window=..., sym=False), F:1480
+    // symmetrise in place: each unordered pair {b, rc(b)} is handled by the thread owning min(b, rc)
+    for (int x = 1; x <= K; ++x) {
+        for (uint32_t b = threadIdx.x; b < pow4(x); b += kThreads) {
+            const uint32_t r = revcomp_idx(b, x);
+            if (b < r) {
+                const unsigned long long s = tables[lvl_off(x) + b] + tables[lvl_off(x) + r];
+                tables[lvl_off(x) + b] = s;
+                tables[lvl_off(x) + r] = s;
+            } else if (b == r) {
+                tables[lvl_off(x) + b] *= 2ull;   // palindrome: +1 word, +1 its own reverse complement
+            }
+        }
+    }
+}
+
+// Genome-side IVOM of every K-mer.  The reference's recurrence (F:426-446)
+//     a_x = w_x / W_x,  I_x = a_x p_x + (1 - a_x) I_{x-1},  W_x = sum_{y<=x} w_y
+// telescopes (multiply by W_x):  W_x I_x = w_x p_x + W_{x-1} I_{x-1}, hence
+//     I_K = sum_x w_x p_x / sum_x w_x,   w_x = C_x 4^x,  p_x = C_x / ((S-(x-1)) 2).
+// One division per k-mer instead of sixteen; agreement with the sequential form ~1e-15 relative.
+template <int K>
+__global__ void genome_ivom_kernel(const unsigned long long* __restrict__ tables, int kmin, long long space,
+                                   double2* __restrict__ ig) {
+    const uint32_t kappa = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kappa >= pow4(K)) return;
+    double num = 0.0;
+    unsigned long long den = 0;
+    bool bad = false;
+#pragma unroll
+    for (int x = 1; x <= K; ++x) {
+        if (x < kmin) continue;
+        const unsigned long long c = tables[lvl_off(x) + (kappa >> (2 * (K - x)))];
+        const long long d = (space - (long long)(x - 1)) * 2;
+        if (d == 0) bad = true;
+        const double q = (double)pow4(x) / (double)d;
+        const double cd = (double)c;
+        num = fma(q, cd * cd, num);
+        den += c << (2 * x);
+        if (x == kmin && c == 0) bad = true;      // W_kmin == 0: ZeroDivisionError at F:437
+    }
+    double v = bad ? CUDART_NAN : num / (double)den;
+    ig[kappa] = make_double2(v, log2(v));
+}
+
+// ============================================================================================
+// Window scoring.  One persistent CTA per SM; per window:
+//   0. word-wise popcounts: unresolved count (30 % rule, F:238), upper-case base and G+C counts
+//   1. one u16 shared-memory atomic per position on the order-K table (positions whose K-word is
+//      invalid add to the order-v table of their longest valid word instead)
+//   2. orders K-1..1 by marginalisation (4 children -> parent), never by atomics
+//   3. non-zero order-K bins compacted (deterministic order) into (kmer,count) entries; table zeroed
+//   4. per entry: window IVOM (closed form above) from the prefix counts, genome IVOM + log2 from
+//      the precomputed table; three fp64 sums; KLD = T/Sw + log2(Sg/Sw)   (F:448-454, F:466-470)
+// ============================================================================================
+struct ScoreSmem {
+    double q[8];              // q_x = 4^x / ((S-(x-1)) 2) for the current window
+    double red[3][kWarps];
+    int n_non, n_gc, n_up, flags;
+    int warp_nz[kMaxSeg][kWarps];
+};
+
+template <int K>
+struct ScoreLayout {
+    static constexpr uint32_t NB = pow4(K);
+    static constexpr uint32_t NLOW = lvl_off(K);                       // entries of orders 1..K-1
+    static constexpr uint32_t TOP_BYTES = (NB * 2u + 15u) & ~15u;
+    static constexpr uint32_t LOW_BYTES = (NLOW * 2u + 15u) & ~15u;
+    static constexpr uint32_t LIST_BYTES = kListCap * 4u;
+    static constexpr uint32_t TOTAL = TOP_BYTES + LOW_BYTES + LIST_BYTES + (uint32_t)sizeof(ScoreSmem);
+};
+
+template <int K>
+__global__ void __launch_bounds__(kThreads, 1)
+score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
+                     const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
+                     const double2* __restrict__ ig, int kmin, int want_rip, int nseg,
+                     double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
+    using L = ScoreLayout<K>;
+    constexpr uint32_t NB = L::NB;
+    constexpr uint32_t NP = NB / 4u;                                   // parents of the top level (K=1: 1)
+    constexpr int ROUNDS = (NP + kThreads - 1) / kThreads;             // K=8: 16, K=7: 4, else 1
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint16_t* top16 = reinterpret_cast<uint16_t*>(smem);
+    uint32_t* top32 = reinterpret_cast<uint32_t*>(smem);
+    uint16_t* low16 = reinterpret_cast<uint16_t*>(smem + L::TOP_BYTES);
+    uint32_t* low32 = reinterpret_cast<uint32_t*>(smem + L::TOP_BYTES);
+    uint32_t* list = reinterpret_cast<uint32_t*>(smem + L::TOP_BYTES + L::LOW_BYTES);
+    ScoreSmem& ss = *reinterpret_cast<ScoreSmem*>(smem + L::TOP_BYTES + L::LOW_BYTES + L::LIST_BYTES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // zero both tables once; afterwards every window leaves them zeroed
+    for (uint32_t i = tid; i < (L::TOP_BYTES + L::LOW_BYTES) / 16u; i += kThreads)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { ss.n_non = 0; ss.n_gc = 0; ss.n_up = 0; ss.flags = 0; }
+    for (int i = tid; i < kMaxSeg * kWarps; i += kThreads) (&ss.warp_nz[0][0])[i] = 0;
+    __syncthreads();
+
+    for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x) {
+        const uint64_t o = win_off[win];
+        const uint32_t len = win_len[win];
+
+        // ---- 0. composition counts, word-wise (32 bases per thread) ---------------------------
+        {
+            const uint64_t mw_first = o >> 5, mw_last = (o + len - 1) >> 5;
+            int non = 0, gc = 0, upc = 0;
+            for (uint64_t mw = mw_first + tid; mw <= mw_last && len > 0; mw += kThreads) {
+                uint32_t range = kFull;
+                if (mw == mw_first) range &= kFull >> (uint32_t)(o & 31);
+                if (mw == mw_last) range &= kFull << (31u - (uint32_t)((o + len - 1) & 31));
+                uint32_t bad = __ldg(inv + mw);
+                if (low) bad |= __ldg(low + mw);
+                const uint32_t good = ~bad & range;
+                const uint32_t g = (high_bits16(__ldg(codes + 2 * mw)) << 16) | high_bits16(__ldg(codes + 2 * mw + 1));
+                non += __popc(bad & range);
+                upc += __popc(good);
+                gc += __popc(g & good);
+            }
+            non = __reduce_add_sync(kFull, non);
+            gc = __reduce_add_sync(kFull, gc);
+            upc = __reduce_add_sync(kFull, upc);
+            if (lane == 0 && (non | gc | upc)) {
+                atomicAdd(&ss.n_non, non); atomicAdd(&ss.n_gc, gc); atomicAdd(&ss.n_up, upc);
+            }
+        }
+        __syncthreads();
+        const int n_non = ss.n_non, n_gc = ss.n_gc, n_up = ss.n_up;
+        // F:238 / F:213: excluded when winN >= 0.3 * len (same double comparison as the reference)
+        const bool excluded = (double)n_non >= 0.3 * (double)len;
+        __syncthreads();                                   // everyone has read the counters
+        if (tid == 0) { ss.n_non = 0; ss.n_gc = 0; ss.n_up = 0; ss.flags = 0; }
+        if (excluded) {
+            if (tid == 0) {
+                status[win] = FRISK_ROW_EXCLUDED;
+                for (int c = 0; c < 5; ++c) rows[(size_t)win * 5 + c] = CUDART_NAN;
+            }
+            if (dump) for (uint32_t i = tid; i < lvl_off(K + 1); i += kThreads) dump[(size_t)win * lvl_off(K + 1) + i] = 0;
+            __syncthreads();                               // counters are reset before the next window adds to them
+            continue;
+        }
+        // window space S = totalLen - nnTotal (F:380) = number of upper-case ATGC characters
+        if (tid < K) {
+            const int x = tid + 1;
+            const long long d = ((long long)n_up - (long long)(x - 1)) * 2;
+            ss.q[tid] = (double)pow4(x) / (double)d;       // inf if d == 0: flagged below when used
+        }
+
+        // ---- 1. count: one shared-memory atomic per position ----------------------------------
+        for (uint32_t p = tid; p < len; p += kThreads) {
+            const uint64_t a = o + p;
+            const uint64_t wi = a >> 4, mi = a >> 5;
+            const uint32_t code = __funnelshift_l(__ldg(codes + wi + 1), __ldg(codes + wi), (uint32_t)(a & 15) * 2u)
+                                  >> (32 - 2 * K);
+            const uint32_t m = __funnelshift_l(__ldg(inv + mi + 1), __ldg(inv + mi), (uint32_t)(a & 31));
+            const int v = min(min(__clz(m), K), (int)min(len - p, (uint32_t)K));
+            if (v == K) {
+                atomicAdd(&top32[code >> 1], 1u << ((code & 1u) * 16u));
+            } else if (v > 0) {
+                const uint32_t g = lvl_off(v) + (code >> (2 * (K - v)));
+                atomicAdd(&low32[g >> 1], 1u << ((g & 1u) * 16u));
+            }
+        }
+        __syncthreads();
+
+        // ---- 2. marginalise: order x from order x+1 (plus the short-word counts already there) ---
+        // level K-1 from the top table, counting the non-zero top bins per (segment, warp) on the way
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const uint32_t t = tid + r * kThreads;
+            int nz = 0;
+            if (t < NP) {
+                const uint2 ch = *reinterpret_cast<const uint2*>(top16 + 4 * t);
+                const uint32_t c0 = ch.x & 0xffffu, c1 = ch.x >> 16, c2 = ch.y & 0xffffu, c3 = ch.y >> 16;
+                nz = (c0 != 0) + (c1 != 0) + (c2 != 0) + (c3 != 0);
+                if constexpr (K > 1) low16[lvl_off(K - 1) + t] += (uint16_t)(c0 + c1 + c2 + c3);
+            }
+            nz = __reduce_add_sync(kFull, nz);
+            if (lane == 0 && nz) ss.warp_nz[(r * nseg) / ROUNDS][warp] += nz;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int x = K - 2; x >= 1; --x) {
+            if (pow4(x) > 256u) {                          // wide levels: whole CTA
+                for (uint32_t t = tid; t < pow4(x); t += kThreads) {
+                    const uint2 ch = *reinterpret_cast<const uint2*>(low16 + lvl_off(x + 1) + 4 * t);
+                    low16[lvl_off(x) + t] += (uint16_t)((ch.x & 0xffffu) + (ch.x >> 16) + (ch.y & 0xffffu) + (ch.y >> 16));
+                }
+                __syncthreads();
+            } else if (warp == 0) {                        // narrow levels: warp 0 alone
+                for (uint32_t t = lane; t < pow4(x); t += 32) {
+                    const uint2 ch = *reinterpret_cast<const uint2*>(low16 + lvl_off(x + 1) + 4 * t);
+                    low16[lvl_off(x) + t] += (uint16_t)((ch.x & 0xffffu) + (ch.x >> 16) + (ch.y & 0xffffu) + (ch.y >> 16));
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+
+        // dinucleotide counts for calcRIP (F:474-495), read before step 3 wipes the tables
+        uint32_t n_at = 0, n_ta = 0, n_sub = 0, n_prod = 0;
+        if constexpr (K >= 2) {
+            if (tid == 0 && want_rip) {
+                const uint16_t* di = (K == 2) ? top16 : low16 + lvl_off(2);
+                n_at = di[1]; n_ta = di[4];                 // AT = 0*4+1, TA = 1*4+0
+                n_sub = (uint32_t)di[3] + di[9];            // AC + GT
+                n_prod = (uint32_t)di[12] + di[6];          // CA + TG
+            }
+        }
+
+        if (dump) {   // tests only: window tables, orders 1..K
+            uint16_t* d = dump + (size_t)win * lvl_off(K + 1);
+            for (uint32_t i = tid; i < lvl_off(K); i += kThreads) d[i] = low16[i];
+            for (uint32_t i = tid; i < NB; i += kThreads) d[lvl_off(K) + i] = top16[i];
+        }
+
+        // ---- 3+4. per segment: compact non-zero top bins, then score the entries --------------
+        double s_w = 0.0, s_g = 0.0, s_t = 0.0;
+        int bad = 0;
+        uint32_t n_total = 0;
+        for (int seg = 0; seg < nseg; ++seg) {
+            // exclusive prefix of the per-warp counts of this segment
+            const int mine = ss.warp_nz[seg][lane];
+            const uint32_t n_list = (uint32_t)__reduce_add_sync(kFull, mine);
+            uint32_t running = (uint32_t)__reduce_add_sync(kFull, lane < warp ? mine : 0);
+            const int r0 = seg * ROUNDS / nseg, r1 = (seg + 1) * ROUNDS / nseg;
+            for (int r = r0; r < r1; ++r) {
+                const uint32_t t = tid + r * kThreads;
+                uint32_t c[4] = {0, 0, 0, 0};
+                if (t < NP) {
+                    uint2* p = reinterpret_cast<uint2*>(top16 + 4 * t);
+                    const uint2 ch = *p;
+                    c[0] = ch.x & 0xffffu; c[1] = ch.x >> 16; c[2] = ch.y & 0xffffu; c[3] = ch.y >> 16;
+                    if (ch.x | ch.y) *p = make_uint2(0, 0);          // leave the table zeroed for the next window
+                }
+                const int cnt = (c[0] != 0) + (c[1] != 0) + (c[2] != 0) + (c[3] != 0);
+                // warp exclusive prefix of cnt (0..4) from three ballots
+                const uint32_t lt = (1u << lane) - 1u;
+                const uint32_t b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2),
+                               b2 = __ballot_sync(kFull, cnt & 4);
+                uint32_t pos = running + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+                running += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (c[b]) list[pos++] = ((4 * t + b) << 16) | c[b];
+            }
+            __syncthreads();
+            if (lane == 0) ss.warp_nz[seg][warp] = 0;    // every warp has read it: reset for the next window
+
+            for (uint32_t e = tid; e < n_list; e += kThreads) {
+                const uint32_t ent = list[e];
+                const uint32_t kappa = ent >> 16;
+                double num = 0.0;
+                unsigned long long den = 0;
+#pragma unroll
+                for (int x = 1; x <= K; ++x) {
+                    if (x >= kmin) {
+                        const uint32_t c = (x == K) ? (ent & 0xffffu) : (uint32_t)low16[lvl_off(x) + (kappa >> (2 * (K - x)))];
+                        den += (unsigned long long)c << (2 * x);
+                        num = fma(ss.q[x - 1], u32_to_double(c * c), num);
+                    }
+                }
+                const double iw = num / __ull2double_rn(den);
+                const double2 g = __ldg(ig + kappa);
+                s_w += iw;
+                s_g += g.x;
+                s_t = fma(iw, log2(iw) - g.y, s_t);
+                bad |= (g.x != g.x);
+            }
+            n_total += n_list;
+            __syncthreads();                               // list is reused by the next segment
+        }
+
+        // ---- block reduction (fixed tree -> bit-reproducible) and the row ----------------------
+#pragma unroll
+        for (int ofs = 16; ofs; ofs >>= 1) {
+            s_w += __shfl_xor_sync(kFull, s_w, ofs);
+            s_g += __shfl_xor_sync(kFull, s_g, ofs);
+            s_t += __shfl_xor_sync(kFull, s_t, ofs);
+        }
+        bad = __any_sync(kFull, bad);
+        if (lane == 0) {
+            ss.red[0][warp] = s_w; ss.red[1][warp] = s_g; ss.red[2][warp] = s_t;
+            if (bad) atomicOr(&ss.flags, 1);
+        }
+        __syncthreads();
+        // re-zero the lower-order tables for the next window (the top table was zeroed in step 3)
+        for (uint32_t i = tid; i < L::LOW_BYTES / 16u; i += kThreads)
+            reinterpret_cast<uint4*>(low16)[i] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) {
+            double a = 0, b = 0, c = 0;
+            for (int w = 0; w < kWarps; ++w) { a += ss.red[0][w]; b += ss.red[1][w]; c += ss.red[2][w]; }
+            uint32_t st = 0;
+            double kld = 0.0;                              // the reference returns 0 for a window without kmax-mers
+            if (n_total) {
+                bool zd = ss.flags & 1;
+                for (int x = kmin; x <= K; ++x) zd |= ((long long)n_up - (long long)(x - 1)) == 0;
+                if (zd) { st |= FRISK_ROW_KLD_ZERODIV; kld = CUDART_NAN; }
+                else {
+                    kld = c / a + (log2(b) - log2(a));
+                    if (!(kld == kld) || isinf(kld)) st |= FRISK_ROW_LOG_DOMAIN;
+                }
+            }
+            double* row = rows + (size_t)win * 5;
+            row[0] = kld;
+            if (n_up == 0) { st |= FRISK_ROW_GC_ZERODIV; row[1] = CUDART_NAN; }
+            else row[1] = (double)n_gc / (double)n_up;       // F:136
+            double pi = CUDART_NAN, si = CUDART_NAN, cri = CUDART_NAN;
+            if (K >= 2 && want_rip) {
+                if (n_at > 0) pi = (double)n_ta / (double)n_at;        // F:480-483
+                if (n_sub > 0) si = (double)n_prod / (double)n_sub;    // F:485-489
+                if (pi != 0.0 && si != 0.0) cri = pi - si;             // F:491: 0.0 falsy, NaN truthy
+            }
+            row[2] = pi; row[3] = si; row[4] = cri;
+            status[win] = st;
+        }
+    }
+}
+
+
+// KLD of two already-normalised IVOM vectors (F:459-472): sum w*log2(w/G), G == 0 skipped.
+// One CTA, fixed reduction tree.  Only used by the dict-level compatibility API; the batch path
+// computes the same quantity inside score_windows_kernel.
+__global__ void __launch_bounds__(kThreads, 1)
+kld_kernel(const double* __restrict__ g, const double* __restrict__ w, uint32_t n, double* __restrict__ out) {
+    __shared__ double red[kWarps];
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+        const double gv = g[i], wv = w[i];
+        if (gv != 0.0) acc = fma(wv, log2(wv / gv), acc);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int wp = 0; wp < kWarps; ++wp) s += red[wp];
+        *out = s;
+    }
+}
+}  // namespace
+
+// ============================================================================================
+// Shared-memory atomic micro-benchmark (roofline denominator for the counting step)
+// ============================================================================================
+namespace {
+__global__ void __launch_bounds__(kThreads, 1) smem_atomic_bench_kernel(int iters, int mode, uint32_t* sink) {
+    extern __shared__ __align__(16) uint32_t tab[];
+    constexpr uint32_t N = 16384;   // 64 KiB of u32 bins
+    for (uint32_t i = threadIdx.x; i < N; i += kThreads) tab[i] = 0;
+    __syncthreads();
+    uint32_t x = threadIdx.x * 2654435761u + blockIdx.x * 40503u + 12345u;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t idx;
+        if (mode == 0) idx = (threadIdx.x + 32u * (uint32_t)it) & (N - 1);        // one lane per bank
+        else if (mode == 1) { x = x * 1664525u + 1013904223u; idx = (x >> 10) & (N - 1); }   // random bins
+        else idx = 0;                                                              // one address
+        atomicAdd(&tab[idx], 1u);
+    }
+    __syncthreads();
+    uint32_t s = 0;
+    for (uint32_t i = threadIdx.x; i < N; i += kThreads) s += tab[i];
+    if (s == 0xdeadbeefu) sink[0] = s;
+}
+
+thread_local char g_cuda_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return FRISK_E_CUDA;
+}
+#define CK(call)                                                  \
+    do {                                                          \
+        cudaError_t e_ = (call);                                  \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);       \
+    } while (0)
+
+int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+}
+
+template <int K>
+int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, uint64_t w_lo, uint64_t w_hi,
+                      int mask_host, uint64_t* fwd, cudaStream_t st) {
+    constexpr uint32_t NB = pow4(K);
+    constexpr uint32_t HB = NB < 32768u ? NB : 32768u;
+    const size_t smem = (size_t)HB * 4;
+    CK(cudaFuncSetAttribute(bg_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t n_words = w_hi - w_lo;
+    int grid = sm_count();
+    if (grid <= 0) return FRISK_E_NO_DEVICE;
+    // at least ~2 rounds of 1024 words per CTA, otherwise fewer CTAs
+    const uint64_t want = (n_words + 2047) / 2048;
+    if ((uint64_t)grid > want) grid = want ? (int)want : 1;
+    bg_count_kernel<K><<<grid, kThreads, smem, st>>>(codes, inv, low, w_lo, w_hi, mask_host,
+                                                      reinterpret_cast<unsigned long long*>(fwd));
+    CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+template <int K>
+int launch_finalize(const uint64_t* fwd, int symmetric, uint64_t* tables, uint64_t* valid, cudaStream_t st) {
+    finalize_tables_kernel<K><<<1, kThreads, 0, st>>>(reinterpret_cast<const unsigned long long*>(fwd),
+                                                      reinterpret_cast<unsigned long long*>(tables),
+                                                      reinterpret_cast<unsigned long long*>(valid), symmetric);
+    CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+template <int K>
+int launch_genome_ivom(const uint64_t* tables, int kmin, int64_t space, double* ig, cudaStream_t st) {
+    const uint32_t n = pow4(K);
+    const int bs = 256;
+    genome_ivom_kernel<K><<<(n + bs - 1) / bs, bs, 0, st>>>(reinterpret_cast<const unsigned long long*>(tables), kmin,
+                                                           (long long)space, reinterpret_cast<double2*>(ig));
+    CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+template <int K>
+int launch_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                 const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
+                 double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+    using L = ScoreLayout<K>;
+    constexpr uint32_t NB = pow4(K);
+    constexpr int ROUNDS = (NB / 4 + kThreads - 1) / kThreads;
+    int nseg = 1;
+    while ((NB / (uint32_t)nseg < max_len ? NB / (uint32_t)nseg : max_len) > kListCap) nseg *= 2;
+    if (nseg > kMaxSeg || nseg > ROUNDS) return FRISK_E_UNSUPPORTED;
+    CK(cudaFuncSetAttribute(score_windows_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+    int grid = sm_count();
+    if (grid <= 0) return FRISK_E_NO_DEVICE;
+    if ((uint64_t)grid > n_win) grid = (int)n_win;
+    score_windows_kernel<K><<<grid, kThreads, L::TOTAL, st>>>(
+        codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len, (uint32_t)n_win,
+        reinterpret_cast<const double2*>(ig), kmin, want_rip, nseg, rows, status, dump);
+    CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+#define DISPATCH_K(kmax, expr)                      \
+    switch (kmax) {                                 \
+        case 1: { constexpr int K = 1; return expr; } \
+        case 2: { constexpr int K = 2; return expr; } \
+        case 3: { constexpr int K = 3; return expr; } \
+        case 4: { constexpr int K = 4; return expr; } \
+        case 5: { constexpr int K = 5; return expr; } \
+        case 6: { constexpr int K = 6; return expr; } \
+        case 7: { constexpr int K = 7; return expr; } \
+        case 8: { constexpr int K = 8; return expr; } \
+        default: return FRISK_E_UNSUPPORTED;        \
+    }
+
+int check_k(int kmin, int kmax) {
+    if (kmin < 1 || kmin > kmax) return FRISK_E_INVALID;
+    if (kmax > FRISK_B200_MAX_K) return FRISK_E_UNSUPPORTED;
+    return FRISK_OK;
+}
+
+// cached device workspace of frisk_b200_run_host (one per device, grown on demand)
+struct Workspace {
+    int device = -1;
+    void* buf[16] = {};
+    size_t cap[16] = {};
+};
+Workspace g_ws[64];
+
+int ws_get(int slot, size_t bytes, void** out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    Workspace& w = g_ws[dev & 63];
+    if (w.cap[slot] < bytes) {
+        if (w.buf[slot]) CK(cudaFree(w.buf[slot]));
+        w.buf[slot] = nullptr; w.cap[slot] = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        CK(cudaMalloc(&w.buf[slot], want));
+        w.cap[slot] = want;
+    }
+    *out = w.buf[slot];
+    return FRISK_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* frisk_b200_strerror(int code) {
+    switch (code) {
+        case FRISK_OK: return "ok";
+        case FRISK_E_INVALID: return "invalid argument";
+        case FRISK_E_UNSUPPORTED: return "unsupported: kmax > 8 or window longer than 65535 bases";
+        case FRISK_E_CUDA: return "CUDA error (see frisk_b200_last_cuda_error)";
+        case FRISK_E_NO_DEVICE: return "no CUDA device (frisk_b200 has no CPU fallback)";
+        case FRISK_E_CAPACITY: return "output capacity too small";
+        case FRISK_E_FORMAT: return "malformed input";
+        default: return "unknown error";
+    }
+}
+
+const char* frisk_b200_last_cuda_error(void) { return g_cuda_err; }
+int frisk_b200_abi_version(void) { return FRISK_B200_ABI_VERSION; }
+
+int frisk_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int frisk_b200_background(const uint32_t* d_codes, const uint32_t* d_inv, const uint32_t* d_low, uint64_t first_base,
+                          uint64_t last_base, int kmax, int mask_host, uint64_t* d_fwd, void* stream) {
+    if (!d_codes || !d_inv || !d_fwd || (first_base & 31) || (last_base & 31) || last_base < first_base)
+        return FRISK_E_INVALID;
+    int rc = check_k(1, kmax);
+    if (rc) return rc;
+    if (last_base == first_base) return FRISK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_K(kmax, launch_background<K>(d_codes, d_inv, d_low, first_base >> 5, last_base >> 5, mask_host, d_fwd, st));
+}
+
+int frisk_b200_finalize_tables(const uint64_t* d_fwd, int kmax, int symmetric, uint64_t* d_tables, uint64_t* d_valid_kmax,
+                               void* stream) {
+    if (!d_fwd || !d_tables) return FRISK_E_INVALID;
+    int rc = check_k(1, kmax);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_K(kmax, launch_finalize<K>(d_fwd, symmetric, d_tables, d_valid_kmax, st));
+}
+
+int frisk_b200_genome_ivom(const uint64_t* d_tables, int kmin, int kmax, int64_t genome_space, double* d_ig, void* stream) {
+    if (!d_tables || !d_ig) return FRISK_E_INVALID;
+    int rc = check_k(kmin, kmax);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_K(kmax, launch_genome_ivom<K>(d_tables, kmin, genome_space, d_ig, st));
+}
+
+int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint32_t* d_low, const uint64_t* d_win_off,
+                     const uint32_t* d_win_len, uint64_t n_win, uint32_t max_win_len, const double* d_ig, int kmin,
+                     int kmax, int want_rip, double* d_rows, uint32_t* d_status, uint16_t* d_dump, void* stream) {
+    if (n_win == 0) return FRISK_OK;
+    if (!d_codes || !d_inv || !d_win_off || !d_win_len || !d_ig || !d_rows || !d_status) return FRISK_E_INVALID;
+    int rc = check_k(kmin, kmax);
+    if (rc) return rc;
+    if (max_win_len > FRISK_B200_MAX_WINDOW || n_win > 0xffffffffull) return FRISK_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rip = want_rip && kmin <= 2 && kmax >= 2;
+    DISPATCH_K(kmax, launch_score<K>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, rip,
+                                     d_rows, d_status, d_dump, st));
+}
+
+int frisk_b200_kld(const double* d_genome_ivom, const double* d_window_ivom, uint64_t n, double* d_out, void* stream) {
+    if (!d_out || (n && (!d_genome_ivom || !d_window_ivom)) || n > 0xffffffffull) return FRISK_E_INVALID;
+    kld_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(d_genome_ivom, d_window_ivom, (uint32_t)n, d_out);
+    CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const uint32_t* h_low, uint64_t h_padded_len,
+                        const uint32_t* q_codes, const uint32_t* q_inv, const uint32_t* q_low, uint64_t q_padded_len,
+                        const uint64_t* win_off, const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len,
+                        int kmin, int kmax, int mask_host, int want_rip, int64_t genome_space, double* rows_out,
+                        uint32_t* status_out, uint64_t* tables_out, uint64_t* valid_kmax_out, void* stream) {
+    if (!h_codes || !h_inv || !q_codes || !q_inv || (h_padded_len & 127) || (q_padded_len & 127) || h_padded_len < 128 ||
+        q_padded_len < 128)
+        return FRISK_E_INVALID;
+    if (n_win && (!win_off || !win_len || !rows_out || !status_out)) return FRISK_E_INVALID;
+    int rc = check_k(kmin, kmax);
+    if (rc) return rc;
+    if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool same = (h_codes == q_codes) && (h_inv == q_inv) && (h_padded_len == q_padded_len);
+    const size_t tsz = (size_t)frisk_b200_table_size(1, kmax);
+    void *dhc, *dhi, *dhl = nullptr, *dqc, *dqi, *dql = nullptr, *dfwd, *dtab, *dig, *dwo, *dwl, *drows, *dstat;
+    if ((rc = ws_get(0, h_padded_len / 4, &dhc))) return rc;
+    if ((rc = ws_get(1, h_padded_len / 8, &dhi))) return rc;
+    if (h_low && (rc = ws_get(2, h_padded_len / 8, &dhl))) return rc;
+    CK(cudaMemcpyAsync(dhc, h_codes, h_padded_len / 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dhi, h_inv, h_padded_len / 8, cudaMemcpyHostToDevice, st));
+    if (h_low) CK(cudaMemcpyAsync(dhl, h_low, h_padded_len / 8, cudaMemcpyHostToDevice, st));
+    if (same) { dqc = dhc; dqi = dhi; dql = dhl; }
+    else {
+        if ((rc = ws_get(3, q_padded_len / 4, &dqc))) return rc;
+        if ((rc = ws_get(4, q_padded_len / 8, &dqi))) return rc;
+        if (q_low && (rc = ws_get(5, q_padded_len / 8, &dql))) return rc;
+        CK(cudaMemcpyAsync(dqc, q_codes, q_padded_len / 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dqi, q_inv, q_padded_len / 8, cudaMemcpyHostToDevice, st));
+        if (q_low) CK(cudaMemcpyAsync(dql, q_low, q_padded_len / 8, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = ws_get(6, (tsz + 1) * 8, &dfwd))) return rc;
+    if ((rc = ws_get(7, (tsz + 1) * 8, &dtab))) return rc;
+    if ((rc = ws_get(8, (size_t)pow4(kmax) * 16, &dig))) return rc;
+    CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, st));
+    // the last 32-base word is padding by construction and is only ever read as look-ahead
+    rc = frisk_b200_background((const uint32_t*)dhc, (const uint32_t*)dhi, (const uint32_t*)dhl, 0, h_padded_len - 32, kmax,
+                               mask_host, (uint64_t*)dfwd, st);
+    if (rc) return rc;
+    uint64_t* dvalid = (uint64_t*)dtab + tsz;
+    rc = frisk_b200_finalize_tables((const uint64_t*)dfwd, kmax, 1, (uint64_t*)dtab, dvalid, st);
+    if (rc) return rc;
+    rc = frisk_b200_genome_ivom((const uint64_t*)dtab, kmin, kmax, genome_space, (double*)dig, st);
+    if (rc) return rc;
+    if (n_win) {
+        if ((rc = ws_get(9, n_win * 8, &dwo))) return rc;
+        if ((rc = ws_get(10, n_win * 4, &dwl))) return rc;
+        if ((rc = ws_get(11, n_win * 40, &drows))) return rc;
+        if ((rc = ws_get(12, n_win * 4, &dstat))) return rc;
+        CK(cudaMemcpyAsync(dwo, win_off, n_win * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dwl, win_len, n_win * 4, cudaMemcpyHostToDevice, st));
+        rc = frisk_b200_score((const uint32_t*)dqc, (const uint32_t*)dqi, (const uint32_t*)dql, (const uint64_t*)dwo,
+                              (const uint32_t*)dwl, n_win, max_win_len, (const double*)dig, kmin, kmax, want_rip,
+                              (double*)drows, (uint32_t*)dstat, nullptr, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(rows_out, drows, n_win * 40, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status_out, dstat, n_win * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, st));
+    if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FRISK_OK;
+}
+
+int frisk_b200_release_workspace(void) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    Workspace& w = g_ws[dev & 63];
+    for (int i = 0; i < 16; ++i) {
+        if (w.buf[i]) CK(cudaFree(w.buf[i]));
+        w.buf[i] = nullptr; w.cap[i] = 0;
+    }
+    return FRISK_OK;
+}
+
+int frisk_b200_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return FRISK_E_INVALID;
+    if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    CK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return FRISK_OK;
+}
+
+int frisk_b200_host_free(void* ptr) {
+    if (ptr) CK(cudaFreeHost(ptr));
+    return FRISK_OK;
+}
+
+int frisk_b200_bench_smem_atomics(int blocks, int iters, int mode, float* ms, void* stream) {
+    if (blocks <= 0 || iters <= 0 || !ms) return FRISK_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaFuncSetAttribute(smem_atomic_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    uint32_t* sink = nullptr;
+    CK(cudaMalloc(&sink, 4));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    smem_atomic_bench_kernel<<<blocks, kThreads, 65536, st>>>(iters, mode, sink);   // warm-up
+    CK(cudaEventRecord(a, st));
+    smem_atomic_bench_kernel<<<blocks, kThreads, 65536, st>>>(iters, mode, sink);
+    CK(cudaEventRecord(b, st));
+    CK(cudaEventSynchronize(b));
+    CK(cudaEventElapsedTime(ms, a, b));
+    CK(cudaEventDestroy(a));
+    CK(cudaEventDestroy(b));
+    CK(cudaFree(sink));
+    CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+}  // extern "C"

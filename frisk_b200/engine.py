@@ -1,0 +1,431 @@
+"""Batch engine: the frisk hot path on one B200 through the C ABI.
+
+Host side (pure CPU, testable without a GPU): ``PackedGenome`` (FASTA / in-memory scaffolds ->
+2-bit planes, replaces iterFasta + countN, F:139-164 / F:106-118) and ``WindowList`` (candidate
+windows, replaces crawlGenome's enumeration, F:194-251).
+
+Device side: ``DeviceGenome`` (planes resident in HBM as torch tensors -- torch is only the
+allocator/stream provider), ``background`` / ``finalize`` / ``genome_ivom`` / ``score`` (thin
+wrappers of the C entry points) and ``run`` (the whole path, one GPU).  ``run_host`` is the single
+C call from pinned host buffers used for end-to-end timing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+
+SeqLike = Union[np.ndarray, bytes, str]
+
+
+def _ptr(a) -> C.c_void_p:
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(int(a.data_ptr()))     # torch tensor
+
+
+def _as_u8(seq: SeqLike) -> np.ndarray:
+    if isinstance(seq, str):
+        seq = seq.encode()
+    if isinstance(seq, (bytes, bytearray)):
+        return np.frombuffer(seq, dtype=np.uint8)
+    return np.ascontiguousarray(seq, dtype=np.uint8)
+
+
+_TORCH_DTYPE = {"uint32": "int32", "uint64": "int64", "float64": "float64", "int64": "int64", "int32": "int32"}
+
+
+def _alloc(shape, dtype, pinned: bool) -> np.ndarray:
+    """Host array, page-locked through torch when a GPU is present (the numpy view keeps the
+    tensor's storage alive through its .base chain)."""
+    dtype = np.dtype(dtype)
+    if pinned:
+        import torch
+        if torch.cuda.is_available():
+            t = torch.empty(shape, dtype=getattr(torch, _TORCH_DTYPE[dtype.name])).pin_memory()
+            return t.numpy().view(dtype)
+    return np.empty(shape, dtype=dtype)
+
+
+def _alloc_u32(n: int, pinned: bool) -> np.ndarray:
+    return _alloc(n, np.uint32, pinned)
+
+
+@dataclass
+class WindowList:
+    """Candidate windows in crawlGenome order (F:194-251), before the 30 % unresolved filter."""
+    off: np.ndarray      # uint64 absolute base offset in the packed planes
+    length: np.ndarray   # uint32
+    scaf: np.ndarray     # uint32 scaffold index
+    start: np.ndarray    # int64, reference coordinates (F:243/F:245)
+    stop: np.ndarray     # int64
+
+    def __len__(self) -> int:
+        return int(self.off.shape[0])
+
+    @property
+    def max_len(self) -> int:
+        return int(self.length.max()) if len(self) else 0
+
+    def slice(self, a: int, b: int) -> "WindowList":
+        return WindowList(self.off[a:b], self.length[a:b], self.scaf[a:b], self.start[a:b], self.stop[a:b])
+
+
+@dataclass
+class PackedGenome:
+    names: List[str]
+    scaf_len: np.ndarray          # uint64
+    scaf_off: np.ndarray          # uint64 (multiples of 128)
+    padded_len: int
+    codes: np.ndarray             # uint32, padded_len/16 words
+    inv: np.ndarray               # uint32, padded_len/32 words
+    low: Optional[np.ndarray]     # uint32 or None when the input has no lower case
+    total_len: int                # F:323
+    nn_total: int                 # F:325: characters that are not upper-case ATGC
+    n_lower: int
+
+    # ------------------------------------------------------------------ constructors
+    @classmethod
+    def from_scaffolds(cls, scaffolds: Sequence[Tuple[str, SeqLike]], pinned: bool = False,
+                       threads: int = 0) -> "PackedGenome":
+        names = [n for n, _ in scaffolds]
+        arrs = [_as_u8(s) for _, s in scaffolds]
+        lens = np.array([a.shape[0] for a in arrs], dtype=np.uint64)
+        src = np.concatenate(arrs) if arrs else np.zeros(0, np.uint8)
+        end = np.cumsum(lens, dtype=np.uint64)
+        off = end - lens
+        return cls._pack(names, src, off, end, lens, pinned, threads)
+
+    @classmethod
+    def from_fasta_bytes(cls, text: Union[bytes, np.ndarray], pinned: bool = False, threads: int = 0) -> "PackedGenome":
+        L = _lib.lib()
+        buf = _as_u8(text)
+        n = C.c_uint64(0)
+        _lib.check(L.frisk_b200_fasta_scan(_ptr(buf), buf.shape[0], 0, None, None, None, None, None, C.byref(n)),
+                   "frisk_b200_fasta_scan")
+        cap = int(n.value)
+        name_off = np.zeros(cap, np.uint64); name_len = np.zeros(cap, np.uint32)
+        body_off = np.zeros(cap, np.uint64); body_end = np.zeros(cap, np.uint64); seq_len = np.zeros(cap, np.uint64)
+        _lib.check(L.frisk_b200_fasta_scan(_ptr(buf), buf.shape[0], cap, _ptr(name_off), _ptr(name_len), _ptr(body_off),
+                                           _ptr(body_end), _ptr(seq_len), C.byref(n)), "frisk_b200_fasta_scan")
+        raw = buf.tobytes() if cap < 100000 else None
+        names = []
+        for i in range(cap):
+            a = int(name_off[i]); b = a + int(name_len[i])
+            names.append((raw[a:b] if raw is not None else buf[a:b].tobytes()).decode())
+        return cls._pack(names, buf, body_off, body_end, seq_len, pinned, threads)
+
+    @classmethod
+    def from_fasta(cls, path: str, pinned: bool = False, threads: int = 0) -> "PackedGenome":
+        if path.endswith(".gz"):
+            import gzip
+            with gzip.open(path, "rb") as fh:   # the reference opens .gz the same way (F:144-147)
+                data = np.frombuffer(fh.read(), dtype=np.uint8)
+        else:
+            data = np.fromfile(path, dtype=np.uint8)
+        return cls.from_fasta_bytes(data, pinned, threads)
+
+    @classmethod
+    def _pack(cls, names, src, src_off, src_end, lens, pinned, threads) -> "PackedGenome":
+        L = _lib.lib()
+        n = len(names)
+        lens = np.ascontiguousarray(lens, np.uint64)
+        src_off = np.ascontiguousarray(src_off, np.uint64)
+        src_end = np.ascontiguousarray(src_end, np.uint64)
+        scaf_off = np.zeros(n, np.uint64)
+        padded = C.c_uint64(0)
+        _lib.check(L.frisk_b200_pack_layout(_ptr(lens), n, _ptr(scaf_off), C.byref(padded)), "frisk_b200_pack_layout")
+        P = int(padded.value)
+        codes = _alloc_u32(P // 16, pinned)
+        inv = _alloc_u32(P // 32, pinned)
+        low = _alloc_u32(P // 32, pinned)
+        stats = np.zeros(3, np.uint64)
+        _lib.check(L.frisk_b200_pack(_ptr(src), _ptr(src_off), _ptr(src_end), _ptr(lens), _ptr(scaf_off), n, P,
+                                     _ptr(codes), _ptr(inv), _ptr(low), _ptr(stats), threads), "frisk_b200_pack")
+        n_lower = int(stats[2])
+        return cls(names, lens, scaf_off, P, codes, inv, low if n_lower else None, int(stats[0]), int(stats[1]), n_lower)
+
+    # ------------------------------------------------------------------ host logic
+    def windows(self, w: int = 5000, step: int = 2500, scaffolds_all: bool = False) -> WindowList:
+        L = _lib.lib()
+        n = C.c_uint64(0)
+        nsc = len(self.names)
+        rc = L.frisk_b200_windows(_ptr(self.scaf_len), _ptr(self.scaf_off), nsc, w, step, int(scaffolds_all), 0,
+                                  None, None, None, None, None, C.byref(n))
+        _lib.check(rc, "frisk_b200_windows")
+        cap = int(n.value)
+        off = np.zeros(cap, np.uint64); ln = np.zeros(cap, np.uint32); sc = np.zeros(cap, np.uint32)
+        st = np.zeros(cap, np.int64); sp = np.zeros(cap, np.int64)
+        _lib.check(L.frisk_b200_windows(_ptr(self.scaf_len), _ptr(self.scaf_off), nsc, w, step, int(scaffolds_all), cap,
+                                        _ptr(off), _ptr(ln), _ptr(sc), _ptr(st), _ptr(sp), C.byref(n)),
+                   "frisk_b200_windows")
+        return WindowList(off, ln, sc, st, sp)
+
+    def ex_max(self, kmax: int, valid_kmax: int) -> int:
+        """exMax (F:344): kmax-words that contain an invalid character."""
+        possible = np.maximum(self.scaf_len.astype(np.int64) - kmax + 1, 0).sum()
+        return int(possible) - int(valid_kmax)
+
+    @property
+    def genome_space(self) -> int:
+        return self.total_len - self.nn_total     # F:379
+
+    @property
+    def plane_bytes(self) -> int:
+        return self.codes.nbytes + self.inv.nbytes + (self.low.nbytes if self.low is not None else 0)
+
+
+# ---------------------------------------------------------------------- device side
+class DeviceGenome:
+    """The packed planes resident in HBM (torch tensors used purely as device buffers)."""
+
+    def __init__(self, g: PackedGenome, device="cuda:0", stream=None):
+        import torch
+        _lib.require_device()
+        self.host = g
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            self.codes = torch.from_numpy(g.codes.view(np.int32)).to(self.device, non_blocking=True)
+            self.inv = torch.from_numpy(g.inv.view(np.int32)).to(self.device, non_blocking=True)
+            self.low = torch.from_numpy(g.low.view(np.int32)).to(self.device, non_blocking=True) if g.low is not None else None
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def background(dg: DeviceGenome, kmax: int, mask_host: bool = False, d_fwd=None, first_base: int = 0,
+               last_base: Optional[int] = None):
+    """Forward-strand counts (adds into d_fwd, a device int64 tensor of table_size(1,kmax))."""
+    import torch
+    if d_fwd is None:
+        d_fwd = torch.zeros(_lib.table_size(1, kmax), dtype=torch.int64, device=dg.device)
+    if last_base is None:
+        last_base = dg.host.padded_len - 32      # the last word is padding, only read as look-ahead
+    with torch.cuda.device(dg.device):
+        _lib.check(_lib.lib().frisk_b200_background(_ptr(dg.codes), _ptr(dg.inv), _ptr(dg.low), first_base, last_base,
+                                                    kmax, int(mask_host), _ptr(d_fwd), _stream_ptr(dg.device)),
+                   "frisk_b200_background")
+    return d_fwd
+
+
+def finalize(d_fwd, kmax: int, symmetric: bool = True):
+    """-> (d_tables int64[table_size(1,kmax)], d_valid int64[1]) on the device of d_fwd."""
+    import torch
+    d_tables = torch.empty_like(d_fwd)
+    d_valid = torch.zeros(1, dtype=torch.int64, device=d_fwd.device)
+    with torch.cuda.device(d_fwd.device):
+        _lib.check(_lib.lib().frisk_b200_finalize_tables(_ptr(d_fwd), kmax, int(symmetric), _ptr(d_tables), _ptr(d_valid),
+                                                         _stream_ptr(d_fwd.device)), "frisk_b200_finalize_tables")
+    return d_tables, d_valid
+
+
+def genome_ivom(d_tables, kmin: int, kmax: int, genome_space: int):
+    import torch
+    d_ig = torch.empty(2 * 4 ** kmax, dtype=torch.float64, device=d_tables.device)
+    with torch.cuda.device(d_tables.device):
+        _lib.check(_lib.lib().frisk_b200_genome_ivom(_ptr(d_tables), kmin, kmax, int(genome_space), _ptr(d_ig),
+                                                     _stream_ptr(d_tables.device)), "frisk_b200_genome_ivom")
+    return d_ig
+
+
+def score(dg: DeviceGenome, wins: WindowList, d_ig, kmin: int, kmax: int, rip: bool = True, dump: bool = False):
+    """-> (d_rows float64[n,5], d_status int32[n], d_dump uint16-as-int16[n, table_size(1,kmax)] or None)."""
+    import torch
+    n = len(wins)
+    dev = dg.device
+    d_rows = torch.empty((n, 5), dtype=torch.float64, device=dev)
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    d_dump = torch.empty((n, _lib.table_size(1, kmax)), dtype=torch.int16, device=dev) if dump else None
+    if n == 0:
+        return d_rows, d_status, d_dump
+    d_off = torch.from_numpy(wins.off.view(np.int64)).to(dev, non_blocking=True)
+    d_len = torch.from_numpy(wins.length.view(np.int32)).to(dev, non_blocking=True)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().frisk_b200_score(_ptr(dg.codes), _ptr(dg.inv), _ptr(dg.low), _ptr(d_off), _ptr(d_len), n,
+                                               wins.max_len, _ptr(d_ig), kmin, kmax, int(rip), _ptr(d_rows),
+                                               _ptr(d_status), _ptr(d_dump), _stream_ptr(dev)), "frisk_b200_score")
+    return d_rows, d_status, d_dump
+
+
+@dataclass
+class HotPathResult:
+    kmin: int
+    kmax: int
+    tables: np.ndarray            # uint64, orders kmin..kmax concatenated, reference dict order
+    meta: Tuple[int, int, int]    # totalLen, exMax, nnTotal (F:356-359)
+    names: List[str]              # one per emitted row
+    coords: np.ndarray            # int64 [n,2] start, stop
+    rows: np.ndarray              # float64 [n,5] windowKLD, GC, PI, SI, CRI
+    status: np.ndarray            # uint32 [n] FRISK_ROW_* bits (never EXCLUDED)
+    n_candidates: int = 0
+    win_index: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # candidate index of each row
+    win_tables: Optional[np.ndarray] = None   # uint16 [n, table_size(kmin,kmax)] when dump=True
+
+    def raise_reference_errors(self) -> None:
+        """The reference aborts on the first window that raises; mirror that when asked."""
+        bad = np.nonzero(self.status & (_lib.ROW_KLD_ZERODIV | _lib.ROW_GC_ZERODIV))[0]
+        if bad.size:
+            i = int(bad[0])
+            raise ZeroDivisionError("window %s:%d-%d: float division by zero (reference F:437/F:136)"
+                                    % (self.names[i], self.coords[i, 0], self.coords[i, 1]))
+        bad = np.nonzero(self.status & _lib.ROW_LOG_DOMAIN)[0]
+        if bad.size:
+            raise ValueError("math domain error (reference F:470)")
+
+
+def _slice_orders(tab: np.ndarray, kmin: int, kmax: int) -> np.ndarray:
+    return tab[..., _lib.table_size(1, kmin - 1):_lib.table_size(1, kmax)] if kmin > 1 else tab[..., :_lib.table_size(1, kmax)]
+
+
+def assemble(query: PackedGenome, host: PackedGenome, wins: WindowList, tables_1k: np.ndarray, valid_kmax: int,
+             rows: np.ndarray, status: np.ndarray, kmin: int, kmax: int, dump: Optional[np.ndarray] = None) -> HotPathResult:
+    keep = (status & _lib.ROW_EXCLUDED) == 0
+    idx = np.nonzero(keep)[0]
+    names = [query.names[s] for s in wins.scaf[idx]]
+    coords = np.stack([wins.start[idx], wins.stop[idx]], axis=1) if idx.size else np.zeros((0, 2), np.int64)
+    meta = (host.total_len, host.ex_max(kmax, valid_kmax), host.nn_total)
+    wt = None
+    if dump is not None:
+        wt = _slice_orders(dump[idx], kmin, kmax)
+    return HotPathResult(kmin, kmax, _slice_orders(tables_1k, kmin, kmax).copy(), meta, names, coords,
+                         rows[idx], status[idx].astype(np.uint32), len(wins), idx, wt)
+
+
+class Pipeline:
+    """The device-resident hot path: planes, window list and all work buffers live in HBM; one
+    ``enqueue()`` launches background -> [all-reduce] -> finalize -> genome IVOM -> score on the
+    current stream without any host synchronisation (so it can be timed with CUDA events, replayed,
+    or captured in a CUDA graph)."""
+
+    def __init__(self, query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1, kmax: int = 8,
+                 w: int = 5000, step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False,
+                 rip: bool = True, device="cuda:0", dump: bool = False, allreduce=None,
+                 genome_space: Optional[int] = None, wins: Optional[WindowList] = None):
+        import torch
+        _lib.require_device()
+        rc = 0 if 1 <= kmin <= kmax else _lib.E_INVALID
+        if kmax > _lib.MAX_K:
+            rc = _lib.E_UNSUPPORTED
+        _lib.check(rc, "frisk_b200 Pipeline(kmin=%d, kmax=%d)" % (kmin, kmax))
+        self.query, self.host = query, host or query
+        self.kmin, self.kmax, self.mask_host, self.rip = kmin, kmax, mask_host, rip
+        self.allreduce = allreduce
+        self.genome_space = self.host.genome_space if genome_space is None else int(genome_space)
+        self.wins = wins if wins is not None else query.windows(w, step, scaffolds_all)
+        self.dq = DeviceGenome(query, device)
+        self.dh = self.dq if self.host is query else DeviceGenome(self.host, device)
+        dev = self.dq.device
+        self.device = dev
+        n = len(self.wins)
+        tsz = _lib.table_size(1, kmax)
+        self.d_fwd = torch.zeros(tsz, dtype=torch.int64, device=dev)
+        self.d_tables = torch.empty(tsz, dtype=torch.int64, device=dev)
+        self.d_valid = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.d_ig = torch.empty(2 * 4 ** kmax, dtype=torch.float64, device=dev)
+        self.d_rows = torch.empty((n, 5), dtype=torch.float64, device=dev)
+        self.d_status = torch.empty(n, dtype=torch.int32, device=dev)
+        self.d_dump = torch.empty((n, tsz), dtype=torch.int16, device=dev) if dump else None
+        self.d_off = torch.from_numpy(self.wins.off.view(np.int64)).to(dev, non_blocking=True)
+        self.d_len = torch.from_numpy(self.wins.length.view(np.int32)).to(dev, non_blocking=True)
+        self.launches_per_step = 4          # bg_count, finalize_tables, genome_ivom, score_windows
+
+    def enqueue(self, marks=None) -> None:
+        """Launch one pass.  ``marks`` (optional list) receives a CUDA event after each stage:
+        [start, background done, tables+IVOM done, score done]."""
+        import torch
+        L = _lib.lib()
+        dev = self.device
+
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream(dev))
+                marks.append(ev)
+
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            self.d_fwd.zero_()
+            mark()
+            dh = self.dh
+            _lib.check(L.frisk_b200_background(_ptr(dh.codes), _ptr(dh.inv), _ptr(dh.low), 0, dh.host.padded_len - 32,
+                                               self.kmax, int(self.mask_host), _ptr(self.d_fwd), st), "frisk_b200_background")
+            mark()
+            space = self.genome_space
+            if self.allreduce is not None:
+                space = self.allreduce(self.d_fwd, space)
+            _lib.check(L.frisk_b200_finalize_tables(_ptr(self.d_fwd), self.kmax, 1, _ptr(self.d_tables), _ptr(self.d_valid), st),
+                       "frisk_b200_finalize_tables")
+            _lib.check(L.frisk_b200_genome_ivom(_ptr(self.d_tables), self.kmin, self.kmax, int(space), _ptr(self.d_ig), st),
+                       "frisk_b200_genome_ivom")
+            mark()
+            n = len(self.wins)
+            if n:
+                dq = self.dq
+                _lib.check(L.frisk_b200_score(_ptr(dq.codes), _ptr(dq.inv), _ptr(dq.low), _ptr(self.d_off), _ptr(self.d_len),
+                                              n, self.wins.max_len, _ptr(self.d_ig), self.kmin, self.kmax, int(self.rip),
+                                              _ptr(self.d_rows), _ptr(self.d_status), _ptr(self.d_dump), st),
+                           "frisk_b200_score")
+            mark()
+
+    def result(self) -> HotPathResult:
+        import torch
+        torch.cuda.synchronize(self.device)
+        tables = self.d_tables.cpu().numpy().view(np.uint64)
+        rows = self.d_rows.cpu().numpy()
+        status = self.d_status.cpu().numpy().view(np.uint32)
+        dmp = self.d_dump.cpu().numpy().view(np.uint16) if self.d_dump is not None else None
+        return assemble(self.query, self.host, self.wins, tables, int(self.d_valid.item()), rows, status,
+                        self.kmin, self.kmax, dmp)
+
+
+def run(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1, kmax: int = 8, w: int = 5000,
+        step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True,
+        device="cuda:0", dump: bool = False, allreduce=None, genome_space: Optional[int] = None,
+        wins: Optional[WindowList] = None) -> HotPathResult:
+    """Stages 2+3 of the reference's main() (F:1442, F:1478-1494) on one GPU: H2D of the planes,
+    one Pipeline pass, D2H of tables and rows.  ``allreduce`` (multi-GPU): see frisk_b200/dist.py;
+    ``host`` is then this rank's shard and the returned tables are the global ones (meta's
+    totalLen/exMax/nnTotal stay per-shard and are summed by the caller)."""
+    pipe = Pipeline(query, host, kmin, kmax, w, step, mask_host, scaffolds_all, rip, device, dump, allreduce,
+                    genome_space, wins)
+    pipe.enqueue()
+    return pipe.result()
+
+
+def run_host(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1, kmax: int = 8, w: int = 5000,
+             step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True,
+             wins: Optional[WindowList] = None, out=None, stream: int = 0) -> HotPathResult:
+    """Same path as ``run`` but as ONE C call from host buffers (frisk_b200_run_host): H2D of the
+    planes and window list, all kernels, D2H of rows/status/tables.  Used for end-to-end timing."""
+    _lib.require_device()
+    host = host or query
+    if wins is None:
+        wins = query.windows(w, step, scaffolds_all)
+    n = len(wins)
+    if out is None:
+        out = HostOutputs(n, kmax)
+    rc = _lib.lib().frisk_b200_run_host(
+        _ptr(host.codes), _ptr(host.inv), _ptr(host.low), host.padded_len,
+        _ptr(query.codes), _ptr(query.inv), _ptr(query.low), query.padded_len,
+        _ptr(wins.off), _ptr(wins.length), n, wins.max_len, kmin, kmax, int(mask_host), int(rip),
+        int(host.genome_space), _ptr(out.rows), _ptr(out.status), _ptr(out.tables), _ptr(out.valid), C.c_void_p(stream))
+    _lib.check(rc, "frisk_b200_run_host")
+    return assemble(query, host, wins, out.tables, int(out.valid[0]), out.rows[:n], out.status[:n], kmin, kmax)
+
+
+class HostOutputs:
+    """Reusable (pinned when possible) host buffers for run_host."""
+
+    def __init__(self, n_win: int, kmax: int, pinned: bool = True):
+        self.rows = _alloc((max(n_win, 1), 5), np.float64, pinned)
+        self.status = _alloc((max(n_win, 1),), np.uint32, pinned)
+        self.tables = _alloc((_lib.table_size(1, kmax),), np.uint64, pinned)
+        self.valid = _alloc((1,), np.uint64, pinned)

@@ -1,0 +1,192 @@
+/*
+ * frisk_b200 -- C ABI of the B200-native frisk hot path (k-mer background tables + per-window
+ * IVOM/KLD scoring).  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * The reference (Adamtaranto/frisk) has no FFI of its own: its hot path is a set of Python
+ * functions called from main() (frisk/__init__.py, "F:" below).  Every entry point here names
+ * the reference code it replaces; INTEGRATION.md shows the ctypes binding a frisk maintainer
+ * would add.  Conventions:
+ *   - return 0 on success, a negative FRISK_E_* code otherwise (never throws, never exits);
+ *     frisk_b200_strerror() explains a code, frisk_b200_last_cuda_error() the CUDA detail;
+ *   - "d_" pointers are device memory owned by the caller (e.g. torch tensors' data_ptr());
+ *     the library never frees caller memory;
+ *   - `stream` is a cudaStream_t passed as void*; device entry points only enqueue work on it;
+ *   - k-mer table index = base-4 number, digits A=0,T=1,G=2,C=3, first base most significant:
+ *     exactly the key order of the reference's dict tables (F:70, F:253-274).
+ *
+ * Packed sequence layout ("planes"), shared by host and device:
+ *   codes: uint32 words, 16 bases/word, base j of a word in bits [31-2j, 30-2j] (big-endian),
+ *          invalid bases coded 0;
+ *   inv  : uint32 words, 32 bases/word, base j at bit 31-j; 1 = not one of ACGTacgt (or padding);
+ *   low  : same layout; 1 = lower-case acgt (soft-masked).  May be NULL when the input has none.
+ *   Scaffold i starts at base offset scaf_off[i] (a multiple of 128) and is followed by >= 1
+ *   padding base; padded_len is a multiple of 128 and includes >= 128 trailing padding bases.
+ *   codes has padded_len/16 words, inv/low padded_len/32 words.
+ */
+#ifndef FRISK_B200_H
+#define FRISK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRISK_B200_ABI_VERSION 1
+#define FRISK_B200_MAX_K 8          /* largest supported --maxWordSize (4^8 u16 bins live in one SM's smem) */
+#define FRISK_B200_MAX_WINDOW 65535 /* largest window length (u16 window counters) */
+
+enum {
+    FRISK_OK = 0,
+    FRISK_E_INVALID = -1,     /* bad argument (null pointer, kmin > kmax, ...) */
+    FRISK_E_UNSUPPORTED = -2, /* kmax > FRISK_B200_MAX_K or window longer than FRISK_B200_MAX_WINDOW */
+    FRISK_E_CUDA = -3,        /* a CUDA call failed; see frisk_b200_last_cuda_error() */
+    FRISK_E_NO_DEVICE = -4,   /* no CUDA device: there is deliberately no CPU fallback */
+    FRISK_E_CAPACITY = -5,    /* an output array is too small; the required count is still reported */
+    FRISK_E_FORMAT = -6       /* malformed FASTA */
+};
+
+/* Per-window status bits written by frisk_b200_score (0 = a normal row). */
+#define FRISK_ROW_KLD_ZERODIV 1u /* the reference would raise ZeroDivisionError in IvomBuild (F:401-437) */
+#define FRISK_ROW_GC_ZERODIV 2u  /* ... in calcGC (F:136): no upper-case base in the window */
+#define FRISK_ROW_LOG_DOMAIN 4u  /* ... ValueError in KLD's math.log (F:470) */
+#define FRISK_ROW_EXCLUDED 8u    /* dropped by the >= 30 % unresolved rule (F:213, F:238): not a row */
+
+const char *frisk_b200_strerror(int code);
+const char *frisk_b200_last_cuda_error(void);
+int frisk_b200_abi_version(void);
+/* Number of CUDA devices visible (0 when none / no driver). */
+int frisk_b200_device_count(void);
+
+/* Number of table entries for orders kmin..kmax: sum 4^k (F:267-274 rangeMaps). */
+uint64_t frisk_b200_table_size(int kmin, int kmax);
+
+/* ------------------------------------------------------------------ host side: ingest (F:139-164, F:106-118)
+ *
+ * frisk_b200_fasta_scan: one pass over FASTA text, replaces iterFasta's record splitting
+ * (F:148-163).  Record i has its name at text[name_off[i] .. name_off[i]+name_len[i]) (first
+ * whitespace token after stripping '>' characters, F:156), its sequence lines inside
+ * text[body_off[i] .. body_end[i]) and seq_len[i] bases after whitespace is stripped.
+ * Outputs may be NULL to only count.  *n_records always receives the record count;
+ * FRISK_E_CAPACITY if cap is too small.
+ */
+int frisk_b200_fasta_scan(const char *text, uint64_t n, uint64_t cap, uint64_t *name_off, uint32_t *name_len,
+                          uint64_t *body_off, uint64_t *body_end, uint64_t *seq_len, uint64_t *n_records);
+
+/* Layout of n scaffolds of the given lengths: fills scaf_off[n] and *padded_len. */
+int frisk_b200_pack_layout(const uint64_t *scaf_len, uint64_t n, uint64_t *scaf_off, uint64_t *padded_len);
+
+/*
+ * frisk_b200_pack: 2-bit pack scaffolds into the planes (host buffers, ideally pinned).
+ * Scaffold i's characters are src[src_off[i] .. src_end[i]) with ASCII whitespace skipped (so a
+ * FASTA body can be packed in place); exactly scaf_len[i] non-space characters are expected
+ * (FRISK_E_FORMAT otherwise).  low may be NULL only if the caller knows there is no lower case
+ * (then *n_lower reports how many were seen and FRISK_E_FORMAT is returned if any).
+ * stats[0] = totalLen (F:323), stats[1] = nnTotal: characters that are not upper-case ATGC
+ * (F:106-118 countN, case-sensitive), stats[2] = number of lower-case acgt.
+ * threads <= 0 means "all hardware threads".
+ */
+int frisk_b200_pack(const char *src, const uint64_t *src_off, const uint64_t *src_end, const uint64_t *scaf_len,
+                    const uint64_t *scaf_off, uint64_t n, uint64_t padded_len, uint32_t *codes, uint32_t *inv,
+                    uint32_t *low, uint64_t stats[3], int threads);
+
+/*
+ * frisk_b200_windows: candidate windows per crawlGenome (F:194-251) WITHOUT the 30 % filter
+ * (the score kernel applies it and flags FRISK_ROW_EXCLUDED, so no second pass over the bases is
+ * needed): minimum-size rule (F:211, F:222), j = 0, step, ... (F:228), tail jump-back and its
+ * sticky coordinates (F:230-232, F:243), 1-based inclusive coords (F:245), --scaffoldsAll rescue
+ * (F:211-221).  win_off is the absolute base offset in the packed planes.  Arrays may be NULL to
+ * only count; *n_windows always receives the count.
+ */
+int frisk_b200_windows(const uint64_t *scaf_len, const uint64_t *scaf_off, uint64_t n_scaf, int w, int step,
+                       int scaffolds_all, uint64_t cap, uint64_t *win_off, uint32_t *win_len, uint32_t *win_scaf,
+                       int64_t *win_start, int64_t *win_stop, uint64_t *n_windows);
+
+/* ------------------------------------------------------------------ device side
+ *
+ * frisk_b200_background: forward-strand k-mer counts of the packed bases [first_base, last_base)
+ * (multiples of 32) -- the counting half of computeKmers(genomeMode=True), F:321-351.  ADDS into
+ * d_fwd, a uint64 array of frisk_b200_table_size(1, kmax) entries (orders 1..kmax concatenated):
+ * order kmax holds the count of every position whose kmax-word is valid, order x < kmax only the
+ * positions whose longest valid word has length exactly x (scaffold ends, N boundaries).
+ * frisk_b200_finalize_tables turns this into the reference's tables.  mask_host != 0 drops words
+ * containing lower-case bases (--maskHost, F:336).  Zero d_fwd before the first call; ranks of a
+ * multi-GPU job sum their d_fwd (one allreduce) before finalising.
+ */
+int frisk_b200_background(const uint32_t *d_codes, const uint32_t *d_inv, const uint32_t *d_low, uint64_t first_base,
+                          uint64_t last_base, int kmax, int mask_host, uint64_t *d_fwd, void *stream);
+
+/*
+ * frisk_b200_finalize_tables: F_x = full forward count of order x (marginals of order x+1 plus
+ * the short-word counts in d_fwd).  symmetric != 0 (genomeMode or sym, F:350): d_tables[x][kmer]
+ * = F_x[kmer] + F_x[revcomp(kmer)] -- bit-identical to the reference's "+1 word, +1
+ * revComplement(word)" (F:348-351); symmetric == 0: d_tables = F (window mode, F:1480).
+ * d_tables has frisk_b200_table_size(1, kmax) entries.  d_valid_kmax (1 uint64, nullable)
+ * receives the number of valid forward kmax-words; exMax (F:344) = sum_i max(0, len_i-kmax+1) - that.
+ */
+int frisk_b200_finalize_tables(const uint64_t *d_fwd, int kmax, int symmetric, uint64_t *d_tables,
+                               uint64_t *d_valid_kmax, void *stream);
+
+/*
+ * frisk_b200_genome_ivom: for every kmax-mer, the un-normalised genome IVOM value of
+ * IvomBuild(isGenomeIVOM=True) (F:411-450) and its log2, as pairs of doubles (4^kmax pairs).
+ * It depends only on the genome tables, so it is computed once instead of once per window.
+ * genome_space = totalLen - nnTotal (F:379).  An entry whose reference evaluation would raise
+ * ZeroDivisionError is NaN.
+ */
+int frisk_b200_genome_ivom(const uint64_t *d_tables, int kmin, int kmax, int64_t genome_space, double *d_ig,
+                           void *stream);
+
+/*
+ * frisk_b200_score: the per-window loop of main() (F:1478-1494): window k-mer tables
+ * (computeKmers, forward strand, upper-cased, F:1480), IvomBuild x2 + KLD (F:1481-1483), calcGC
+ * (F:1484) and calcRIP (F:1486), fused in one kernel; window tables live only in shared memory.
+ * d_rows: n_win x 5 doubles {windowKLD, GC, PI, SI, CRI} (PI/SI/CRI NaN unless want_rip and
+ * kmin <= 2 <= kmax).  d_status: n_win FRISK_ROW_* words.  d_dump (nullable, tests only):
+ * n_win x frisk_b200_table_size(1,kmax) uint16 window tables, orders 1..kmax.
+ * max_win_len: the largest win_len (<= FRISK_B200_MAX_WINDOW).
+ */
+int frisk_b200_score(const uint32_t *d_codes, const uint32_t *d_inv, const uint32_t *d_low,
+                     const uint64_t *d_win_off, const uint32_t *d_win_len, uint64_t n_win, uint32_t max_win_len,
+                     const double *d_ig, int kmin, int kmax, int want_rip, double *d_rows, uint32_t *d_status,
+                     uint16_t *d_dump, void *stream);
+
+/*
+ * frisk_b200_kld: KLD(GenomeIVOM, windowIVOM) (F:459-472) of two normalised IVOM vectors of n
+ * doubles in the same k-mer order: sum w*log2(w/G), terms with G == 0 skipped; *d_out gets the
+ * sum.  Serves the dict-level compatibility API; frisk_b200_score fuses the same computation.
+ */
+int frisk_b200_kld(const double *d_genome_ivom, const double *d_window_ivom, uint64_t n, double *d_out, void *stream);
+
+/*
+ * frisk_b200_run_host: the whole path from HOST buffers: H2D of the packed planes and window
+ * list, background + finalize + genome IVOM + score, D2H of rows/status/tables.  Query planes are
+ * scored against the host planes' background (pass the same planes for the default -Q == -H).
+ * All host pointers should be pinned for the copies to be asynchronous.  Device workspace is
+ * cached per device between calls.  tables_out: frisk_b200_table_size(1,kmax) uint64 (nullable);
+ * valid_kmax_out: 1 uint64 (nullable).  Synchronises `stream` before returning.
+ */
+int frisk_b200_run_host(const uint32_t *h_codes, const uint32_t *h_inv, const uint32_t *h_low, uint64_t h_padded_len,
+                        const uint32_t *q_codes, const uint32_t *q_inv, const uint32_t *q_low, uint64_t q_padded_len,
+                        const uint64_t *win_off, const uint32_t *win_len, uint64_t n_win, uint32_t max_win_len,
+                        int kmin, int kmax, int mask_host, int want_rip, int64_t genome_space, double *rows_out,
+                        uint32_t *status_out, uint64_t *tables_out, uint64_t *valid_kmax_out, void *stream);
+
+/* Free the cached device workspace of frisk_b200_run_host on the current device. */
+int frisk_b200_release_workspace(void);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so Python can build pinned planes. */
+int frisk_b200_host_alloc(void **ptr, uint64_t bytes);
+int frisk_b200_host_free(void *ptr);
+
+/* Shared-memory atomic micro-benchmark used for the smem-atomic roofline:
+ * every thread of `blocks` x 1024 threads issues `iters` u32 atomicAdd's on a 64 KiB shared table
+ * with (mode 0) conflict-free, (mode 1) uniformly random, (mode 2) single-address indices.
+ * *ms receives the kernel time; updates = blocks*1024*iters. */
+int frisk_b200_bench_smem_atomics(int blocks, int iters, int mode, float *ms, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRISK_B200_H */

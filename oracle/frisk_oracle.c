@@ -147,20 +147,19 @@ static size_t ivom_raw(const uint64_t *wtab_kmax, const uint64_t *tabs, int64_t 
  * nnTotal}.  out = {KLD, GC, PI, SI, CRI}.  wtabs_out (nullable) receives the window tables and
  * wmeta_out (nullable) the window's meta.  Returns the FO_ERR_* status.
  */
-unsigned frisk_oracle_window(const unsigned char *win, size_t len, int kmin, int kmax, const uint64_t *gtabs,
-                             const uint64_t gmeta[3], int rip, double out[5], uint64_t *wtabs_out,
-                             uint64_t wmeta_out[3]) {
+static unsigned window_ws(const unsigned char *win, size_t len, int kmin, int kmax, const uint64_t *gtabs,
+                          const uint64_t gmeta[3], int rip, double out[5], uint64_t *wtabs_out, uint64_t wmeta_out[3],
+                          uint64_t *wt, double *gi, double *wi) {
+    /* wt/gi/wi: caller-provided scratch (tsz u64, 4^kmax doubles x2) so worker threads do not
+     * fight over the allocator; wt is re-zeroed here like the reference's deepcopy of the blank map (F:317) */
     size_t tsz = frisk_oracle_table_size(kmin, kmax);
-    size_t nk = (size_t)1 << (2 * kmax);
-    uint64_t *wt = (uint64_t *)calloc(tsz, sizeof(uint64_t));
+    memset(wt, 0, tsz * sizeof(uint64_t));
     uint64_t wmeta[3] = {0, 0, 0};
     unsigned err = 0;
     frisk_oracle_count(win, len, kmin, kmax, 0, 1, wt, wmeta); /* F:1480 */
     int64_t gspace = (int64_t)gmeta[0] - (int64_t)gmeta[2];   /* F:379 */
     int64_t wspace = (int64_t)wmeta[0] - (int64_t)wmeta[2];   /* F:380 */
     const uint64_t *wmax = wt + table_offset(kmin, kmax);
-    double *gi = (double *)malloc(nk * sizeof(double));
-    double *wi = (double *)malloc(nk * sizeof(double));
     double gsum = 0, wsum = 0;
     size_t n = ivom_raw(wmax, gtabs, gspace, kmin, kmax, gi, &gsum, &err); /* F:1481 */
     size_t n2 = err ? 0 : ivom_raw(wmax, wt, wspace, kmin, kmax, wi, &wsum, &err); /* F:1482 */
@@ -202,6 +201,18 @@ unsigned frisk_oracle_window(const unsigned char *win, size_t len, int kmin, int
     }
     if (wtabs_out) memcpy(wtabs_out, wt, tsz * sizeof(uint64_t));
     if (wmeta_out) memcpy(wmeta_out, wmeta, sizeof(wmeta));
+    return err;
+}
+
+unsigned frisk_oracle_window(const unsigned char *win, size_t len, int kmin, int kmax, const uint64_t *gtabs,
+                             const uint64_t gmeta[3], int rip, double out[5], uint64_t *wtabs_out,
+                             uint64_t wmeta_out[3]) {
+    size_t tsz = frisk_oracle_table_size(kmin, kmax);
+    size_t nk = (size_t)1 << (2 * kmax);
+    uint64_t *wt = (uint64_t *)malloc(tsz * sizeof(uint64_t));
+    double *gi = (double *)malloc(nk * sizeof(double));
+    double *wi = (double *)malloc(nk * sizeof(double));
+    unsigned err = window_ws(win, len, kmin, kmax, gtabs, gmeta, rip, out, wtabs_out, wmeta_out, wt, gi, wi);
     free(wt); free(gi); free(wi);
     return err;
 }
@@ -299,9 +310,15 @@ typedef struct {
 
 static void *win_worker(void *p) {
     win_job *j = (win_job *)p;
+    size_t tsz = frisk_oracle_table_size(j->kmin, j->kmax);
+    size_t nk = (size_t)1 << (2 * j->kmax);
+    uint64_t *wt = (uint64_t *)malloc(tsz * sizeof(uint64_t));
+    double *gi = (double *)malloc(nk * sizeof(double));
+    double *wi = (double *)malloc(nk * sizeof(double));
     for (size_t i = j->first; i < j->last; ++i)
-        j->status[i] = frisk_oracle_window(j->seq + j->win_off[i], j->win_len[i], j->kmin, j->kmax, j->gtabs, j->gmeta,
-                                           j->rip, j->rows + 5 * i, NULL, NULL);
+        j->status[i] = window_ws(j->seq + j->win_off[i], j->win_len[i], j->kmin, j->kmax, j->gtabs, j->gmeta, j->rip,
+                                 j->rows + 5 * i, NULL, NULL, wt, gi, wi);
+    free(wt); free(gi); free(wi);
     return NULL;
 }
 

@@ -1,0 +1,166 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libfrisk_b200.so); the oracle (oracle/) and the golden fixtures are only the checker."""
+import numpy as np
+import pytest
+
+from tests.helpers import Golden, SMALL_CASES, assert_rows_close, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from frisk_b200 import _lib, engine
+    _lib.require_device()          # fail loudly: no CPU fallback exists
+    return engine
+
+
+def _run_case(eng, g, host_path=False, dump=False):
+    q = eng.PackedGenome.from_scaffolds(g.scaffolds(), pinned=host_path)
+    h = eng.PackedGenome.from_scaffolds(g.host(), pinned=host_path) if g.host() is not None else None
+    kw = g.kwargs()
+    if host_path:
+        return eng.run_host(q, h, **kw)
+    return eng.run(q, h, dump=dump, **kw)
+
+
+def _check_against_golden(res, g, what):
+    from frisk_b200 import _lib
+    assert np.array_equal(res.tables, g.tables), what + ": genome tables must be bit-exact"
+    assert list(res.meta) == [int(x) for x in g.genome_meta], what + ": totalLen/exMax/nnTotal"
+    assert res.names == g.names, what
+    assert np.array_equal(res.coords, g.coords), what
+    ref = g.vals.copy()
+    zd = np.isinf(ref[:, 0])          # rows on which the reference raised ZeroDivisionError
+    assert np.array_equal(zd, (res.status & _lib.ROW_KLD_ZERODIV) != 0), what + ": ZeroDivisionError rows"
+    rows = res.rows.copy()
+    ref[zd, 0] = 0.0
+    rows[zd, 0] = 0.0
+    # north_star tolerance: 1e-6 relative on KLD; GC/PI/SI/CRI are single divisions -> exact
+    assert_rows_close(rows, ref, rtol_kld=1e-6, rtol_other=1e-15, what=what)
+    return max_rel_err(rows[:, 0], ref[:, 0])
+
+
+@pytest.mark.parametrize("case", SMALL_CASES)
+def test_staged_path_matches_reference_golden(eng, case):
+    g = Golden(case)
+    err = _check_against_golden(_run_case(eng, g), g, case)
+    assert err < 1e-10, "KLD agreement is expected ~1e-13, got %.2e" % err
+
+
+@pytest.mark.parametrize("case", ["edge_default", "edge_scaffoldsAll", "edge_maskHost", "c2_small_query_vs_c1_host",
+                                  "edge_k2_5_w1000_i250"])
+def test_host_buffer_path_matches_reference_golden(eng, case):
+    g = Golden(case)
+    res = _run_case(eng, g, host_path=True)
+    _check_against_golden(res, g, case + "[run_host]")
+    staged = _run_case(eng, g)
+    assert np.array_equal(res.rows, staged.rows, equal_nan=True), "both entry paths run the same kernels"
+
+
+@pytest.mark.parametrize("case", ["edge_default", "edge_k2_5_w1000_i250", "edge_scaffoldsAll", "edge_k1_1"])
+def test_window_tables_bit_exact(eng, case):
+    """Window k-mer tables (debug dump of the shared-memory histograms) vs the reference's."""
+    from oracle import c_oracle
+    g = Golden(case)
+    res = _run_case(eng, g, dump=True)
+    kw = g.kwargs()
+    for slot, idx in enumerate(g.win_pick):
+        assert np.array_equal(res.win_tables[idx].astype(np.uint32), g.win_tables[slot]), (case, int(idx))
+    # and every window against the C oracle
+    sc = g.scaffolds()
+    seq, off = c_oracle.concat(sc)
+    _, woff, wlen, _, _ = c_oracle.crawl(seq, off, kw["w"], kw["step"], kw["scaffolds_all"])
+    assert len(woff) == len(res.rows)
+    for i in range(len(woff)):
+        win = seq[int(woff[i]):int(woff[i]) + int(wlen[i])]
+        _, _, wt, _ = c_oracle.window_tables(win, g.tables, g.genome_meta, kw["kmin"], kw["kmax"])
+        assert np.array_equal(res.win_tables[i].astype(np.uint64), wt), (case, i)
+
+
+def test_bit_reproducible(eng):
+    g = Golden("c1_small")
+    a = _run_case(eng, g)
+    b = _run_case(eng, g)
+    assert np.array_equal(a.rows, b.rows, equal_nan=True)
+    assert np.array_equal(a.tables, b.tables)
+
+
+@pytest.mark.parametrize("config,scale,kw", [
+    ("C1", 0.2, {}),
+    ("C2", 0.05, dict(scaffolds_all=True)),
+    ("C3", 0.01, dict(kmin=1, kmax=6)),
+    ("C5", 0.0002, dict(scaffolds_all=True)),
+    ("C4", 0.0005, dict(w=2000, step=500)),
+])
+def test_against_c_oracle_on_fresh_genomes(eng, config, scale, kw):
+    from frisk_b200 import synth
+    from oracle import c_oracle
+    sc = synth.make(config, scale)
+    full = dict(kmin=1, kmax=8, w=5000, step=2500, mask_host=False, scaffolds_all=False, rip=True)
+    full.update(kw)
+    ref = c_oracle.run(sc, threads=8, **full)
+    res = eng.run(eng.PackedGenome.from_scaffolds(sc), **full)
+    kmin, kmax = full["kmin"], full["kmax"]
+    assert np.array_equal(res.tables, ref["tables"])
+    assert list(res.meta) == [int(x) for x in ref["meta"]]
+    assert res.names == ref["names"]
+    assert np.array_equal(res.coords, ref["coords"])
+    assert np.array_equal(res.status & 7, ref["status"] & 7)
+    ok = ref["status"] == 0
+    assert_rows_close(res.rows[ok], ref["rows"][ok], rtol_kld=1e-6, rtol_other=1e-15, what=config)
+    assert max_rel_err(res.rows[ok, 0], ref["rows"][ok, 0]) < 1e-10
+
+
+def test_full_size_c2_properties_and_sampled_parity(eng):
+    """BASELINE config C2 at full size (40 Mbp, ~16 k windows): size-independent properties of the
+    tables plus parity of the background and of 400 sampled windows against the C oracle."""
+    from frisk_b200 import _lib, synth
+    from oracle import c_oracle
+    sc = synth.make("C2", 1.0)
+    g = eng.PackedGenome.from_scaffolds(sc)
+    res = eng.run(g)
+    K = 8
+    off = 0
+    sums = []
+    for k in range(1, K + 1):
+        t = res.tables[off:off + 4 ** k].astype(np.int64)
+        # strand symmetry: count(kmer) == count(revcomp(kmer))
+        idx = np.arange(4 ** k)
+        rc = np.zeros_like(idx)
+        tmp = idx.copy()
+        for _ in range(k):
+            rc = (rc << 2) | ((tmp & 3) ^ 1)
+            tmp >>= 2
+        assert np.array_equal(t, t[rc]), "order %d not reverse-complement symmetric" % k
+        sums.append(int(t.sum()))
+        off += 4 ** k
+    # both strands: total of order k = 2 * (#valid k-words) which is non-increasing in k, and
+    # exMax closes the books for kmax: valid + excluded = all kmax-word start positions
+    assert all(a >= b for a, b in zip(sums, sums[1:]))
+    possible = int(np.maximum(g.scaf_len.astype(np.int64) - K + 1, 0).sum())
+    assert sums[-1] // 2 + res.meta[1] == possible
+    assert sums[0] // 2 == g.total_len - (g.nn_total - g.n_lower)
+    # background vs C oracle (bit-exact), windows sampled
+    seq, soff = c_oracle.concat(sc)
+    tabs, meta = c_oracle.background(seq, soff, 1, 8, False, threads=8)
+    assert np.array_equal(res.tables, tabs)
+    assert list(res.meta) == [int(x) for x in meta]
+    sidx, woff, wlen, st, sp = c_oracle.crawl(seq, soff)
+    assert len(woff) == len(res.rows)
+    assert np.array_equal(res.coords, np.stack([st, sp], 1))
+    rng = np.random.Generator(np.random.PCG64(5))
+    pick = np.sort(rng.choice(len(woff), 400, replace=False))
+    rows, status = c_oracle.score(seq, woff[pick], wlen[pick], tabs, meta, threads=8)
+    assert np.all(status == 0) and np.all(res.status[pick] == 0)
+    assert_rows_close(res.rows[pick], rows, rtol_kld=1e-6, rtol_other=1e-15, what="C2 full")
+    assert max_rel_err(res.rows[pick, 0], rows[:, 0]) < 1e-10
+    assert np.all(np.isfinite(res.rows[:, 0])) and np.all(res.rows[:, 0] >= 0)
+
+
+def test_no_silent_fallback_symbols_loaded(eng):
+    """The product library is the thing that ran: it is loaded in this process and reports a GPU."""
+    from frisk_b200 import _lib
+    assert _lib.device_count() >= 1
+    with open("/proc/self/maps") as fh:
+        assert "libfrisk_b200.so" in fh.read()

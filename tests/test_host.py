@@ -1,0 +1,139 @@
+"""CPU tests of the host side of the product (packing, FASTA scan, window enumeration) and of the
+C-ABI surface.  No compute kernels are called (there is no GPU here and no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from frisk_b200 import _lib, engine, synth
+from oracle import c_oracle
+from tests.helpers import Golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "frisk_b200.h")).read()
+    declared = set(re.findall(r"\b(frisk_b200_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.PROTOTYPES), "header and ctypes prototypes must list the same entry points"
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.frisk_b200_abi_version() == 1
+    assert _lib.table_size(1, 8) == 87380 and _lib.table_size(4, 8) == 87380 - 84
+
+
+def test_fails_loudly_without_a_gpu():
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    g = engine.PackedGenome.from_scaffolds(synth.make("edge"))
+    with pytest.raises(_lib.FriskError) as ei:
+        engine.run(g)
+    assert ei.value.code == _lib.E_NO_DEVICE
+    with pytest.raises(_lib.FriskError):
+        engine.run_host(g)
+
+
+def _unpack(g, s):
+    off, ln = int(g.scaf_off[s]), int(g.scaf_len[s])
+    pos = off + np.arange(ln)
+    code = (g.codes[pos >> 4] >> (30 - 2 * (pos & 15)).astype(np.uint32)) & 3
+    inv = (g.inv[pos >> 5] >> (31 - (pos & 31)).astype(np.uint32)) & 1
+    low = ((g.low[pos >> 5] >> (31 - (pos & 31)).astype(np.uint32)) & 1) if g.low is not None else np.zeros(ln, np.uint32)
+    return code, inv.astype(bool), low.astype(bool)
+
+
+def test_pack_round_trip_and_stats():
+    sc = synth.make("edge")
+    g = engine.PackedGenome.from_scaffolds(sc, threads=3)
+    letters = np.frombuffer(b"ATGC", dtype=np.uint8)
+    for s, (name, seq) in enumerate(sc):
+        code, inv, low = _unpack(g, s)
+        rebuilt = letters[code]
+        rebuilt = np.where(low, rebuilt + 32, rebuilt)
+        valid = ~inv
+        assert np.array_equal(rebuilt[valid], seq[valid]), name
+        is_acgt = np.isin(seq, np.frombuffer(b"ACGTacgt", dtype=np.uint8))
+        assert np.array_equal(valid, is_acgt), name
+        # >= 1 padding base after the scaffold, flagged invalid
+        p = int(g.scaf_off[s]) + len(seq)
+        assert (g.inv[p >> 5] >> (31 - (p & 31))) & 1
+    assert g.total_len == synth.total_bases(sc)
+    upper = sum(int(np.isin(s, np.frombuffer(b"ACGT", dtype=np.uint8)).sum()) for _, s in sc)
+    assert g.nn_total == g.total_len - upper              # countN semantics, F:106-118
+    assert np.all(g.scaf_off % 128 == 0) and g.padded_len % 128 == 0
+    assert g.padded_len - (int(g.scaf_off[-1]) + int(g.scaf_len[-1])) >= 128
+    # trailing padding is all-invalid
+    assert np.all(g.inv[-4:] == 0xFFFFFFFF)
+
+
+def test_no_lowercase_means_no_low_plane():
+    g = engine.PackedGenome.from_scaffolds(synth.make("C1", 0.004))
+    assert g.low is None and g.n_lower == 0 and g.nn_total == 0
+
+
+def test_fasta_scan_matches_reference_rules(tmp_path):
+    text = (b"leading junk before any header\n"
+            b">>seq1 description words\nACGT\n  \nacgtNN\r\n"
+            b">seq2\tother\n\nAC\nGT\n"
+            b">empty_record\n"
+            b">last\nTTTT")
+    g = engine.PackedGenome.from_fasta_bytes(text)
+    assert g.names == ["seq1", "seq2", "empty_record", "last"]         # F:156 token rule
+    assert list(g.scaf_len) == [10, 4, 0, 4]
+    assert g.total_len == 18 and g.nn_total == 6 and g.n_lower == 4
+    sc = synth.make("edge")
+    p = tmp_path / "edge.fa"
+    synth.write_fasta(sc, str(p))
+    a = engine.PackedGenome.from_fasta(str(p))
+    b = engine.PackedGenome.from_scaffolds(sc)
+    assert a.names == b.names
+    for f in ("codes", "inv", "low"):
+        assert np.array_equal(getattr(a, f), getattr(b, f))
+    import gzip
+    with gzip.open(str(p) + ".gz", "wb") as fh:
+        fh.write(p.read_bytes())
+    c = engine.PackedGenome.from_fasta(str(p) + ".gz")
+    assert np.array_equal(c.codes, b.codes)
+
+
+@pytest.mark.parametrize("w,step,sa", [(5000, 2500, False), (5000, 2500, True), (1000, 250, False), (3000, 1000, True),
+                                       (4000, 1000, False), (5000, 5000, False), (700, 900, True)])
+def test_window_enumeration_matches_oracle(w, step, sa):
+    """Candidates minus the 30 % rule (applied on the device) == crawlGenome (oracle)."""
+    sc = synth.make("edge") + synth.make("C5", 0.00002, seed=3)
+    g = engine.PackedGenome.from_scaffolds(sc)
+    wins = g.windows(w, step, sa)
+    seq, off = c_oracle.concat(sc)
+    sidx, woff, wlen, st, sp = c_oracle.crawl(seq, off, w, step, sa)
+    # apply the reference's 30 % rule on the host for the comparison
+    keep = []
+    for i in range(len(wins)):
+        s = int(wins.scaf[i]); o = int(wins.off[i] - g.scaf_off[s]); l = int(wins.length[i])
+        chunk = sc[s][1][o:o + l]
+        bad = l - int(np.isin(chunk, np.frombuffer(b"ACGT", dtype=np.uint8)).sum())
+        keep.append(not (bad >= 0.3 * l))
+    keep = np.array(keep, bool)
+    assert np.array_equal(wins.scaf[keep].astype(np.int64), sidx)
+    assert np.array_equal(wins.start[keep], st) and np.array_equal(wins.stop[keep], sp)
+    assert np.array_equal(wins.length[keep], wlen)
+    rel = wins.off[keep] - g.scaf_off[wins.scaf[keep]]
+    assert np.array_equal(rel, woff - off[sidx])
+
+
+def test_window_rows_match_reference_golden_coords():
+    g = Golden("edge_default")
+    pg = engine.PackedGenome.from_scaffolds(g.scaffolds())
+    wins = pg.windows()
+    # duplicate tail window when size % step == 0: 15001-20000 then 15000-20000
+    a = [(int(s), int(e)) for s, e, c in zip(wins.start, wins.stop, wins.scaf) if c == 0]
+    assert a[-2:] == [(15001, 20000), (15000, 20000)]
+
+
+def test_too_long_window_is_refused():
+    g = engine.PackedGenome.from_scaffolds([("big", synth.iid_bases(np.random.default_rng(1), 300_000, 0.5))])
+    with pytest.raises(_lib.FriskError) as ei:
+        g.windows(70_000, 35_000)
+    assert ei.value.code == _lib.E_UNSUPPORTED

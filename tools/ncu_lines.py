@@ -1,0 +1,39 @@
+"""Aggregate an `ncu --page source --csv --print-source cuda,sass` dump per CUDA source line."""
+import csv, sys, re, collections
+path = sys.argv[1]
+thresh = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
+rows = list(csv.reader(open(path)))
+hdr = None
+agg = collections.OrderedDict()
+cur = None
+stall_cols = None
+for r in rows:
+    if 'Instructions Executed' in r:
+        hdr = r
+        ie = hdr.index('Instructions Executed'); isamp = hdr.index('# Samples'); isrc = hdr.index('Source')
+        stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
+        continue
+    if hdr is None or len(r) < len(hdr) - 2:
+        continue
+    first = r[0]
+    # cuda source lines have a line number in column 0; sass lines have an address
+    if re.fullmatch(r'\d+', first):
+        cur = (int(first), r[isrc].strip())
+        agg.setdefault(cur, [0, 0, collections.Counter()])
+        continue
+    if cur is None:
+        continue
+    try:
+        n = int(r[ie]); s = int(r[isamp])
+    except ValueError:
+        continue
+    a = agg[cur]; a[0] += n; a[1] += s
+    for i, h in stall_cols:
+        try: a[2][h] += int(r[i])
+        except ValueError: pass
+tot = sum(a[0] for a in agg.values()); ts = sum(a[1] for a in agg.values())
+print("total warp-instructions %d, samples %d" % (tot, ts))
+for (ln, text), (n, s, st) in agg.items():
+    if n > tot * thresh / 100 or s > ts * thresh / 100:
+        top = ", ".join("%s %d" % (k.replace('stall_', ''), v) for k, v in st.most_common(3))
+        print("%5d inst %5.1f%% samp %5.1f%% [%s] | %s" % (ln, 100 * n / tot, 100 * s / max(ts, 1), top, text[:100]))
