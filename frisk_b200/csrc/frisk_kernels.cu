@@ -181,31 +181,78 @@ __global__ void genome_ivom_kernel(const unsigned long long* __restrict__ tables
 }
 
 // ============================================================================================
-// Window scoring.  One persistent CTA per SM; per window:
+// Window scoring.  One persistent CTA per SM (the 4^8 u16 order-K table alone is 128 KiB).
+// Per window:
 //   0. word-wise popcounts: unresolved count (30 % rule, F:238), upper-case base and G+C counts
-//   1. one u16 shared-memory atomic per position on the order-K table (positions whose K-word is
-//      invalid add to the order-v table of their longest valid word instead)
-//   2. orders K-1..1 by marginalisation (4 children -> parent), never by atomics
-//   3. non-zero order-K bins compacted (deterministic order) into (kmer,count) entries; table zeroed
-//   4. per entry: window IVOM (closed form above) from the prefix counts, genome IVOM + log2 from
-//      the precomputed table; three fp64 sums; KLD = T/Sw + log2(Sg/Sw)   (F:448-454, F:466-470)
+//   1. count: per position one u16 shared-memory atomic on each of the orders LD..K (LD = 5: the
+//      orders with >= 1024 bins, where a warp's 32 updates rarely collide) plus one atomicOr on an
+//      occupancy bitmap of the order-K table.  A position whose longest valid word is v < LD
+//      (window end, N boundary) adds 1 to order v only.
+//   2. orders LD-1..1 by marginalisation (4 children -> parent) in one warp: <= 340 bins.
+//   3. per order-LP node (LP = 5) the partial sums  sum_{x<=LP} q_x c_x^2  and  sum_{x<=LP} 4^x c_x
+//      shared by every k-mer below it; bitmap popcounts + block scan -> sorted list of the
+//      distinct K-mers (no pass over the 65,536 bins, 93 % of which are empty).
+//   4. per distinct K-mer: window IVOM = N/D (closed form, see genome_ivom_kernel) from the prefix
+//      counts, genome IVOM and its log2 from the precomputed table, three fp64 sums;
+//      KLD = T/Sw + log2(Sg/Sw)  ==  sum_k w_k log2(w_k/g_k) with w, g normalised (F:448-454, F:466-470)
 // ============================================================================================
 struct ScoreSmem {
     double q[8];              // q_x = 4^x / ((S-(x-1)) 2) for the current window
     double red[3][kWarps];
     int n_non, n_gc, n_up, flags;
-    int warp_nz[kMaxSeg][kWarps];
+    uint32_t warp_tot[kWarps];
+    uint32_t seg_base[kMaxSeg + 1];
 };
 
 template <int K>
 struct ScoreLayout {
     static constexpr uint32_t NB = pow4(K);
+    static constexpr int LD = K < 5 ? K : 5;                            // lowest order counted by atomics
+    static constexpr int LP = K > 5 ? 5 : K - 1;                        // order of the shared partial sums (0: none)
+    static constexpr uint32_t NPRE = LP > 0 ? pow4(LP) : 1u;
     static constexpr uint32_t NLOW = lvl_off(K);                       // entries of orders 1..K-1
+    static constexpr uint32_t BM_WORDS = NB >= 32u ? NB / 32u : 1u;
     static constexpr uint32_t TOP_BYTES = (NB * 2u + 15u) & ~15u;
     static constexpr uint32_t LOW_BYTES = (NLOW * 2u + 15u) & ~15u;
-    static constexpr uint32_t LIST_BYTES = kListCap * 4u;
-    static constexpr uint32_t TOTAL = TOP_BYTES + LOW_BYTES + LIST_BYTES + (uint32_t)sizeof(ScoreSmem);
+    static constexpr uint32_t BM_BYTES = (BM_WORDS * 4u + 15u) & ~15u;
+    static constexpr uint32_t LIST_BYTES = kListCap * 2u;
+    static constexpr uint32_t PRE_BYTES = NPRE * 16u;                  // double num + u64 den per node
+    static constexpr uint32_t LOG_BYTES = 128u * 16u;
+    static constexpr uint32_t OFF_LOW = TOP_BYTES;
+    static constexpr uint32_t OFF_BM = OFF_LOW + LOW_BYTES;
+    static constexpr uint32_t OFF_LIST = OFF_BM + BM_BYTES;
+    static constexpr uint32_t OFF_PRE = OFF_LIST + LIST_BYTES;
+    static constexpr uint32_t OFF_LOG = OFF_PRE + PRE_BYTES;
+    static constexpr uint32_t OFF_SS = OFF_LOG + LOG_BYTES;
+    static constexpr uint32_t TOTAL = OFF_SS + (uint32_t)sizeof(ScoreSmem);
 };
+
+// log2 of a positive normal double: x = 2^e * m, m in [1,2); m = c (1 + r) with c the midpoint of
+// one of 128 mantissa intervals, |r| <= 2^-8; log2(1+r) by a degree-6 Taylor polynomial
+// (truncation < 3e-18).  tab[i] = {1/c_i rounded, -log2 of that rounded value}.  ~20 instructions
+// against ~75 for the library log2 (which also handles zero, denormals, inf, NaN).
+__device__ __forceinline__ double log2_pos(double x, const double2* __restrict__ tab) {
+    const int hi = __double2hiint(x);
+    const double2 t = tab[(hi >> 13) & 127];
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double r = fma(m, t.x, -1.0);
+    double p = fma(r, -0.24044917348149390, 0.28853900817779268);
+    p = fma(r, p, -0.36067376022224085);
+    p = fma(r, p, 0.48089834696298783);
+    p = fma(r, p, -0.72134752044448170);
+    p = fma(r, p, 1.4426950408889634);
+    return fma(r, p, (double)((hi >> 20) - 1023) + t.y);
+}
+
+// n / d for a positive normal d: hardware reciprocal seed + two Newton steps + one residual step
+__device__ __forceinline__ double div_pos(double n, double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    const double q = n * r;
+    return fma(fma(-d, q, n), r, q);
+}
 
 template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -215,23 +262,29 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
                      double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
     using L = ScoreLayout<K>;
     constexpr uint32_t NB = L::NB;
-    constexpr uint32_t NP = NB / 4u;                                   // parents of the top level (K=1: 1)
-    constexpr int ROUNDS = (NP + kThreads - 1) / kThreads;             // K=8: 16, K=7: 4, else 1
+    constexpr int LD = L::LD, LP = L::LP;
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t* top16 = reinterpret_cast<uint16_t*>(smem);
     uint32_t* top32 = reinterpret_cast<uint32_t*>(smem);
-    uint16_t* low16 = reinterpret_cast<uint16_t*>(smem + L::TOP_BYTES);
-    uint32_t* low32 = reinterpret_cast<uint32_t*>(smem + L::TOP_BYTES);
-    uint32_t* list = reinterpret_cast<uint32_t*>(smem + L::TOP_BYTES + L::LOW_BYTES);
-    ScoreSmem& ss = *reinterpret_cast<ScoreSmem*>(smem + L::TOP_BYTES + L::LOW_BYTES + L::LIST_BYTES);
+    uint16_t* low16 = reinterpret_cast<uint16_t*>(smem + L::OFF_LOW);
+    uint32_t* low32 = reinterpret_cast<uint32_t*>(smem + L::OFF_LOW);
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem + L::OFF_BM);
+    uint16_t* list = reinterpret_cast<uint16_t*>(smem + L::OFF_LIST);
+    double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);       // .x = num, .y = den (as a double bit pattern of u64)
+    double2* logtab = reinterpret_cast<double2*>(smem + L::OFF_LOG);
+    ScoreSmem& ss = *reinterpret_cast<ScoreSmem*>(smem + L::OFF_SS);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // zero both tables once; afterwards every window leaves them zeroed
-    for (uint32_t i = tid; i < (L::TOP_BYTES + L::LOW_BYTES) / 16u; i += kThreads)
+    // zero tables + bitmap once; afterwards every window leaves them zeroed
+    for (uint32_t i = tid; i < L::OFF_LIST / 16u; i += kThreads)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) { ss.n_non = 0; ss.n_gc = 0; ss.n_up = 0; ss.flags = 0; }
-    for (int i = tid; i < kMaxSeg * kWarps; i += kThreads) (&ss.warp_nz[0][0])[i] = 0;
+    if (tid < 128) {
+        const double c = 1.0 + ((double)tid + 0.5) / 128.0;
+        const double ic = 1.0 / c;
+        logtab[tid] = make_double2(ic, -log2(ic));
+    }
     __syncthreads();
 
     for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x) {
@@ -254,11 +307,11 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
                 upc += __popc(good);
                 gc += __popc(g & good);
             }
-            non = __reduce_add_sync(kFull, non);
-            gc = __reduce_add_sync(kFull, gc);
-            upc = __reduce_add_sync(kFull, upc);
-            if (lane == 0 && (non | gc | upc)) {
-                atomicAdd(&ss.n_non, non); atomicAdd(&ss.n_gc, gc); atomicAdd(&ss.n_up, upc);
+            if (__any_sync(kFull, (non | upc) != 0)) {
+                non = __reduce_add_sync(kFull, non);
+                gc = __reduce_add_sync(kFull, gc);
+                upc = __reduce_add_sync(kFull, upc);
+                if (lane == 0) { atomicAdd(&ss.n_non, non); atomicAdd(&ss.n_gc, gc); atomicAdd(&ss.n_up, upc); }
             }
         }
         __syncthreads();
@@ -283,7 +336,7 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
             ss.q[tid] = (double)pow4(x) / (double)d;       // inf if d == 0: flagged below when used
         }
 
-        // ---- 1. count: one shared-memory atomic per position ----------------------------------
+        // ---- 1. count ---------------------------------------------------------------------------
         for (uint32_t p = tid; p < len; p += kThreads) {
             const uint64_t a = o + p;
             const uint64_t wi = a >> 4, mi = a >> 5;
@@ -293,6 +346,16 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
             const int v = min(min(__clz(m), K), (int)min(len - p, (uint32_t)K));
             if (v == K) {
                 atomicAdd(&top32[code >> 1], 1u << ((code & 1u) * 16u));
+                atomicOr(&bitmap[code >> 5], 1u << (code & 31u));
+            }
+            if (v >= LD) {
+#pragma unroll
+                for (int x = LD; x < K; ++x) {
+                    if (x <= v) {
+                        const uint32_t g = lvl_off(x) + (code >> (2 * (K - x)));
+                        atomicAdd(&low32[g >> 1], 1u << ((g & 1u) * 16u));
+                    }
+                }
             } else if (v > 0) {
                 const uint32_t g = lvl_off(v) + (code >> (2 * (K - v)));
                 atomicAdd(&low32[g >> 1], 1u << ((g & 1u) * 16u));
@@ -300,41 +363,61 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
         }
         __syncthreads();
 
-        // ---- 2. marginalise: order x from order x+1 (plus the short-word counts already there) ---
-        // level K-1 from the top table, counting the non-zero top bins per (segment, warp) on the way
+        // ---- 2. orders LD-1..1 from order LD (warp 0); every thread: its two bitmap words ----------
+        if (warp == 0) {
 #pragma unroll
-        for (int r = 0; r < ROUNDS; ++r) {
-            const uint32_t t = tid + r * kThreads;
-            int nz = 0;
-            if (t < NP) {
-                const uint2 ch = *reinterpret_cast<const uint2*>(top16 + 4 * t);
-                const uint32_t c0 = ch.x & 0xffffu, c1 = ch.x >> 16, c2 = ch.y & 0xffffu, c3 = ch.y >> 16;
-                nz = (c0 != 0) + (c1 != 0) + (c2 != 0) + (c3 != 0);
-                if constexpr (K > 1) low16[lvl_off(K - 1) + t] += (uint16_t)(c0 + c1 + c2 + c3);
-            }
-            nz = __reduce_add_sync(kFull, nz);
-            if (lane == 0 && nz) ss.warp_nz[(r * nseg) / ROUNDS][warp] += nz;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int x = K - 2; x >= 1; --x) {
-            if (pow4(x) > 256u) {                          // wide levels: whole CTA
-                for (uint32_t t = tid; t < pow4(x); t += kThreads) {
-                    const uint2 ch = *reinterpret_cast<const uint2*>(low16 + lvl_off(x + 1) + 4 * t);
-                    low16[lvl_off(x) + t] += (uint16_t)((ch.x & 0xffffu) + (ch.x >> 16) + (ch.y & 0xffffu) + (ch.y >> 16));
-                }
-                __syncthreads();
-            } else if (warp == 0) {                        // narrow levels: warp 0 alone
+            for (int x = LD - 1; x >= 1; --x) {
+                const uint16_t* child = (x + 1 == K) ? top16 : low16 + lvl_off(x + 1);
                 for (uint32_t t = lane; t < pow4(x); t += 32) {
-                    const uint2 ch = *reinterpret_cast<const uint2*>(low16 + lvl_off(x + 1) + 4 * t);
+                    const uint2 ch = *reinterpret_cast<const uint2*>(child + 4 * t);
                     low16[lvl_off(x) + t] += (uint16_t)((ch.x & 0xffffu) + (ch.x >> 16) + (ch.y & 0xffffu) + (ch.y >> 16));
                 }
                 __syncwarp();
             }
         }
+        uint32_t w0 = 0, w1 = 0;
+        if (2u * tid < L::BM_WORDS) {
+            if (L::BM_WORDS >= 2u) {
+                const uint2 ww = *reinterpret_cast<const uint2*>(bitmap + 2 * tid);
+                w0 = ww.x; w1 = ww.y;
+                if (w0 | w1) *reinterpret_cast<uint2*>(bitmap + 2 * tid) = make_uint2(0, 0);
+            } else {
+                w0 = bitmap[0];
+                bitmap[0] = 0;
+            }
+        }
+        const uint32_t cnt = __popc(w0) + __popc(w1);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int ofs = 1; ofs < 32; ofs <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, incl, ofs);
+            if (lane >= ofs) incl += y;
+        }
+        if (lane == 31) ss.warp_tot[warp] = incl;
         __syncthreads();
 
-        // dinucleotide counts for calcRIP (F:474-495), read before step 3 wipes the tables
+        // ---- 3. shared partial sums per order-LP node; offsets of every thread's k-mers ------------
+        const uint32_t wt = ss.warp_tot[lane];
+        const uint32_t n_total = __reduce_add_sync(kFull, wt);
+        uint32_t my_off = __reduce_add_sync(kFull, lane < warp ? wt : 0u) + incl - cnt;   // exclusive, window-wide
+        constexpr int OWN = L::BM_WORDS >= 2u ? (int)(L::BM_WORDS / 2u) : 1;   // threads that own bitmap words
+        const int tps = OWN / nseg > 0 ? OWN / nseg : 1;                       // of them, per segment
+        if (tid < OWN && tid % tps == 0) ss.seg_base[tid / tps] = my_off;
+        if (tid == 0) ss.seg_base[nseg] = n_total;
+        if (LP > 0 && tid < (int)L::NPRE) {
+            double num = 0.0;
+            unsigned long long den = 0;
+#pragma unroll
+            for (int x = 1; x <= LP; ++x) {
+                if (x >= kmin) {
+                    const uint32_t c = low16[lvl_off(x) + ((uint32_t)tid >> (2 * (LP - x)))];
+                    den += (unsigned long long)c << (2 * x);
+                    num = fma(ss.q[x - 1], u32_to_double(c * c), num);
+                }
+            }
+            pre[tid] = make_double2(num, __longlong_as_double((long long)den));
+        }
+        // dinucleotide counts for calcRIP (F:474-495), read before the epilogue wipes the top table
         uint32_t n_at = 0, n_ta = 0, n_sub = 0, n_prod = 0;
         if constexpr (K >= 2) {
             if (tid == 0 && want_rip) {
@@ -344,67 +427,54 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
                 n_prod = (uint32_t)di[12] + di[6];          // CA + TG
             }
         }
-
-        if (dump) {   // tests only: window tables, orders 1..K
+        if (dump) {   // tests only: window tables, orders 1..K (orders < LD are final: warp 0 finished before the barrier)
             uint16_t* d = dump + (size_t)win * lvl_off(K + 1);
             for (uint32_t i = tid; i < lvl_off(K); i += kThreads) d[i] = low16[i];
             for (uint32_t i = tid; i < NB; i += kThreads) d[lvl_off(K) + i] = top16[i];
         }
+        __syncthreads();
 
-        // ---- 3+4. per segment: compact non-zero top bins, then score the entries --------------
+        // ---- 4. per segment: expand bitmap words into the sorted k-mer list, then score -----------
         double s_w = 0.0, s_g = 0.0, s_t = 0.0;
         int bad = 0;
-        uint32_t n_total = 0;
         for (int seg = 0; seg < nseg; ++seg) {
-            // exclusive prefix of the per-warp counts of this segment
-            const int mine = ss.warp_nz[seg][lane];
-            const uint32_t n_list = (uint32_t)__reduce_add_sync(kFull, mine);
-            uint32_t running = (uint32_t)__reduce_add_sync(kFull, lane < warp ? mine : 0);
-            const int r0 = seg * ROUNDS / nseg, r1 = (seg + 1) * ROUNDS / nseg;
-            for (int r = r0; r < r1; ++r) {
-                const uint32_t t = tid + r * kThreads;
-                uint32_t c[4] = {0, 0, 0, 0};
-                if (t < NP) {
-                    uint2* p = reinterpret_cast<uint2*>(top16 + 4 * t);
-                    const uint2 ch = *p;
-                    c[0] = ch.x & 0xffffu; c[1] = ch.x >> 16; c[2] = ch.y & 0xffffu; c[3] = ch.y >> 16;
-                    if (ch.x | ch.y) *p = make_uint2(0, 0);          // leave the table zeroed for the next window
-                }
-                const int cnt = (c[0] != 0) + (c[1] != 0) + (c[2] != 0) + (c[3] != 0);
-                // warp exclusive prefix of cnt (0..4) from three ballots
-                const uint32_t lt = (1u << lane) - 1u;
-                const uint32_t b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2),
-                               b2 = __ballot_sync(kFull, cnt & 4);
-                uint32_t pos = running + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-                running += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (c[b]) list[pos++] = ((4 * t + b) << 16) | c[b];
+            const uint32_t base = ss.seg_base[seg];
+            const uint32_t n_list = ss.seg_base[seg + 1] - base;
+            if (tid < OWN && tid / tps == seg) {
+                uint32_t pos = my_off - base;
+                uint32_t w = w0;
+                while (w) { const int b = __ffs(w) - 1; w &= w - 1; list[pos++] = (uint16_t)(64u * tid + b); }
+                w = w1;
+                while (w) { const int b = __ffs(w) - 1; w &= w - 1; list[pos++] = (uint16_t)(64u * tid + 32u + b); }
             }
             __syncthreads();
-            if (lane == 0) ss.warp_nz[seg][warp] = 0;    // every warp has read it: reset for the next window
 
             for (uint32_t e = tid; e < n_list; e += kThreads) {
-                const uint32_t ent = list[e];
-                const uint32_t kappa = ent >> 16;
+                const uint32_t kappa = list[e];
+                const uint32_t ck = top16[kappa];
+                top16[kappa] = 0;                              // leave the table zeroed for the next window
                 double num = 0.0;
                 unsigned long long den = 0;
+                if (LP > 0) {
+                    const double2 pp = pre[kappa >> (2 * (K - LP))];
+                    num = pp.x;
+                    den = (unsigned long long)__double_as_longlong(pp.y);
+                }
 #pragma unroll
-                for (int x = 1; x <= K; ++x) {
+                for (int x = LP + 1; x <= K; ++x) {
                     if (x >= kmin) {
-                        const uint32_t c = (x == K) ? (ent & 0xffffu) : (uint32_t)low16[lvl_off(x) + (kappa >> (2 * (K - x)))];
+                        const uint32_t c = (x == K) ? ck : (uint32_t)low16[lvl_off(x) + (kappa >> (2 * (K - x)))];
                         den += (unsigned long long)c << (2 * x);
                         num = fma(ss.q[x - 1], u32_to_double(c * c), num);
                     }
                 }
-                const double iw = num / __ull2double_rn(den);
+                const double iw = div_pos(num, __ull2double_rn(den));
                 const double2 g = __ldg(ig + kappa);
                 s_w += iw;
                 s_g += g.x;
-                s_t = fma(iw, log2(iw) - g.y, s_t);
+                s_t = fma(iw, log2_pos(iw, logtab) - g.y, s_t);
                 bad |= (g.x != g.x);
             }
-            n_total += n_list;
             __syncthreads();                               // list is reused by the next segment
         }
 
@@ -420,10 +490,10 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
             ss.red[0][warp] = s_w; ss.red[1][warp] = s_g; ss.red[2][warp] = s_t;
             if (bad) atomicOr(&ss.flags, 1);
         }
-        __syncthreads();
-        // re-zero the lower-order tables for the next window (the top table was zeroed in step 3)
+        // re-zero the lower-order tables for the next window (top table and bitmap are already clean)
         for (uint32_t i = tid; i < L::LOW_BYTES / 16u; i += kThreads)
             reinterpret_cast<uint4*>(low16)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
         if (tid == 0) {
             double a = 0, b = 0, c = 0;
             for (int w = 0; w < kWarps; ++w) { a += ss.red[0][w]; b += ss.red[1][w]; c += ss.red[2][w]; }
@@ -453,7 +523,6 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
         }
     }
 }
-
 
 // KLD of two already-normalised IVOM vectors (F:459-472): sum w*log2(w/G), G == 0 skipped.
 // One CTA, fixed reduction tree.  Only used by the dict-level compatibility API; the batch path
@@ -563,10 +632,11 @@ int launch_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* low
                  double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
     using L = ScoreLayout<K>;
     constexpr uint32_t NB = pow4(K);
-    constexpr int ROUNDS = (NB / 4 + kThreads - 1) / kThreads;
+    // a segment = a contiguous 1/nseg of the k-mer space (and of the threads owning its bitmap words);
+    // its distinct k-mers (<= bins in it, <= window length) must fit the list
     int nseg = 1;
     while ((NB / (uint32_t)nseg < max_len ? NB / (uint32_t)nseg : max_len) > kListCap) nseg *= 2;
-    if (nseg > kMaxSeg || nseg > ROUNDS) return FRISK_E_UNSUPPORTED;
+    if (nseg > kMaxSeg || (uint32_t)nseg > (L::BM_WORDS >= 2u ? L::BM_WORDS / 2u : 1u)) return FRISK_E_UNSUPPORTED;
     CK(cudaFuncSetAttribute(score_windows_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
     int grid = sm_count();
     if (grid <= 0) return FRISK_E_NO_DEVICE;
