@@ -152,6 +152,10 @@ int frisk_b200_score(const uint32_t *d_codes, const uint32_t *d_inv, const uint3
                      const double *d_ig, int kmin, int kmax, int want_rip, double *d_rows, uint32_t *d_status,
                      uint16_t *d_dump, void *stream);
 
+/* Tuning/test switches.  "force_dense_kernel" = 1 makes frisk_b200_score use the dense-table
+ * kernel (the general path for kmax < 4 or windows > 8192 bases) for every input. */
+int frisk_b200_set_option(const char *name, int value);
+
 /*
  * frisk_b200_kld: KLD(GenomeIVOM, windowIVOM) (F:459-472) of two normalised IVOM vectors of n
  * doubles in the same k-mer order: sum w*log2(w/G), terms with G == 0 skipped; *d_out gets the

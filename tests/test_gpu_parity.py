@@ -78,6 +78,63 @@ def test_window_tables_bit_exact(eng, case):
         assert np.array_equal(res.win_tables[i].astype(np.uint64), wt), (case, i)
 
 
+@pytest.mark.parametrize("case", ["edge_default", "edge_scaffoldsAll", "edge_k4_8", "c1_small", "edge_k2_5_w1000_i250"])
+def test_dense_table_kernel_matches_reference_golden(eng, case):
+    """frisk_b200_score has two kernels: the bucketed one (default for 4 <= kmax <= 8 and windows
+    <= 8192) and the dense-table one (everything else).  Force the dense one on the same cases."""
+    from frisk_b200 import _lib
+    g = Golden(case)
+    _lib.check(_lib.lib().frisk_b200_set_option(b"force_dense_kernel", 1), "set_option")
+    try:
+        res = _run_case(eng, g, dump=True)
+    finally:
+        _lib.lib().frisk_b200_set_option(b"force_dense_kernel", 0)
+    _check_against_golden(res, g, case + "[dense]")
+    default = _run_case(eng, g, dump=True)
+    assert np.array_equal(res.win_tables, default.win_tables)
+    assert max_rel_err(res.rows[:, 0], default.rows[:, 0]) < 1e-12
+
+
+def test_long_windows_use_segments(eng):
+    """Windows longer than the bucketed kernel's 8192-base buffer (and longer than the dense
+    kernel's 8192-entry k-mer list) against the C oracle."""
+    from frisk_b200 import synth
+    from oracle import c_oracle
+    sc = synth.make("C1", 0.06, seed=77)
+    kw = dict(kmin=1, kmax=8, w=30000, step=12000, mask_host=False, scaffolds_all=False, rip=True)
+    ref = c_oracle.run(sc, threads=8, **kw)
+    res = eng.run(eng.PackedGenome.from_scaffolds(sc), **kw)
+    assert np.array_equal(res.tables, ref["tables"])
+    assert np.array_equal(res.coords, ref["coords"])
+    assert_rows_close(res.rows, ref["rows"], rtol_kld=1e-6, rtol_other=1e-15, what="long windows")
+    assert max_rel_err(res.rows[:, 0], ref["rows"][:, 0]) < 1e-10
+
+
+def test_low_complexity_windows(eng):
+    """Homopolymer / dinucleotide-repeat windows: one bucket holds thousands of entries (the slow
+    path of the bucketed kernel, maximal atomic contention in both kernels)."""
+    from frisk_b200 import synth
+    from oracle import c_oracle
+    rng = np.random.Generator(np.random.PCG64(3))
+    a = synth.iid_bases(rng, 40_000, 0.5)
+    a[5_000:11_000] = ord("A")
+    a[15_000:21_000] = np.tile(np.frombuffer(b"AT", dtype=np.uint8), 3000)
+    a[25_000:30_000] = np.tile(np.frombuffer(b"ACGTTGCA", dtype=np.uint8), 625)
+    a[31_000:31_040] = ord("N")
+    sc = [("lowcomplex", a)]
+    ref = c_oracle.run(sc, threads=4)
+    res = eng.run(eng.PackedGenome.from_scaffolds(sc), dump=True)
+    assert np.array_equal(res.tables, ref["tables"])
+    print("low-complexity KLDs:", ref["rows"][:, 0], "abs diff:", np.abs(res.rows[:, 0] - ref["rows"][:, 0]))
+    assert_rows_close(res.rows, ref["rows"], rtol_kld=1e-6, rtol_other=1e-15, what="low complexity")
+    assert max_rel_err(res.rows[:, 0], ref["rows"][:, 0]) < 1e-10
+    seq, off = c_oracle.concat(sc)
+    for i in range(len(ref["rows"])):
+        win = seq[int(ref["win_off"][i]):int(ref["win_off"][i]) + int(ref["win_len"][i])]
+        _, _, wt, _ = c_oracle.window_tables(win, ref["tables"], ref["meta"], 1, 8)
+        assert np.array_equal(res.win_tables[i].astype(np.uint64), wt), i
+
+
 def test_bit_reproducible(eng):
     g = Golden("c1_small")
     a = _run_case(eng, g)

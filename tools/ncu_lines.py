@@ -37,3 +37,17 @@ for (ln, text), (n, s, st) in agg.items():
     if n > tot * thresh / 100 or s > ts * thresh / 100:
         top = ", ".join("%s %d" % (k.replace('stall_', ''), v) for k, v in st.most_common(3))
         print("%5d inst %5.1f%% samp %5.1f%% [%s] | %s" % (ln, 100 * n / tot, 100 * s / max(ts, 1), top, text[:100]))
+
+# optional phase summary: extra args "name:lo-hi" ...
+phases = [a for a in sys.argv[3:] if ':' in a]
+if phases:
+    print("\nphase summary (share of warp-instructions / of stall samples)")
+    for ph in phases:
+        name, rng = ph.split(':'); lo, hi = map(int, rng.split('-'))
+        n = sum(v[0] for (ln, _), v in agg.items() if lo <= ln <= hi)
+        s = sum(v[1] for (ln, _), v in agg.items() if lo <= ln <= hi)
+        st = collections.Counter()
+        for (ln, _), v in agg.items():
+            if lo <= ln <= hi: st.update(v[2])
+        top = ", ".join("%s %.0f%%" % (k.replace('stall_', ''), 100 * c / max(s, 1)) for k, c in st.most_common(4))
+        print("%-12s inst %5.1f%%  samples %5.1f%%  [%s]" % (name, 100 * n / tot, 100 * s / max(ts, 1), top))
