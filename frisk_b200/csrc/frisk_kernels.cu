@@ -525,22 +525,24 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
 }
 
 // ============================================================================================
-// Window scoring, bucketed formulation ("v3"): the default path (4 <= K <= 8, windows <= 8192).
+// Window scoring, bucketed formulation: the default path (4 <= K <= 8, windows <= 8192 bases).
 //
 // The dense 4^K table of score_windows_kernel costs 128 KiB and forces one CTA per SM, whose phases
 // (count / scan / score) then run back to back with barriers between them.  A window of L bases has
 // at most L distinct K-mers, so instead the K-mers are counting-sorted by their (K-2)-prefix:
 //   P1  per position: u16 shared-memory atomics on the orders LD..B only (B = K-2, 4^B buckets;
-//       LD = min(5,B)), composition counts on the way (30 % rule, GC)
+//       LD = min(5,B)); composition counts on the way (30 % rule, GC)
 //   P2  warp 0 marginalises orders LD-1..1; exclusive scan of the order-B counts -> bucket cursors
 //   P3  per position: claim a slot in its bucket (atomic on the cursor) and store a 5-bit code: the
-//       2-base suffix (0..15), or 16+b for a word that is valid for K-1 bases only, or 20 for K-2;
-//       per order-LD node the partial sums  sum q_x c_x^2 ,  sum 4^x c_x  shared by all K-mers below it
-//   P4  per bucket: suffix multiplicities (packed 4-bit counters; generic slow path above 15
-//       entries) give the order-K and order-(K-1) counts of its distinct K-mers in sorted order;
-//       each is scored exactly as in score_windows_kernel.
-// Footprint for K = 8: 46 KiB -> 4 CTAs of 256 threads per SM, so four windows in different phases
-// overlap on every SM and barriers only span 8 warps.
+//       2-base suffix (0..15), or 16+b for a word valid for K-1 bases only, or 20 for K-2 only;
+//       OR the suffix into the bucket's 16-bit presence mask.  Per order-LP node (LP = min(4,B)) the
+//       partial sums  sum q_x c_x^2 ,  sum 4^x c_x  shared by every K-mer below it.
+//   P4a popcounts of the presence masks + block scan -> sorted list of the distinct K-mers
+//   P4b one list entry per thread per round (converged): order-K / order-(K-1) counts are 1 and
+//       popc(mask group) when every entry of the bucket is a distinct K-mer (the common case),
+//       otherwise recounted from the bucket; then the same closed-form IVOM / KLD terms as above.
+// Footprint for K = 8, w = 5000: 48 KiB -> 4 CTAs of 256 threads per SM: four windows in
+// different phases overlap on every SM and barriers span 8 warps only.
 // ============================================================================================
 constexpr int kT3 = 256;
 constexpr int kW3 = kT3 / 32;
@@ -549,7 +551,7 @@ constexpr uint32_t kBuf3 = 8192;      // longest window handled by this kernel
 struct Score3Smem {
     double q[8];
     double red[3][kW3];
-    int cnt[2][4];                    // [window parity][n_non, n_gc, n_up, distinct k-mers]
+    int cnt[2][4];                    // [window parity][n_non, n_gc, n_up, -]
     int flags[2];
     uint32_t warp_tot[kW3];
 };
@@ -558,13 +560,16 @@ template <int K>
 struct Score3Layout {
     static constexpr int B = K - 2;                                     // bucket order
     static constexpr uint32_t NBK = pow4(B);
-    static constexpr int LD = B < 5 ? B : 5;                            // lowest order counted by atomics; also the partial-sum order
-    static constexpr uint32_t NPRE = pow4(LD);
+    static constexpr int LD = B < 5 ? B : 5;                            // lowest order counted by atomics
+    static constexpr int LP = B < 4 ? B : 4;                            // order of the shared partial sums
+    static constexpr uint32_t NPRE = pow4(LP);
     static constexpr uint32_t PER = NBK >= (uint32_t)kT3 ? NBK / kT3 : 1u;   // buckets per thread (contiguous)
     static constexpr uint32_t TAB_BYTES = (lvl_off(B + 1) * 2u + 15u) & ~15u;  // orders 1..B, u16
-    static constexpr uint32_t CUR_BYTES = (NBK * 2u + 15u) & ~15u;
-    static constexpr uint32_t OFF_CUR = TAB_BYTES;
-    static constexpr uint32_t OFF_PRE = OFF_CUR + CUR_BYTES;
+    static constexpr uint32_t MASK_BYTES = (NBK * 2u + 15u) & ~15u;     // suffix-presence masks, u16 per bucket
+    static constexpr uint32_t OFF_MASK = TAB_BYTES;                     // (tables and masks are zeroed together)
+    static constexpr uint32_t ZERO_BYTES = TAB_BYTES + MASK_BYTES;
+    static constexpr uint32_t OFF_CUR = ZERO_BYTES;
+    static constexpr uint32_t OFF_PRE = OFF_CUR + MASK_BYTES;
     static constexpr uint32_t OFF_LOG = OFF_PRE + NPRE * 16u;
     static constexpr uint32_t OFF_SS = OFF_LOG + 128u * 16u;
     static constexpr uint32_t OFF_BUF = (OFF_SS + (uint32_t)sizeof(Score3Smem) + 15u) & ~15u;
@@ -573,50 +578,31 @@ struct Score3Layout {
     static constexpr uint32_t total(uint32_t cap) { return OFF_BUF + cap + 2u * cap; }
 };
 
-// sequential reader of the packed planes: code of the K-mer starting at base a and the validity
-// mask of the 32 bases from a (bit 31 = base a), reloading words only when a crosses a boundary
-struct PlaneReader {
-    const uint32_t* __restrict__ codes;
-    const uint32_t* __restrict__ inv;
-    const uint32_t* __restrict__ low;
-    uint32_t c_hi, c_lo, m_hi, m_lo, l_hi;
-    __device__ __forceinline__ void start(uint64_t a) {
-        c_hi = __ldg(codes + (a >> 4)); c_lo = __ldg(codes + (a >> 4) + 1);
-        m_hi = __ldg(inv + (a >> 5)); m_lo = __ldg(inv + (a >> 5) + 1);
-        l_hi = low ? __ldg(low + (a >> 5)) : 0u;
-    }
-    __device__ __forceinline__ void advance_to(uint64_t a) {     // a = previous + 1
-        if ((a & 15) == 0) { c_hi = c_lo; c_lo = __ldg(codes + (a >> 4) + 1); }
-        if ((a & 31) == 0) { m_hi = m_lo; m_lo = __ldg(inv + (a >> 5) + 1); l_hi = low ? __ldg(low + (a >> 5)) : 0u; }
-    }
-    __device__ __forceinline__ uint32_t code32(uint64_t a) const { return __funnelshift_l(c_lo, c_hi, (uint32_t)(a & 15) * 2u); }
-    __device__ __forceinline__ uint32_t mask32(uint64_t a) const { return __funnelshift_l(m_lo, m_hi, (uint32_t)(a & 31)); }
-    __device__ __forceinline__ uint32_t lower(uint64_t a) const { return (l_hi << (uint32_t)(a & 31)) >> 31; }
-};
-
-template <int K>
+template <int K, bool DUMP>
 __global__ void __launch_bounds__(kT3, 4)
 score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                             const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
                             const double2* __restrict__ ig, int kmin, int want_rip, uint32_t cap,
                             double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
     using L = Score3Layout<K>;
-    constexpr int B = L::B, LD = L::LD;
+    constexpr int B = L::B, LD = L::LD, LP = L::LP;
     constexpr uint32_t NBK = L::NBK, PER = L::PER;
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem);                 // orders 1..B
     uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem);
+    uint16_t* mask16 = reinterpret_cast<uint16_t*>(smem + L::OFF_MASK);
+    uint32_t* mask32 = reinterpret_cast<uint32_t*>(smem + L::OFF_MASK);
     uint16_t* cur16 = reinterpret_cast<uint16_t*>(smem + L::OFF_CUR);
     uint32_t* cur32 = reinterpret_cast<uint32_t*>(smem + L::OFF_CUR);
-    uint8_t* buf = smem + L::OFF_BUF;
-    uint16_t* list = reinterpret_cast<uint16_t*>(smem + L::OFF_BUF + cap);
-    double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);
+    double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);       // .x = num, .y = den (exact integer as double)
     double2* logtab = reinterpret_cast<double2*>(smem + L::OFF_LOG);
     Score3Smem& ss = *reinterpret_cast<Score3Smem*>(smem + L::OFF_SS);
+    uint8_t* buf = smem + L::OFF_BUF;
+    uint16_t* list = reinterpret_cast<uint16_t*>(smem + L::OFF_BUF + cap);
     const uint16_t* tabB = tab16 + lvl_off(B);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t i = tid; i < L::TAB_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid < 8) { ss.cnt[tid >> 2][tid & 3] = 0; ss.flags[tid & 1] = 0; }
     if (tid < 128) {
         const double c = 1.0 + ((double)tid + 0.5) / 128.0;
@@ -629,23 +615,24 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
     for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x, par ^= 1) {
         const uint64_t o = win_off[win];
         const uint32_t len = win_len[win];
-        const uint32_t chunk = (len + kT3 - 1) / kT3;
-        const uint32_t p0 = min(len, (uint32_t)tid * chunk), p1 = min(len, p0 + chunk);
-        PlaneReader rd{codes, inv, low, 0, 0, 0, 0, 0};
+        // 32-bit addressing relative to the window's first mask word
+        const uint32_t o_lo = (uint32_t)(o & 31);
+        const uint32_t* __restrict__ cw = codes + (o >> 5) * 2;
+        const uint32_t* __restrict__ mw = inv + (o >> 5);
+        const uint32_t* __restrict__ lw = low ? low + (o >> 5) : nullptr;
 
         // ---- P1: count orders LD..B (and short words), composition ------------------------------
         {
-            int non = 0, gc = 0, upc = 0;
-            if (p0 < p1) rd.start(o + p0);
-            for (uint32_t p = p0; p < p1; ++p) {
-                const uint64_t a = o + p;
-                if (p != p0) rd.advance_to(a);
-                const uint32_t c32 = rd.code32(a), m = rd.mask32(a);
+            int non = 0, gc = 0;
+            for (uint32_t p = tid; p < len; p += kT3) {
+                const uint32_t a = o_lo + p, wi = a >> 4, mi = a >> 5;
+                const uint32_t c32 = __funnelshift_l(__ldg(cw + wi + 1), __ldg(cw + wi), (a & 15u) * 2u);
+                const uint32_t m = __funnelshift_l(__ldg(mw + mi + 1), __ldg(mw + mi), a & 31u);
                 const int v = min(min(__clz(m), K), (int)min(len - p, (uint32_t)K));
-                const uint32_t unres = (m >> 31) | rd.lower(a);          // not an upper-case ATGC (F:106-118)
+                uint32_t unres = m >> 31;                                    // not an upper-case ATGC (F:106-118)
+                if (lw) unres |= (__ldg(lw + mi) << (a & 31u)) >> 31;
                 non += unres;
-                upc += 1 - unres;
-                gc += (1 - unres) & (c32 >> 31);                         // G = 2, C = 3: bit 1 of the first base
+                gc += (1 - unres) & (c32 >> 31);                             // G = 2, C = 3: bit 1 of the first base
                 if (v >= LD) {
 #pragma unroll
                     for (int x = LD; x <= B; ++x) {
@@ -661,21 +648,21 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             }
             non = __reduce_add_sync(kFull, non);
             gc = __reduce_add_sync(kFull, gc);
-            upc = __reduce_add_sync(kFull, upc);
-            if (lane == 0) { atomicAdd(&ss.cnt[par][0], non); atomicAdd(&ss.cnt[par][1], gc); atomicAdd(&ss.cnt[par][2], upc); }
+            if (lane == 0) { atomicAdd(&ss.cnt[par][0], non); atomicAdd(&ss.cnt[par][1], gc); }
         }
         __syncthreads();                                                   // (1)
-        const int n_non = ss.cnt[par][0], n_gc = ss.cnt[par][1], n_up = ss.cnt[par][2];
+        const int n_non = ss.cnt[par][0], n_gc = ss.cnt[par][1], n_up = (int)len - n_non;
         if (tid < 4) ss.cnt[par ^ 1][tid] = 0;                              // next window's counters (idle until its P1)
         if (tid == 4) ss.flags[par ^ 1] = 0;
         const bool excluded = (double)n_non >= 0.3 * (double)len;          // F:238 / F:213
+        uint16_t* dmp = DUMP ? dump + (size_t)win * lvl_off(K + 1) : nullptr;
         if (excluded) {
             for (uint32_t i = tid; i < L::TAB_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
             if (tid == 0) {
                 status[win] = FRISK_ROW_EXCLUDED;
                 for (int c = 0; c < 5; ++c) rows[(size_t)win * 5 + c] = CUDART_NAN;
             }
-            if (dump) for (uint32_t i = tid; i < lvl_off(K + 1); i += kT3) dump[(size_t)win * lvl_off(K + 1) + i] = 0;
+            if (DUMP) for (uint32_t i = tid; i < lvl_off(K + 1); i += kT3) dmp[i] = 0;
             __syncthreads();
             continue;
         }
@@ -724,33 +711,35 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         }
         __syncthreads();                                                   // (2b)
 
-        // ---- P3: scatter suffix codes into buckets; shared partial sums per order-LD node --------
-        if (p0 < p1) rd.start(o + p0);
-        for (uint32_t p = p0; p < p1; ++p) {
-            const uint64_t a = o + p;
-            if (p != p0) rd.advance_to(a);
-            const uint32_t c32 = rd.code32(a), m = rd.mask32(a);
+        // ---- P3: scatter suffix codes into buckets; presence masks; partial sums per order-LP node --
+        for (uint32_t p = tid; p < len; p += kT3) {
+            const uint32_t a = o_lo + p, wi = a >> 4, mi = a >> 5;
+            const uint32_t c32 = __funnelshift_l(__ldg(cw + wi + 1), __ldg(cw + wi), (a & 15u) * 2u);
+            const uint32_t m = __funnelshift_l(__ldg(mw + mi + 1), __ldg(mw + mi), a & 31u);
             const int v = min(min(__clz(m), K), (int)min(len - p, (uint32_t)K));
             if (v >= B) {
                 const uint32_t b = c32 >> (32 - 2 * B);
                 const uint32_t sfx = (c32 >> (32 - 2 * K)) & 15u;
-                const uint32_t code5 = (v == K) ? sfx : (v == K - 1 ? 16u + (sfx >> 2) : 20u);
-                const uint32_t old = atomicAdd(&cur32[b >> 1], 1u << ((b & 1u) * 16u));
-                buf[(old >> ((b & 1u) * 16u)) & 0xffffu] = (uint8_t)code5;
+                const uint32_t sh = (b & 1u) * 16u;
+                const uint32_t old = atomicAdd(&cur32[b >> 1], 1u << sh);
+                uint32_t code5 = 20u;
+                if (v == K) { code5 = sfx; atomicOr(&mask32[b >> 1], (1u << sfx) << sh); }
+                else if (v == K - 1) code5 = 16u + (sfx >> 2);
+                buf[(old >> sh) & 0xffffu] = (uint8_t)code5;
             }
         }
         for (uint32_t node = tid; node < L::NPRE; node += kT3) {
             double num = 0.0;
-            unsigned long long den = 0;
+            uint32_t den = 0;
 #pragma unroll
-            for (int x = 1; x <= LD; ++x) {
+            for (int x = 1; x <= LP; ++x) {
                 if (x >= kmin) {
-                    const uint32_t c = tab16[lvl_off(x) + (node >> (2 * (LD - x)))];
-                    den += (unsigned long long)c << (2 * x);
+                    const uint32_t c = tab16[lvl_off(x) + (node >> (2 * (LP - x)))];
+                    den += c << (2 * x);
                     num = fma(ss.q[x - 1], u32_to_double(c * c), num);
                 }
             }
-            pre[node] = make_double2(num, __longlong_as_double((long long)den));
+            pre[node] = make_double2(num, __hiloint2double(0, (int)den));
         }
         uint32_t n_at = 0, n_ta = 0, n_sub = 0, n_prod = 0;
         if (tid == 0 && want_rip) {                        // orders < LD are final since barrier (2a); K >= 4 so B >= 2
@@ -759,39 +748,39 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             n_sub = (uint32_t)di[3] + di[9];
             n_prod = (uint32_t)di[12] + di[6];
         }
-        uint16_t* dmp = dump ? dump + (size_t)win * lvl_off(K + 1) : nullptr;
-        if (dmp) {
+        if (DUMP) {
             for (uint32_t i = tid; i < lvl_off(B + 1); i += kT3) dmp[i] = tab16[i];
             for (uint32_t i = lvl_off(B + 1) + tid; i < lvl_off(K + 1); i += kT3) dmp[i] = 0;
         }
         __syncthreads();                                                   // (3)
 
-        // ---- P4a: per bucket, which 2-base suffixes occur -> sorted list of the distinct K-mers -----
-        // (data-dependent and divergent, but only a few instructions per position)
+        // ---- P4a: popcounts of the presence masks -> sorted list of the distinct K-mers -----------
         uint32_t masks[(PER + 1) / 2];
         uint32_t dcount = 0;
 #pragma unroll
-        for (uint32_t i = 0; i < (PER + 1) / 2; ++i) masks[i] = 0;
-#pragma unroll
-        for (uint32_t i = 0; i < PER; ++i) {
-            const uint32_t b = tid * PER + i;
-            uint32_t mask = 0;
-            if (b < NBK) {
-                const uint32_t nb = tabB[b];
-                if (nb) {
-                    const uint32_t end = cur16[b];                         // the cursor finished at the bucket's end
+        for (uint32_t i = 0; i < (PER + 1) / 2; ++i) {
+            masks[i] = 0;
+            if ((uint32_t)tid * PER + 2 * i < NBK) {
+                if (PER >= 2) masks[i] = mask32[(tid * PER) / 2 + i];
+                else masks[i] = mask16[tid];
+            }
+            dcount += __popc(masks[i]);
+        }
+        if (DUMP) {   // tests only: order K-1 counts of the window, straight from the bucket entries
+#pragma unroll 1
+            for (uint32_t i = 0; i < PER; ++i) {
+                const uint32_t b = tid * PER + i;
+                if (b < NBK) {
+                    const uint32_t nb = tabB[b], end = cur16[b];
                     for (uint32_t e = end - nb; e < end; ++e) {
                         const uint32_t c5 = buf[e];
-                        if (c5 < 16u) mask |= 1u << c5;
-                        if (dmp && c5 < 20u) {                             // tests only: order K-1 counts of the window
+                        if (c5 < 20u) {
                             const uint32_t g = lvl_off(K - 1) + 4 * b + (c5 < 16u ? c5 >> 2 : c5 - 16u);
                             atomicAdd(reinterpret_cast<unsigned int*>(dmp + (g & ~1u)), 1u << (16 * (g & 1u)));
                         }
                     }
                 }
             }
-            masks[i / 2] |= mask << (16 * (i & 1));
-            dcount += __popc(mask);
         }
         uint32_t dincl = dcount;
 #pragma unroll
@@ -827,61 +816,62 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             const uint32_t kappa = list[e];
             const uint32_t b = kappa >> 4, sfx = kappa & 15u, j = sfx >> 2;
             const uint32_t nb = tabB[b];
-            const uint32_t end = cur16[b];
-            uint32_t c8 = 0, c7 = 0;                                       // order-K and order-(K-1) counts of this K-mer
-            for (uint32_t i = end - nb; i < end; ++i) {
-                const uint32_t c5 = buf[i];
-                c8 += (c5 == sfx);
-                c7 += (c5 < 16u) ? ((c5 >> 2) == j) : (c5 == 16u + j);
+            const uint32_t msk = mask16[b];
+            uint32_t c8 = 1, c7 = __popc((msk >> (4 * j)) & 15u);           // right when every entry is a distinct K-mer
+            if (nb != (uint32_t)__popc(msk)) {                              // repeats or short words in the bucket: recount
+                const uint32_t end = cur16[b];                             // the cursor finished at the bucket's end
+                c8 = 0; c7 = 0;
+                for (uint32_t i = end - nb; i < end; ++i) {
+                    const uint32_t c5 = buf[i];
+                    c8 += (c5 == sfx);
+                    c7 += (c5 < 16u) ? ((c5 >> 2) == j) : (c5 == 16u + j);
+                }
             }
-            if (dmp) dmp[lvl_off(K) + kappa] = (uint16_t)c8;
-            // orders <= LD from `pre`, orders LD+1..B from the tables, then K-1 and K
-            const double2 pp = pre[b >> (2 * (B - LD))];
+            if (DUMP) dmp[lvl_off(K) + kappa] = (uint16_t)c8;
+            // orders <= LP from `pre`, orders LP+1..B from the tables, then K-1 and K
+            const double2 pp = pre[b >> (2 * (B - LP))];
             double num = pp.x;
-            unsigned long long den = (unsigned long long)__double_as_longlong(pp.y);
+            uint32_t den = (uint32_t)__double2loint(pp.y);
 #pragma unroll
-            for (int x = LD + 1; x <= B; ++x) {
+            for (int x = LP + 1; x <= B; ++x) {
                 if (x >= kmin) {
                     const uint32_t c = (x == B) ? nb : (uint32_t)tab16[lvl_off(x) + (b >> (2 * (B - x)))];
-                    den += (unsigned long long)c << (2 * x);
+                    den += c << (2 * x);
                     num = fma(ss.q[x - 1], u32_to_double(c * c), num);
                 }
             }
             if (K - 1 >= kmin) {
-                den += (unsigned long long)c7 << (2 * (K - 1));
+                den += c7 << (2 * (K - 1));
                 num = fma(q7, u32_to_double(c7 * c7), num);
             }
-            den += (unsigned long long)c8 << (2 * K);
+            den += c8 << (2 * K);
             num = fma(q8, u32_to_double(c8 * c8), num);
-            const double iw = div_pos(num, __ull2double_rn(den));
+            const double iw = div_pos(num, (double)den);
             const double2 g = __ldg(ig + kappa);
             s_w += iw;
             s_g += g.x;
             s_t = fma(iw, log2_pos(iw, logtab) - g.y, s_t);
             bad |= (g.x != g.x);
         }
-        int n_distinct = (tid == 0) ? (int)n_list : 0;
 #pragma unroll
         for (int ofs = 16; ofs; ofs >>= 1) {
             s_w += __shfl_xor_sync(kFull, s_w, ofs);
             s_g += __shfl_xor_sync(kFull, s_g, ofs);
             s_t += __shfl_xor_sync(kFull, s_t, ofs);
         }
-        n_distinct = __reduce_add_sync(kFull, n_distinct);
         bad = __any_sync(kFull, bad);
         if (lane == 0) {
             ss.red[0][warp] = s_w; ss.red[1][warp] = s_g; ss.red[2][warp] = s_t;
-            atomicAdd(&ss.cnt[par][3], n_distinct);
             if (bad) atomicOr(&ss.flags[par], 1);
         }
         __syncthreads();                                                   // (4) everyone is done with the tables
-        for (uint32_t i = tid; i < L::TAB_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) {
             double a = 0, bsum = 0, c = 0;
             for (int w = 0; w < kW3; ++w) { a += ss.red[0][w]; bsum += ss.red[1][w]; c += ss.red[2][w]; }
             uint32_t st = 0;
             double kld = 0.0;                              // the reference returns 0 for a window without kmax-mers
-            if (ss.cnt[par][3]) {
+            if (n_list) {
                 bool zd = ss.flags[par] & 1;
                 for (int x = kmin; x <= K; ++x) zd |= ((long long)n_up - (long long)(x - 1)) == 0;
                 if (zd) { st |= FRISK_ROW_KLD_ZERODIV; kld = CUDART_NAN; }
@@ -903,7 +893,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             row[2] = pi; row[3] = si; row[4] = cri;
             status[win] = st;
         }
-        __syncthreads();                                                   // (5) tables zeroed, ss.red/cnt consumed
+        __syncthreads();                                                   // (5) tables zeroed, ss.red consumed
     }
 }
 
@@ -1032,26 +1022,35 @@ int launch_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* low
     return FRISK_OK;
 }
 
-template <int K>
-int launch_score_bucket(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
-                        const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
-                        double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+template <int K, bool DUMP>
+int launch_score_bucket2(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                         const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
+                         double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
     using L = Score3Layout<K>;
     const uint32_t cap = (max_len + 15u) & ~15u;
     const size_t smem = L::total(cap);
-    CK(cudaFuncSetAttribute(score_windows_bucket_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = score_windows_bucket_kernel<K, DUMP>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_windows_bucket_kernel<K>, kT3, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT3, smem));
     if (per_sm < 1) per_sm = 1;
     int sms = sm_count();
     if (sms <= 0) return FRISK_E_NO_DEVICE;
     uint64_t grid = (uint64_t)sms * (uint64_t)per_sm;
     if (grid > n_win) grid = n_win;
-    score_windows_bucket_kernel<K><<<(unsigned)grid, kT3, smem, st>>>(
+    kern<<<(unsigned)grid, kT3, smem, st>>>(
         codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len, (uint32_t)n_win,
         reinterpret_cast<const double2*>(ig), kmin, want_rip, cap, rows, status, dump);
     CK(cudaGetLastError());
     return FRISK_OK;
+}
+
+template <int K>
+int launch_score_bucket(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                        const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
+                        double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+    if (dump) return launch_score_bucket2<K, true>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
+    return launch_score_bucket2<K, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
 }
 
 #define DISPATCH_K(kmax, expr)                      \
