@@ -578,15 +578,41 @@ struct Score3Layout {
     static constexpr uint32_t total(uint32_t cap) { return OFF_BUF + cap + 2u * cap; }
 };
 
-template <int K, bool DUMP>
+// Visits every position of a window, four absolute-aligned bases per thread per round so the
+// two code words / two mask words they need are loaded once (32-bit addressing relative to the
+// window's first mask word).  f(p, c32, m, low_bit): p = position in the window, c32 = the 16 bases
+// from p (2 bits each, first base on top), m = unresolved mask of the 32 bases from p (bit 31 = p),
+// low_bit = 1 when base p is lower case.
+template <int NT, typename F>
+__device__ __forceinline__ void for_each_position(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ mw,
+                                                  const uint32_t* __restrict__ lw, uint32_t o_lo, uint32_t len, int tid, F f) {
+    const uint32_t g0 = o_lo >> 2;
+    const uint32_t ngroups = ((o_lo + len + 3u) >> 2) - g0;
+    for (uint32_t gi = tid; gi < ngroups; gi += NT) {
+        const uint32_t a0 = (g0 + gi) << 2, wi = a0 >> 4, mi = a0 >> 5;
+        const uint32_t chi = __ldg(cw + wi), clo = __ldg(cw + wi + 1);
+        const uint32_t mhi = __ldg(mw + mi), mlo = __ldg(mw + mi + 1);
+        const uint32_t lhi = lw ? __ldg(lw + mi) : 0u;
+        const uint32_t cs = (a0 & 15u) * 2u, ms = a0 & 31u;           // cs <= 24, ms <= 28
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t p = a0 + j - o_lo;                          // wraps for bases before the window
+            if (p < len)
+                f(p, __funnelshift_l(clo, chi, cs + 2u * j), __funnelshift_l(mlo, mhi, ms + j), (lhi << (ms + j)) >> 31);
+        }
+    }
+}
+
+template <int K, bool DUMP, bool ALLK>
 __global__ void __launch_bounds__(kT3, 4)
 score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                             const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
-                            const double2* __restrict__ ig, int kmin, int want_rip, uint32_t cap,
+                            const double2* __restrict__ ig, int kmin_arg, int want_rip, uint32_t cap,
                             double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
     using L = Score3Layout<K>;
     constexpr int B = L::B, LD = L::LD, LP = L::LP;
     constexpr uint32_t NBK = L::NBK, PER = L::PER;
+    const int kmin = ALLK ? 1 : kmin_arg;                                // ALLK: the default --minWordSize 1, predicates fold away
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem);                 // orders 1..B
     uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem);
@@ -624,13 +650,9 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         // ---- P1: count orders LD..B (and short words), composition ------------------------------
         {
             int non = 0, gc = 0;
-            for (uint32_t p = tid; p < len; p += kT3) {
-                const uint32_t a = o_lo + p, wi = a >> 4, mi = a >> 5;
-                const uint32_t c32 = __funnelshift_l(__ldg(cw + wi + 1), __ldg(cw + wi), (a & 15u) * 2u);
-                const uint32_t m = __funnelshift_l(__ldg(mw + mi + 1), __ldg(mw + mi), a & 31u);
+            for_each_position<kT3>(cw, mw, lw, o_lo, len, tid, [&](uint32_t p, uint32_t c32, uint32_t m, uint32_t lowbit) {
                 const int v = min(min(__clz(m), K), (int)min(len - p, (uint32_t)K));
-                uint32_t unres = m >> 31;                                    // not an upper-case ATGC (F:106-118)
-                if (lw) unres |= (__ldg(lw + mi) << (a & 31u)) >> 31;
+                const uint32_t unres = (m >> 31) | lowbit;                   // not an upper-case ATGC (F:106-118)
                 non += unres;
                 gc += (1 - unres) & (c32 >> 31);                             // G = 2, C = 3: bit 1 of the first base
                 if (v >= LD) {
@@ -645,7 +667,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                     const uint32_t g = lvl_off(v) + (c32 >> (32 - 2 * v));
                     atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
                 }
-            }
+            });
             non = __reduce_add_sync(kFull, non);
             gc = __reduce_add_sync(kFull, gc);
             if (lane == 0) { atomicAdd(&ss.cnt[par][0], non); atomicAdd(&ss.cnt[par][1], gc); }
@@ -712,10 +734,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         __syncthreads();                                                   // (2b)
 
         // ---- P3: scatter suffix codes into buckets; presence masks; partial sums per order-LP node --
-        for (uint32_t p = tid; p < len; p += kT3) {
-            const uint32_t a = o_lo + p, wi = a >> 4, mi = a >> 5;
-            const uint32_t c32 = __funnelshift_l(__ldg(cw + wi + 1), __ldg(cw + wi), (a & 15u) * 2u);
-            const uint32_t m = __funnelshift_l(__ldg(mw + mi + 1), __ldg(mw + mi), a & 31u);
+        for_each_position<kT3>(cw, mw, lw, o_lo, len, tid, [&](uint32_t p, uint32_t c32, uint32_t m, uint32_t) {
             const int v = min(min(__clz(m), K), (int)min(len - p, (uint32_t)K));
             if (v >= B) {
                 const uint32_t b = c32 >> (32 - 2 * B);
@@ -727,7 +746,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 else if (v == K - 1) code5 = 16u + (sfx >> 2);
                 buf[(old >> sh) & 0xffffu] = (uint8_t)code5;
             }
-        }
+        });
         for (uint32_t node = tid; node < L::NPRE; node += kT3) {
             double num = 0.0;
             uint32_t den = 0;
@@ -754,17 +773,27 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         }
         __syncthreads();                                                   // (3)
 
-        // ---- P4a: popcounts of the presence masks -> sorted list of the distinct K-mers -----------
-        uint32_t masks[(PER + 1) / 2];
-        uint32_t dcount = 0;
+        // ---- P4a: popcounts of the presence masks -> sorted lists of the distinct K-mers -----------
+        // A bucket is "clean" when every entry is a distinct K-mer (count == popc(mask)): its K-mers
+        // have order-K count 1 and order-(K-1) count popc(mask group).  Clean K-mers fill the list
+        // from the front, the others ("dirty": repeats or short words in the bucket, recounted from
+        // the bucket entries) from the back, so each scoring loop below runs converged.
+        uint32_t masks[(PER + 1) / 2];          // this thread's PER buckets: 16 presence bits each, bucket i at bits 16i..16i+15
+        uint32_t dirty = 0;                     // same layout: 0xffff over a dirty bucket
+        uint32_t cnt2 = 0;                      // clean count | dirty count << 16
 #pragma unroll
         for (uint32_t i = 0; i < (PER + 1) / 2; ++i) {
             masks[i] = 0;
             if ((uint32_t)tid * PER + 2 * i < NBK) {
-                if (PER >= 2) masks[i] = mask32[(tid * PER) / 2 + i];
-                else masks[i] = mask16[tid];
+                uint32_t nb2;
+                if (PER >= 2) { masks[i] = mask32[(tid * PER) / 2 + i]; nb2 = reinterpret_cast<const uint32_t*>(tabB)[(tid * PER) / 2 + i]; }
+                else { masks[i] = mask16[tid]; nb2 = tabB[tid]; }
+                const uint32_t lo = masks[i] & 0xffffu, hi = masks[i] >> 16;
+                const uint32_t plo = __popc(lo), phi = __popc(hi);
+                const bool dlo = (nb2 & 0xffffu) != plo, dhi = (nb2 >> 16) != phi;
+                if (i < 16) dirty |= ((dlo ? 1u : 0u) | (dhi ? 2u : 0u)) << (2 * i);
+                cnt2 += (dlo ? plo << 16 : plo) + (dhi ? phi << 16 : phi);
             }
-            dcount += __popc(masks[i]);
         }
         if (DUMP) {   // tests only: order K-1 counts of the window, straight from the bucket entries
 #pragma unroll 1
@@ -782,51 +811,41 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 }
             }
         }
-        uint32_t dincl = dcount;
+        uint32_t incl2 = cnt2;
 #pragma unroll
         for (int ofs = 1; ofs < 32; ofs <<= 1) {
-            const uint32_t y = __shfl_up_sync(kFull, dincl, ofs);
-            if (lane >= ofs) dincl += y;
+            const uint32_t y = __shfl_up_sync(kFull, incl2, ofs);
+            if (lane >= ofs) incl2 += y;
         }
-        if (lane == 31) ss.warp_tot[warp] = dincl;                         // (its use by the bucket scan ended before barrier 2b)
+        if (lane == 31) ss.warp_tot[warp] = incl2;                         // (its use by the bucket scan ended before barrier 2b)
         __syncthreads();                                                   // (3c)
-        uint32_t n_list = 0;
+        uint32_t n_clean, n_dirty;
         {
-            uint32_t off = dincl - dcount;
+            uint32_t tot2 = 0, off2 = incl2 - cnt2;
 #pragma unroll
-            for (int w = 0; w < kW3; ++w) { const uint32_t t = ss.warp_tot[w]; n_list += t; off += (w < warp) ? t : 0u; }
+            for (int w = 0; w < kW3; ++w) { const uint32_t t = ss.warp_tot[w]; tot2 += t; off2 += (w < warp) ? t : 0u; }
+            n_clean = tot2 & 0xffffu; n_dirty = tot2 >> 16;
+            uint32_t offc = off2 & 0xffffu;                 // clean K-mers: list[0 .. n_clean)
+            uint32_t offd = cap - 1u - (off2 >> 16);        // dirty K-mers: list[cap-1] downwards
 #pragma unroll
-            for (uint32_t i = 0; i < PER; ++i) {
-                uint32_t mask = (masks[i / 2] >> (16 * (i & 1))) & 0xffffu;
-                const uint32_t b = tid * PER + i;
-                while (mask) {
-                    const uint32_t sfx = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    list[off++] = (uint16_t)((b << 4) | sfx);
-                }
+            for (uint32_t i = 0; i < (PER + 1) / 2; ++i) {
+                const uint32_t dm = ((dirty >> (2 * i)) & 1u ? 0xffffu : 0u) | ((dirty >> (2 * i)) & 2u ? 0xffff0000u : 0u);
+                const uint32_t base = (tid * PER + 2 * i) << 4;          // K-mer index of bit 0 of this word
+                uint32_t w = masks[i] & ~dm;
+                while (w) { const uint32_t bit = __ffs(w) - 1; w &= w - 1; list[offc++] = (uint16_t)(base + bit); }
+                w = masks[i] & dm;
+                while (w) { const uint32_t bit = __ffs(w) - 1; w &= w - 1; list[offd--] = (uint16_t)(base + bit); }
             }
         }
         __syncthreads();                                                   // (3d)
 
-        // ---- P4b: score the distinct K-mers (converged: one list entry per thread per round) ------
+        // ---- P4b: score the distinct K-mers, one list entry per thread per round -------------------
         double s_w = 0.0, s_g = 0.0, s_t = 0.0;
         int bad = 0;
-        const double q7 = ss.q[K - 2], q8 = ss.q[K - 1];
-        for (uint32_t e = tid; e < n_list; e += kT3) {
-            const uint32_t kappa = list[e];
-            const uint32_t b = kappa >> 4, sfx = kappa & 15u, j = sfx >> 2;
-            const uint32_t nb = tabB[b];
-            const uint32_t msk = mask16[b];
-            uint32_t c8 = 1, c7 = __popc((msk >> (4 * j)) & 15u);           // right when every entry is a distinct K-mer
-            if (nb != (uint32_t)__popc(msk)) {                              // repeats or short words in the bucket: recount
-                const uint32_t end = cur16[b];                             // the cursor finished at the bucket's end
-                c8 = 0; c7 = 0;
-                for (uint32_t i = end - nb; i < end; ++i) {
-                    const uint32_t c5 = buf[i];
-                    c8 += (c5 == sfx);
-                    c7 += (c5 < 16u) ? ((c5 >> 2) == j) : (c5 == 16u + j);
-                }
-            }
+        double qr[K - LP];                                                 // q of the orders LP+1..K
+#pragma unroll
+        for (int x = LP + 1; x <= K; ++x) qr[x - LP - 1] = ss.q[x - 1];
+        auto score_one = [&](uint32_t kappa, uint32_t b, uint32_t nb, uint32_t c7, uint32_t c8) {
             if (DUMP) dmp[lvl_off(K) + kappa] = (uint16_t)c8;
             // orders <= LP from `pre`, orders LP+1..B from the tables, then K-1 and K
             const double2 pp = pre[b >> (2 * (B - LP))];
@@ -837,22 +856,40 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 if (x >= kmin) {
                     const uint32_t c = (x == B) ? nb : (uint32_t)tab16[lvl_off(x) + (b >> (2 * (B - x)))];
                     den += c << (2 * x);
-                    num = fma(ss.q[x - 1], u32_to_double(c * c), num);
+                    num = fma(qr[x - LP - 1], u32_to_double(c * c), num);
                 }
             }
             if (K - 1 >= kmin) {
                 den += c7 << (2 * (K - 1));
-                num = fma(q7, u32_to_double(c7 * c7), num);
+                num = fma(qr[K - LP - 2], u32_to_double(c7 * c7), num);
             }
             den += c8 << (2 * K);
-            num = fma(q8, u32_to_double(c8 * c8), num);
+            num = fma(qr[K - LP - 1], u32_to_double(c8 * c8), num);
             const double iw = div_pos(num, (double)den);
             const double2 g = __ldg(ig + kappa);
             s_w += iw;
             s_g += g.x;
             s_t = fma(iw, log2_pos(iw, logtab) - g.y, s_t);
             bad |= (g.x != g.x);
+        };
+        for (uint32_t e = tid; e < n_clean; e += kT3) {
+            const uint32_t kappa = list[e];
+            const uint32_t b = kappa >> 4, j = (kappa >> 2) & 3u;
+            score_one(kappa, b, tabB[b], __popc(((uint32_t)mask16[b] >> (4 * j)) & 15u), 1u);
         }
+        for (uint32_t e = tid; e < n_dirty; e += kT3) {
+            const uint32_t kappa = list[cap - 1u - e];
+            const uint32_t b = kappa >> 4, sfx = kappa & 15u, j = sfx >> 2;
+            const uint32_t nb = tabB[b], end = cur16[b];                   // the cursor finished at the bucket's end
+            uint32_t c8 = 0, c7 = 0;
+            for (uint32_t i = end - nb; i < end; ++i) {
+                const uint32_t c5 = buf[i];
+                c8 += (c5 == sfx);
+                c7 += (c5 < 16u) ? ((c5 >> 2) == j) : (c5 == 16u + j);
+            }
+            score_one(kappa, b, nb, c7, c8);
+        }
+        const uint32_t n_list = n_clean + n_dirty;
 #pragma unroll
         for (int ofs = 16; ofs; ofs >>= 1) {
             s_w += __shfl_xor_sync(kFull, s_w, ofs);
@@ -1022,14 +1059,14 @@ int launch_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* low
     return FRISK_OK;
 }
 
-template <int K, bool DUMP>
+template <int K, bool DUMP, bool ALLK>
 int launch_score_bucket2(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                          const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
                          double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
     using L = Score3Layout<K>;
     const uint32_t cap = (max_len + 15u) & ~15u;
     const size_t smem = L::total(cap);
-    auto kern = score_windows_bucket_kernel<K, DUMP>;
+    auto kern = score_windows_bucket_kernel<K, DUMP, ALLK>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT3, smem));
@@ -1049,8 +1086,12 @@ template <int K>
 int launch_score_bucket(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                         const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
                         double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
-    if (dump) return launch_score_bucket2<K, true>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
-    return launch_score_bucket2<K, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
+    // the test-only table dump and kmin > 1 share the generic instantiation; the production default
+    // (no dump, --minWordSize 1) gets the specialised one
+    if (dump || kmin != 1)
+        return dump ? launch_score_bucket2<K, true, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st)
+                    : launch_score_bucket2<K, false, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
+    return launch_score_bucket2<K, false, true>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
 }
 
 #define DISPATCH_K(kmax, expr)                      \

@@ -1,7 +1,7 @@
 #!/bin/bash
 # parity tests + smoke + bench (no profiling)
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q -s 2>&1 | tail -25
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 python bench.py --steps 20 --warmup 3 --profile > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; python - <<'PY'
 import json
