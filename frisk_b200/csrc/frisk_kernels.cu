@@ -107,47 +107,79 @@ bg_count_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__
     }
 }
 
-// One CTA.  F_x = short-word counts of order x + marginal of F_{x+1}; tables = F + F(revcomp).
+// Finalising the tables: F_x = short-word counts of order x + marginal of F_{x+1}; then
+// tables = F + F(revcomp).  Three small launches instead of one serial CTA:
+//   forward_totals_kernel   one CTA per order-R subtree (R = K-4): F_x for x = R..K
+//   forward_low_kernel      one CTA: F_x for x = R-1..1 (<= 84 bins)
+//   symmetrise_kernel       one thread per table entry, each {kmer, revcomp} pair handled once
 template <int K>
-__global__ void __launch_bounds__(kThreads, 1)
-finalize_tables_kernel(const unsigned long long* __restrict__ fwd, unsigned long long* __restrict__ tables,
-                       unsigned long long* __restrict__ valid_kmax, int symmetric) {
-    // `tables` doubles as scratch for the forward totals F_x until the symmetrise step.
-    __shared__ unsigned long long red[kWarps];
-    unsigned long long local = 0;
-    for (uint32_t b = threadIdx.x; b < pow4(K); b += kThreads) {
-        const unsigned long long c = fwd[lvl_off(K) + b];
-        tables[lvl_off(K) + b] = c;
-        local += c;
+__global__ void __launch_bounds__(256)
+forward_totals_kernel(const unsigned long long* __restrict__ fwd, unsigned long long* __restrict__ tables,
+                      unsigned long long* __restrict__ valid_kmax) {
+    constexpr int R = K > 4 ? K - 4 : 0;
+    __shared__ unsigned long long lvl[2][256];
+    __shared__ unsigned long long red[8];
+    const uint32_t root = blockIdx.x, t = threadIdx.x;
+    uint32_t n = pow4(K - R);                         // subtree nodes at the current order
+    unsigned long long v = 0;
+    if (t < n) {
+        v = fwd[lvl_off(K) + root * n + t];
+        tables[lvl_off(K) + root * n + t] = v;
+        lvl[0][t] = v;
     }
+    unsigned long long local = v;                     // valid K-words of this subtree
     for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(kFull, local, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    if ((t & 31) == 0) red[t >> 5] = local;
     __syncthreads();
-    if (threadIdx.x == 0 && valid_kmax) {
-        unsigned long long s = 0;
-        for (int w = 0; w < kWarps; ++w) s += red[w];
-        *valid_kmax = s;
+    if (t == 0 && valid_kmax) {
+        unsigned long long sum = 0;
+        for (int w = 0; w < 8; ++w) sum += red[w];
+        if (sum) atomicAdd(valid_kmax, sum);
     }
-    for (int x = K - 1; x >= 1; --x) {
-        for (uint32_t b = threadIdx.x; b < pow4(x); b += kThreads) {
-            const unsigned long long* ch = tables + lvl_off(x + 1) + 4 * b;
-            tables[lvl_off(x) + b] = fwd[lvl_off(x) + b] + ch[0] + ch[1] + ch[2] + ch[3];
+    int cur = 0;
+    for (int x = K - 1; x >= (R > 1 ? R : 1); --x) {
+        n >>= 2;
+        if (t < n) {
+            const unsigned long long* ch = &lvl[cur][4 * t];
+            const unsigned long long f = fwd[lvl_off(x) + root * n + t] + ch[0] + ch[1] + ch[2] + ch[3];
+            tables[lvl_off(x) + root * n + t] = f;
+            lvl[cur ^ 1][t] = f;
+        }
+        cur ^= 1;
+        __syncthreads();
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(64)
+forward_low_kernel(const unsigned long long* __restrict__ fwd, unsigned long long* __restrict__ tables) {
+    constexpr int R = K > 4 ? K - 4 : 0;
+    for (int x = R - 1; x >= 1; --x) {
+        const uint32_t t = threadIdx.x;
+        if (t < pow4(x)) {
+            const unsigned long long* ch = tables + lvl_off(x + 1) + 4 * t;
+            tables[lvl_off(x) + t] = fwd[lvl_off(x) + t] + ch[0] + ch[1] + ch[2] + ch[3];
         }
         __syncthreads();
     }
-    if (!symmetric) return;       // forward strand only: computeKmers(window=..., sym=False), F:1480
-    // symmetrise in place: each unordered pair {b, rc(b)} is handled by the thread owning min(b, rc)
-    for (int x = 1; x <= K; ++x) {
-        for (uint32_t b = threadIdx.x; b < pow4(x); b += kThreads) {
-            const uint32_t r = revcomp_idx(b, x);
-            if (b < r) {
-                const unsigned long long s = tables[lvl_off(x) + b] + tables[lvl_off(x) + r];
-                tables[lvl_off(x) + b] = s;
-                tables[lvl_off(x) + r] = s;
-            } else if (b == r) {
-                tables[lvl_off(x) + b] *= 2ull;   // palindrome: +1 word, +1 its own reverse complement
-            }
-        }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+symmetrise_kernel(unsigned long long* __restrict__ tables) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= lvl_off(K + 1)) return;
+    int x = 1;
+#pragma unroll
+    for (int y = 2; y <= K; ++y) x += (i >= lvl_off(y));
+    const uint32_t b = i - lvl_off(x);
+    const uint32_t r = revcomp_idx(b, x);
+    if (b < r) {
+        const unsigned long long sum = tables[i] + tables[lvl_off(x) + r];
+        tables[i] = sum;
+        tables[lvl_off(x) + r] = sum;
+    } else if (b == r) {
+        tables[i] *= 2ull;                          // palindrome: +1 word, +1 its own reverse complement
     }
 }
 
@@ -530,9 +562,10 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
 // The dense 4^K table of score_windows_kernel costs 128 KiB and forces one CTA per SM, whose phases
 // (count / scan / score) then run back to back with barriers between them.  A window of L bases has
 // at most L distinct K-mers, so instead the K-mers are counting-sorted by their (K-2)-prefix:
-//   P1  per position: u16 shared-memory atomics on the orders LD..B only (B = K-2, 4^B buckets;
-//       LD = min(5,B)); composition counts on the way (30 % rule, GC)
-//   P2  warp 0 marginalises orders LD-1..1; exclusive scan of the order-B counts -> bucket cursors
+//   P1  per position: ONE u16 shared-memory atomic, on order B = K-2 (4^B buckets), or on order v
+//       for a word valid for v < B bases only; composition counts on the way (30 % rule, GC)
+//   P2  exclusive scan of the order-B counts -> bucket cursors; orders B-1..1 by marginalisation
+//       (4 children -> parent) inside the same pass
 //   P3  per position: claim a slot in its bucket (atomic on the cursor) and store a 5-bit code: the
 //       2-base suffix (0..15), or 16+b for a word valid for K-1 bases only, or 20 for K-2 only;
 //       OR the suffix into the bucket's 16-bit presence mask.  Per order-LP node (LP = min(4,B)) the
@@ -560,7 +593,6 @@ template <int K>
 struct Score3Layout {
     static constexpr int B = K - 2;                                     // bucket order
     static constexpr uint32_t NBK = pow4(B);
-    static constexpr int LD = B < 5 ? B : 5;                            // lowest order counted by atomics
     static constexpr int LP = B < 4 ? B : 4;                            // order of the shared partial sums
     static constexpr uint32_t NPRE = pow4(LP);
     static constexpr uint32_t PER = NBK >= (uint32_t)kT3 ? NBK / kT3 : 1u;   // buckets per thread (contiguous)
@@ -610,7 +642,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                             const double2* __restrict__ ig, int kmin_arg, int want_rip, uint32_t cap,
                             double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
     using L = Score3Layout<K>;
-    constexpr int B = L::B, LD = L::LD, LP = L::LP;
+    constexpr int B = L::B, LP = L::LP;
     constexpr uint32_t NBK = L::NBK, PER = L::PER;
     const int kmin = ALLK ? 1 : kmin_arg;                                // ALLK: the default --minWordSize 1, predicates fold away
     extern __shared__ __align__(16) unsigned char smem[];
@@ -647,7 +679,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         const uint32_t* __restrict__ mw = inv + (o >> 5);
         const uint32_t* __restrict__ lw = low ? low + (o >> 5) : nullptr;
 
-        // ---- P1: count orders LD..B (and short words), composition ------------------------------
+        // ---- P1: count order B (and short words), composition ------------------------------------
         {
             int non = 0, gc = 0;
             for_each_position<kT3>(cw, mw, lw, o_lo, len, tid, [&](uint32_t p, uint32_t c32, uint32_t m, uint32_t lowbit) {
@@ -655,16 +687,9 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 const uint32_t unres = (m >> 31) | lowbit;                   // not an upper-case ATGC (F:106-118)
                 non += unres;
                 gc += (1 - unres) & (c32 >> 31);                             // G = 2, C = 3: bit 1 of the first base
-                if (v >= LD) {
-#pragma unroll
-                    for (int x = LD; x <= B; ++x) {
-                        if (x <= v) {
-                            const uint32_t g = lvl_off(x) + (c32 >> (32 - 2 * x));
-                            atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
-                        }
-                    }
-                } else if (v > 0) {
-                    const uint32_t g = lvl_off(v) + (c32 >> (32 - 2 * v));
+                if (v > 0) {                                               // one atomic: order min(v, B)
+                    const int x = v < B ? v : B;
+                    const uint32_t g = lvl_off(x) + (c32 >> (32 - 2 * x));
                     atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
                 }
             });
@@ -694,21 +719,27 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             ss.q[tid] = (double)pow4(x) / (double)d;
         }
 
-        // ---- P2: orders LD-1..1 (warp 0); exclusive scan of the order-B counts -------------------
-        if (warp == 0) {
-#pragma unroll
-            for (int x = LD - 1; x >= 1; --x) {
-                for (uint32_t t = lane; t < pow4(x); t += 32) {
-                    const uint2 ch = *reinterpret_cast<const uint2*>(tab16 + lvl_off(x + 1) + 4 * t);
-                    tab16[lvl_off(x) + t] += (uint16_t)((ch.x & 0xffffu) + (ch.x >> 16) + (ch.y & 0xffffu) + (ch.y >> 16));
-                }
-                __syncwarp();
-            }
-        }
+        // ---- P2: exclusive scan of the order-B counts; lower orders by marginalisation ------------
+        // A thread's PER contiguous order-B bins are the children of PER/4 order-(B-1) bins and of
+        // PER/16 order-(B-2) bins, summed here on the way; warp 0 finishes orders LW-1..1 below.
         uint32_t mine = 0;
         if ((uint32_t)tid * PER < NBK) {
+            if constexpr (PER >= 4) {
+                uint32_t quad = 0;
 #pragma unroll
-            for (uint32_t j = 0; j < PER; ++j) mine += tabB[tid * PER + j];
+                for (uint32_t g = 0; g < PER / 4; ++g) {
+                    const uint2 ch = *reinterpret_cast<const uint2*>(tabB + tid * PER + 4 * g);
+                    uint32_t sum4 = (ch.x & 0xffffu) + (ch.x >> 16) + (ch.y & 0xffffu) + (ch.y >> 16);
+                    mine += sum4;
+                    uint16_t* par1 = tab16 + lvl_off(B - 1) + (tid * PER) / 4 + g;
+                    sum4 += *par1;                                           // + the short words of order B-1
+                    *par1 = (uint16_t)sum4;
+                    quad += sum4;
+                }
+                if constexpr (PER >= 16) tab16[lvl_off(B - 2) + tid] += (uint16_t)quad;
+            } else {
+                mine = tabB[tid];
+            }
         }
         uint32_t incl = mine;
 #pragma unroll
@@ -718,6 +749,17 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         }
         if (lane == 31) ss.warp_tot[warp] = incl;
         __syncthreads();                                                   // (2a)
+        if (warp == 0) {
+            constexpr int LW = B - (PER >= 16 ? 2 : (PER >= 4 ? 1 : 0));  // lowest order that is complete by now
+#pragma unroll
+            for (int x = LW - 1; x >= 1; --x) {
+                for (uint32_t t = lane; t < pow4(x); t += 32) {
+                    const uint2 ch = *reinterpret_cast<const uint2*>(tab16 + lvl_off(x + 1) + 4 * t);
+                    tab16[lvl_off(x) + t] += (uint16_t)((ch.x & 0xffffu) + (ch.x >> 16) + (ch.y & 0xffffu) + (ch.y >> 16));
+                }
+                __syncwarp();
+            }
+        }
         {
             uint32_t run = incl - mine;
 #pragma unroll
@@ -761,7 +803,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             pre[node] = make_double2(num, __hiloint2double(0, (int)den));
         }
         uint32_t n_at = 0, n_ta = 0, n_sub = 0, n_prod = 0;
-        if (tid == 0 && want_rip) {                        // orders < LD are final since barrier (2a); K >= 4 so B >= 2
+        if (tid == 0 && want_rip) {                        // all orders are final since barrier (2b); K >= 4 so B >= 2
             const uint16_t* di = tab16 + lvl_off(2);
             n_at = di[1]; n_ta = di[4];
             n_sub = (uint32_t)di[3] + di[9];
@@ -1020,9 +1062,13 @@ int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t
 
 template <int K>
 int launch_finalize(const uint64_t* fwd, int symmetric, uint64_t* tables, uint64_t* valid, cudaStream_t st) {
-    finalize_tables_kernel<K><<<1, kThreads, 0, st>>>(reinterpret_cast<const unsigned long long*>(fwd),
-                                                      reinterpret_cast<unsigned long long*>(tables),
-                                                      reinterpret_cast<unsigned long long*>(valid), symmetric);
+    constexpr int R = K > 4 ? K - 4 : 0;
+    auto f = reinterpret_cast<const unsigned long long*>(fwd);
+    auto t = reinterpret_cast<unsigned long long*>(tables);
+    if (valid) CK(cudaMemsetAsync(valid, 0, sizeof(uint64_t), st));
+    forward_totals_kernel<K><<<pow4(R), 256, 0, st>>>(f, t, reinterpret_cast<unsigned long long*>(valid));
+    if (R > 1) forward_low_kernel<K><<<1, 64, 0, st>>>(f, t);
+    if (symmetric) symmetrise_kernel<K><<<(lvl_off(K + 1) + 255) / 256, 256, 0, st>>>(t);
     CK(cudaGetLastError());
     return FRISK_OK;
 }
