@@ -620,11 +620,20 @@ __device__ __forceinline__ void for_each_position(const uint32_t* __restrict__ c
                                                   const uint32_t* __restrict__ lw, uint32_t o_lo, uint32_t len, int tid, F f) {
     const uint32_t g0 = o_lo >> 2;
     const uint32_t ngroups = ((o_lo + len + 3u) >> 2) - g0;
-    for (uint32_t gi = tid; gi < ngroups; gi += NT) {
-        const uint32_t a0 = (g0 + gi) << 2, wi = a0 >> 4, mi = a0 >> 5;
-        const uint32_t chi = __ldg(cw + wi), clo = __ldg(cw + wi + 1);
-        const uint32_t mhi = __ldg(mw + mi), mlo = __ldg(mw + mi + 1);
-        const uint32_t lhi = lw ? __ldg(lw + mi) : 0u;
+    uint32_t gi = tid;
+    if (gi >= ngroups) return;
+    uint32_t a0 = (g0 + gi) << 2;
+    uint32_t chi = __ldg(cw + (a0 >> 4)), clo = __ldg(cw + (a0 >> 4) + 1);
+    uint32_t mhi = __ldg(mw + (a0 >> 5)), mlo = __ldg(mw + (a0 >> 5) + 1);
+    uint32_t lhi = lw ? __ldg(lw + (a0 >> 5)) : 0u;
+    for (;;) {
+        // issue the next round's loads before working on this round (hides the L2 latency)
+        const uint32_t gn = gi + NT;
+        const bool more = gn < ngroups;
+        const uint32_t an = (g0 + (more ? gn : gi)) << 2;
+        const uint32_t nchi = __ldg(cw + (an >> 4)), nclo = __ldg(cw + (an >> 4) + 1);
+        const uint32_t nmhi = __ldg(mw + (an >> 5)), nmlo = __ldg(mw + (an >> 5) + 1);
+        const uint32_t nlhi = lw ? __ldg(lw + (an >> 5)) : 0u;
         const uint32_t cs = (a0 & 15u) * 2u, ms = a0 & 31u;           // cs <= 24, ms <= 28
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
@@ -632,6 +641,8 @@ __device__ __forceinline__ void for_each_position(const uint32_t* __restrict__ c
             if (p < len)
                 f(p, __funnelshift_l(clo, chi, cs + 2u * j), __funnelshift_l(mlo, mhi, ms + j), (lhi << (ms + j)) >> 31);
         }
+        if (!more) break;
+        gi = gn; a0 = an; chi = nchi; clo = nclo; mhi = nmhi; mlo = nmlo; lhi = nlhi;
     }
 }
 
@@ -683,14 +694,18 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         {
             int non = 0, gc = 0;
             for_each_position<kT3>(cw, mw, lw, o_lo, len, tid, [&](uint32_t p, uint32_t c32, uint32_t m, uint32_t lowbit) {
-                const int v = min(min(__clz(m), K), (int)min(len - p, (uint32_t)K));
                 const uint32_t unres = (m >> 31) | lowbit;                   // not an upper-case ATGC (F:106-118)
                 non += unres;
                 gc += (1 - unres) & (c32 >> 31);                             // G = 2, C = 3: bit 1 of the first base
-                if (v > 0) {                                               // one atomic: order min(v, B)
-                    const int x = v < B ? v : B;
-                    const uint32_t g = lvl_off(x) + (c32 >> (32 - 2 * x));
+                if ((m >> (32 - B)) == 0u && p + B <= len) {                 // the common case: >= B valid bases ahead
+                    const uint32_t g = lvl_off(B) + (c32 >> (32 - 2 * B));
                     atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
+                } else {                                                     // window end / N boundary: order v < B
+                    const int v = min(__clz(m), (int)(len - p));
+                    if (v > 0) {
+                        const uint32_t g = lvl_off(v) + (c32 >> (32 - 2 * v));
+                        atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
+                    }
                 }
             });
             non = __reduce_add_sync(kFull, non);
@@ -777,16 +792,19 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
 
         // ---- P3: scatter suffix codes into buckets; presence masks; partial sums per order-LP node --
         for_each_position<kT3>(cw, mw, lw, o_lo, len, tid, [&](uint32_t p, uint32_t c32, uint32_t m, uint32_t) {
-            const int v = min(min(__clz(m), K), (int)min(len - p, (uint32_t)K));
-            if (v >= B) {
-                const uint32_t b = c32 >> (32 - 2 * B);
-                const uint32_t sfx = (c32 >> (32 - 2 * K)) & 15u;
-                const uint32_t sh = (b & 1u) * 16u;
+            const uint32_t b = c32 >> (32 - 2 * B);
+            const uint32_t sfx = (c32 >> (32 - 2 * K)) & 15u;
+            const uint32_t sh = (b & 1u) * 16u;
+            if ((m >> (32 - K)) == 0u && p + K <= len) {                     // the common case: a full K-word
                 const uint32_t old = atomicAdd(&cur32[b >> 1], 1u << sh);
-                uint32_t code5 = 20u;
-                if (v == K) { code5 = sfx; atomicOr(&mask32[b >> 1], (1u << sfx) << sh); }
-                else if (v == K - 1) code5 = 16u + (sfx >> 2);
-                buf[(old >> sh) & 0xffffu] = (uint8_t)code5;
+                atomicOr(&mask32[b >> 1], (1u << sfx) << sh);
+                buf[(old >> sh) & 0xffffu] = (uint8_t)sfx;
+            } else {
+                const int v = min(__clz(m), (int)(len - p));
+                if (v >= B) {                                                // valid for K-1 or K-2 bases only
+                    const uint32_t old = atomicAdd(&cur32[b >> 1], 1u << sh);
+                    buf[(old >> sh) & 0xffffu] = (uint8_t)(v == K - 1 ? 16u + (sfx >> 2) : 20u);
+                }
             }
         });
         for (uint32_t node = tid; node < L::NPRE; node += kT3) {

@@ -56,3 +56,47 @@ def reduce_counts_cpu(tables: np.ndarray, genome_space: int, group=None) -> Tupl
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     out = buf.numpy()
     return out[:-1].astype(np.uint64), int(out[-1])
+
+
+def score_sharded(scaffolds, group=None, device=None, **params):
+    """Multi-GPU hot path, one call per rank: this rank packs and scores its own scaffolds against
+    the background of ALL ranks' scaffolds (one NCCL all-reduce inside the pipeline).
+
+    Returns (local HotPathResult whose ``tables`` are the global ones and ``meta`` the global
+    (totalLen, exMax, nnTotal), list of this rank's scaffold indices)."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    mine = shard_scaffolds([len(s) for _, s in scaffolds], world)[rank]
+    genome = engine.PackedGenome.from_scaffolds([scaffolds[i] for i in mine], pinned=True)
+    space = global_genome_space(genome.genome_space, device, group)
+    pipe = engine.Pipeline(genome, device=device, allreduce=make_allreduce(group), genome_space=space, **params)
+    pipe.enqueue()
+    res = pipe.result()
+    meta = torch.tensor(list(res.meta), dtype=torch.int64, device=device)
+    dist.all_reduce(meta, op=dist.ReduceOp.SUM, group=group)        # totalLen, exMax, nnTotal are sums over scaffolds
+    res.meta = tuple(int(x) for x in meta.tolist())
+    return res, mine
+
+
+def gather_rows(res, mine, group=None, dst: int = 0):
+    """Collect every rank's rows on rank `dst` in the reference's order (scaffold order of the
+    input, windows in order inside a scaffold).  Returns (names, coords, rows, status) or None."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    original = np.asarray(mine, dtype=np.int64)[res.row_scaf] if len(res.row_scaf) else np.zeros(0, np.int64)
+    payload = (original, res.names, res.coords, res.rows, res.status)
+    out = [None] * world if rank == dst else None
+    dist.gather_object(payload, out, dst=dst, group=group)
+    if rank != dst:
+        return None
+    key = np.concatenate([o[0] for o in out])
+    names = [n for o in out for n in o[1]]
+    coords = np.concatenate([o[2].reshape(-1, 2) for o in out])
+    rows = np.concatenate([o[3].reshape(-1, 5) for o in out])
+    status = np.concatenate([o[4] for o in out])
+    order = np.argsort(key, kind="stable")
+    return [names[i] for i in order], coords[order], rows[order], status[order]

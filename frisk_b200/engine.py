@@ -267,6 +267,7 @@ class HotPathResult:
     status: np.ndarray            # uint32 [n] FRISK_ROW_* bits (never EXCLUDED)
     n_candidates: int = 0
     win_index: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # candidate index of each row
+    row_scaf: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))   # scaffold index (in the query) of each row
     win_tables: Optional[np.ndarray] = None   # uint16 [n, table_size(kmin,kmax)] when dump=True
 
     def raise_reference_errors(self) -> None:
@@ -296,7 +297,7 @@ def assemble(query: PackedGenome, host: PackedGenome, wins: WindowList, tables_1
     if dump is not None:
         wt = _slice_orders(dump[idx], kmin, kmax)
     return HotPathResult(kmin, kmax, _slice_orders(tables_1k, kmin, kmax).copy(), meta, names, coords,
-                         rows[idx], status[idx].astype(np.uint32), len(wins), idx, wt)
+                         rows[idx], status[idx].astype(np.uint32), len(wins), idx, wins.scaf[idx].astype(np.int64), wt)
 
 
 class Pipeline:

@@ -1,0 +1,102 @@
+"""GPU tests of the reference-facing function surface (computeKmers / IvomBuild / KLD / main)."""
+import pickle
+import types
+
+import numpy as np
+import pytest
+
+from tests.helpers import Golden, assert_rows_close, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(path, g, tmp, **extra):
+    p = g.params
+    d = dict(hostSeq=path, querySeq=None, minWordSize=p["kmin"], maxWordSize=p["kmax"], windowlen=p["w"], increment=p["i"],
+             maskHost=p["maskHost"], scaffoldsAll=p["scaffoldsAll"], RIP=p["RIP"], pcaMin=1, pcaMax=6, tempDir=str(tmp))
+    d.update(extra)
+    return types.SimpleNamespace(**d)
+
+
+def _arr(maps, kmin, kmax):
+    return np.concatenate([np.fromiter(maps[k - kmin].values(), dtype=np.uint64) for k in range(kmin, kmax + 1)])
+
+
+@pytest.mark.parametrize("case", ["edge_default", "edge_maskHost", "edge_k2_5_w1000_i250"])
+def test_compute_kmers_and_scoring_functions(tmp_path, case):
+    import frisk
+    from frisk_b200 import synth
+    from oracle import frisk_oracle
+    g = Golden(case)
+    path = str(tmp_path / "g.fa")
+    synth.write_fasta(g.scaffolds(), path)
+    args = _args(path, g, tmp_path)
+    kmin, kmax = args.minWordSize, args.maxWordSize
+    blank = frisk.rangeMaps(kmin, kmax)
+    pk = str(tmp_path / "genome.p")
+    genome = frisk.computeKmers(args, genomepickle=pk, window=None, genomeMode=True, kmerMap=blank, getMeta=True)
+    assert np.array_equal(_arr(genome, kmin, kmax), g.tables)
+    kr = kmax - kmin
+    assert [genome[kr + 1]["totalLen"], genome[kr + 2]["exMax"], genome[kr + 3]["nnTotal"]] == [int(x) for x in g.genome_meta]
+    assert list(genome[0].keys()) == list(blank[0].keys())                      # reference dict order
+    assert pickle.load(open(pk, "rb")) == genome                               # F:363
+    # the per-window loop of the reference's main(), function by function (F:1478-1488), first 3 windows
+    rows = []
+    for n, (seq, name, start, stop) in enumerate(frisk.crawlGenome(args, path)):
+        if n == 3:
+            break
+        win = frisk.computeKmers(args, window=[(name, seq)], genomeMode=False, kmerMap=blank, getMeta=True)
+        ref_win = frisk_oracle.compute_kmers([(name, seq)], kmin, kmax, both_strands=False)
+        assert win == ref_win
+        gi = frisk.IvomBuild(win, args, genome, True)
+        wi = frisk.IvomBuild(win, args, genome, False)
+        ref_gi = frisk_oracle.ivom_build(ref_win, genome, kmin, kmax, True)
+        assert list(gi.keys()) == list(ref_gi.keys())
+        assert max_rel_err(list(gi.values()), list(ref_gi.values()), atol=0) < 1e-12
+        kld = frisk.KLD(gi, wi, args)
+        rows.append((name, start, stop, kld, frisk.calcGC(seq)) + tuple(frisk.calcRIP(win, args)))
+    vals = np.array([r[3:] for r in rows], float)
+    assert [r[0] for r in rows] == g.names[:3]
+    assert_rows_close(vals, g.vals[:3], rtol_kld=1e-6, rtol_other=0.0, what=case + "[function API]")
+    # symmetric (PCA-feature) counting: second caller of the counting kernel (F:1571-1578)
+    seq, name = rows and frisk_oracle.iter_fasta(path).__next__()[1][:4000], "x"
+    sym = frisk.computeKmers(types.SimpleNamespace(pcaMin=1, pcaMax=6, maskHost=False), window=[(name, seq)], pcaMode=True,
+                             kmerMap=frisk.rangeMaps(1, 6), getMeta=False, sym=True)
+    assert sym == frisk_oracle.compute_kmers([(name, seq)], 1, 6, both_strands=True)[:6]
+
+
+@pytest.mark.parametrize("case,flags", [("edge_default", ["--RIP"]), ("edge_scaffoldsAll", ["--RIP", "--scaffoldsAll"]),
+                                        ("edge_k2_5_w1000_i250", ["--RIP", "-m", "2", "-k", "5", "-w", "1000", "-i", "250"])])
+def test_cli_main_writes_reference_products(tmp_path, case, flags, capsys):
+    import frisk
+    import pandas as pd
+    from frisk_b200 import synth
+    g = Golden(case)
+    path = str(tmp_path / "genome.fa")
+    synth.write_fasta(g.scaffolds(), path)
+    tmp = tmp_path / "temp"
+    argv = ["-H", path, "-t", str(tmp), "--exitAfter", "WindowKLD"] + flags
+    with pytest.raises(SystemExit) as ei:
+        frisk.main(argv)
+    assert ei.value.code == 0
+    out = capsys.readouterr().out
+    # raw TSV (F:1475, F:1493)
+    tsv = pd.read_csv(tmp / "raw_window_scores.bed", sep="\t")
+    assert list(tsv.columns) == ["name", "start", "stop", "windowKLD", "GC", "PI", "SI", "CRI"]
+    assert list(tsv["name"]) == g.names
+    assert np.array_equal(tsv[["start", "stop"]].to_numpy(), g.coords)
+    assert_rows_close(tsv[["windowKLD", "GC", "PI", "SI", "CRI"]].to_numpy(float), g.vals, rtol_kld=1e-6, rtol_other=1e-15,
+                      what=case + "[TSV]")
+    assert out.count("\n") >= len(g.names)                                     # rows echoed to stdout (F:1494)
+    # caches (F:501, F:505)
+    a = frisk.mainArgs(argv)
+    genome = pickle.load(open(frisk.makePicklePath(a, space="genome"), "rb"))
+    kmin, kmax = a.minWordSize, a.maxWordSize
+    assert np.array_equal(_arr(genome, kmin, kmax), g.tables)
+    kr = kmax - kmin
+    assert [genome[kr + 1]["totalLen"], genome[kr + 2]["exMax"], genome[kr + 3]["nnTotal"]] == [int(x) for x in g.genome_meta]
+    frame = pd.read_pickle(frisk.makePicklePath(a, space="window"))
+    assert list(frame["name"]) == g.names and np.array_equal(frame["windowKLD"].to_numpy(), tsv["windowKLD"].to_numpy())
+    # second run re-uses both caches (default: --recalc / --recalcWin not given) and returns the frame
+    frame2 = frisk.main(["-H", path, "-t", str(tmp), "--quiet"] + flags)
+    assert frame2.equals(frame)
