@@ -89,6 +89,7 @@ class PackedGenome:
     total_len: int                # F:323
     nn_total: int                 # F:325: characters that are not upper-case ATGC
     n_lower: int
+    pinned: bool = False          # planes (and the window arrays derived from them) are page-locked
 
     # ------------------------------------------------------------------ constructors
     @classmethod
@@ -149,7 +150,8 @@ class PackedGenome:
         _lib.check(L.frisk_b200_pack(_ptr(src), _ptr(src_off), _ptr(src_end), _ptr(lens), _ptr(scaf_off), n, P,
                                      _ptr(codes), _ptr(inv), _ptr(low), _ptr(stats), threads), "frisk_b200_pack")
         n_lower = int(stats[2])
-        return cls(names, lens, scaf_off, P, codes, inv, low if n_lower else None, int(stats[0]), int(stats[1]), n_lower)
+        return cls(names, lens, scaf_off, P, codes, inv, low if n_lower else None, int(stats[0]), int(stats[1]), n_lower,
+                   bool(pinned))
 
     # ------------------------------------------------------------------ host logic
     def windows(self, w: int = 5000, step: int = 2500, scaffolds_all: bool = False) -> WindowList:
@@ -160,7 +162,9 @@ class PackedGenome:
                                   None, None, None, None, None, C.byref(n))
         _lib.check(rc, "frisk_b200_windows")
         cap = int(n.value)
-        off = np.zeros(cap, np.uint64); ln = np.zeros(cap, np.uint32); sc = np.zeros(cap, np.uint32)
+        pinned = self.pinned
+        off = _alloc(cap, np.uint64, pinned); ln = _alloc(cap, np.uint32, pinned)     # these two go to the device
+        sc = np.zeros(cap, np.uint32)
         st = np.zeros(cap, np.int64); sp = np.zeros(cap, np.int64)
         _lib.check(L.frisk_b200_windows(_ptr(self.scaf_len), _ptr(self.scaf_off), nsc, w, step, int(scaffolds_all), cap,
                                         _ptr(off), _ptr(ln), _ptr(sc), _ptr(st), _ptr(sp), C.byref(n)),
@@ -403,9 +407,11 @@ def run(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1,
 
 def run_host(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1, kmax: int = 8, w: int = 5000,
              step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True,
-             wins: Optional[WindowList] = None, out=None, stream: int = 0) -> HotPathResult:
+             wins: Optional[WindowList] = None, out=None, stream: int = 0, assemble_result: bool = True):
     """Same path as ``run`` but as ONE C call from host buffers (frisk_b200_run_host): H2D of the
-    planes and window list, all kernels, D2H of rows/status/tables.  Used for end-to-end timing."""
+    planes and window list, all kernels, D2H of rows/status/tables.  Used for end-to-end timing;
+    ``assemble_result=False`` returns the raw HostOutputs (rows of every candidate window, status
+    flags, tables) without building the Python-side row list."""
     _lib.require_device()
     host = host or query
     if wins is None:
@@ -419,6 +425,8 @@ def run_host(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int
         _ptr(wins.off), _ptr(wins.length), n, wins.max_len, kmin, kmax, int(mask_host), int(rip),
         int(host.genome_space), _ptr(out.rows), _ptr(out.status), _ptr(out.tables), _ptr(out.valid), C.c_void_p(stream))
     _lib.check(rc, "frisk_b200_run_host")
+    if not assemble_result:
+        return out
     return assemble(query, host, wins, out.tables, int(out.valid[0]), out.rows[:n], out.status[:n], kmin, kmax)
 
 

@@ -81,7 +81,7 @@ def test_cli_main_writes_reference_products(tmp_path, case, flags, capsys):
     assert ei.value.code == 0
     out = capsys.readouterr().out
     # raw TSV (F:1475, F:1493)
-    tsv = pd.read_csv(tmp / "raw_window_scores.bed", sep="\t")
+    tsv = pd.read_csv(tmp / "raw_window_scores.bed", sep="\t", float_precision="round_trip")
     assert list(tsv.columns) == ["name", "start", "stop", "windowKLD", "GC", "PI", "SI", "CRI"]
     assert list(tsv["name"]) == g.names
     assert np.array_equal(tsv[["start", "stop"]].to_numpy(), g.coords)

@@ -1,0 +1,7 @@
+#!/bin/bash
+# 2-GPU session: all gpu tests (incl. the 2-rank one), bench at N=1 and N=2
+mkdir -p gpurun_out
+nvidia-smi -L
+python -m pytest tests -m gpu -x -q 2>&1 | tail -12
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 2500 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 2500 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
