@@ -76,9 +76,15 @@ def score_sharded(scaffolds, group=None, device=None, **params):
     pipe = engine.Pipeline(genome, device=device, allreduce=make_allreduce(group), genome_space=space, **params)
     pipe.enqueue()
     res = pipe.result()
-    meta = torch.tensor(list(res.meta), dtype=torch.int64, device=device)
-    dist.all_reduce(meta, op=dist.ReduceOp.SUM, group=group)        # totalLen, exMax, nnTotal are sums over scaffolds
-    res.meta = tuple(int(x) for x in meta.tolist())
+    # totalLen and nnTotal are sums over scaffolds; exMax = (all kmax-word start positions) - (valid
+    # kmax-words), where the valid count finalised from the all-reduced counters is already global
+    kmax = pipe.kmax
+    possible = int(np.maximum(genome.scaf_len.astype(np.int64) - kmax + 1, 0).sum())
+    valid_global = possible - res.meta[1]
+    meta = torch.tensor([res.meta[0], possible, res.meta[2]], dtype=torch.int64, device=device)
+    dist.all_reduce(meta, op=dist.ReduceOp.SUM, group=group)
+    tot = [int(x) for x in meta.tolist()]
+    res.meta = (tot[0], tot[1] - valid_global, tot[2])
     return res, mine
 
 
