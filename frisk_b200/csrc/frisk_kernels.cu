@@ -587,6 +587,7 @@ struct Score3Smem {
     int cnt[2][4];                    // [window parity][n_non, n_gc, n_up, -]
     int flags[2];
     uint32_t warp_tot[kW3];
+    uint32_t warp_tot2[kW3];
 };
 
 template <int K>
@@ -601,7 +602,8 @@ struct Score3Layout {
     static constexpr uint32_t OFF_MASK = TAB_BYTES;                     // (tables and masks are zeroed together)
     static constexpr uint32_t ZERO_BYTES = TAB_BYTES + MASK_BYTES;
     static constexpr uint32_t OFF_CUR = ZERO_BYTES;
-    static constexpr uint32_t OFF_PRE = OFF_CUR + MASK_BYTES;
+    static constexpr uint32_t OFF_DST = OFF_CUR + MASK_BYTES;
+    static constexpr uint32_t OFF_PRE = OFF_DST + MASK_BYTES;
     static constexpr uint32_t OFF_LOG = OFF_PRE + NPRE * 16u;
     static constexpr uint32_t OFF_SS = OFF_LOG + 128u * 16u;
     static constexpr uint32_t OFF_BUF = (OFF_SS + (uint32_t)sizeof(Score3Smem) + 15u) & ~15u;
@@ -610,43 +612,36 @@ struct Score3Layout {
     static constexpr uint32_t total(uint32_t cap) { return OFF_BUF + cap + 2u * cap; }
 };
 
-// Visits every position of a window, four absolute-aligned bases per thread per round so the
-// two code words / two mask words they need are loaded once (32-bit addressing relative to the
-// window's first mask word).  f(p, c32, m, low_bit): p = position in the window, c32 = the 16 bases
-// from p (2 bits each, first base on top), m = unresolved mask of the 32 bases from p (bit 31 = p),
-// low_bit = 1 when base p is lower case.
-template <int NT, typename F>
-__device__ __forceinline__ void for_each_position(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ mw,
-                                                  const uint32_t* __restrict__ lw, uint32_t o_lo, uint32_t len, int tid, F f) {
-    const uint32_t g0 = o_lo >> 2;
-    const uint32_t ngroups = ((o_lo + len + 3u) >> 2) - g0;
-    uint32_t gi = tid;
-    if (gi >= ngroups) return;
-    uint32_t a0 = (g0 + gi) << 2;
-    uint32_t chi = __ldg(cw + (a0 >> 4)), clo = __ldg(cw + (a0 >> 4) + 1);
-    uint32_t mhi = __ldg(mw + (a0 >> 5)), mlo = __ldg(mw + (a0 >> 5) + 1);
-    uint32_t lhi = lw ? __ldg(lw + (a0 >> 5)) : 0u;
-    for (;;) {
-        // issue the next round's loads before working on this round (hides the L2 latency)
-        const uint32_t gn = gi + NT;
-        const bool more = gn < ngroups;
-        const uint32_t an = (g0 + (more ? gn : gi)) << 2;
-        const uint32_t nchi = __ldg(cw + (an >> 4)), nclo = __ldg(cw + (an >> 4) + 1);
-        const uint32_t nmhi = __ldg(mw + (an >> 5)), nmlo = __ldg(mw + (an >> 5) + 1);
-        const uint32_t nlhi = lw ? __ldg(lw + (an >> 5)) : 0u;
-        const uint32_t cs = (a0 & 15u) * 2u, ms = a0 & 31u;           // cs <= 24, ms <= 28
+// One round of the position walk: the four absolute-aligned bases of group `gi` (see below), with
+// the words they need loaded once.  f(j, p, c32, m, low_bit) for the positions inside the window:
+// j = 0..3, p = position in the window, c32 = the 16 bases from p (2 bits each, first base on top),
+// m = unresolved mask of the 32 bases from p (bit 31 = p), low_bit = 1 when base p is lower case.
+struct GroupWords { uint32_t chi, clo, mhi, mlo, lhi; };
+
+__device__ __forceinline__ GroupWords load_group(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ mw,
+                                                 const uint32_t* __restrict__ lw, uint32_t a0) {
+    GroupWords g;
+    g.chi = __ldg(cw + (a0 >> 4)); g.clo = __ldg(cw + (a0 >> 4) + 1);
+    g.mhi = __ldg(mw + (a0 >> 5)); g.mlo = __ldg(mw + (a0 >> 5) + 1);
+    g.lhi = lw ? __ldg(lw + (a0 >> 5)) : 0u;
+    return g;
+}
+
+template <typename F>
+__device__ __forceinline__ void visit_group(const GroupWords& g, uint32_t a0, uint32_t o_lo, uint32_t len, F f) {
+    const uint32_t cs = (a0 & 15u) * 2u, ms = a0 & 31u;               // cs <= 24, ms <= 28
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t p = a0 + j - o_lo;                          // wraps for bases before the window
-            if (p < len)
-                f(p, __funnelshift_l(clo, chi, cs + 2u * j), __funnelshift_l(mlo, mhi, ms + j), (lhi << (ms + j)) >> 31);
-        }
-        if (!more) break;
-        gi = gn; a0 = an; chi = nchi; clo = nclo; mhi = nmhi; mlo = nmlo; lhi = nlhi;
+    for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t p = a0 + j - o_lo;                              // wraps for bases before the window
+        if (p < len)
+            f(j, p, __funnelshift_l(g.clo, g.chi, cs + 2u * j), __funnelshift_l(g.mlo, g.mhi, ms + j), (g.lhi << (ms + j)) >> 31);
     }
 }
 
-template <int K, bool DUMP, bool ALLK>
+// ROUNDS rounds of 4 positions per thread cover a window of up to 4*NT*ROUNDS - 3 bases; what a
+// position contributes (bucket, suffix code, arrival rank in its bucket) stays in registers
+// between the counting pass and the placement pass, so the sequence is read and decoded once.
+template <int K, int ROUNDS, bool DUMP, bool ALLK>
 __global__ void __launch_bounds__(kT3, 4)
 score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                             const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
@@ -655,15 +650,16 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
     using L = Score3Layout<K>;
     constexpr int B = L::B, LP = L::LP;
     constexpr uint32_t NBK = L::NBK, PER = L::PER;
+    constexpr uint32_t kNone = 31u;                                      // suffix code of "nothing to place"
     const int kmin = ALLK ? 1 : kmin_arg;                                // ALLK: the default --minWordSize 1, predicates fold away
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem);                 // orders 1..B
     uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem);
     uint16_t* mask16 = reinterpret_cast<uint16_t*>(smem + L::OFF_MASK);
     uint32_t* mask32 = reinterpret_cast<uint32_t*>(smem + L::OFF_MASK);
-    uint16_t* cur16 = reinterpret_cast<uint16_t*>(smem + L::OFF_CUR);
-    uint32_t* cur32 = reinterpret_cast<uint32_t*>(smem + L::OFF_CUR);
-    double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);       // .x = num, .y = den (exact integer as double)
+    uint16_t* cur16 = reinterpret_cast<uint16_t*>(smem + L::OFF_CUR);   // start of a dirty bucket's entries in buf
+    uint16_t* dst16 = reinterpret_cast<uint16_t*>(smem + L::OFF_DST);   // start of a bucket's K-mers in its list | 0x8000 if dirty
+    double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);       // .x = num, .y = den (u32 bit pattern)
     double2* logtab = reinterpret_cast<double2*>(smem + L::OFF_LOG);
     Score3Smem& ss = *reinterpret_cast<Score3Smem*>(smem + L::OFF_SS);
     uint8_t* buf = smem + L::OFF_BUF;
@@ -689,25 +685,49 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         const uint32_t* __restrict__ cw = codes + (o >> 5) * 2;
         const uint32_t* __restrict__ mw = inv + (o >> 5);
         const uint32_t* __restrict__ lw = low ? low + (o >> 5) : nullptr;
+        const uint32_t g0 = o_lo >> 2;
+        const uint32_t ngroups = ((o_lo + len + 3u) >> 2) - g0;          // <= NT * ROUNDS (checked by the launcher)
 
-        // ---- P1: count order B (and short words), composition ------------------------------------
+        // ---- P1: one pass over the positions: composition, order-B counts (-> rank), presence masks ---
+        uint32_t place[4 * ROUNDS];                    // per position: bucket << 18 | rank << 5 | suffix code
         {
             int non = 0, gc = 0;
-            for_each_position<kT3>(cw, mw, lw, o_lo, len, tid, [&](uint32_t p, uint32_t c32, uint32_t m, uint32_t lowbit) {
-                const uint32_t unres = (m >> 31) | lowbit;                   // not an upper-case ATGC (F:106-118)
-                non += unres;
-                gc += (1 - unres) & (c32 >> 31);                             // G = 2, C = 3: bit 1 of the first base
-                if ((m >> (32 - B)) == 0u && p + B <= len) {                 // the common case: >= B valid bases ahead
-                    const uint32_t g = lvl_off(B) + (c32 >> (32 - 2 * B));
-                    atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
-                } else {                                                     // window end / N boundary: order v < B
-                    const int v = min(__clz(m), (int)(len - p));
-                    if (v > 0) {
-                        const uint32_t g = lvl_off(v) + (c32 >> (32 - 2 * v));
-                        atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
-                    }
+            GroupWords gw = load_group(cw, mw, lw, (g0 + (tid < (int)ngroups ? tid : 0)) << 2);
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) {
+                const uint32_t gi = tid + r * kT3;
+                // next round's words are requested before this round is processed (hides the L2 latency)
+                const uint32_t gn = gi + kT3;
+                GroupWords nx = gw;
+                if (r + 1 < ROUNDS) nx = load_group(cw, mw, lw, (g0 + (gn < ngroups ? gn : 0u)) << 2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) place[4 * r + j] = kNone;
+                if (gi < ngroups) {
+                    visit_group(gw, (g0 + gi) << 2, o_lo, len, [&](uint32_t j, uint32_t p, uint32_t c32, uint32_t m, uint32_t lowbit) {
+                        const uint32_t unres = (m >> 31) | lowbit;               // not an upper-case ATGC (F:106-118)
+                        non += unres;
+                        gc += (1 - unres) & (c32 >> 31);                         // G = 2, C = 3: bit 1 of the first base
+                        const uint32_t b = c32 >> (32 - 2 * B);
+                        const uint32_t sfx = (c32 >> (32 - 2 * K)) & 15u;
+                        const uint32_t sh = (b & 1u) * 16u;
+                        if ((m >> (32 - K)) == 0u && p + K <= len) {             // the common case: a full K-word
+                            const uint32_t old = atomicAdd(&tab32[(lvl_off(B) + b) >> 1], 1u << sh);
+                            atomicOr(&mask32[b >> 1], (1u << sfx) << sh);
+                            place[4 * r + j] = (b << 18) | (((old >> sh) & 0x1fffu) << 5) | sfx;
+                        } else {                                                 // window end / N boundary
+                            const int v = min(__clz(m), (int)(len - p));
+                            if (v >= B) {                                        // valid for K-1 or K-2 bases only
+                                const uint32_t old = atomicAdd(&tab32[(lvl_off(B) + b) >> 1], 1u << sh);
+                                place[4 * r + j] = (b << 18) | (((old >> sh) & 0x1fffu) << 5) | (v == K - 1 ? 16u + (sfx >> 2) : 20u);
+                            } else if (v > 0) {                                  // order v < B only
+                                const uint32_t g = lvl_off(v) + (c32 >> (32 - 2 * v));
+                                atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
+                            }
+                        }
+                    });
                 }
-            });
+                gw = nx;
+            }
             non = __reduce_add_sync(kFull, non);
             gc = __reduce_add_sync(kFull, gc);
             if (lane == 0) { atomicAdd(&ss.cnt[par][0], non); atomicAdd(&ss.cnt[par][1], gc); }
@@ -719,7 +739,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         const bool excluded = (double)n_non >= 0.3 * (double)len;          // F:238 / F:213
         uint16_t* dmp = DUMP ? dump + (size_t)win * lvl_off(K + 1) : nullptr;
         if (excluded) {
-            for (uint32_t i = tid; i < L::TAB_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
             if (tid == 0) {
                 status[win] = FRISK_ROW_EXCLUDED;
                 for (int c = 0; c < 5; ++c) rows[(size_t)win * 5 + c] = CUDART_NAN;
@@ -734,35 +754,40 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             ss.q[tid] = (double)pow4(x) / (double)d;
         }
 
-        // ---- P2: exclusive scan of the order-B counts; lower orders by marginalisation ------------
-        // A thread's PER contiguous order-B bins are the children of PER/4 order-(B-1) bins and of
-        // PER/16 order-(B-2) bins, summed here on the way; warp 0 finishes orders LW-1..1 below.
-        uint32_t mine = 0;
+        // ---- P2: per bucket: clean (every entry a distinct K-mer) or dirty; three exclusive scans
+        //          (clean K-mers, dirty K-mers, dirty entries); orders B-1..1 by marginalisation -----------
+        uint32_t scanA = 0, scanB = 0;                 // A: clean K-mers | dirty K-mers << 16;  B: entries of dirty buckets
+        uint32_t dirtybits = 0;
         if ((uint32_t)tid * PER < NBK) {
-            if constexpr (PER >= 4) {
-                uint32_t quad = 0;
+            uint32_t quad = 0, hexa = 0;
 #pragma unroll
-                for (uint32_t g = 0; g < PER / 4; ++g) {
-                    const uint2 ch = *reinterpret_cast<const uint2*>(tabB + tid * PER + 4 * g);
-                    uint32_t sum4 = (ch.x & 0xffffu) + (ch.x >> 16) + (ch.y & 0xffffu) + (ch.y >> 16);
-                    mine += sum4;
-                    uint16_t* par1 = tab16 + lvl_off(B - 1) + (tid * PER) / 4 + g;
-                    sum4 += *par1;                                           // + the short words of order B-1
-                    *par1 = (uint16_t)sum4;
-                    quad += sum4;
+            for (uint32_t j = 0; j < PER; ++j) {
+                const uint32_t b = tid * PER + j;
+                const uint32_t nb = tabB[b], pc = __popc((uint32_t)mask16[b]);
+                const bool dirty = nb != pc;
+                dirtybits |= (dirty ? 1u : 0u) << j;
+                scanA += dirty ? pc << 16 : pc;
+                scanB += dirty ? nb : 0u;
+                if constexpr (PER >= 4) {
+                    quad += nb;
+                    if ((j & 3u) == 3u) {                                  // the four children of an order-(B-1) bin
+                        uint16_t* par1 = tab16 + lvl_off(B - 1) + (tid * PER + j) / 4;
+                        quad += *par1;                                     // + the short words of order B-1
+                        *par1 = (uint16_t)quad;
+                        hexa += quad;
+                        quad = 0;
+                    }
                 }
-                if constexpr (PER >= 16) tab16[lvl_off(B - 2) + tid] += (uint16_t)quad;
-            } else {
-                mine = tabB[tid];
             }
+            if constexpr (PER >= 16) tab16[lvl_off(B - 2) + tid] += (uint16_t)hexa;   // sixteen children of an order-(B-2) bin
         }
-        uint32_t incl = mine;
+        uint32_t inclA = scanA, inclB = scanB;
 #pragma unroll
         for (int ofs = 1; ofs < 32; ofs <<= 1) {
-            const uint32_t y = __shfl_up_sync(kFull, incl, ofs);
-            if (lane >= ofs) incl += y;
+            const uint32_t ya = __shfl_up_sync(kFull, inclA, ofs), yb = __shfl_up_sync(kFull, inclB, ofs);
+            if (lane >= ofs) { inclA += ya; inclB += yb; }
         }
-        if (lane == 31) ss.warp_tot[warp] = incl;
+        if (lane == 31) { ss.warp_tot[warp] = inclA; ss.warp_tot2[warp] = inclB; }
         __syncthreads();                                                   // (2a)
         if (warp == 0) {
             constexpr int LW = B - (PER >= 16 ? 2 : (PER >= 4 ? 1 : 0));  // lowest order that is complete by now
@@ -775,38 +800,54 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 __syncwarp();
             }
         }
+        uint32_t n_clean, n_dirty;
         {
-            uint32_t run = incl - mine;
+            uint32_t totA = 0, runA = inclA - scanA, runB = inclB - scanB;
 #pragma unroll
-            for (int w = 0; w < kW3; ++w) run += (w < warp) ? ss.warp_tot[w] : 0u;
+            for (int w = 0; w < kW3; ++w) {
+                const uint32_t ta = ss.warp_tot[w], tb = ss.warp_tot2[w];
+                totA += ta;
+                if (w < warp) { runA += ta; runB += tb; }
+            }
+            n_clean = totA & 0xffffu; n_dirty = totA >> 16;
             if ((uint32_t)tid * PER < NBK) {
 #pragma unroll
                 for (uint32_t j = 0; j < PER; ++j) {
                     const uint32_t b = tid * PER + j;
-                    cur16[b] = (uint16_t)run;
-                    run += tabB[b];
+                    const uint32_t pc = __popc((uint32_t)mask16[b]);
+                    if ((dirtybits >> j) & 1u) {
+                        dst16[b] = (uint16_t)(0x8000u | (runA >> 16));
+                        cur16[b] = (uint16_t)runB;
+                        runA += pc << 16;
+                        runB += tabB[b];
+                    } else {
+                        dst16[b] = (uint16_t)(runA & 0xffffu);
+                        runA += pc;
+                    }
                 }
             }
         }
         __syncthreads();                                                   // (2b)
 
-        // ---- P3: scatter suffix codes into buckets; presence masks; partial sums per order-LP node --
-        for_each_position<kT3>(cw, mw, lw, o_lo, len, tid, [&](uint32_t p, uint32_t c32, uint32_t m, uint32_t) {
-            const uint32_t b = c32 >> (32 - 2 * B);
-            const uint32_t sfx = (c32 >> (32 - 2 * K)) & 15u;
-            const uint32_t sh = (b & 1u) * 16u;
-            if ((m >> (32 - K)) == 0u && p + K <= len) {                     // the common case: a full K-word
-                const uint32_t old = atomicAdd(&cur32[b >> 1], 1u << sh);
-                atomicOr(&mask32[b >> 1], (1u << sfx) << sh);
-                buf[(old >> sh) & 0xffffu] = (uint8_t)sfx;
-            } else {
-                const int v = min(__clz(m), (int)(len - p));
-                if (v >= B) {                                                // valid for K-1 or K-2 bases only
-                    const uint32_t old = atomicAdd(&cur32[b >> 1], 1u << sh);
-                    buf[(old >> sh) & 0xffffu] = (uint8_t)(v == K - 1 ? 16u + (sfx >> 2) : 20u);
+        // ---- P3: place every remembered position: its K-mer into the sorted list of distinct K-mers
+        //          (slot = bucket start + rank of the suffix among the bucket's present suffixes: the same
+        //          for every occurrence, so duplicates write the same value), dirty buckets' entries into buf --
+#pragma unroll
+        for (int i = 0; i < 4 * ROUNDS; ++i) {
+            const uint32_t pl = place[i], c5 = pl & 31u;
+            if (c5 != kNone) {
+                const uint32_t b = pl >> 18, rank = (pl >> 5) & 0x1fffu;
+                const uint32_t d = dst16[b];
+                if (c5 < 16u) {
+                    const uint32_t slot = (d & 0x7fffu) + __popc((uint32_t)mask16[b] & ((1u << c5) - 1u));
+                    const uint16_t kappa = (uint16_t)((b << 4) | c5);
+                    if (d & 0x8000u) { list[cap - 1u - slot] = kappa; buf[cur16[b] + rank] = (uint8_t)c5; }
+                    else list[slot] = kappa;
+                } else {
+                    buf[cur16[b] + rank] = (uint8_t)c5;                    // a short word makes its bucket dirty
                 }
             }
-        });
+        }
         for (uint32_t node = tid; node < L::NPRE; node += kT3) {
             double num = 0.0;
             uint32_t den = 0;
@@ -832,76 +873,26 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             for (uint32_t i = lvl_off(B + 1) + tid; i < lvl_off(K + 1); i += kT3) dmp[i] = 0;
         }
         __syncthreads();                                                   // (3)
-
-        // ---- P4a: popcounts of the presence masks -> sorted lists of the distinct K-mers -----------
-        // A bucket is "clean" when every entry is a distinct K-mer (count == popc(mask)): its K-mers
-        // have order-K count 1 and order-(K-1) count popc(mask group).  Clean K-mers fill the list
-        // from the front, the others ("dirty": repeats or short words in the bucket, recounted from
-        // the bucket entries) from the back, so each scoring loop below runs converged.
-        uint32_t masks[(PER + 1) / 2];          // this thread's PER buckets: 16 presence bits each, bucket i at bits 16i..16i+15
-        uint32_t dirty = 0;                     // same layout: 0xffff over a dirty bucket
-        uint32_t cnt2 = 0;                      // clean count | dirty count << 16
-#pragma unroll
-        for (uint32_t i = 0; i < (PER + 1) / 2; ++i) {
-            masks[i] = 0;
-            if ((uint32_t)tid * PER + 2 * i < NBK) {
-                uint32_t nb2;
-                if (PER >= 2) { masks[i] = mask32[(tid * PER) / 2 + i]; nb2 = reinterpret_cast<const uint32_t*>(tabB)[(tid * PER) / 2 + i]; }
-                else { masks[i] = mask16[tid]; nb2 = tabB[tid]; }
-                const uint32_t lo = masks[i] & 0xffffu, hi = masks[i] >> 16;
-                const uint32_t plo = __popc(lo), phi = __popc(hi);
-                const bool dlo = (nb2 & 0xffffu) != plo, dhi = (nb2 >> 16) != phi;
-                if (i < 16) dirty |= ((dlo ? 1u : 0u) | (dhi ? 2u : 0u)) << (2 * i);
-                cnt2 += (dlo ? plo << 16 : plo) + (dhi ? phi << 16 : phi);
-            }
-        }
-        if (DUMP) {   // tests only: order K-1 counts of the window, straight from the bucket entries
-#pragma unroll 1
-            for (uint32_t i = 0; i < PER; ++i) {
-                const uint32_t b = tid * PER + i;
-                if (b < NBK) {
-                    const uint32_t nb = tabB[b], end = cur16[b];
-                    for (uint32_t e = end - nb; e < end; ++e) {
+        if (DUMP) {   // tests only: order K-1 counts of the window, per bucket
+            for (uint32_t b = tid; b < NBK; b += kT3) {
+                const uint32_t nb = tabB[b], msk = mask16[b];
+                if (nb == 0) continue;
+                uint32_t c7[4] = {0, 0, 0, 0};
+                if (!(dst16[b] & 0x8000u)) {
+                    for (int j = 0; j < 4; ++j) c7[j] = __popc((msk >> (4 * j)) & 15u);
+                } else {
+                    const uint32_t beg = cur16[b];
+                    for (uint32_t e = beg; e < beg + nb; ++e) {
                         const uint32_t c5 = buf[e];
-                        if (c5 < 20u) {
-                            const uint32_t g = lvl_off(K - 1) + 4 * b + (c5 < 16u ? c5 >> 2 : c5 - 16u);
-                            atomicAdd(reinterpret_cast<unsigned int*>(dmp + (g & ~1u)), 1u << (16 * (g & 1u)));
-                        }
+                        if (c5 < 16u) c7[c5 >> 2]++; else if (c5 < 20u) c7[c5 - 16u]++;
                     }
                 }
+                for (int j = 0; j < 4; ++j) dmp[lvl_off(K - 1) + 4 * b + j] = (uint16_t)c7[j];
             }
         }
-        uint32_t incl2 = cnt2;
-#pragma unroll
-        for (int ofs = 1; ofs < 32; ofs <<= 1) {
-            const uint32_t y = __shfl_up_sync(kFull, incl2, ofs);
-            if (lane >= ofs) incl2 += y;
-        }
-        if (lane == 31) ss.warp_tot[warp] = incl2;                         // (its use by the bucket scan ended before barrier 2b)
-        __syncthreads();                                                   // (3c)
-        uint32_t n_clean, n_dirty;
-        {
-            uint32_t tot2 = 0, off2 = incl2 - cnt2;
-#pragma unroll
-            for (int w = 0; w < kW3; ++w) { const uint32_t t = ss.warp_tot[w]; tot2 += t; off2 += (w < warp) ? t : 0u; }
-            n_clean = tot2 & 0xffffu; n_dirty = tot2 >> 16;
-            uint32_t offc = off2 & 0xffffu;                 // clean K-mers: list[0 .. n_clean)
-            uint32_t offd = cap - 1u - (off2 >> 16);        // dirty K-mers: list[cap-1] downwards
-#pragma unroll
-            for (uint32_t i = 0; i < (PER + 1) / 2; ++i) {
-                const uint32_t dm = ((dirty >> (2 * i)) & 1u ? 0xffffu : 0u) | ((dirty >> (2 * i)) & 2u ? 0xffff0000u : 0u);
-                const uint32_t base = (tid * PER + 2 * i) << 4;          // K-mer index of bit 0 of this word
-                uint32_t w = masks[i] & ~dm;
-                while (w) { const uint32_t bit = __ffs(w) - 1; w &= w - 1; list[offc++] = (uint16_t)(base + bit); }
-                w = masks[i] & dm;
-                while (w) { const uint32_t bit = __ffs(w) - 1; w &= w - 1; list[offd--] = (uint16_t)(base + bit); }
-            }
-        }
-        __syncthreads();                                                   // (3d)
 
-        // ---- P4b: score the distinct K-mers, one list entry per thread per round -------------------
+        // ---- P4: score the distinct K-mers, one list entry per thread per round -------------------
         double s_w = 0.0, s_g = 0.0, s_t = 0.0;
-        int bad = 0;
         double qr[K - LP];                                                 // q of the orders LP+1..K
 #pragma unroll
         for (int x = LP + 1; x <= K; ++x) qr[x - LP - 1] = ss.q[x - 1];
@@ -928,9 +919,8 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             const double iw = div_pos(num, (double)den);
             const double2 g = __ldg(ig + kappa);
             s_w += iw;
-            s_g += g.x;
+            s_g += g.x;                                    // a NaN entry (reference: ZeroDivisionError) poisons the sum
             s_t = fma(iw, log2_pos(iw, logtab) - g.y, s_t);
-            bad |= (g.x != g.x);
         };
         for (uint32_t e = tid; e < n_clean; e += kT3) {
             const uint32_t kappa = list[e];
@@ -940,9 +930,9 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         for (uint32_t e = tid; e < n_dirty; e += kT3) {
             const uint32_t kappa = list[cap - 1u - e];
             const uint32_t b = kappa >> 4, sfx = kappa & 15u, j = sfx >> 2;
-            const uint32_t nb = tabB[b], end = cur16[b];                   // the cursor finished at the bucket's end
+            const uint32_t nb = tabB[b], beg = cur16[b];
             uint32_t c8 = 0, c7 = 0;
-            for (uint32_t i = end - nb; i < end; ++i) {
+            for (uint32_t i = beg; i < beg + nb; ++i) {
                 const uint32_t c5 = buf[i];
                 c8 += (c5 == sfx);
                 c7 += (c5 < 16u) ? ((c5 >> 2) == j) : (c5 == 16u + j);
@@ -956,11 +946,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             s_g += __shfl_xor_sync(kFull, s_g, ofs);
             s_t += __shfl_xor_sync(kFull, s_t, ofs);
         }
-        bad = __any_sync(kFull, bad);
-        if (lane == 0) {
-            ss.red[0][warp] = s_w; ss.red[1][warp] = s_g; ss.red[2][warp] = s_t;
-            if (bad) atomicOr(&ss.flags[par], 1);
-        }
+        if (lane == 0) { ss.red[0][warp] = s_w; ss.red[1][warp] = s_g; ss.red[2][warp] = s_t; }
         __syncthreads();                                                   // (4) everyone is done with the tables
         for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) {
@@ -969,7 +955,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             uint32_t st = 0;
             double kld = 0.0;                              // the reference returns 0 for a window without kmax-mers
             if (n_list) {
-                bool zd = ss.flags[par] & 1;
+                bool zd = bsum != bsum;                    // NaN genome IVOM entry: ZeroDivisionError at F:437
                 for (int x = kmin; x <= K; ++x) zd |= ((long long)n_up - (long long)(x - 1)) == 0;
                 if (zd) { st |= FRISK_ROW_KLD_ZERODIV; kld = CUDART_NAN; }
                 else {
@@ -1123,14 +1109,14 @@ int launch_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* low
     return FRISK_OK;
 }
 
-template <int K, bool DUMP, bool ALLK>
-int launch_score_bucket2(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+template <int K, int ROUNDS, bool DUMP, bool ALLK>
+int launch_score_bucket3(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                          const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
                          double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
     using L = Score3Layout<K>;
     const uint32_t cap = (max_len + 15u) & ~15u;
     const size_t smem = L::total(cap);
-    auto kern = score_windows_bucket_kernel<K, DUMP, ALLK>;
+    auto kern = score_windows_bucket_kernel<K, ROUNDS, DUMP, ALLK>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT3, smem));
@@ -1144,6 +1130,16 @@ int launch_score_bucket2(const uint32_t* codes, const uint32_t* inv, const uint3
         reinterpret_cast<const double2*>(ig), kmin, want_rip, cap, rows, status, dump);
     CK(cudaGetLastError());
     return FRISK_OK;
+}
+
+template <int K, bool DUMP, bool ALLK>
+int launch_score_bucket2(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                         const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
+                         double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+    // positions per thread = 4 * ROUNDS, held in registers: 5 rounds cover the default 5,000-base windows
+    if (max_len <= kT3 * 4u * 5u - 6u)
+        return launch_score_bucket3<K, 5, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
+    return launch_score_bucket3<K, 8, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
 }
 
 template <int K>
@@ -1264,7 +1260,7 @@ int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint3
     cudaStream_t st = (cudaStream_t)stream;
     const int rip = want_rip && kmin <= 2 && kmax >= 2;
     // default path: bucketed kernel (4 CTAs/SM); the dense-table kernel covers K < 4 and long windows
-    if (kmax >= 4 && max_win_len <= kBuf3 && !g_force_dense) {
+    if (kmax >= 4 && max_win_len <= kBuf3 - 6u && !g_force_dense) {
         switch (kmax) {
             case 4: return launch_score_bucket<4>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
             case 5: return launch_score_bucket<5>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
