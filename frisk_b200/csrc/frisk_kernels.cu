@@ -601,9 +601,8 @@ struct Score3Layout {
     static constexpr uint32_t MASK_BYTES = (NBK * 2u + 15u) & ~15u;     // suffix-presence masks, u16 per bucket
     static constexpr uint32_t OFF_MASK = TAB_BYTES;                     // (tables and masks are zeroed together)
     static constexpr uint32_t ZERO_BYTES = TAB_BYTES + MASK_BYTES;
-    static constexpr uint32_t OFF_CUR = ZERO_BYTES;
-    static constexpr uint32_t OFF_DST = OFF_CUR + MASK_BYTES;
-    static constexpr uint32_t OFF_PRE = OFF_DST + MASK_BYTES;
+    static constexpr uint32_t OFF_CUR = ZERO_BYTES;                     // u32 per bucket (list start, dirty flag, buf start)
+    static constexpr uint32_t OFF_PRE = OFF_CUR + 2u * MASK_BYTES;
     static constexpr uint32_t OFF_LOG = OFF_PRE + NPRE * 16u;
     static constexpr uint32_t OFF_SS = OFF_LOG + 128u * 16u;
     static constexpr uint32_t OFF_BUF = (OFF_SS + (uint32_t)sizeof(Score3Smem) + 15u) & ~15u;
@@ -611,6 +610,23 @@ struct Score3Layout {
     // cap = longest window of the launch rounded up to 16
     static constexpr uint32_t total(uint32_t cap) { return OFF_BUF + cap + 2u * cap; }
 };
+
+// PER consecutive u16 values starting at p (8-byte aligned when PER >= 4) with the widest loads:
+// a thread's contiguous bins are 32 bytes apart from its neighbour's, so single u16 loads would be
+// 8-way bank-conflicted.
+template <uint32_t PER>
+__device__ __forceinline__ void load_u16s(const uint16_t* p, uint32_t (&out)[PER]) {
+    if constexpr (PER >= 4) {
+#pragma unroll
+        for (uint32_t g = 0; g < PER / 4; ++g) {
+            const uint2 v = *reinterpret_cast<const uint2*>(p + 4 * g);
+            out[4 * g] = v.x & 0xffffu; out[4 * g + 1] = v.x >> 16; out[4 * g + 2] = v.y & 0xffffu; out[4 * g + 3] = v.y >> 16;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t g = 0; g < PER; ++g) out[g] = p[g];
+    }
+}
 
 // One round of the position walk: the four absolute-aligned bases of group `gi` (see below), with
 // the words they need loaded once.  f(j, p, c32, m, low_bit) for the positions inside the window:
@@ -657,8 +673,8 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
     uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem);
     uint16_t* mask16 = reinterpret_cast<uint16_t*>(smem + L::OFF_MASK);
     uint32_t* mask32 = reinterpret_cast<uint32_t*>(smem + L::OFF_MASK);
-    uint16_t* cur16 = reinterpret_cast<uint16_t*>(smem + L::OFF_CUR);   // start of a dirty bucket's entries in buf
-    uint16_t* dst16 = reinterpret_cast<uint16_t*>(smem + L::OFF_DST);   // start of a bucket's K-mers in its list | 0x8000 if dirty
+    // per bucket: bits 0-14 start of its K-mers in its list, bit 15 dirty, bits 16-31 start of a dirty bucket's entries in buf
+    uint32_t* dst32 = reinterpret_cast<uint32_t*>(smem + L::OFF_CUR);
     double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);       // .x = num, .y = den (u32 bit pattern)
     double2* logtab = reinterpret_cast<double2*>(smem + L::OFF_LOG);
     Score3Smem& ss = *reinterpret_cast<Score3Smem*>(smem + L::OFF_SS);
@@ -757,15 +773,16 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         // ---- P2: per bucket: clean (every entry a distinct K-mer) or dirty; three exclusive scans
         //          (clean K-mers, dirty K-mers, dirty entries); orders B-1..1 by marginalisation -----------
         uint32_t scanA = 0, scanB = 0;                 // A: clean K-mers | dirty K-mers << 16;  B: entries of dirty buckets
-        uint32_t dirtybits = 0;
-        if ((uint32_t)tid * PER < NBK) {
+        const bool owner = (uint32_t)tid * PER < NBK;
+        if (owner) {
+            uint32_t nbs[PER], mks[PER];
+            load_u16s<PER>(tabB + tid * PER, nbs);
+            load_u16s<PER>(mask16 + tid * PER, mks);
             uint32_t quad = 0, hexa = 0;
 #pragma unroll
             for (uint32_t j = 0; j < PER; ++j) {
-                const uint32_t b = tid * PER + j;
-                const uint32_t nb = tabB[b], pc = __popc((uint32_t)mask16[b]);
+                const uint32_t nb = nbs[j], pc = __popc(mks[j]);
                 const bool dirty = nb != pc;
-                dirtybits |= (dirty ? 1u : 0u) << j;
                 scanA += dirty ? pc << 16 : pc;
                 scanB += dirty ? nb : 0u;
                 if constexpr (PER >= 4) {
@@ -810,20 +827,28 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 if (w < warp) { runA += ta; runB += tb; }
             }
             n_clean = totA & 0xffffu; n_dirty = totA >> 16;
-            if ((uint32_t)tid * PER < NBK) {
+            if (owner) {
+                uint32_t nbs[PER], mks[PER], outv[PER];
+                load_u16s<PER>(tabB + tid * PER, nbs);
+                load_u16s<PER>(mask16 + tid * PER, mks);
 #pragma unroll
                 for (uint32_t j = 0; j < PER; ++j) {
-                    const uint32_t b = tid * PER + j;
-                    const uint32_t pc = __popc((uint32_t)mask16[b]);
-                    if ((dirtybits >> j) & 1u) {
-                        dst16[b] = (uint16_t)(0x8000u | (runA >> 16));
-                        cur16[b] = (uint16_t)runB;
+                    const uint32_t pc = __popc(mks[j]);
+                    if (nbs[j] != pc) {                                    // dirty: list start | flag, and the start of its entries in buf
+                        outv[j] = 0x8000u | (runA >> 16) | (runB << 16);
                         runA += pc << 16;
-                        runB += tabB[b];
+                        runB += nbs[j];
                     } else {
-                        dst16[b] = (uint16_t)(runA & 0xffffu);
+                        outv[j] = runA & 0xffffu;
                         runA += pc;
                     }
+                }
+                if constexpr (PER >= 4) {
+#pragma unroll
+                    for (uint32_t g = 0; g < PER / 4; ++g)
+                        reinterpret_cast<uint4*>(dst32 + tid * PER)[g] = make_uint4(outv[4 * g], outv[4 * g + 1], outv[4 * g + 2], outv[4 * g + 3]);
+                } else {
+                    dst32[tid] = outv[0];
                 }
             }
         }
@@ -837,14 +862,14 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             const uint32_t pl = place[i], c5 = pl & 31u;
             if (c5 != kNone) {
                 const uint32_t b = pl >> 18, rank = (pl >> 5) & 0x1fffu;
-                const uint32_t d = dst16[b];
+                const uint32_t d = dst32[b];
                 if (c5 < 16u) {
                     const uint32_t slot = (d & 0x7fffu) + __popc((uint32_t)mask16[b] & ((1u << c5) - 1u));
                     const uint16_t kappa = (uint16_t)((b << 4) | c5);
-                    if (d & 0x8000u) { list[cap - 1u - slot] = kappa; buf[cur16[b] + rank] = (uint8_t)c5; }
+                    if (d & 0x8000u) { list[cap - 1u - slot] = kappa; buf[(d >> 16) + rank] = (uint8_t)c5; }
                     else list[slot] = kappa;
                 } else {
-                    buf[cur16[b] + rank] = (uint8_t)c5;                    // a short word makes its bucket dirty
+                    buf[(d >> 16) + rank] = (uint8_t)c5;                   // a short word makes its bucket dirty
                 }
             }
         }
@@ -878,10 +903,10 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 const uint32_t nb = tabB[b], msk = mask16[b];
                 if (nb == 0) continue;
                 uint32_t c7[4] = {0, 0, 0, 0};
-                if (!(dst16[b] & 0x8000u)) {
+                if (!(dst32[b] & 0x8000u)) {
                     for (int j = 0; j < 4; ++j) c7[j] = __popc((msk >> (4 * j)) & 15u);
                 } else {
-                    const uint32_t beg = cur16[b];
+                    const uint32_t beg = dst32[b] >> 16;
                     for (uint32_t e = beg; e < beg + nb; ++e) {
                         const uint32_t c5 = buf[e];
                         if (c5 < 16u) c7[c5 >> 2]++; else if (c5 < 20u) c7[c5 - 16u]++;
@@ -930,7 +955,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         for (uint32_t e = tid; e < n_dirty; e += kT3) {
             const uint32_t kappa = list[cap - 1u - e];
             const uint32_t b = kappa >> 4, sfx = kappa & 15u, j = sfx >> 2;
-            const uint32_t nb = tabB[b], beg = cur16[b];
+            const uint32_t nb = tabB[b], beg = dst32[b] >> 16;
             uint32_t c8 = 0, c7 = 0;
             for (uint32_t i = beg; i < beg + nb; ++i) {
                 const uint32_t c5 = buf[i];
