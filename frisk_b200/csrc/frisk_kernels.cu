@@ -772,39 +772,57 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
 
         // ---- P2: per bucket: clean (every entry a distinct K-mer) or dirty; three exclusive scans
         //          (clean K-mers, dirty K-mers, dirty entries); orders B-1..1 by marginalisation -----------
-        uint32_t scanA = 0, scanB = 0;                 // A: clean K-mers | dirty K-mers << 16;  B: entries of dirty buckets
+        // Bucket ownership: a thread owns G groups of GS contiguous buckets; group g of lane l in warp w
+        // starts at bucket w*32*PER + g*32*GS + l*GS, so a warp's lanes read contiguous 8-byte units (no
+        // bank conflicts) and (warp, group, lane, bucket-in-group) order is bucket order: the lists stay sorted.
+        constexpr uint32_t GS = PER >= 4 ? 4u : PER, G = PER / GS;
         const bool owner = (uint32_t)tid * PER < NBK;
-        if (owner) {
-            uint32_t nbs[PER], mks[PER];
-            load_u16s<PER>(tabB + tid * PER, nbs);
-            load_u16s<PER>(mask16 + tid * PER, mks);
-            uint32_t quad = 0, hexa = 0;
+        const uint32_t wbase = (uint32_t)warp * 32u * PER + (uint32_t)lane * GS;
+        uint32_t gA[G], gB[G];                         // per group: A = clean K-mers | dirty K-mers << 16;  B = entries of dirty buckets
 #pragma unroll
-            for (uint32_t j = 0; j < PER; ++j) {
-                const uint32_t nb = nbs[j], pc = __popc(mks[j]);
-                const bool dirty = nb != pc;
-                scanA += dirty ? pc << 16 : pc;
-                scanB += dirty ? nb : 0u;
-                if constexpr (PER >= 4) {
-                    quad += nb;
-                    if ((j & 3u) == 3u) {                                  // the four children of an order-(B-1) bin
-                        uint16_t* par1 = tab16 + lvl_off(B - 1) + (tid * PER + j) / 4;
-                        quad += *par1;                                     // + the short words of order B-1
-                        *par1 = (uint16_t)quad;
-                        hexa += quad;
-                        quad = 0;
-                    }
+        for (uint32_t g = 0; g < G; ++g) {
+            gA[g] = 0; gB[g] = 0;
+            uint32_t sum4 = 0;
+            if (owner) {
+                uint32_t nbs[GS], mks[GS];
+                load_u16s<GS>(tabB + wbase + g * 32u * GS, nbs);
+                load_u16s<GS>(mask16 + wbase + g * 32u * GS, mks);
+#pragma unroll
+                for (uint32_t j = 0; j < GS; ++j) {
+                    const uint32_t pc = __popc(mks[j]);
+                    const bool dirty = nbs[j] != pc;
+                    gA[g] += dirty ? pc << 16 : pc;
+                    gB[g] += dirty ? nbs[j] : 0u;
+                    sum4 += nbs[j];
+                }
+                if constexpr (PER >= 4) {              // the four buckets are the children of one order-(B-1) bin
+                    uint16_t* par1 = tab16 + lvl_off(B - 1) + (wbase + g * 32u * GS) / 4;
+                    sum4 += *par1;                     // + the short words of order B-1
+                    *par1 = (uint16_t)sum4;
                 }
             }
-            if constexpr (PER >= 16) tab16[lvl_off(B - 2) + tid] += (uint16_t)hexa;   // sixteen children of an order-(B-2) bin
+            if constexpr (PER >= 16) {                 // four consecutive lanes hold the children of one order-(B-2) bin
+                sum4 += __shfl_xor_sync(kFull, sum4, 1);
+                sum4 += __shfl_xor_sync(kFull, sum4, 2);
+                if (owner && (lane & 3) == 0) tab16[lvl_off(B - 2) + (wbase + g * 32u * GS) / 16] += (uint16_t)sum4;
+            }
         }
-        uint32_t inclA = scanA, inclB = scanB;
+        // inclusive scans over lanes per group, then groups chained inside the warp
+        uint32_t iA[G], iB[G], warpA = 0, warpB = 0;
 #pragma unroll
-        for (int ofs = 1; ofs < 32; ofs <<= 1) {
-            const uint32_t ya = __shfl_up_sync(kFull, inclA, ofs), yb = __shfl_up_sync(kFull, inclB, ofs);
-            if (lane >= ofs) { inclA += ya; inclB += yb; }
+        for (uint32_t g = 0; g < G; ++g) {
+            iA[g] = gA[g]; iB[g] = gB[g];
+#pragma unroll
+            for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                const uint32_t ya = __shfl_up_sync(kFull, iA[g], ofs), yb = __shfl_up_sync(kFull, iB[g], ofs);
+                if (lane >= ofs) { iA[g] += ya; iB[g] += yb; }
+            }
+            const uint32_t ta = __shfl_sync(kFull, iA[g], 31), tb = __shfl_sync(kFull, iB[g], 31);
+            iA[g] += warpA - gA[g];                    // -> exclusive prefix inside the warp
+            iB[g] += warpB - gB[g];
+            warpA += ta; warpB += tb;
         }
-        if (lane == 31) { ss.warp_tot[warp] = inclA; ss.warp_tot2[warp] = inclB; }
+        if (lane == 31) { ss.warp_tot[warp] = warpA; ss.warp_tot2[warp] = warpB; }
         __syncthreads();                                                   // (2a)
         if (warp == 0) {
             constexpr int LW = B - (PER >= 16 ? 2 : (PER >= 4 ? 1 : 0));  // lowest order that is complete by now
@@ -819,36 +837,39 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         }
         uint32_t n_clean, n_dirty;
         {
-            uint32_t totA = 0, runA = inclA - scanA, runB = inclB - scanB;
+            uint32_t totA = 0, preA = 0, preB = 0;
 #pragma unroll
             for (int w = 0; w < kW3; ++w) {
                 const uint32_t ta = ss.warp_tot[w], tb = ss.warp_tot2[w];
                 totA += ta;
-                if (w < warp) { runA += ta; runB += tb; }
+                if (w < warp) { preA += ta; preB += tb; }
             }
             n_clean = totA & 0xffffu; n_dirty = totA >> 16;
             if (owner) {
-                uint32_t nbs[PER], mks[PER], outv[PER];
-                load_u16s<PER>(tabB + tid * PER, nbs);
-                load_u16s<PER>(mask16 + tid * PER, mks);
 #pragma unroll
-                for (uint32_t j = 0; j < PER; ++j) {
-                    const uint32_t pc = __popc(mks[j]);
-                    if (nbs[j] != pc) {                                    // dirty: list start | flag, and the start of its entries in buf
-                        outv[j] = 0x8000u | (runA >> 16) | (runB << 16);
-                        runA += pc << 16;
-                        runB += nbs[j];
-                    } else {
-                        outv[j] = runA & 0xffffu;
-                        runA += pc;
+                for (uint32_t g = 0; g < G; ++g) {
+                    uint32_t nbs[GS], mks[GS], outv[GS];
+                    load_u16s<GS>(tabB + wbase + g * 32u * GS, nbs);
+                    load_u16s<GS>(mask16 + wbase + g * 32u * GS, mks);
+                    uint32_t runA = preA + iA[g], runB = preB + iB[g];
+#pragma unroll
+                    for (uint32_t j = 0; j < GS; ++j) {
+                        const uint32_t pc = __popc(mks[j]);
+                        if (nbs[j] != pc) {                                // dirty: list start | flag, and the start of its entries in buf
+                            outv[j] = 0x8000u | (runA >> 16) | (runB << 16);
+                            runA += pc << 16;
+                            runB += nbs[j];
+                        } else {
+                            outv[j] = runA & 0xffffu;
+                            runA += pc;
+                        }
                     }
-                }
-                if constexpr (PER >= 4) {
+                    if constexpr (GS == 4) {
+                        *reinterpret_cast<uint4*>(dst32 + wbase + g * 32u * GS) = make_uint4(outv[0], outv[1], outv[2], outv[3]);
+                    } else {
 #pragma unroll
-                    for (uint32_t g = 0; g < PER / 4; ++g)
-                        reinterpret_cast<uint4*>(dst32 + tid * PER)[g] = make_uint4(outv[4 * g], outv[4 * g + 1], outv[4 * g + 2], outv[4 * g + 3]);
-                } else {
-                    dst32[tid] = outv[0];
+                        for (uint32_t j = 0; j < GS; ++j) dst32[wbase + g * 32u * GS + j] = outv[j];
+                    }
                 }
             }
         }
