@@ -62,7 +62,8 @@ __device__ __forceinline__ uint32_t high_bits16(uint32_t w) {
 template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
 bg_count_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
-                uint64_t word_lo, uint64_t word_hi, int mask_host, unsigned long long* __restrict__ fwd) {
+                uint64_t word_lo, uint64_t word_hi, int mask_host, unsigned long long* __restrict__ fwd,
+                uint32_t* __restrict__ partial) {
     constexpr uint32_t NB = pow4(K);
     constexpr uint32_t HB = NB < 32768u ? NB : 32768u;   // bins held in smem per pass
     constexpr int PASSES = NB / HB;
@@ -82,29 +83,55 @@ bg_count_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__
             if (use_low) { m0 |= __ldg(low + wd); m1 |= __ldg(low + wd + 1); }
             const uint32_t c0 = __ldg(codes + 2 * wd), c1 = __ldg(codes + 2 * wd + 1), c2 = __ldg(codes + 2 * wd + 2);
             const bool all_valid = (m0 == 0u) && (K == 1 || (m1 >> (33 - K)) == 0u);
+            if (all_valid) {                                   // the common word: 32 full K-words, no per-position checks
 #pragma unroll
-            for (int p = 0; p < 32; ++p) {
-                const uint32_t code = (p < 16 ? __funnelshift_l(c1, c0, 2 * p) : __funnelshift_l(c2, c1, 2 * (p - 16)))
-                                      >> (32 - 2 * K);
-                int v = K;
-                if (!all_valid) {
-                    const uint32_t m = __funnelshift_l(m1, m0, p);
-                    v = min(__clz(m), K);
+                for (int p = 0; p < 32; ++p) {
+                    const uint32_t code = (p < 16 ? __funnelshift_l(c1, c0, 2 * p) : __funnelshift_l(c2, c1, 2 * (p - 16)))
+                                          >> (32 - 2 * K);
+                    // branch-free: words of the other half go to one spare bin (same-address lanes are
+                    // aggregated by the hardware's POPC.INC form of the atomic)
+                    const uint32_t bin = (PASSES == 1 || (int)(code / HB) == pass) ? code % HB : HB;
+                    atomicAdd(&tab[bin], 1u);
                 }
-                if (v == K) {
-                    if (PASSES == 1 || (int)(code / HB) == pass) atomicAdd(&tab[code % HB], 1u);
-                } else if (v > 0 && pass == 0) {
-                    atomicAdd(&fwd[lvl_off(v) + (code >> (2 * (K - v)))], 1ull);
+            } else {
+#pragma unroll 4
+                for (int p = 0; p < 32; ++p) {
+                    const uint32_t code = (p < 16 ? __funnelshift_l(c1, c0, 2 * p) : __funnelshift_l(c2, c1, 2 * (p - 16)))
+                                          >> (32 - 2 * K);
+                    const int v = min(__clz(__funnelshift_l(m1, m0, p)), K);
+                    if (v == K) {
+                        if (PASSES == 1 || (int)(code / HB) == pass) atomicAdd(&tab[code % HB], 1u);
+                    } else if (v > 0 && pass == 0) {
+                        atomicAdd(&fwd[lvl_off(v) + (code >> (2 * (K - v)))], 1ull);
+                    }
                 }
             }
         }
         __syncthreads();
-        for (uint32_t b = threadIdx.x; b < HB; b += kThreads) {
-            const uint32_t c = tab[b];
-            if (c) atomicAdd(&fwd[lvl_off(K) + (uint32_t)pass * HB + b], (unsigned long long)c);
+        if (partial) {   // per-CTA partial table, coalesced stores; bg_reduce_kernel sums them into fwd
+            uint32_t* dst = partial + (size_t)blockIdx.x * NB + (uint32_t)pass * HB;
+            for (uint32_t b = threadIdx.x * 4u; b < HB; b += kThreads * 4u)
+                *reinterpret_cast<uint4*>(dst + b) = *reinterpret_cast<const uint4*>(tab + b);
+        } else {
+            for (uint32_t b = threadIdx.x; b < HB; b += kThreads) {
+                const uint32_t c = tab[b];
+                if (c) atomicAdd(&fwd[lvl_off(K) + (uint32_t)pass * HB + b], (unsigned long long)c);
+            }
         }
         __syncthreads();
     }
+}
+
+// fwd[order K][b] += sum over CTAs of partial[cta][b]   (one thread per bin, coalesced across bins)
+template <int K>
+__global__ void __launch_bounds__(256)
+bg_reduce_kernel(const uint32_t* __restrict__ partial, int n_parts, unsigned long long* __restrict__ fwd) {
+    const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+    if (b >= pow4(K)) return;
+    unsigned long long sum = 0;
+#pragma unroll 4
+    for (int c = 0; c < n_parts; ++c) sum += partial[(size_t)c * pow4(K) + b];
+    if (sum) fwd[lvl_off(K) + b] += sum;
 }
 
 // Finalising the tables: F_x = short-word counts of order x + marginal of F_{x+1}; then
@@ -1091,12 +1118,14 @@ int sm_count() {
     return n;
 }
 
+int ws_get(int slot, size_t bytes, void** out);
+
 template <int K>
 int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, uint64_t w_lo, uint64_t w_hi,
                       int mask_host, uint64_t* fwd, cudaStream_t st) {
     constexpr uint32_t NB = pow4(K);
     constexpr uint32_t HB = NB < 32768u ? NB : 32768u;
-    const size_t smem = (size_t)HB * 4;
+    const size_t smem = (size_t)HB * 4 + 16;            // + the spare bin
     CK(cudaFuncSetAttribute(bg_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t n_words = w_hi - w_lo;
     int grid = sm_count();
@@ -1104,8 +1133,18 @@ int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t
     // at least ~2 rounds of 1024 words per CTA, otherwise fewer CTAs
     const uint64_t want = (n_words + 2047) / 2048;
     if ((uint64_t)grid > want) grid = want ? (int)want : 1;
+    // large tables: per-CTA partial tables + one reduction instead of ~65 k global atomics per CTA
+    uint32_t* partial = nullptr;
+    if (NB >= 4096u && grid > 1) {
+        void* p = nullptr;
+        int rc = ws_get(13, (size_t)grid * NB * sizeof(uint32_t), &p);
+        if (rc) return rc;
+        partial = (uint32_t*)p;
+    }
     bg_count_kernel<K><<<grid, kThreads, smem, st>>>(codes, inv, low, w_lo, w_hi, mask_host,
-                                                      reinterpret_cast<unsigned long long*>(fwd));
+                                                      reinterpret_cast<unsigned long long*>(fwd), partial);
+    if (partial)
+        bg_reduce_kernel<K><<<(NB + 255) / 256, 256, 0, st>>>(partial, grid, reinterpret_cast<unsigned long long*>(fwd));
     CK(cudaGetLastError());
     return FRISK_OK;
 }

@@ -215,6 +215,65 @@ def test_full_size_c2_properties_and_sampled_parity(eng):
     assert np.all(np.isfinite(res.rows[:, 0])) and np.all(res.rows[:, 0] >= 0)
 
 
+def test_hmm_anomaly_calls_identical_on_full_c1(eng):
+    """north_star: "HMM anomaly calls on those scores must be identical".  Scores of the full-size C1
+    config (5 Mbp, 2,000 rows) from the GPU vs the reference's own (golden c1_full, produced by executing
+    the reference source): fit the 2-state HMM on each and compare the decoded state paths (tests/hmm_ref.py
+    documents the hmmlearn stand-in)."""
+    from tests import hmm_ref
+    g = Golden("c1_full")
+    res = _run_case(eng, g)
+    err = _check_against_golden(res, g, "c1_full")
+    assert err < 1e-10
+    ref_kld, gpu_kld = g.vals[:, 0], res.rows[:, 0]
+    m_ref, m_gpu = hmm_ref.fit(ref_kld), hmm_ref.fit(gpu_kld)
+    path_ref, path_gpu = hmm_ref.predict(m_ref, ref_kld), hmm_ref.predict(m_gpu, gpu_kld)
+    assert np.array_equal(path_ref, path_gpu)
+    hi = int(np.argmax(m_ref[2]))
+    called = int((path_ref == hi).sum())
+    assert 0 < called < len(path_ref), "the planted islands are called, the background is not"
+
+
+def test_addressing_beyond_2_pow_32_bases(eng):
+    """A small genome placed behind > 2^32 padding bases (C4/C5-scale offsets): every kernel must use
+    64-bit base offsets.  Same tables and the same rows as the genome on its own."""
+    import torch
+    from frisk_b200 import _lib, synth
+    sc = synth.make("C2", 0.01, seed=21) + synth.make("edge")
+    g = eng.PackedGenome.from_scaffolds(sc)
+    ref = eng.run(g, scaffolds_all=True)
+    shift = (1 << 32) + (1 << 20)                       # bases, multiple of 128
+    big_len = shift + g.padded_len
+    dev = torch.device("cuda:0")
+    codes = torch.zeros(big_len // 16, dtype=torch.int32, device=dev)
+    inv = torch.full((big_len // 32,), -1, dtype=torch.int32, device=dev)      # all padding
+    codes[shift // 16:] = torch.from_numpy(g.codes.view(np.int32)).to(dev)
+    inv[shift // 32:] = torch.from_numpy(g.inv.view(np.int32)).to(dev)
+    low = None
+    if g.low is not None:
+        low = torch.zeros(big_len // 32, dtype=torch.int32, device=dev)
+        low[shift // 32:] = torch.from_numpy(g.low.view(np.int32)).to(dev)
+
+    class Shifted:      # a DeviceGenome whose planes start 2^32 bases in
+        pass
+    dg = Shifted()
+    dg.codes, dg.inv, dg.low, dg.device = codes, inv, low, dev
+    dg.host = type("H", (), {"padded_len": big_len})()
+    d_fwd = eng.background(dg, 8, False)
+    d_tables, d_valid = eng.finalize(d_fwd, 8)
+    d_ig = eng.genome_ivom(d_tables, 1, 8, g.genome_space)
+    wins = g.windows(5000, 2500, True)
+    moved = eng.WindowList(wins.off + np.uint64(shift), wins.length, wins.scaf, wins.start, wins.stop)
+    d_rows, d_status, _ = eng.score(dg, moved, d_ig, 1, 8, True)
+    torch.cuda.synchronize()
+    out = eng.assemble(g, g, wins, d_tables.cpu().numpy().view(np.uint64), int(d_valid.item()), d_rows.cpu().numpy(),
+                       d_status.cpu().numpy().view(np.uint32), 1, 8)
+    assert np.array_equal(out.tables, ref.tables)
+    assert out.meta == ref.meta
+    assert np.array_equal(out.rows, ref.rows, equal_nan=True)
+    assert np.array_equal(out.status, ref.status)
+
+
 def test_no_silent_fallback_symbols_loaded(eng):
     """The product library is the thing that ran: it is loaded in this process and reports a GPU."""
     from frisk_b200 import _lib
