@@ -41,6 +41,12 @@ PROTOTYPES = {
     "frisk_b200_score": (_i, [_p, _p, _p, _p, _p, _u64, C.c_uint32, _p, _i, _i, _i, _p, _p, _p, _p]),
     "frisk_b200_run_host": (_i, [_p, _p, _p, _u64, _p, _p, _p, _u64, _p, _p, _u64, C.c_uint32, _i, _i, _i, _i,
                                  C.c_int64, _p, _p, _p, _p, _p]),
+    "frisk_b200_run_resident": (_i, [_p, _p, _p, _u64, _p, _p, _p, _u64, _p, _p, _u64, C.c_uint32, _i, _i, _i, _i,
+                                     C.c_int64, _p, _p, _p, _p, _p]),
+    "frisk_b200_fasta_open": (_i, [_p, _u64, _p, C.POINTER(C.c_void_p), C.POINTER(_u64), C.POINTER(_u64), _p]),
+    "frisk_b200_fasta_records": (_i, [_p, _p, _p, _p, _p]),
+    "frisk_b200_fasta_pack": (_i, [_p, _p, _p, _p, _p]),
+    "frisk_b200_fasta_close": (_i, [_p, _p]),
     "frisk_b200_release_workspace": (_i, []),
     "frisk_b200_host_alloc": (_i, [C.POINTER(C.c_void_p), _u64]),
     "frisk_b200_host_free": (_i, [_p]),
@@ -59,7 +65,7 @@ class FriskError(RuntimeError):
 def build(force: bool = False) -> str:
     """Compile the shared library in-tree (nvcc, sm_100a).  Cross-compiles without a GPU."""
     src_dir = os.path.join(HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("frisk_kernels.cu", "frisk_host.cpp", "Makefile")]
+    srcs = [os.path.join(src_dir, f) for f in ("frisk_kernels.cu", "frisk_ingest.cu", "frisk_host.cpp", "frisk_internal.h", "Makefile")]
     srcs.append(os.path.join(os.path.dirname(HERE), "include", "frisk_b200.h"))
     stale = not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/frisk_b200.h"
+#include "frisk_internal.h"
 
 namespace {
 
@@ -78,6 +79,25 @@ int pack_one(const unsigned char* s, const unsigned char* e, uint64_t expect, ui
 
 }  // namespace
 
+bool frisk_internal::parse_header_name(const unsigned char* t, uint64_t n, uint64_t line_start, uint64_t* name_off,
+                                       uint32_t* name_len) {
+    const void* nl = memchr(t + line_start, '\n', n - line_start);
+    uint64_t a = line_start, b = nl ? (uint64_t)((const unsigned char*)nl - t) : n;
+    while (a < b && is_space(t[a])) ++a;            // line.strip()
+    while (b > a && is_space(t[b - 1])) --b;
+    // name = line.strip('>').split()[0]  (F:156)
+    uint64_t x = a, y = b;
+    while (x < y && t[x] == '>') ++x;
+    while (y > x && t[y - 1] == '>') --y;
+    while (x < y && is_space(t[x])) ++x;
+    uint64_t z = x;
+    while (z < y && !is_space(t[z])) ++z;
+    if (z == x) return false;
+    *name_off = x;
+    *name_len = (uint32_t)(z - x);
+    return true;
+}
+
 extern "C" {
 
 uint64_t frisk_b200_table_size(int kmin, int kmax) {
@@ -115,15 +135,9 @@ int frisk_b200_fasta_scan(const char* text, uint64_t n, uint64_t cap, uint64_t* 
         if (a < b) {
             if (t[a] == '>') {
                 if (have) emit(i);
-                // name = line.strip('>').split()[0]  (F:156)
-                uint64_t x = a, y = b;
-                while (x < y && t[x] == '>') ++x;
-                while (y > x && t[y - 1] == '>') --y;
-                while (x < y && is_space(t[x])) ++x;
-                uint64_t z = x;
-                while (z < y && !is_space(t[z])) ++z;
-                if (z == x) return FRISK_E_FORMAT;  // the reference raises IndexError on an empty header
-                cur_name = x; cur_nlen = (uint32_t)(z - x); cur_body = nl ? j + 1 : n; cur_len = 0;
+                if (!frisk_internal::parse_header_name(t, n, i, &cur_name, &cur_nlen))
+                    return FRISK_E_FORMAT;          // the reference raises IndexError on an empty header
+                cur_body = nl ? j + 1 : n; cur_len = 0;
                 have = true;                         // a non-empty name is truthy
             } else if (have) {
                 // interior whitespace stays part of the reference's string; treat it as such only for

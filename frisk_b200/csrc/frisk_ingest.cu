@@ -1,0 +1,510 @@
+// frisk_b200 device-side FASTA ingest: FASTA text in, packed 2-bit planes out, on the GPU.
+//
+// Replaces the reference's iterFasta (F:139-164: line.strip(), blank lines skipped, '>' lines start
+// a record, everything else is sequence) and countN (F:106-118) -- which the reference runs three
+// times per file (F:170, F:203, F:297) in pure Python -- and this library's own host packer
+// (frisk_b200_fasta_scan + frisk_b200_pack), whose outputs it reproduces bit for bit.  The host
+// only copies the raw text to the device and reads back one small record table.
+//
+// The text is cut into tiles of 4096 bytes (256 threads x 16 bytes).  What a byte means depends on
+// the line it is in (header or sequence) and on the record it belongs to, i.e. on everything before
+// it, so the work is three tile passes separated by two scans over per-tile summaries:
+//   fasta_lines_kernel     per tile: number of header lines starting in it, and whether the last
+//                          line starting in it is a header
+//   fasta_scan1_kernel     over tiles: records before the tile, header state carried into the tile
+//   fasta_tile_kernel<0>   per tile: classify every byte; per record: header position and length
+//                          (one atomic per record piece, not per base); per tile: bases before the
+//                          first / after the last header; countN statistics
+//   fasta_scan2_kernel     over tiles (segmented): bases of the open record before the tile
+//   [host: names from the header positions, 128-base aligned layout -> scaf_off]
+//   fasta_tile_kernel<1>   per tile: scatter the class of every base to its packed position
+//   fasta_pack_kernel      32 classes -> two code words, one invalid word, one lower-case word
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/frisk_b200.h"
+#include "frisk_internal.h"
+
+namespace {
+
+constexpr int kTT = 256;                    // threads per tile
+constexpr uint32_t kTile = kTT * 16u;       // text bytes per tile
+constexpr int kST = 1024;                   // threads of the (single-CTA) tile scans
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+// class of a byte: 0..3 = A,T,G,C (F:70 order); 4..7 = a,t,g,c; 8 = anything else; 9 = whitespace
+// removed by the reference's line.strip() (F:149)
+__device__ __forceinline__ uint32_t class_of(uint32_t c) {
+    switch (c) {
+        case 'A': return 0; case 'T': return 1; case 'G': return 2; case 'C': return 3;
+        case 'a': return 4; case 't': return 5; case 'g': return 6; case 'c': return 7;
+        case ' ': case '\t': case '\n': case '\r': case '\v': case '\f': return 9;
+        default: return 8;
+    }
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint4& v, int k) {
+    const uint32_t w = k < 4 ? v.x : (k < 8 ? v.y : (k < 12 ? v.z : v.w));
+    return (w >> (8 * (k & 3))) & 0xffu;
+}
+
+// Is the line starting at byte i a header?  Its first non-blank character decides (the reference
+// strips the line before looking at it, F:149-153).
+__device__ bool line_is_header(const uint8_t* __restrict__ t, uint64_t i, uint64_t n) {
+    while (i < n) {
+        const uint32_t c = t[i];
+        if (c == '\n') return false;                 // blank line
+        if (class_of(c) != 9u) return c == '>';
+        ++i;
+    }
+    return false;
+}
+
+// bit k of start_mask: a line starts at byte i0 + k; of hdr_mask: ... and it is a header line
+__device__ __forceinline__ void find_starts(const uint8_t* __restrict__ t, uint64_t n, uint64_t i0, const uint4& raw,
+                                            uint32_t& start_mask, uint32_t& hdr_mask) {
+    start_mask = 0; hdr_mask = 0;
+    uint32_t prev = i0 ? (uint32_t)t[i0 - 1] : (uint32_t)'\n';
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (prev == '\n') {
+            start_mask |= 1u << k;
+            if (line_is_header(t, i0 + k, n)) hdr_mask |= 1u << k;
+        }
+        prev = byte_of(raw, k);
+    }
+}
+
+// state of the last line start of a thread / tile: 0 = no line starts here, 1 = sequence line, 2 = header
+__device__ __forceinline__ uint32_t last_key(uint32_t start_mask, uint32_t hdr_mask) {
+    return start_mask ? 1u + ((hdr_mask >> (31 - __clz(start_mask))) & 1u) : 0u;
+}
+
+// ---- block-wide scans (blockDim.x a multiple of 32, <= 1024); sm: >= 64 words of shared memory ----------
+template <typename T>
+__device__ __forceinline__ T block_excl_sum(T v, T* sm, T* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        const T y = __shfl_up_sync(kFullMask, incl, ofs);
+        if (lane >= ofs) incl += y;
+    }
+    if (lane == 31) sm[warp] = incl;
+    __syncthreads();
+    T before = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+        const T x = sm[w];
+        if (w < warp) before += x;
+        tot += x;
+    }
+    __syncthreads();
+    *total = tot;
+    return before + incl - v;
+}
+
+// "last writer wins": the last non-zero key among the threads before this one (0 if none);
+// *last = the last non-zero key of the whole block
+__device__ __forceinline__ uint32_t block_excl_last(uint32_t key, uint32_t* sm, uint32_t* last) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t ball = __ballot_sync(kFullMask, key != 0u);
+    const uint32_t prior = ball & ((1u << lane) - 1u);
+    uint32_t v = __shfl_sync(kFullMask, key, prior ? 31 - __clz(prior) : 0);
+    if (!prior) v = 0;
+    const uint32_t wl = __shfl_sync(kFullMask, key, ball ? 31 - __clz(ball) : 0);
+    if (lane == 0) sm[warp] = ball ? wl : 0u;
+    __syncthreads();
+    uint32_t carry = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+        const uint32_t x = sm[w];
+        if (x) { tot = x; if (w < warp) carry = x; }
+    }
+    __syncthreads();
+    *last = tot;
+    return v ? v : carry;
+}
+
+// Segmented sum.  Element = (f, v): f = "a reset happens inside this element", v = the amount after
+// its last reset (the whole amount when !f).  Returns the amount accumulated since the last reset
+// before this thread; *reset_before = some earlier thread has a reset.
+template <typename T>
+__device__ __forceinline__ T block_excl_seg(bool f, T v, T* smv, uint32_t* smf, bool* reset_before) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T iv = v;
+    uint32_t fl = f ? 1u : 0u;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        const T uv = __shfl_up_sync(kFullMask, iv, ofs);
+        const uint32_t uf = __shfl_up_sync(kFullMask, fl, ofs);
+        if (lane >= ofs) { if (!fl) iv += uv; fl |= uf; }
+    }
+    T ev = __shfl_up_sync(kFullMask, iv, 1);
+    uint32_t ef = __shfl_up_sync(kFullMask, fl, 1);
+    if (lane == 0) { ev = 0; ef = 0; }
+    if (lane == 31) { smv[warp] = iv; smf[warp] = fl; }
+    __syncthreads();
+    T c = 0;
+    uint32_t cf = 0;
+    for (int w = 0; w < warp; ++w) {
+        if (smf[w]) { c = smv[w]; cf = 1; } else c += smv[w];
+    }
+    __syncthreads();
+    if (!ef) ev += c;
+    *reset_before = (ef | cf) != 0u;
+    return ev;
+}
+
+// ---- pass 1: line starts ------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTT)
+fasta_lines_kernel(const uint8_t* __restrict__ t, uint64_t n, uint32_t* __restrict__ tile_nhdr, uint8_t* __restrict__ tile_key) {
+    __shared__ uint32_t sm[64];
+    const uint64_t tile = blockIdx.x;
+    const uint64_t i0 = tile * kTile + threadIdx.x * 16u;
+    const uint4 raw = *reinterpret_cast<const uint4*>(t + i0);
+    uint32_t sm_, hm_;
+    find_starts(t, n, i0, raw, sm_, hm_);
+    uint32_t total, last;
+    block_excl_sum<uint32_t>(__popc(hm_), sm, &total);
+    block_excl_last(last_key(sm_, hm_), sm, &last);
+    if (threadIdx.x == 0) { tile_nhdr[tile] = total; tile_key[tile] = (uint8_t)last; }
+}
+
+// ---- scan 1 over tiles: records before each tile, header state carried into it -----------------
+__global__ void __launch_bounds__(kST)
+fasta_scan1_kernel(const uint32_t* __restrict__ tile_nhdr, const uint8_t* __restrict__ tile_key, uint64_t n_tiles,
+                   uint32_t* __restrict__ tile_rec_base, uint8_t* __restrict__ tile_carry_hdr,
+                   unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t sm[64];
+    const uint64_t per = (n_tiles + kST - 1) / kST;
+    const uint64_t lo = min((uint64_t)threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
+    uint32_t sum = 0, key = 0;
+    for (uint64_t i = lo; i < hi; ++i) {
+        sum += tile_nhdr[i];
+        const uint32_t k = tile_key[i];
+        if (k) key = k;
+    }
+    uint32_t total, last;
+    uint32_t run = block_excl_sum<uint32_t>(sum, sm, &total);
+    uint32_t rk = block_excl_last(key, sm, &last);
+    for (uint64_t i = lo; i < hi; ++i) {
+        tile_rec_base[i] = run;
+        tile_carry_hdr[i] = (uint8_t)(rk == 2u);
+        run += tile_nhdr[i];
+        const uint32_t k = tile_key[i];
+        if (k) rk = k;
+    }
+    if (threadIdx.x == 0) counters[0] = total;
+}
+
+// ---- scan 2 over tiles (segmented by headers): bases of the open record before each tile ------------
+__global__ void __launch_bounds__(kST)
+fasta_scan2_kernel(const uint32_t* __restrict__ tile_nhdr, const uint32_t* __restrict__ tile_pre,
+                   const uint32_t* __restrict__ tile_post, uint64_t n_tiles, unsigned long long* __restrict__ tile_base_in) {
+    __shared__ unsigned long long smv[32];
+    __shared__ uint32_t smf[32];
+    const uint64_t per = (n_tiles + kST - 1) / kST;
+    const uint64_t lo = min((uint64_t)threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
+    bool f = false;
+    unsigned long long v = 0;
+    for (uint64_t i = lo; i < hi; ++i) {
+        if (tile_nhdr[i]) { f = true; v = tile_post[i]; } else v += tile_pre[i];
+    }
+    bool rb;
+    unsigned long long run = block_excl_seg<unsigned long long>(f, v, smv, smf, &rb);
+    for (uint64_t i = lo; i < hi; ++i) {
+        tile_base_in[i] = run;
+        if (tile_nhdr[i]) run = tile_post[i]; else run += tile_pre[i];
+    }
+}
+
+// ---- passes 2 and 3: classify every byte of a tile -------------------------------------------------
+// MODE 0: record table (header position, length), per-tile base counts, countN statistics.
+// MODE 1: scatter the class of every base to compact[scaf_off[record] + index in record].
+template <int MODE>
+__global__ void __launch_bounds__(kTT)
+fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __restrict__ tile_rec_base,
+                  const uint8_t* __restrict__ tile_carry_hdr,
+                  unsigned long long* __restrict__ rec_hdr_pos, unsigned long long* __restrict__ rec_len,
+                  uint32_t* __restrict__ tile_pre, uint32_t* __restrict__ tile_post, unsigned long long* __restrict__ counters,
+                  const unsigned long long* __restrict__ tile_base_in, const unsigned long long* __restrict__ scaf_off,
+                  uint8_t* __restrict__ compact) {
+    __shared__ uint32_t sm[64];
+    __shared__ uint32_t smf[32];
+    __shared__ uint8_t cls_tab[256];
+    const int tid = threadIdx.x;
+    cls_tab[tid] = (uint8_t)class_of((uint32_t)tid);
+    const uint64_t tile = blockIdx.x;
+    const uint64_t i0 = tile * kTile + (uint64_t)tid * 16u;
+    const uint4 raw = *reinterpret_cast<const uint4*>(t + i0);
+    uint32_t start_mask, hdr_mask;
+    find_starts(t, n, i0, raw, start_mask, hdr_mask);
+    const uint32_t n_hdr_t = __popc(hdr_mask);
+    uint32_t tile_hdrs, last;
+    const uint32_t hdr_before = block_excl_sum<uint32_t>(n_hdr_t, sm, &tile_hdrs);     // (also orders cls_tab)
+    const uint32_t key_before = block_excl_last(last_key(start_mask, hdr_mask), sm, &last);
+    bool in_hdr = key_before ? key_before == 2u : tile_carry_hdr[tile] != 0;
+    const uint32_t rec_start = tile_rec_base[tile] + hdr_before;       // headers before this thread; open record = rec_start - 1
+
+    // walk the 16 bytes: which are bases, how many before the first / after the last header
+    uint32_t base_mask = 0, cnt = 0, pre = 0, non_upper = 0, lower = 0;
+    uint32_t cls16[2] = {0, 0};                                        // 4 bits per byte
+    bool seen_hdr = false;
+    {
+        uint32_t rec = rec_start;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if ((start_mask >> k) & 1u) {
+                const bool h = (hdr_mask >> k) & 1u;
+                if (h) {
+                    if (!seen_hdr) { pre = cnt; seen_hdr = true; }
+                    else if (MODE == 0 && cnt && rec >= 1u) atomicAdd(&rec_len[rec - 1u], (unsigned long long)cnt);
+                    cnt = 0;
+                    ++rec;
+                    if (MODE == 0) rec_hdr_pos[rec - 1u] = i0 + k;
+                }
+                in_hdr = h;
+            }
+            const uint32_t c = cls_tab[byte_of(raw, k)];
+            if (!in_hdr && c != 9u && rec >= 1u) {
+                base_mask |= 1u << k;
+                ++cnt;
+                non_upper += c >= 4u;
+                lower += (c >= 4u) & (c < 8u);
+                cls16[k >> 3] |= c << (4 * (k & 7));
+            }
+        }
+    }
+    bool reset_before;
+    const uint32_t carry = block_excl_seg<uint32_t>(seen_hdr, cnt, sm, smf, &reset_before);
+
+    if (MODE == 0) {
+        if (seen_hdr) {
+            const uint32_t amount = carry + pre;                        // this tile's share of the record the header closes
+            if (rec_start >= 1u && amount) atomicAdd(&rec_len[rec_start - 1u], (unsigned long long)amount);
+            if (!reset_before) tile_pre[tile] = amount;
+        }
+        if (tid == kTT - 1) {
+            const uint32_t s = seen_hdr ? cnt : carry + cnt;            // bases after the tile's last header (all, if none)
+            const uint32_t rec_end = rec_start + n_hdr_t;
+            if (rec_end >= 1u && s) atomicAdd(&rec_len[rec_end - 1u], (unsigned long long)s);
+            tile_post[tile] = s;
+            if (!reset_before && !seen_hdr) tile_pre[tile] = s;
+        }
+        uint32_t tot_non, tot_low;
+        block_excl_sum<uint32_t>(non_upper, sm, &tot_non);
+        block_excl_sum<uint32_t>(lower, sm, &tot_low);
+        if (tid == 0) {
+            if (tot_non) atomicAdd(&counters[1], (unsigned long long)tot_non);
+            if (tot_low) atomicAdd(&counters[2], (unsigned long long)tot_low);
+        }
+    } else {
+        if (base_mask) {
+            uint32_t rec = rec_start;
+            unsigned long long run = (unsigned long long)carry + (reset_before ? 0ull : tile_base_in[tile]);
+            unsigned long long dst = rec >= 1u ? scaf_off[rec - 1u] : 0ull;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if ((hdr_mask >> k) & 1u) { ++rec; run = 0; dst = scaf_off[rec - 1u]; }
+                if ((base_mask >> k) & 1u) {
+                    compact[dst + run] = (uint8_t)((cls16[k >> 3] >> (4 * (k & 7))) & 15u);
+                    ++run;
+                }
+            }
+        }
+    }
+}
+
+// ---- pass 4: 32 classes -> packed words (layout: include/frisk_b200.h) ---------------------------
+__global__ void __launch_bounds__(256)
+fasta_pack_kernel(const uint8_t* __restrict__ compact, uint64_t n_words, uint32_t* __restrict__ codes,
+                  uint32_t* __restrict__ inv, uint32_t* __restrict__ low) {
+    const uint64_t w = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    if (w >= n_words) return;
+    const uint4* p = reinterpret_cast<const uint4*>(compact + w * 32u);
+    const uint4 a = p[0], b = p[1];
+    uint32_t c0 = 0, c1 = 0, iv = 0, lw = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t x = byte_of(a, k), y = byte_of(b, k);
+        c0 |= (x < 8u ? x & 3u : 0u) << (30 - 2 * k);
+        c1 |= (y < 8u ? y & 3u : 0u) << (30 - 2 * k);
+        iv |= (uint32_t)(x >= 8u) << (31 - k) | (uint32_t)(y >= 8u) << (15 - k);
+        lw |= (uint32_t)((x >= 4u) & (x < 8u)) << (31 - k) | (uint32_t)((y >= 4u) & (y < 8u)) << (15 - k);
+    }
+    *reinterpret_cast<uint2*>(codes + 2 * w) = make_uint2(c0, c1);
+    inv[w] = iv;
+    if (low) low[w] = lw;
+}
+
+
+int pool_ready(int dev) {
+    static bool done[64] = {};
+    if (!done[dev & 63]) {
+        cudaMemPool_t pool;
+        FRISK_CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = ~0ull;                      // keep freed blocks cached: repeated ingests do not hit the allocator
+        FRISK_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        done[dev & 63] = true;
+    }
+    return FRISK_OK;
+}
+
+}  // namespace
+
+struct frisk_b200_fasta {
+    uint64_t n = 0, n_tiles = 0, n_rec = 0, padded_len = 128;
+    uint64_t stats[3] = {0, 0, 0};
+    uint8_t* d_text = nullptr;
+    uint32_t *d_nhdr = nullptr, *d_rec_base = nullptr, *d_pre = nullptr, *d_post = nullptr;
+    uint8_t *d_key = nullptr, *d_carry = nullptr;
+    unsigned long long *d_base_in = nullptr, *d_hdr_pos = nullptr, *d_len = nullptr, *d_scaf_off = nullptr, *d_counters = nullptr;
+    std::vector<uint64_t> name_off, seq_len, scaf_off, hdr_pos;
+    std::vector<uint32_t> name_len;
+};
+
+namespace {
+int free_all(frisk_b200_fasta* h, cudaStream_t st) {
+    void* ptrs[] = {h->d_text, h->d_nhdr, h->d_rec_base, h->d_pre, h->d_post, h->d_key, h->d_carry,
+                    h->d_base_in, h->d_hdr_pos, h->d_len, h->d_scaf_off, h->d_counters};
+    for (void* p : ptrs)
+        if (p) FRISK_CK(cudaFreeAsync(p, st));
+    h->d_text = nullptr; h->d_nhdr = h->d_rec_base = h->d_pre = h->d_post = nullptr; h->d_key = h->d_carry = nullptr;
+    h->d_base_in = h->d_hdr_pos = h->d_len = h->d_scaf_off = h->d_counters = nullptr;
+    return FRISK_OK;
+}
+
+int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st) {
+    int dev = 0;
+    FRISK_CK(cudaGetDevice(&dev));
+    int rc = pool_ready(dev);
+    if (rc) return rc;
+    h->n = n;
+    h->n_tiles = n ? (n + kTile - 1) / kTile : 0;
+    if (h->n_tiles > 0x7fffffffull) return FRISK_E_UNSUPPORTED;         // 8 TB of text per call
+    const uint64_t T = h->n_tiles;
+    if (T) {
+        const uint64_t padded_text = T * kTile + 16;
+        FRISK_CK(cudaMallocAsync((void**)&h->d_text, padded_text, st));
+        FRISK_CK(cudaMemsetAsync(h->d_text + n, '\n', padded_text - n, st));
+        FRISK_CK(cudaMemcpyAsync(h->d_text, text, n, cudaMemcpyHostToDevice, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_nhdr, T * 4, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_rec_base, T * 4, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_pre, T * 4, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_post, T * 4, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_key, T, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_carry, T, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_base_in, T * 8, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_counters, 3 * 8, st));
+        FRISK_CK(cudaMemsetAsync(h->d_counters, 0, 3 * 8, st));
+        fasta_lines_kernel<<<(unsigned)T, kTT, 0, st>>>(h->d_text, n, h->d_nhdr, h->d_key);
+        fasta_scan1_kernel<<<1, kST, 0, st>>>(h->d_nhdr, h->d_key, T, h->d_rec_base, h->d_carry, h->d_counters);
+        FRISK_CK(cudaGetLastError());
+        unsigned long long n_rec = 0;
+        FRISK_CK(cudaMemcpyAsync(&n_rec, h->d_counters, 8, cudaMemcpyDeviceToHost, st));
+        FRISK_CK(cudaStreamSynchronize(st));
+        h->n_rec = n_rec;
+        const uint64_t R = n_rec ? n_rec : 1;
+        FRISK_CK(cudaMallocAsync((void**)&h->d_hdr_pos, R * 8, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_len, R * 8, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_scaf_off, R * 8, st));
+        FRISK_CK(cudaMemsetAsync(h->d_len, 0, R * 8, st));
+        fasta_tile_kernel<0><<<(unsigned)T, kTT, 0, st>>>(h->d_text, n, h->d_rec_base, h->d_carry, h->d_hdr_pos, h->d_len,
+                                                          h->d_pre, h->d_post, h->d_counters, nullptr, nullptr, nullptr);
+        fasta_scan2_kernel<<<1, kST, 0, st>>>(h->d_nhdr, h->d_pre, h->d_post, T, h->d_base_in);
+        FRISK_CK(cudaGetLastError());
+        h->seq_len.resize(n_rec);
+        h->hdr_pos.resize(n_rec);
+        unsigned long long ctr[3] = {0, 0, 0};
+        if (n_rec) {
+            FRISK_CK(cudaMemcpyAsync(h->seq_len.data(), h->d_len, n_rec * 8, cudaMemcpyDeviceToHost, st));
+            FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data(), h->d_hdr_pos, n_rec * 8, cudaMemcpyDeviceToHost, st));
+        }
+        FRISK_CK(cudaMemcpyAsync(ctr, h->d_counters, 3 * 8, cudaMemcpyDeviceToHost, st));
+        FRISK_CK(cudaStreamSynchronize(st));
+        h->stats[1] = ctr[1];
+        h->stats[2] = ctr[2];
+    }
+    // names (F:156) and the 128-base aligned layout
+    const uint64_t R = h->n_rec;
+    h->name_off.resize(R); h->name_len.resize(R); h->scaf_off.resize(R);
+    const unsigned char* tt = reinterpret_cast<const unsigned char*>(text);
+    uint64_t total = 0;
+    for (uint64_t r = 0; r < R; ++r) {
+        if (!frisk_internal::parse_header_name(tt, n, h->hdr_pos[r], &h->name_off[r], &h->name_len[r])) return FRISK_E_FORMAT;
+        total += h->seq_len[r];
+    }
+    h->stats[0] = total;
+    rc = frisk_b200_pack_layout(h->seq_len.data(), R, h->scaf_off.data(), &h->padded_len);
+    if (rc) return rc;
+    if (R) FRISK_CK(cudaMemcpyAsync(h->d_scaf_off, h->scaf_off.data(), R * 8, cudaMemcpyHostToDevice, st));
+    return FRISK_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int frisk_b200_fasta_open(const char* text, uint64_t n, void* stream, frisk_b200_fasta** out, uint64_t* n_records,
+                          uint64_t* padded_len, uint64_t stats[3]) {
+    if (!out || (!text && n)) return FRISK_E_INVALID;
+    *out = nullptr;
+    if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    frisk_b200_fasta* h = new (std::nothrow) frisk_b200_fasta();
+    if (!h) return FRISK_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    try {
+        rc = open_impl(h, text, n, st);
+    } catch (...) {                                   // std::bad_alloc of the record table: nothing crosses the ABI
+        rc = FRISK_E_CAPACITY;
+    }
+    if (rc) {
+        free_all(h, st);
+        delete h;
+        return rc;
+    }
+    if (n_records) *n_records = h->n_rec;
+    if (padded_len) *padded_len = h->padded_len;
+    if (stats) { stats[0] = h->stats[0]; stats[1] = h->stats[1]; stats[2] = h->stats[2]; }
+    *out = h;
+    return FRISK_OK;
+}
+
+int frisk_b200_fasta_records(const frisk_b200_fasta* h, uint64_t* name_off, uint32_t* name_len, uint64_t* seq_len,
+                             uint64_t* scaf_off) {
+    if (!h) return FRISK_E_INVALID;
+    const size_t R = (size_t)h->n_rec;
+    if (name_off && R) memcpy(name_off, h->name_off.data(), R * 8);
+    if (name_len && R) memcpy(name_len, h->name_len.data(), R * 4);
+    if (seq_len && R) memcpy(seq_len, h->seq_len.data(), R * 8);
+    if (scaf_off && R) memcpy(scaf_off, h->scaf_off.data(), R * 8);
+    return FRISK_OK;
+}
+
+int frisk_b200_fasta_pack(frisk_b200_fasta* h, uint32_t* d_codes, uint32_t* d_inv, uint32_t* d_low, void* stream) {
+    if (!h || !d_codes || !d_inv) return FRISK_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* compact = nullptr;
+    FRISK_CK(cudaMallocAsync((void**)&compact, h->padded_len, st));
+    FRISK_CK(cudaMemsetAsync(compact, 8, h->padded_len, st));          // padding = "not a base": invalid, code 0
+    if (h->n_tiles && h->n_rec)
+        fasta_tile_kernel<1><<<(unsigned)h->n_tiles, kTT, 0, st>>>(h->d_text, h->n, h->d_rec_base, h->d_carry, nullptr, nullptr,
+                                                                   nullptr, nullptr, nullptr, h->d_base_in, h->d_scaf_off, compact);
+    const uint64_t n_words = h->padded_len / 32;
+    fasta_pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(compact, n_words, d_codes, d_inv, d_low);
+    FRISK_CK(cudaGetLastError());
+    FRISK_CK(cudaFreeAsync(compact, st));
+    return FRISK_OK;
+}
+
+int frisk_b200_fasta_close(frisk_b200_fasta* h, void* stream) {
+    if (!h) return FRISK_OK;
+    const int rc = free_all(h, (cudaStream_t)stream);
+    delete h;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+// Shared by the translation units of libfrisk_b200.so; not part of the C ABI.
+#ifndef FRISK_INTERNAL_H
+#define FRISK_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace frisk_internal {
+
+// records the CUDA error text for frisk_b200_last_cuda_error() and returns FRISK_E_CUDA
+int cuda_fail(cudaError_t e, const char* what);
+
+// cached per-device workspace (grown on demand, freed by frisk_b200_release_workspace)
+int ws_get(int slot, size_t bytes, void** out);
+
+// FASTA header rule of the reference (F:156): name = line.strip().strip('>').split()[0].
+// The line starts at `line_start`; returns false for an empty name (the reference raises IndexError).
+bool parse_header_name(const unsigned char* t, uint64_t n, uint64_t line_start, uint64_t* name_off, uint32_t* name_len);
+
+}  // namespace frisk_internal
+
+#define FRISK_CK(call)                                                        \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return frisk_internal::cuda_fail(e_, #call);   \
+    } while (0)
+
+#endif

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include "../../include/frisk_b200.h"
+#include "frisk_internal.h"
 
 namespace {
 
@@ -1100,16 +1101,16 @@ __global__ void __launch_bounds__(kThreads, 1) smem_atomic_bench_kernel(int iter
 
 thread_local char g_cuda_err[512] = "";
 int g_force_dense = 0;      // tests: force the dense-table kernel (frisk_b200_set_option)
+}  // namespace
 
-int cuda_fail(cudaError_t e, const char* what) {
+int frisk_internal::cuda_fail(cudaError_t e, const char* what) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
     return FRISK_E_CUDA;
 }
-#define CK(call)                                                  \
-    do {                                                          \
-        cudaError_t e_ = (call);                                  \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #call);       \
-    } while (0)
+
+namespace {
+using frisk_internal::ws_get;
+#define CK(call) FRISK_CK(call)
 
 int sm_count() {
     int dev = 0, n = 0;
@@ -1117,8 +1118,6 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
     return n;
 }
-
-int ws_get(int slot, size_t bytes, void** out);
 
 template <int K>
 int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, uint64_t w_lo, uint64_t w_hi,
@@ -1261,12 +1260,14 @@ int check_k(int kmin, int kmax) {
 // cached device workspace of frisk_b200_run_host (one per device, grown on demand)
 struct Workspace {
     int device = -1;
-    void* buf[16] = {};
-    size_t cap[16] = {};
+    void* buf[32] = {};
+    size_t cap[32] = {};
 };
 Workspace g_ws[64];
 
-int ws_get(int slot, size_t bytes, void** out) {
+}  // namespace
+
+int frisk_internal::ws_get(int slot, size_t bytes, void** out) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     Workspace& w = g_ws[dev & 63];
@@ -1280,7 +1281,6 @@ int ws_get(int slot, size_t bytes, void** out) {
     *out = w.buf[slot];
     return FRISK_OK;
 }
-}  // namespace
 
 extern "C" {
 
@@ -1372,6 +1372,75 @@ int frisk_b200_kld(const double* d_genome_ivom, const double* d_window_ivom, uin
     return FRISK_OK;
 }
 
+// Everything after the planes are on the device: [background], finalize, genome IVOM, window
+// upload, score, download.  `copy` (nullable) already carries the uploads this run must wait for.
+static int run_tail(const uint32_t* dhc, const uint32_t* dhi, const uint32_t* dhl, uint64_t h_padded_len, bool bg_enqueued,
+                    const uint32_t* dqc, const uint32_t* dqi, const uint32_t* dql, const uint64_t* win_off,
+                    const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host,
+                    int want_rip, int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
+                    uint64_t* valid_kmax_out, void* dfwd, cudaStream_t st, cudaStream_t copy, cudaEvent_t copy_done) {
+    const size_t tsz = (size_t)frisk_b200_table_size(1, kmax);
+    void *dtab, *dig, *dwo = nullptr, *dwl = nullptr, *drows = nullptr, *dstat = nullptr;
+    int rc;
+    if ((rc = ws_get(7, (tsz + 1) * 8, &dtab))) return rc;
+    if ((rc = ws_get(8, (size_t)pow4(kmax) * 16, &dig))) return rc;
+    if (n_win) {
+        if ((rc = ws_get(9, n_win * 8, &dwo))) return rc;
+        if ((rc = ws_get(10, n_win * 4, &dwl))) return rc;
+        if ((rc = ws_get(11, n_win * 40, &drows))) return rc;
+        if ((rc = ws_get(12, n_win * 4, &dstat))) return rc;
+        cudaStream_t up = copy ? copy : st;             // the window list rides behind the planes
+        CK(cudaMemcpyAsync(dwo, win_off, n_win * 8, cudaMemcpyHostToDevice, up));
+        CK(cudaMemcpyAsync(dwl, win_len, n_win * 4, cudaMemcpyHostToDevice, up));
+    }
+    if (copy) CK(cudaEventRecord(copy_done, copy));
+    if (!bg_enqueued) {
+        CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, st));
+        // the last 32-base word is padding by construction and is only ever read as look-ahead
+        rc = frisk_b200_background(dhc, dhi, dhl, 0, h_padded_len - 32, kmax, mask_host, (uint64_t*)dfwd, st);
+        if (rc) return rc;
+    }
+    uint64_t* dvalid = (uint64_t*)dtab + tsz;
+    rc = frisk_b200_finalize_tables((const uint64_t*)dfwd, kmax, 1, (uint64_t*)dtab, dvalid, st);
+    if (rc) return rc;
+    rc = frisk_b200_genome_ivom((const uint64_t*)dtab, kmin, kmax, genome_space, (double*)dig, st);
+    if (rc) return rc;
+    if (copy) CK(cudaStreamWaitEvent(st, copy_done, 0));
+    if (n_win) {
+        rc = frisk_b200_score(dqc, dqi, dql, (const uint64_t*)dwo, (const uint32_t*)dwl, n_win, max_win_len,
+                              (const double*)dig, kmin, kmax, want_rip, (double*)drows, (uint32_t*)dstat, nullptr, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(rows_out, drows, n_win * 40, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status_out, dstat, n_win * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, st));
+    if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FRISK_OK;
+}
+
+// per-device copy stream + events of frisk_b200_run_host (uploads overlap the background count)
+namespace {
+constexpr int kMaxChunks = 16;
+struct CopyCtx {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev[kMaxChunks + 2] = {};
+};
+CopyCtx g_copy[64];
+
+int copy_ctx(CopyCtx** out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CopyCtx& c = g_copy[dev & 63];
+    if (!c.copy) {
+        CK(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+        for (auto& e : c.ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    *out = &c;
+    return FRISK_OK;
+}
+}  // namespace
+
 int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const uint32_t* h_low, uint64_t h_padded_len,
                         const uint32_t* q_codes, const uint32_t* q_inv, const uint32_t* q_low, uint64_t q_padded_len,
                         const uint64_t* win_off, const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len,
@@ -1385,62 +1454,81 @@ int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const ui
     if (rc) return rc;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
+    CopyCtx* cc = nullptr;
+    if ((rc = copy_ctx(&cc))) return rc;
     const bool same = (h_codes == q_codes) && (h_inv == q_inv) && (h_padded_len == q_padded_len);
     const size_t tsz = (size_t)frisk_b200_table_size(1, kmax);
-    void *dhc, *dhi, *dhl = nullptr, *dqc, *dqi, *dql = nullptr, *dfwd, *dtab, *dig, *dwo, *dwl, *drows, *dstat;
+    void *dhc, *dhi, *dhl = nullptr, *dqc, *dqi, *dql = nullptr, *dfwd;
     if ((rc = ws_get(0, h_padded_len / 4, &dhc))) return rc;
     if ((rc = ws_get(1, h_padded_len / 8, &dhi))) return rc;
     if (h_low && (rc = ws_get(2, h_padded_len / 8, &dhl))) return rc;
-    CK(cudaMemcpyAsync(dhc, h_codes, h_padded_len / 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dhi, h_inv, h_padded_len / 8, cudaMemcpyHostToDevice, st));
-    if (h_low) CK(cudaMemcpyAsync(dhl, h_low, h_padded_len / 8, cudaMemcpyHostToDevice, st));
+    if ((rc = ws_get(6, (tsz + 1) * 8, &dfwd))) return rc;
+    CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, st));
+    // The planes go up in chunks on the copy stream; the background count of a chunk starts as soon
+    // as the chunk has landed (it stops 128 bases short of the chunk's end: the kernel looks ahead),
+    // so only the last chunk's count is not hidden behind PCIe.
+    CK(cudaEventRecord(cc->ev[kMaxChunks], st));
+    CK(cudaStreamWaitEvent(cc->copy, cc->ev[kMaxChunks], 0));          // order behind earlier work on `stream`
+    uint64_t n_chunks = (h_padded_len + (8ull << 20) - 1) / (8ull << 20);
+    if (n_chunks > (uint64_t)kMaxChunks) n_chunks = kMaxChunks;
+    const uint64_t chunk = ((h_padded_len + n_chunks - 1) / n_chunks + 127) & ~127ull;
+    uint64_t counted = 0;
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        const uint64_t b0 = c * chunk, b1 = (b0 + chunk < h_padded_len) ? b0 + chunk : h_padded_len;
+        if (b0 >= b1) break;
+        CK(cudaMemcpyAsync((char*)dhc + b0 / 4, (const char*)h_codes + b0 / 4, (b1 - b0) / 4, cudaMemcpyHostToDevice, cc->copy));
+        CK(cudaMemcpyAsync((char*)dhi + b0 / 8, (const char*)h_inv + b0 / 8, (b1 - b0) / 8, cudaMemcpyHostToDevice, cc->copy));
+        if (h_low) CK(cudaMemcpyAsync((char*)dhl + b0 / 8, (const char*)h_low + b0 / 8, (b1 - b0) / 8, cudaMemcpyHostToDevice, cc->copy));
+        CK(cudaEventRecord(cc->ev[c], cc->copy));
+        CK(cudaStreamWaitEvent(st, cc->ev[c], 0));
+        const uint64_t upto = (b1 == h_padded_len) ? h_padded_len - 32 : b1 - 128;
+        if (upto > counted) {
+            rc = frisk_b200_background((const uint32_t*)dhc, (const uint32_t*)dhi, (const uint32_t*)dhl, counted, upto, kmax,
+                                       mask_host, (uint64_t*)dfwd, st);
+            if (rc) return rc;
+            counted = upto;
+        }
+    }
     if (same) { dqc = dhc; dqi = dhi; dql = dhl; }
     else {
         if ((rc = ws_get(3, q_padded_len / 4, &dqc))) return rc;
         if ((rc = ws_get(4, q_padded_len / 8, &dqi))) return rc;
         if (q_low && (rc = ws_get(5, q_padded_len / 8, &dql))) return rc;
-        CK(cudaMemcpyAsync(dqc, q_codes, q_padded_len / 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(dqi, q_inv, q_padded_len / 8, cudaMemcpyHostToDevice, st));
-        if (q_low) CK(cudaMemcpyAsync(dql, q_low, q_padded_len / 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dqc, q_codes, q_padded_len / 4, cudaMemcpyHostToDevice, cc->copy));
+        CK(cudaMemcpyAsync(dqi, q_inv, q_padded_len / 8, cudaMemcpyHostToDevice, cc->copy));
+        if (q_low) CK(cudaMemcpyAsync(dql, q_low, q_padded_len / 8, cudaMemcpyHostToDevice, cc->copy));
     }
-    if ((rc = ws_get(6, (tsz + 1) * 8, &dfwd))) return rc;
-    if ((rc = ws_get(7, (tsz + 1) * 8, &dtab))) return rc;
-    if ((rc = ws_get(8, (size_t)pow4(kmax) * 16, &dig))) return rc;
-    CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, st));
-    // the last 32-base word is padding by construction and is only ever read as look-ahead
-    rc = frisk_b200_background((const uint32_t*)dhc, (const uint32_t*)dhi, (const uint32_t*)dhl, 0, h_padded_len - 32, kmax,
-                               mask_host, (uint64_t*)dfwd, st);
+    return run_tail((const uint32_t*)dhc, (const uint32_t*)dhi, (const uint32_t*)dhl, h_padded_len, true,
+                    (const uint32_t*)dqc, (const uint32_t*)dqi, (const uint32_t*)dql, win_off, win_len, n_win, max_win_len,
+                    kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out, valid_kmax_out, dfwd, st,
+                    cc->copy, cc->ev[kMaxChunks + 1]);
+}
+
+int frisk_b200_run_resident(const uint32_t* d_h_codes, const uint32_t* d_h_inv, const uint32_t* d_h_low,
+                            uint64_t h_padded_len, const uint32_t* d_q_codes, const uint32_t* d_q_inv,
+                            const uint32_t* d_q_low, uint64_t q_padded_len, const uint64_t* win_off,
+                            const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax,
+                            int mask_host, int want_rip, int64_t genome_space, double* rows_out, uint32_t* status_out,
+                            uint64_t* tables_out, uint64_t* valid_kmax_out, void* stream) {
+    if (!d_h_codes || !d_h_inv || !d_q_codes || !d_q_inv || (h_padded_len & 127) || (q_padded_len & 127) ||
+        h_padded_len < 128 || q_padded_len < 128)
+        return FRISK_E_INVALID;
+    if (n_win && (!win_off || !win_len || !rows_out || !status_out)) return FRISK_E_INVALID;
+    int rc = check_k(kmin, kmax);
     if (rc) return rc;
-    uint64_t* dvalid = (uint64_t*)dtab + tsz;
-    rc = frisk_b200_finalize_tables((const uint64_t*)dfwd, kmax, 1, (uint64_t*)dtab, dvalid, st);
-    if (rc) return rc;
-    rc = frisk_b200_genome_ivom((const uint64_t*)dtab, kmin, kmax, genome_space, (double*)dig, st);
-    if (rc) return rc;
-    if (n_win) {
-        if ((rc = ws_get(9, n_win * 8, &dwo))) return rc;
-        if ((rc = ws_get(10, n_win * 4, &dwl))) return rc;
-        if ((rc = ws_get(11, n_win * 40, &drows))) return rc;
-        if ((rc = ws_get(12, n_win * 4, &dstat))) return rc;
-        CK(cudaMemcpyAsync(dwo, win_off, n_win * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(dwl, win_len, n_win * 4, cudaMemcpyHostToDevice, st));
-        rc = frisk_b200_score((const uint32_t*)dqc, (const uint32_t*)dqi, (const uint32_t*)dql, (const uint64_t*)dwo,
-                              (const uint32_t*)dwl, n_win, max_win_len, (const double*)dig, kmin, kmax, want_rip,
-                              (double*)drows, (uint32_t*)dstat, nullptr, st);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(rows_out, drows, n_win * 40, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(status_out, dstat, n_win * 4, cudaMemcpyDeviceToHost, st));
-    }
-    if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, st));
-    if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return FRISK_OK;
+    if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    void* dfwd;
+    if ((rc = ws_get(6, ((size_t)frisk_b200_table_size(1, kmax) + 1) * 8, &dfwd))) return rc;
+    return run_tail(d_h_codes, d_h_inv, d_h_low, h_padded_len, false, d_q_codes, d_q_inv, d_q_low, win_off, win_len, n_win,
+                    max_win_len, kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out,
+                    valid_kmax_out, dfwd, (cudaStream_t)stream, nullptr, nullptr);
 }
 
 int frisk_b200_release_workspace(void) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     Workspace& w = g_ws[dev & 63];
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 32; ++i) {
         if (w.buf[i]) CK(cudaFree(w.buf[i]));
         w.buf[i] = nullptr; w.cap[i] = 0;
     }

@@ -38,7 +38,7 @@ def _as_u8(seq: SeqLike) -> np.ndarray:
     return np.ascontiguousarray(seq, dtype=np.uint8)
 
 
-_TORCH_DTYPE = {"uint32": "int32", "uint64": "int64", "float64": "float64", "int64": "int64", "int32": "int32"}
+_TORCH_DTYPE = {"uint8": "uint8", "uint32": "int32", "uint64": "int64", "float64": "float64", "int64": "int64", "int32": "int32"}
 
 
 def _alloc(shape, dtype, pinned: bool) -> np.ndarray:
@@ -55,6 +55,27 @@ def _alloc(shape, dtype, pinned: bool) -> np.ndarray:
 
 def _alloc_u32(n: int, pinned: bool) -> np.ndarray:
     return _alloc(n, np.uint32, pinned)
+
+
+def read_fasta_file(path: str) -> np.ndarray:
+    """The file's bytes; ``.gz`` is inflated the way the reference opens it (F:144-147)."""
+    if path.endswith(".gz"):
+        import gzip
+        with gzip.open(path, "rb") as fh:
+            return np.frombuffer(fh.read(), dtype=np.uint8)
+    return np.fromfile(path, dtype=np.uint8)
+
+
+def _decode_names(buf: np.ndarray, name_off: np.ndarray, name_len: np.ndarray) -> List[str]:
+    if len(name_off) == 0:
+        return []
+    if len(name_off) > 4096:
+        # one pass over the headers only: a 1 M-scaffold assembly must not pay a Python slice of a
+        # multi-GB buffer per record
+        ends = name_off.astype(np.int64) + name_len.astype(np.int64)
+        return [buf[int(a):int(b)].tobytes().decode() for a, b in zip(name_off.astype(np.int64), ends)]
+    raw = memoryview(buf)
+    return [bytes(raw[int(a):int(a) + int(l)]).decode() for a, l in zip(name_off, name_len)]
 
 
 @dataclass
@@ -115,22 +136,11 @@ class PackedGenome:
         body_off = np.zeros(cap, np.uint64); body_end = np.zeros(cap, np.uint64); seq_len = np.zeros(cap, np.uint64)
         _lib.check(L.frisk_b200_fasta_scan(_ptr(buf), buf.shape[0], cap, _ptr(name_off), _ptr(name_len), _ptr(body_off),
                                            _ptr(body_end), _ptr(seq_len), C.byref(n)), "frisk_b200_fasta_scan")
-        raw = buf.tobytes() if cap < 100000 else None
-        names = []
-        for i in range(cap):
-            a = int(name_off[i]); b = a + int(name_len[i])
-            names.append((raw[a:b] if raw is not None else buf[a:b].tobytes()).decode())
-        return cls._pack(names, buf, body_off, body_end, seq_len, pinned, threads)
+        return cls._pack(_decode_names(buf, name_off, name_len), buf, body_off, body_end, seq_len, pinned, threads)
 
     @classmethod
     def from_fasta(cls, path: str, pinned: bool = False, threads: int = 0) -> "PackedGenome":
-        if path.endswith(".gz"):
-            import gzip
-            with gzip.open(path, "rb") as fh:   # the reference opens .gz the same way (F:144-147)
-                data = np.frombuffer(fh.read(), dtype=np.uint8)
-        else:
-            data = np.fromfile(path, dtype=np.uint8)
-        return cls.from_fasta_bytes(data, pinned, threads)
+        return cls.from_fasta_bytes(read_fasta_file(path), pinned, threads)
 
     @classmethod
     def _pack(cls, names, src, src_off, src_end, lens, pinned, threads) -> "PackedGenome":
@@ -182,6 +192,8 @@ class PackedGenome:
 
     @property
     def plane_bytes(self) -> int:
+        if self.codes is None:      # planes exist on the device only (DeviceGenome.from_fasta_bytes)
+            return self.padded_len // 4 + self.padded_len // 8 * (2 if self.n_lower else 1)
         return self.codes.nbytes + self.inv.nbytes + (self.low.nbytes if self.low is not None else 0)
 
 
@@ -189,15 +201,62 @@ class PackedGenome:
 class DeviceGenome:
     """The packed planes resident in HBM (torch tensors used purely as device buffers)."""
 
-    def __init__(self, g: PackedGenome, device="cuda:0", stream=None):
+    def __init__(self, g: PackedGenome, device="cuda:0", stream=None, planes=None):
         import torch
         _lib.require_device()
         self.host = g
         self.device = torch.device(device)
+        if planes is not None:
+            self.codes, self.inv, self.low = planes
+            return
         with torch.cuda.device(self.device):
             self.codes = torch.from_numpy(g.codes.view(np.int32)).to(self.device, non_blocking=True)
             self.inv = torch.from_numpy(g.inv.view(np.int32)).to(self.device, non_blocking=True)
             self.low = torch.from_numpy(g.low.view(np.int32)).to(self.device, non_blocking=True) if g.low is not None else None
+
+    @classmethod
+    def from_fasta_bytes(cls, text: Union[bytes, np.ndarray], device="cuda:0") -> "DeviceGenome":
+        """Device-side ingest (frisk_ingest.cu): the raw FASTA text goes to the GPU once and is
+        tokenised and 2-bit packed there; only the record table comes back.  ``self.host`` is a
+        PackedGenome without host planes (names, lengths, layout, countN statistics)."""
+        import torch
+        _lib.require_device()
+        L = _lib.lib()
+        buf = _as_u8(text)
+        dev = torch.device(device)
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            h = C.c_void_p()
+            nrec, padded = C.c_uint64(0), C.c_uint64(0)
+            stats = np.zeros(3, np.uint64)
+            _lib.check(L.frisk_b200_fasta_open(_ptr(buf), buf.shape[0], st, C.byref(h), C.byref(nrec), C.byref(padded),
+                                               _ptr(stats)), "frisk_b200_fasta_open")
+            try:
+                R, P = int(nrec.value), int(padded.value)
+                name_off = np.zeros(R, np.uint64); name_len = np.zeros(R, np.uint32)
+                seq_len = np.zeros(R, np.uint64); scaf_off = np.zeros(R, np.uint64)
+                _lib.check(L.frisk_b200_fasta_records(h, _ptr(name_off), _ptr(name_len), _ptr(seq_len), _ptr(scaf_off)),
+                           "frisk_b200_fasta_records")
+                codes = torch.empty(P // 16, dtype=torch.int32, device=dev)
+                inv = torch.empty(P // 32, dtype=torch.int32, device=dev)
+                low = torch.empty(P // 32, dtype=torch.int32, device=dev) if int(stats[2]) else None
+                _lib.check(L.frisk_b200_fasta_pack(h, _ptr(codes), _ptr(inv), _ptr(low), st), "frisk_b200_fasta_pack")
+            finally:
+                L.frisk_b200_fasta_close(h, st)
+        names = _decode_names(buf, name_off, name_len)
+        g = PackedGenome(names, seq_len, scaf_off, P, None, None, None, int(stats[0]), int(stats[1]), int(stats[2]), False)
+        return cls(g, dev, planes=(codes, inv, low))
+
+    @classmethod
+    def from_fasta(cls, path: str, device="cuda:0") -> "DeviceGenome":
+        return cls.from_fasta_bytes(read_fasta_file(path), device)
+
+    def to_host(self) -> PackedGenome:
+        """Copy the planes back (tests; the host packer must agree bit for bit)."""
+        g = self.host
+        low = self.low.cpu().numpy().view(np.uint32) if self.low is not None else None
+        return PackedGenome(g.names, g.scaf_len, g.scaf_off, g.padded_len, self.codes.cpu().numpy().view(np.uint32),
+                            self.inv.cpu().numpy().view(np.uint32), low, g.total_len, g.nn_total, g.n_lower, False)
 
 
 def _stream_ptr(device) -> C.c_void_p:
@@ -320,13 +379,16 @@ class Pipeline:
         if kmax > _lib.MAX_K:
             rc = _lib.E_UNSUPPORTED
         _lib.check(rc, "frisk_b200 Pipeline(kmin=%d, kmax=%d)" % (kmin, kmax))
-        self.query, self.host = query, host or query
+        # query / host may be PackedGenome (host planes, uploaded here) or DeviceGenome (already resident)
+        host = host if host is not None else query
+        self.dq = query if isinstance(query, DeviceGenome) else DeviceGenome(query, device)
+        self.dh = self.dq if host is query else (host if isinstance(host, DeviceGenome) else DeviceGenome(host, device))
+        query, host = self.dq.host, self.dh.host
+        self.query, self.host = query, host
         self.kmin, self.kmax, self.mask_host, self.rip = kmin, kmax, mask_host, rip
         self.allreduce = allreduce
         self.genome_space = self.host.genome_space if genome_space is None else int(genome_space)
         self.wins = wins if wins is not None else query.windows(w, step, scaffolds_all)
-        self.dq = DeviceGenome(query, device)
-        self.dh = self.dq if self.host is query else DeviceGenome(self.host, device)
         dev = self.dq.device
         self.device = dev
         n = len(self.wins)
@@ -340,7 +402,7 @@ class Pipeline:
         self.d_dump = torch.empty((n, tsz), dtype=torch.int16, device=dev) if dump else None
         self.d_off = torch.from_numpy(self.wins.off.view(np.int64)).to(dev, non_blocking=True)
         self.d_len = torch.from_numpy(self.wins.length.view(np.int32)).to(dev, non_blocking=True)
-        self.launches_per_step = 4          # bg_count, finalize_tables, genome_ivom, score_windows
+        self.launches_per_step = 7          # bg_count, bg_reduce, forward_totals, forward_low, symmetrise, genome_ivom, score_windows
 
     def enqueue(self, marks=None) -> None:
         """Launch one pass.  ``marks`` (optional list) receives a CUDA event after each stage:
@@ -391,7 +453,7 @@ class Pipeline:
                         self.kmin, self.kmax, dmp)
 
 
-def run(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1, kmax: int = 8, w: int = 5000,
+def run(query, host=None, kmin: int = 1, kmax: int = 8, w: int = 5000,
         step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True,
         device="cuda:0", dump: bool = False, allreduce=None, genome_space: Optional[int] = None,
         wins: Optional[WindowList] = None) -> HotPathResult:
@@ -428,6 +490,42 @@ def run_host(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int
     if not assemble_result:
         return out
     return assemble(query, host, wins, out.tables, int(out.valid[0]), out.rows[:n], out.status[:n], kmin, kmax)
+
+
+def run_resident(dq: DeviceGenome, dh: Optional[DeviceGenome] = None, kmin: int = 1, kmax: int = 8, w: int = 5000,
+                 step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True,
+                 wins: Optional[WindowList] = None, out=None, assemble_result: bool = True):
+    """``run_host`` for planes that are already on the device (frisk_b200_run_resident): one C call
+    that uploads the window list, runs every kernel and downloads rows/status/tables."""
+    _lib.require_device()
+    import torch
+    dh = dh or dq
+    query, host = dq.host, dh.host
+    if wins is None:
+        wins = query.windows(w, step, scaffolds_all)
+    n = len(wins)
+    if out is None:
+        out = HostOutputs(n, kmax)
+    with torch.cuda.device(dq.device):
+        rc = _lib.lib().frisk_b200_run_resident(
+            _ptr(dh.codes), _ptr(dh.inv), _ptr(dh.low), host.padded_len,
+            _ptr(dq.codes), _ptr(dq.inv), _ptr(dq.low), query.padded_len,
+            _ptr(wins.off), _ptr(wins.length), n, wins.max_len, kmin, kmax, int(mask_host), int(rip),
+            int(host.genome_space), _ptr(out.rows), _ptr(out.status), _ptr(out.tables), _ptr(out.valid),
+            _stream_ptr(dq.device))
+    _lib.check(rc, "frisk_b200_run_resident")
+    if not assemble_result:
+        return out
+    return assemble(query, host, wins, out.tables, int(out.valid[0]), out.rows[:n], out.status[:n], kmin, kmax)
+
+
+def run_fasta(query_text, host_text=None, device="cuda:0", out=None, assemble_result: bool = True, **params):
+    """FASTA text (bytes / uint8 array) in, rows out: device-side ingest + frisk_b200_run_resident.
+    This is the whole of the reference's stages 2+3 (F:1442, F:1478-1494) including its three
+    passes over the file (F:170, F:203, F:297) with the host doing nothing but one copy."""
+    dq = DeviceGenome.from_fasta_bytes(query_text, device)
+    dh = DeviceGenome.from_fasta_bytes(host_text, device) if host_text is not None else None
+    return run_resident(dq, dh, out=out, assemble_result=assemble_result, **params)
 
 
 class HostOutputs:

@@ -221,16 +221,23 @@ def digest(scaffolds: List[Scaffold]) -> str:
     return h.hexdigest()
 
 
+def fasta_bytes(scaffolds: List[Scaffold], width: int = 60) -> bytes:
+    """The scaffolds as FASTA text (the reference's input format), `width` bases per line."""
+    parts = []
+    for name, seq in scaffolds:
+        parts.append(b">" + name.encode() + (" len=%d synthetic\n" % len(seq)).encode())
+        n = len(seq)
+        full = (n // width) * width
+        if full:
+            body = np.empty((n // width, width + 1), dtype=np.uint8)
+            body[:, :width] = seq[:full].reshape(-1, width)
+            body[:, width] = 10
+            parts.append(body.tobytes())
+        if n > full:
+            parts.append(seq[full:].tobytes() + b"\n")
+    return b"".join(parts)
+
+
 def write_fasta(scaffolds: List[Scaffold], path: str, width: int = 60) -> None:
     with open(path, "wb") as fh:
-        for name, seq in scaffolds:
-            fh.write(b">" + name.encode() + (" len=%d synthetic\n" % len(seq)).encode())
-            n = len(seq)
-            full = (n // width) * width
-            if full:
-                body = np.empty((n // width, width + 1), dtype=np.uint8)
-                body[:, :width] = seq[:full].reshape(-1, width)
-                body[:, width] = 10
-                fh.write(body.tobytes())
-            if n > full:
-                fh.write(seq[full:].tobytes() + b"\n")
+        fh.write(fasta_bytes(scaffolds, width))

@@ -177,6 +177,42 @@ int frisk_b200_run_host(const uint32_t *h_codes, const uint32_t *h_inv, const ui
                         int kmin, int kmax, int mask_host, int want_rip, int64_t genome_space, double *rows_out,
                         uint32_t *status_out, uint64_t *tables_out, uint64_t *valid_kmax_out, void *stream);
 
+/*
+ * frisk_b200_run_resident: frisk_b200_run_host for planes that are already in device memory (e.g.
+ * written by frisk_b200_fasta_pack): no plane upload; the window list still comes from, and the
+ * results still go to, host memory.
+ */
+int frisk_b200_run_resident(const uint32_t *d_h_codes, const uint32_t *d_h_inv, const uint32_t *d_h_low,
+                            uint64_t h_padded_len, const uint32_t *d_q_codes, const uint32_t *d_q_inv,
+                            const uint32_t *d_q_low, uint64_t q_padded_len, const uint64_t *win_off,
+                            const uint32_t *win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax,
+                            int mask_host, int want_rip, int64_t genome_space, double *rows_out, uint32_t *status_out,
+                            uint64_t *tables_out, uint64_t *valid_kmax_out, void *stream);
+
+/* ------------------------------------------------------------------ device-side FASTA ingest
+ *
+ * The GPU replacement of iterFasta (F:139-164) + countN (F:106-118): the raw FASTA text is copied
+ * to the device once and tokenised, measured and 2-bit packed there (frisk_ingest.cu); the planes
+ * are bit-identical to those of frisk_b200_fasta_scan + frisk_b200_pack_layout + frisk_b200_pack.
+ *
+ * frisk_b200_fasta_open: H2D of text[0..n) (asynchronous when `text` is pinned), record detection
+ * and per-record lengths on the device, names (F:156) and the packed layout on the host.  Blocks
+ * until the record table is known.  *n_records, *padded_len and stats[3] (totalLen, nnTotal,
+ * number of lower-case acgt -- as frisk_b200_pack) describe the result; the caller then allocates
+ * the planes (padded_len/16 and padded_len/32 uint32 words) and calls frisk_b200_fasta_pack, which
+ * only enqueues work on `stream`.  frisk_b200_fasta_records copies the record table (any pointer
+ * may be NULL); name_off/name_len index into `text`.  frisk_b200_fasta_close releases the device
+ * copy of the text (stream-ordered) and the handle.  Use one stream for all calls on a handle.
+ * FRISK_E_FORMAT: a header line without a name (the reference raises IndexError, F:156).
+ */
+typedef struct frisk_b200_fasta frisk_b200_fasta;
+int frisk_b200_fasta_open(const char *text, uint64_t n, void *stream, frisk_b200_fasta **out, uint64_t *n_records,
+                          uint64_t *padded_len, uint64_t stats[3]);
+int frisk_b200_fasta_records(const frisk_b200_fasta *h, uint64_t *name_off, uint32_t *name_len, uint64_t *seq_len,
+                             uint64_t *scaf_off);
+int frisk_b200_fasta_pack(frisk_b200_fasta *h, uint32_t *d_codes, uint32_t *d_inv, uint32_t *d_low, void *stream);
+int frisk_b200_fasta_close(frisk_b200_fasta *h, void *stream);
+
 /* Free the cached device workspace of frisk_b200_run_host on the current device. */
 int frisk_b200_release_workspace(void);
 

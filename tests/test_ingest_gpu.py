@@ -1,0 +1,133 @@
+"""Device-side FASTA ingest (frisk_ingest.cu) against the host packer, which tests/test_host.py holds
+to the reference's iterFasta/countN rules (F:139-164, F:106-118): same records, same layout, and
+bit-identical planes; then the whole FASTA-text-in, rows-out path against the golden fixtures."""
+import numpy as np
+import pytest
+
+from frisk_b200 import _lib, engine, synth
+from tests.helpers import Golden
+
+pytestmark = pytest.mark.gpu
+
+
+def fasta_text(scaffolds, width=60, eol=b"\n", trailing_newline=True):
+    out = []
+    for name, seq in scaffolds:
+        out.append(b">" + name.encode() + b" some description" + eol)
+        b = seq.tobytes() if isinstance(seq, np.ndarray) else seq
+        if width <= 0:
+            out.append(b + eol)
+        else:
+            out.extend(b[i:i + width] + eol for i in range(0, len(b), width))
+    text = b"".join(out)
+    if not trailing_newline and text.endswith(eol):
+        text = text[:-len(eol)]
+    return text
+
+
+def assert_same_genome(text):
+    host = engine.PackedGenome.from_fasta_bytes(text)
+    dev = engine.DeviceGenome.from_fasta_bytes(text).to_host()
+    assert dev.names == host.names
+    assert np.array_equal(dev.scaf_len, host.scaf_len)
+    assert np.array_equal(dev.scaf_off, host.scaf_off)
+    assert dev.padded_len == host.padded_len
+    assert (dev.total_len, dev.nn_total, dev.n_lower) == (host.total_len, host.nn_total, host.n_lower)
+    assert np.array_equal(dev.codes, host.codes)
+    assert np.array_equal(dev.inv, host.inv)
+    assert (dev.low is None) == (host.low is None)
+    if host.low is not None:
+        assert np.array_equal(dev.low, host.low)
+    return host
+
+
+def test_reference_scanning_rules():
+    text = (b"leading junk before any header\n"
+            b">>seq1 description words\nACGT\n  \nacgtNN\r\n"
+            b">seq2\tother\n\nAC\nGT\n"
+            b">empty_record\n"
+            b"  >indented_header x\n AC GT \n"
+            b">last\nTT>TT")
+    g = assert_same_genome(text)
+    assert g.names == ["seq1", "seq2", "empty_record", "indented_header", "last"]
+    assert list(g.scaf_len) == [10, 4, 0, 4, 5]
+
+
+@pytest.mark.parametrize("width,eol,trail", [(60, b"\n", True), (80, b"\r\n", True), (1, b"\n", False), (0, b"\n", True),
+                                             (4095, b"\n", True), (4096, b"\n", False), (7, b"\r\n", False)])
+def test_line_layouts(width, eol, trail):
+    sc = synth.make("edge") + synth.make("C2", 0.003, seed=5)
+    assert_same_genome(fasta_text(sc, width, eol, trail))
+
+
+def test_headers_around_tile_boundaries():
+    rng = np.random.default_rng(3)
+    letters = np.frombuffer(b"ACGTacgtNRY", dtype=np.uint8)
+    for shift in range(4090, 4102):
+        first = letters[rng.integers(0, len(letters), shift)].tobytes()
+        text = b">a\n" + first + b"\n>b\n" + b"ACGT" * 3000 + b"\n>c\n\n>d\nA\n"
+        assert_same_genome(text)
+    # a tile made of headers only, and one made of blank lines only
+    text = b"".join(b">r%05d\n" % i for i in range(2000)) + b"\n" * 9000 + b">z\nACGT\n" + b" " * 5000 + b"\nGG\n"
+    g = assert_same_genome(text)
+    assert len(g.names) == 2001 and int(g.scaf_len[-1]) == 6
+
+
+def test_fuzzed_texts():
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"ACGTACGTACGTacgtNnRYKM-*>", dtype=np.uint8)
+    for trial in range(12):
+        parts = [b"junk line\n"] if trial % 3 == 0 else []
+        for r in range(int(rng.integers(1, 60))):
+            parts.append(b" " * int(rng.integers(0, 3)) + b">" * int(rng.integers(1, 3)) + b"rec%d_%d" % (trial, r) +
+                         (b"\tdesc" if r % 2 else b"") + (b"\r\n" if r % 5 == 0 else b"\n"))
+            n = int(rng.integers(0, 9000)) if r % 7 else 0
+            seq = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
+            width = int(rng.choice([1, 13, 60, 61, 500, 10000]))
+            for i in range(0, n, width):
+                line = seq[i:i + width]
+                if line.lstrip(b" \t").startswith(b">"):
+                    line = b"A" + line[1:]                 # a sequence line must not look like a header
+                parts.append(line + (b"\r\n" if trial % 2 else b"\n"))
+                if rng.random() < 0.05:
+                    parts.append(b"  \t \n")
+        text = b"".join(parts)
+        if trial % 4 == 1:
+            text = text.rstrip(b"\r\n")
+        assert_same_genome(text)
+
+
+def test_empty_and_malformed_inputs():
+    g = engine.DeviceGenome.from_fasta_bytes(b"")
+    assert g.host.names == [] and g.host.padded_len == 128 and g.host.total_len == 0
+    assert np.all(g.to_host().inv == 0xFFFFFFFF)
+    g = engine.DeviceGenome.from_fasta_bytes(b"no header at all\nACGT\n")
+    assert g.host.names == [] and g.host.total_len == 0
+    with pytest.raises(_lib.FriskError) as ei:
+        engine.DeviceGenome.from_fasta_bytes(b">ok\nACGT\n>\nACGT\n")
+    assert ei.value.code == _lib.E_FORMAT                     # the reference raises IndexError at F:156
+
+
+@pytest.mark.parametrize("case", ["edge_default", "edge_scaffoldsAll", "edge_maskHost", "c1_small", "c2_small",
+                                  "c2_small_query_vs_c1_host"])
+def test_fasta_text_to_rows_matches_reference_golden(case):
+    from tests.test_gpu_parity import _check_against_golden
+    gold = Golden(case)
+    host = gold.host()
+    res = engine.run_fasta(fasta_text(gold.scaffolds()), fasta_text(host) if host is not None else None, **gold.kwargs())
+    _check_against_golden(res, gold, case + "[run_fasta]")
+    # same kernels as the packed-plane entry point -> identical bits
+    q = engine.PackedGenome.from_scaffolds(gold.scaffolds())
+    h = engine.PackedGenome.from_scaffolds(host) if host is not None else None
+    ref = engine.run(q, h, **gold.kwargs())
+    assert np.array_equal(res.rows, ref.rows, equal_nan=True) and np.array_equal(res.tables, ref.tables)
+
+
+def test_large_single_line_record_and_many_small_records():
+    big = synth.make("C1", 0.2)                                # one 1 Mbp scaffold on a single line
+    assert_same_genome(fasta_text(big, width=0))
+    small = synth.make("C5", 0.00002)                          # ~20 scaffolds around 9 kbp ...
+    rng = np.random.default_rng(2)
+    tiny = [("t%d" % i, np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(rng.integers(0, 40)))])
+            for i in range(5000)]                              # ... and 5,000 records shorter than a line
+    assert_same_genome(fasta_text(small + tiny, width=60))
