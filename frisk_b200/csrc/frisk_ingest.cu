@@ -17,8 +17,8 @@
 //                          first / after the last header; countN statistics
 //   fasta_scan2_kernel     over tiles (segmented): bases of the open record before the tile
 //   [host: names from the header positions, 128-base aligned layout -> scaf_off]
-//   fasta_tile_kernel<1>   per tile: scatter the class of every base to its packed position
-//   fasta_pack_kernel      32 classes -> two code words, one invalid word, one lower-case word
+//   fasta_tile_kernel<1>   per tile: every thread ORs the <= 16 bases of its 16 bytes into the planes
+//   fasta_padding_kernel   per record: the padding up to the next 128-base boundary is flagged invalid
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -223,7 +223,7 @@ fasta_scan2_kernel(const uint32_t* __restrict__ tile_nhdr, const uint32_t* __res
 
 // ---- passes 2 and 3: classify every byte of a tile -------------------------------------------------
 // MODE 0: record table (header position, length), per-tile base counts, countN statistics.
-// MODE 1: scatter the class of every base to compact[scaf_off[record] + index in record].
+// MODE 1: write every base to the planes at scaf_off[record] + index in record.
 template <int MODE>
 __global__ void __launch_bounds__(kTT)
 fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __restrict__ tile_rec_base,
@@ -231,7 +231,7 @@ fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __r
                   unsigned long long* __restrict__ rec_hdr_pos, unsigned long long* __restrict__ rec_len,
                   uint32_t* __restrict__ tile_pre, uint32_t* __restrict__ tile_post, unsigned long long* __restrict__ counters,
                   const unsigned long long* __restrict__ tile_base_in, const unsigned long long* __restrict__ scaf_off,
-                  uint8_t* __restrict__ compact) {
+                  uint32_t* __restrict__ codes, uint32_t* __restrict__ inv, uint32_t* __restrict__ low) {
     __shared__ uint32_t sm[64];
     __shared__ uint32_t smf[32];
     __shared__ uint8_t cls_tab[256];
@@ -302,44 +302,58 @@ fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __r
             if (tot_low) atomicAdd(&counters[2], (unsigned long long)tot_low);
         }
     } else {
+        // A thread's bases land on consecutive packed positions (per record), i.e. in at most two
+        // code words and two mask words: assemble them in registers and OR them into the zeroed
+        // planes (neighbouring threads share words; all-zero contributions are skipped).
         if (base_mask) {
             uint32_t rec = rec_start;
-            unsigned long long run = (unsigned long long)carry + (reset_before ? 0ull : tile_base_in[tile]);
-            unsigned long long dst = rec >= 1u ? scaf_off[rec - 1u] : 0ull;
+            unsigned long long pos = (rec >= 1u ? scaf_off[rec - 1u] : 0ull) + (unsigned long long)carry +
+                                     (reset_before ? 0ull : tile_base_in[tile]);
+            unsigned long long cidx = pos >> 4, midx = pos >> 5;
+            uint32_t cacc = 0, iacc = 0, lacc = 0;
+            auto flush_codes = [&]() { if (cacc) atomicOr(&codes[cidx], cacc); cacc = 0; };
+            auto flush_masks = [&]() {
+                if (iacc) atomicOr(&inv[midx], iacc);
+                if (lacc && low) atomicOr(&low[midx], lacc);
+                iacc = 0; lacc = 0;
+            };
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                if ((hdr_mask >> k) & 1u) { ++rec; run = 0; dst = scaf_off[rec - 1u]; }
+                if ((hdr_mask >> k) & 1u) {
+                    flush_codes(); flush_masks();
+                    ++rec;
+                    pos = scaf_off[rec - 1u];
+                    cidx = pos >> 4; midx = pos >> 5;
+                }
                 if ((base_mask >> k) & 1u) {
-                    compact[dst + run] = (uint8_t)((cls16[k >> 3] >> (4 * (k & 7))) & 15u);
-                    ++run;
+                    if ((pos >> 4) != cidx) { flush_codes(); cidx = pos >> 4; }
+                    if ((pos >> 5) != midx) { flush_masks(); midx = pos >> 5; }
+                    const uint32_t c = (cls16[k >> 3] >> (4 * (k & 7))) & 15u;
+                    const uint32_t b32 = 0x80000000u >> ((uint32_t)pos & 31u);
+                    if (c < 8u) cacc |= (c & 3u) << (30u - 2u * ((uint32_t)pos & 15u)); else iacc |= b32;
+                    if ((c >= 4u) & (c < 8u)) lacc |= b32;
+                    ++pos;
                 }
             }
+            flush_codes(); flush_masks();
         }
     }
 }
 
-// ---- pass 4: 32 classes -> packed words (layout: include/frisk_b200.h) ---------------------------
+// ---- pass 4: the padding after every record (and the >= 128 trailing bases) is flagged invalid ----
 __global__ void __launch_bounds__(256)
-fasta_pack_kernel(const uint8_t* __restrict__ compact, uint64_t n_words, uint32_t* __restrict__ codes,
-                  uint32_t* __restrict__ inv, uint32_t* __restrict__ low) {
-    const uint64_t w = (uint64_t)blockIdx.x * 256u + threadIdx.x;
-    if (w >= n_words) return;
-    const uint4* p = reinterpret_cast<const uint4*>(compact + w * 32u);
-    const uint4 a = p[0], b = p[1];
-    uint32_t c0 = 0, c1 = 0, iv = 0, lw = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const uint32_t x = byte_of(a, k), y = byte_of(b, k);
-        c0 |= (x < 8u ? x & 3u : 0u) << (30 - 2 * k);
-        c1 |= (y < 8u ? y & 3u : 0u) << (30 - 2 * k);
-        iv |= (uint32_t)(x >= 8u) << (31 - k) | (uint32_t)(y >= 8u) << (15 - k);
-        lw |= (uint32_t)((x >= 4u) & (x < 8u)) << (31 - k) | (uint32_t)((y >= 4u) & (y < 8u)) << (15 - k);
+fasta_padding_kernel(const unsigned long long* __restrict__ scaf_off, const unsigned long long* __restrict__ rec_len,
+                     uint64_t n_rec, uint64_t padded_len, uint32_t* __restrict__ inv) {
+    const uint64_t r = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    if (r >= (n_rec ? n_rec : 1)) return;
+    uint64_t a = n_rec ? scaf_off[r] + rec_len[r] : 0;                  // first padding base
+    const uint64_t b = (r + 1 < n_rec) ? scaf_off[r + 1] : padded_len;  // a multiple of 128
+    if (a & 31u) {
+        atomicOr(&inv[a >> 5], 0xffffffffu >> (uint32_t)(a & 31u));     // shares its word with the record's last bases
+        a = (a | 31u) + 1u;
     }
-    *reinterpret_cast<uint2*>(codes + 2 * w) = make_uint2(c0, c1);
-    inv[w] = iv;
-    if (low) low[w] = lw;
+    for (; a < b; a += 32) inv[a >> 5] = 0xffffffffu;
 }
-
 
 int pool_ready(int dev) {
     static bool done[64] = {};
@@ -413,7 +427,7 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
         FRISK_CK(cudaMallocAsync((void**)&h->d_scaf_off, R * 8, st));
         FRISK_CK(cudaMemsetAsync(h->d_len, 0, R * 8, st));
         fasta_tile_kernel<0><<<(unsigned)T, kTT, 0, st>>>(h->d_text, n, h->d_rec_base, h->d_carry, h->d_hdr_pos, h->d_len,
-                                                          h->d_pre, h->d_post, h->d_counters, nullptr, nullptr, nullptr);
+                                                          h->d_pre, h->d_post, h->d_counters, nullptr, nullptr, nullptr, nullptr, nullptr);
         fasta_scan2_kernel<<<1, kST, 0, st>>>(h->d_nhdr, h->d_pre, h->d_post, T, h->d_base_in);
         FRISK_CK(cudaGetLastError());
         h->seq_len.resize(n_rec);
@@ -487,16 +501,17 @@ int frisk_b200_fasta_records(const frisk_b200_fasta* h, uint64_t* name_off, uint
 int frisk_b200_fasta_pack(frisk_b200_fasta* h, uint32_t* d_codes, uint32_t* d_inv, uint32_t* d_low, void* stream) {
     if (!h || !d_codes || !d_inv) return FRISK_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    uint8_t* compact = nullptr;
-    FRISK_CK(cudaMallocAsync((void**)&compact, h->padded_len, st));
-    FRISK_CK(cudaMemsetAsync(compact, 8, h->padded_len, st));          // padding = "not a base": invalid, code 0
+    const uint64_t P = h->padded_len;
+    FRISK_CK(cudaMemsetAsync(d_codes, 0, P / 4, st));
+    FRISK_CK(cudaMemsetAsync(d_inv, 0, P / 8, st));
+    if (d_low) FRISK_CK(cudaMemsetAsync(d_low, 0, P / 8, st));
     if (h->n_tiles && h->n_rec)
         fasta_tile_kernel<1><<<(unsigned)h->n_tiles, kTT, 0, st>>>(h->d_text, h->n, h->d_rec_base, h->d_carry, nullptr, nullptr,
-                                                                   nullptr, nullptr, nullptr, h->d_base_in, h->d_scaf_off, compact);
-    const uint64_t n_words = h->padded_len / 32;
-    fasta_pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(compact, n_words, d_codes, d_inv, d_low);
+                                                                   nullptr, nullptr, nullptr, h->d_base_in, h->d_scaf_off,
+                                                                   d_codes, d_inv, d_low);
+    const uint64_t R = h->n_rec ? h->n_rec : 1;
+    fasta_padding_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(h->d_scaf_off, h->d_len, h->n_rec, P, d_inv);
     FRISK_CK(cudaGetLastError());
-    FRISK_CK(cudaFreeAsync(compact, st));
     return FRISK_OK;
 }
 

@@ -55,19 +55,37 @@ __device__ __forceinline__ uint32_t high_bits16(uint32_t w) {
 
 // ============================================================================================
 // Background: forward-strand counts.  Each CTA owns a contiguous run of 32-base mask words and
-// histograms the order-K codes into a u32 shared-memory table (all 4^K bins for K<=7; for K=8
-// two passes over the CTA's bases, one per half of the code space), then flushes the non-zero
-// bins to the global u64 table.  Positions whose K-word is invalid but which start a shorter valid
-// word (scaffold ends, N boundaries) add 1 to the order-v table directly in global memory.
+// histograms the order-K codes into a shared-memory table of u16 counters, two per 32-bit word
+// (4^8 bins = 128 KiB: the whole code space in one pass), then stores the table as its partial
+// result; bg_reduce_kernel sums the partials into the global u64 table.  A 16-bit counter that
+// wraps is made exact by the thread whose atomic caused the wrap (it sees the old word): it adds
+// 65,536 to the global bin and, when the low half's carry leaked into the high half, takes that 1
+// back out of the neighbour's global bin -- no second shared-memory operation, so no transient
+// state another thread could misread.  Positions whose K-word is invalid but which start a shorter
+// valid word (scaffold ends, N boundaries) add 1 to the order-v table directly in global memory.
 // ============================================================================================
+__device__ __noinline__ void bg_wrapped(unsigned long long* __restrict__ fwd_k, uint32_t code, uint32_t old) {
+    atomicAdd(&fwd_k[code], 65536ull);
+    if (!(code & 1u))       // low half: its carry bumped the high half (or wrapped it: old word all ones)
+        atomicAdd(&fwd_k[code | 1u], old == 0xffffffffu ? 65535ull : ~0ull);
+}
+
+__device__ __forceinline__ void bg_add(uint32_t* tab, unsigned long long* __restrict__ fwd_k, uint32_t code) {
+    const uint32_t sh = (code & 1u) * 16u;
+    const uint32_t old = atomicAdd(&tab[code >> 1], 1u << sh);
+    if (((old >> sh) & 0xffffu) == 0xffffu) bg_wrapped(fwd_k, code, old);
+}
+
+// ~(old | other half) == 0  <=>  the half that was incremented held 0xffff
+__device__ __forceinline__ uint32_t bg_room(uint32_t old, uint32_t sh) { return ~(old | (0xffff0000u >> sh)); }
+
 template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
 bg_count_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                 uint64_t word_lo, uint64_t word_hi, int mask_host, unsigned long long* __restrict__ fwd,
                 uint32_t* __restrict__ partial) {
     constexpr uint32_t NB = pow4(K);
-    constexpr uint32_t HB = NB < 32768u ? NB : 32768u;   // bins held in smem per pass
-    constexpr int PASSES = NB / HB;
+    constexpr uint32_t NW = NB / 2u;                       // shared words: two u16 bins each
     extern __shared__ __align__(16) uint32_t tab[];
     const uint64_t n_words = word_hi - word_lo;
     const uint64_t per = (n_words + gridDim.x - 1) / gridDim.x;
@@ -75,64 +93,93 @@ bg_count_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__
     uint64_t w1 = w0 + per;
     if (w1 > word_hi) w1 = word_hi;
     const bool use_low = mask_host && low != nullptr;
+    unsigned long long* fwd_k = fwd + lvl_off(K);
 
-    for (int pass = 0; pass < PASSES; ++pass) {
-        for (uint32_t b = threadIdx.x; b < HB; b += kThreads) tab[b] = 0;
-        __syncthreads();
-        for (uint64_t wd = w0 + threadIdx.x; wd < w1; wd += kThreads) {
-            uint32_t m0 = __ldg(inv + wd), m1 = __ldg(inv + wd + 1);
-            if (use_low) { m0 |= __ldg(low + wd); m1 |= __ldg(low + wd + 1); }
-            const uint32_t c0 = __ldg(codes + 2 * wd), c1 = __ldg(codes + 2 * wd + 1), c2 = __ldg(codes + 2 * wd + 2);
-            const bool all_valid = (m0 == 0u) && (K == 1 || (m1 >> (33 - K)) == 0u);
-            if (all_valid) {                                   // the common word: 32 full K-words, no per-position checks
+    for (uint32_t b = threadIdx.x; b < NW; b += kThreads) tab[b] = 0;
+    __syncthreads();
+    for (uint64_t wd = w0 + threadIdx.x; wd < w1; wd += kThreads) {
+        uint32_t m0 = __ldg(inv + wd), m1 = __ldg(inv + wd + 1);
+        if (use_low) { m0 |= __ldg(low + wd); m1 |= __ldg(low + wd + 1); }
+        const uint32_t c0 = __ldg(codes + 2 * wd), c1 = __ldg(codes + 2 * wd + 1), c2 = __ldg(codes + 2 * wd + 2);
+        const bool all_valid = (m0 == 0u) && (K == 1 || (m1 >> (33 - K)) == 0u);
+        if (all_valid) {                                   // the common word: 32 full K-words, no per-position checks
+            // all 32 atomics are issued before any of their results is looked at; a wrap (rare) is
+            // detected through one running minimum and handled after the fact
+            uint32_t olds[32], room = 0xffffffffu;
 #pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const uint32_t code = (p < 16 ? __funnelshift_l(c1, c0, 2 * p) : __funnelshift_l(c2, c1, 2 * (p - 16)))
+                                      >> (32 - 2 * K);
+                const uint32_t sh = (code & 1u) * 16u;
+                olds[p] = atomicAdd(&tab[code >> 1], 1u << sh);
+                room = min(room, bg_room(olds[p], sh));
+            }
+            if (room == 0u) {
+#pragma unroll 1
                 for (int p = 0; p < 32; ++p) {
                     const uint32_t code = (p < 16 ? __funnelshift_l(c1, c0, 2 * p) : __funnelshift_l(c2, c1, 2 * (p - 16)))
                                           >> (32 - 2 * K);
-                    // branch-free: words of the other half go to one spare bin (same-address lanes are
-                    // aggregated by the hardware's POPC.INC form of the atomic)
-                    const uint32_t bin = (PASSES == 1 || (int)(code / HB) == pass) ? code % HB : HB;
-                    atomicAdd(&tab[bin], 1u);
-                }
-            } else {
-#pragma unroll 4
-                for (int p = 0; p < 32; ++p) {
-                    const uint32_t code = (p < 16 ? __funnelshift_l(c1, c0, 2 * p) : __funnelshift_l(c2, c1, 2 * (p - 16)))
-                                          >> (32 - 2 * K);
-                    const int v = min(__clz(__funnelshift_l(m1, m0, p)), K);
-                    if (v == K) {
-                        if (PASSES == 1 || (int)(code / HB) == pass) atomicAdd(&tab[code % HB], 1u);
-                    } else if (v > 0 && pass == 0) {
-                        atomicAdd(&fwd[lvl_off(v) + (code >> (2 * (K - v)))], 1ull);
-                    }
+                    uint32_t old = 0;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) if (q == p) old = olds[q];
+                    if (bg_room(old, (code & 1u) * 16u) == 0u) bg_wrapped(fwd_k, code, old);
                 }
             }
+        } else {
+#pragma unroll 4
+            for (int p = 0; p < 32; ++p) {
+                const uint32_t code = (p < 16 ? __funnelshift_l(c1, c0, 2 * p) : __funnelshift_l(c2, c1, 2 * (p - 16)))
+                                      >> (32 - 2 * K);
+                const int v = min(__clz(__funnelshift_l(m1, m0, p)), K);
+                if (v == K) bg_add(tab, fwd_k, code);
+                else if (v > 0) atomicAdd(&fwd[lvl_off(v) + (code >> (2 * (K - v)))], 1ull);
+            }
         }
-        __syncthreads();
-        if (partial) {   // per-CTA partial table, coalesced stores; bg_reduce_kernel sums them into fwd
-            uint32_t* dst = partial + (size_t)blockIdx.x * NB + (uint32_t)pass * HB;
-            for (uint32_t b = threadIdx.x * 4u; b < HB; b += kThreads * 4u)
+    }
+    __syncthreads();
+    if (partial) {   // per-CTA partial table (raw words), coalesced stores
+        uint32_t* dst = partial + (size_t)blockIdx.x * NW;
+        if constexpr (NW >= 4u * kThreads) {
+            for (uint32_t b = threadIdx.x * 4u; b < NW; b += kThreads * 4u)
                 *reinterpret_cast<uint4*>(dst + b) = *reinterpret_cast<const uint4*>(tab + b);
         } else {
-            for (uint32_t b = threadIdx.x; b < HB; b += kThreads) {
-                const uint32_t c = tab[b];
-                if (c) atomicAdd(&fwd[lvl_off(K) + (uint32_t)pass * HB + b], (unsigned long long)c);
-            }
+            for (uint32_t b = threadIdx.x; b < NW; b += kThreads) dst[b] = tab[b];
         }
-        __syncthreads();
+    } else {
+        for (uint32_t b = threadIdx.x; b < NW; b += kThreads) {
+            const uint32_t c = tab[b];
+            if (c & 0xffffu) atomicAdd(&fwd_k[2u * b], (unsigned long long)(c & 0xffffu));
+            if (c >> 16) atomicAdd(&fwd_k[2u * b + 1u], (unsigned long long)(c >> 16));
+        }
     }
 }
 
-// fwd[order K][b] += sum over CTAs of partial[cta][b]   (one thread per bin, coalesced across bins)
+// fwd[order K][2w], [2w+1] += sum over CTAs of the two halves of partial[cta][w].  A CTA handles 32
+// consecutive words (coalesced across lanes); its 8 warps split the partial tables between them.
 template <int K>
 __global__ void __launch_bounds__(256)
 bg_reduce_kernel(const uint32_t* __restrict__ partial, int n_parts, unsigned long long* __restrict__ fwd) {
-    const uint32_t b = blockIdx.x * 256 + threadIdx.x;
-    if (b >= pow4(K)) return;
-    unsigned long long sum = 0;
+    constexpr uint32_t NW = pow4(K) / 2u;
+    __shared__ unsigned long long acc[8][32][2];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * 32u + lane;
+    unsigned long long lo = 0, hi = 0;
+    if (w < NW) {
 #pragma unroll 4
-    for (int c = 0; c < n_parts; ++c) sum += partial[(size_t)c * pow4(K) + b];
-    if (sum) fwd[lvl_off(K) + b] += sum;
+        for (int c = (int)warp; c < n_parts; c += 8) {
+            const uint32_t v = partial[(size_t)c * NW + w];
+            lo += v & 0xffffu;
+            hi += v >> 16;
+        }
+    }
+    acc[warp][lane][0] = lo; acc[warp][lane][1] = hi;
+    __syncthreads();
+    if (warp == 0 && w < NW) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) { lo += acc[j][lane][0]; hi += acc[j][lane][1]; }
+        if (lo) fwd[lvl_off(K) + 2u * w] += lo;
+        if (hi) fwd[lvl_off(K) + 2u * w + 1u] += hi;
+    }
 }
 
 // Finalising the tables: F_x = short-word counts of order x + marginal of F_{x+1}; then
@@ -1123,8 +1170,8 @@ template <int K>
 int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, uint64_t w_lo, uint64_t w_hi,
                       int mask_host, uint64_t* fwd, cudaStream_t st) {
     constexpr uint32_t NB = pow4(K);
-    constexpr uint32_t HB = NB < 32768u ? NB : 32768u;
-    const size_t smem = (size_t)HB * 4 + 16;            // + the spare bin
+    constexpr uint32_t NW = NB / 2u;
+    const size_t smem = (size_t)NW * 4;
     CK(cudaFuncSetAttribute(bg_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t n_words = w_hi - w_lo;
     int grid = sm_count();
@@ -1136,14 +1183,14 @@ int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t
     uint32_t* partial = nullptr;
     if (NB >= 4096u && grid > 1) {
         void* p = nullptr;
-        int rc = ws_get(13, (size_t)grid * NB * sizeof(uint32_t), &p);
+        int rc = ws_get(13, (size_t)grid * NW * sizeof(uint32_t), &p);
         if (rc) return rc;
         partial = (uint32_t*)p;
     }
     bg_count_kernel<K><<<grid, kThreads, smem, st>>>(codes, inv, low, w_lo, w_hi, mask_host,
                                                       reinterpret_cast<unsigned long long*>(fwd), partial);
     if (partial)
-        bg_reduce_kernel<K><<<(NB + 255) / 256, 256, 0, st>>>(partial, grid, reinterpret_cast<unsigned long long*>(fwd));
+        bg_reduce_kernel<K><<<(NW + 31) / 32, 256, 0, st>>>(partial, grid, reinterpret_cast<unsigned long long*>(fwd));
     CK(cudaGetLastError());
     return FRISK_OK;
 }

@@ -38,6 +38,9 @@ CASES = {
     "edge_k1_3_w3000_i1000": dict(genome=("edge", 1.0), params=dict(kmin=1, kmax=3, w=3000, i=1000, scaffoldsAll=True)),
     "edge_k4_8": dict(genome=("edge", 1.0), params=dict(kmin=4, kmax=8)),
     "edge_k1_1": dict(genome=("edge", 1.0), params=dict(kmin=1, kmax=1)),
+    # beyond the default --maxWordSize 8: served by the general (global-memory) kernels
+    "edge_k1_9": dict(genome=("edge", 1.0), params=dict(kmin=1, kmax=9)),
+    "edge_k9_10_w2500_i2500": dict(genome=("edge", 1.0), params=dict(kmin=9, kmax=10, w=2500, i=2500, scaffoldsAll=True)),
     "c1_small": dict(genome=("C1", 0.04), params={}),
     "c2_small": dict(genome=("C2", 0.01), params={}),
     "c2_small_query_vs_c1_host": dict(genome=("C2", 0.005), host=("C1", 0.02), params={}),

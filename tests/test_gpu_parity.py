@@ -274,6 +274,27 @@ def test_addressing_beyond_2_pow_32_bases(eng):
     assert np.array_equal(out.status, ref.status)
 
 
+def test_background_16bit_counter_wraps_are_exact(eng):
+    """The background kernel counts into 16-bit shared-memory counters, two per word.  Low-complexity
+    sequence makes single bins exceed 65,535 inside one CTA's share: the low half wraps (carry into its
+    neighbour), the high half wraps, and with the period-9 repeat both halves of one word (AAAAAAAA,
+    AAAAAAAT) reach 0xFFFF together.  Tables must stay bit-exact."""
+    from oracle import c_oracle
+    a = np.full(20_000_000, ord("A"), np.uint8)
+    p8 = np.tile(np.frombuffer(b"AAAAAAAT", np.uint8), 10_000_000)
+    p9 = np.tile(np.frombuffer(b"AAAAAAAAT", np.uint8), 10_000_000)
+    sc = [("polyA", a), ("period8", p8), ("period9", p9)]
+    g = eng.PackedGenome.from_scaffolds(sc)
+    dg = eng.DeviceGenome(g)
+    d_tables, d_valid = eng.finalize(eng.background(dg, 8), 8)
+    seq, off = c_oracle.concat(sc)
+    tabs, meta = c_oracle.background(seq, off, 1, 8, False, threads=16)
+    got = d_tables.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, tabs)
+    assert int(got[-4 ** 8]) > 2 * 65536 * 148           # AAAAAAAA: far beyond what 148 16-bit counters hold
+    assert g.ex_max(8, int(d_valid.item())) == int(meta[1])
+
+
 def test_no_silent_fallback_symbols_loaded(eng):
     """The product library is the thing that ran: it is loaded in this process and reports a GPU."""
     from frisk_b200 import _lib

@@ -1,0 +1,255 @@
+"""BASELINE configs C4 (3 Gbp, 24 long scaffolds, Mbp-scale N runs) and C5 (14 Gbp, 1 M short scaffolds,
+many N gaps, --scaffoldsAll) at FULL size.  The oracle cannot run 3-14 Gbp in test time, so the
+genomes are drawn directly in packed form on the GPU (torch is only the random source and the
+buffer owner) and checked through size-independent properties plus sampled parity:
+
+  * books: strand symmetry; sum of order-k counts = 2 x valid k-words; valid + exMax = every
+    kmax-word start; order-1 total = 2 x resolved bases
+  * additivity: the background of two halves of the base range sums to the background of the whole
+  * sampled parity: the bases of ~300 windows (short scaffolds, N-run neighbours and > 2^32 offsets
+    included) are decoded from the planes and scored by the C oracle against the GPU's genome tables
+  * one whole small scaffold's background, bit-exact against the C oracle
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.helpers import assert_rows_close, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+LETTERS = np.frombuffer(b"ATGC", dtype=np.uint8)      # code order of the reference's tables (F:70)
+
+
+def _ranges_to_word_masks(starts, ends):
+    """Bit ranges [s, e) of a 1-bit-per-base plane (bit 31 = first base of a word) -> the distinct
+    partially covered words with their OR-ed masks, and the fully covered word runs [w0, w1)."""
+    starts = np.asarray(starts, np.int64); ends = np.asarray(ends, np.int64)
+    keep = ends > starts
+    starts, ends = starts[keep], ends[keep]
+    fw, lw = starts >> 5, (ends - 1) >> 5
+    full = np.uint64(0xFFFFFFFF)
+    head = (full >> (starts & 31).astype(np.uint64)).astype(np.uint64)
+    tail = (full << (31 - ((ends - 1) & 31)).astype(np.uint64)).astype(np.uint64) & full
+    same = fw == lw
+    idx = np.concatenate([fw[same], fw[~same], lw[~same]])
+    msk = np.concatenate([head[same] & tail[same], head[~same], tail[~same]])
+    uniq, inverse = np.unique(idx, return_inverse=True)
+    merged = np.zeros(len(uniq), np.uint64)
+    np.bitwise_or.at(merged, inverse, msk)
+    return uniq, merged.astype(np.uint32), fw[~same] + 1, lw[~same]
+
+
+def build_device_genome(eng, scaf_len, n_runs, seed, at_rich_block=0):
+    """A random genome straight into device planes: uniform codes (optionally AT-rich blocks), N runs
+    (scaffold[], offset[], length[]; non-overlapping), invalid padding between scaffolds."""
+    import torch
+    from frisk_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    scaf_len = np.ascontiguousarray(scaf_len, np.uint64)
+    n = len(scaf_len)
+    scaf_off = np.zeros(n, np.uint64)
+    padded = C.c_uint64(0)
+    _lib.check(L.frisk_b200_pack_layout(eng._ptr(scaf_len), n, eng._ptr(scaf_off), C.byref(padded)), "layout")
+    P = int(padded.value)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    codes = torch.randint(-2 ** 63, 2 ** 63 - 1, (P // 32,), dtype=torch.int64, device=dev, generator=gen).view(torch.int32)
+    if at_rich_block:
+        # every other block of `at_rich_block` code words: P(G or C) = 1/4 (high bit of a code = G/C)
+        r = torch.randint(-2 ** 63, 2 ** 63 - 1, (P // 32,), dtype=torch.int64, device=dev, generator=gen).view(torch.int32)
+        blk = (torch.arange(P // 16, device=dev, dtype=torch.int64) // at_rich_block) & 1
+        lowgc = codes & (r | 0x55555555)
+        codes = torch.where(blk.bool(), lowgc, codes)
+        del r, blk, lowgc
+    inv = torch.zeros(P // 32, dtype=torch.int32, device=dev)
+    so, sl = scaf_off.astype(np.int64), scaf_len.astype(np.int64)
+    pad_s = so + sl
+    pad_e = np.concatenate([so[1:], [P]])
+    run_s, run_o, run_l = (np.asarray(x, np.int64) for x in n_runs)
+    rs = so[run_s] + run_o
+    re = rs + run_l
+    uniq, masks, f0, f1 = _ranges_to_word_masks(np.concatenate([pad_s, rs]), np.concatenate([pad_e, re]))
+    t_idx = torch.from_numpy(uniq).to(dev)
+    inv[t_idx] = inv[t_idx] | torch.from_numpy(masks.view(np.int32)).to(dev)
+    # fully covered words: +1 / -1 difference array over words, prefix sum > 0
+    keep = f1 > f0
+    if keep.any():
+        delta = torch.zeros(P // 32 + 1, dtype=torch.int32, device=dev)
+        ones = torch.ones(int(keep.sum()), dtype=torch.int32, device=dev)
+        delta.index_add_(0, torch.from_numpy(f0[keep]).to(dev), ones)
+        delta.index_add_(0, torch.from_numpy(f1[keep]).to(dev), -ones)
+        inv = torch.where(torch.cumsum(delta[:-1], 0, dtype=torch.int32) > 0, torch.full_like(inv, -1), inv)
+        del delta
+    # invalid bases carry code 0 (plane convention): clear the codes under the mask, word-wise
+    # (expand each mask bit to the two code bits of its base)
+    m = inv.to(torch.int64) & 0xFFFFFFFF
+    def spread16(x):                       # 16 mask bits -> 32 bits, each bit doubled
+        x = (x | (x << 8)) & 0x00FF00FF
+        x = (x | (x << 4)) & 0x0F0F0F0F
+        x = (x | (x << 2)) & 0x33333333
+        x = (x | (x << 1)) & 0x55555555
+        return x | (x << 1)
+    hi, lo = spread16(m >> 16), spread16(m & 0xFFFF)
+    kill = torch.stack([hi, lo], 1).reshape(-1)
+    kill = torch.where(kill >= 2 ** 31, kill - 2 ** 32, kill).to(torch.int32)
+    codes = codes & ~kill
+    del m, hi, lo, kill
+    nn_total = int(run_l.sum())
+    names = ["s%d" % i for i in range(n)]
+    g = eng.PackedGenome(names, scaf_len, scaf_off, P, None, None, None, int(sl.sum()), nn_total, 0, False)
+    return eng.DeviceGenome(g, dev, planes=(codes, inv, None))
+
+
+def decode(dg, off, length):
+    """ASCII bases [off, off+length) of the device planes ('N' where the invalid bit is set)."""
+    w0, w1 = off >> 4, (off + length + 15) >> 4
+    cw = dg.codes[w0:w1].cpu().numpy().view(np.uint32)
+    m0, m1 = off >> 5, (off + length + 31) >> 5
+    mw = dg.inv[m0:m1].cpu().numpy().view(np.uint32)
+    pos = off + np.arange(length, dtype=np.int64)
+    code = (cw[(pos >> 4) - w0] >> (30 - 2 * (pos & 15)).astype(np.uint32)) & 3
+    bad = (mw[(pos >> 5) - m0] >> (31 - (pos & 31)).astype(np.uint32)) & 1
+    out = LETTERS[code]
+    out[bad.astype(bool)] = ord("N")
+    return out
+
+
+def check_books(res, g, kmax=8):
+    off, sums = 0, []
+    for k in range(1, kmax + 1):
+        t = res.tables[off:off + 4 ** k].astype(np.int64)
+        idx = np.arange(4 ** k)
+        rc = np.zeros_like(idx)
+        tmp = idx.copy()
+        for _ in range(k):
+            rc = (rc << 2) | ((tmp & 3) ^ 1)
+            tmp >>= 2
+        assert np.array_equal(t, t[rc]), "order %d not reverse-complement symmetric" % k
+        sums.append(int(t.sum()))
+        off += 4 ** k
+    assert all(a >= b for a, b in zip(sums, sums[1:]))
+    possible = int(np.maximum(g.scaf_len.astype(np.int64) - kmax + 1, 0).sum())
+    assert sums[-1] // 2 + res.meta[1] == possible                      # valid + exMax (F:344)
+    assert sums[0] // 2 == g.total_len - g.nn_total                     # every resolved base once per strand
+
+
+def check_additivity(eng, dg, kmax=8):
+    import torch
+    P = dg.host.padded_len
+    mid = (P // 2) & ~31
+    whole = eng.background(dg, kmax)
+    parts = eng.background(dg, kmax, first_base=0, last_base=mid)
+    eng.background(dg, kmax, d_fwd=parts, first_base=mid, last_base=P - 32)
+    assert torch.equal(whole, parts), "background of the halves must sum to the background of the whole"
+
+
+def check_sampled_windows(eng, dg, res, wins, pick, kmax=8):
+    from oracle import c_oracle
+    cand = res.win_index[pick]
+    seqs = [decode(dg, int(wins.off[c]), int(wins.length[c])) for c in cand]
+    lens = np.array([len(s) for s in seqs], np.uint32)
+    woff = np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.uint64)]).astype(np.uint64)
+    seq = np.ascontiguousarray(np.concatenate(seqs))
+    meta = np.array(res.meta, dtype=np.uint64)
+    rows, status = c_oracle.score(seq, woff, lens, np.ascontiguousarray(res.tables), meta, 1, kmax, True, threads=8)
+    assert np.array_equal(status & 7, res.status[pick] & 7)
+    ok = status == 0
+    assert ok.sum() > 0.9 * len(pick)
+    assert_rows_close(res.rows[pick][ok], rows[ok], rtol_kld=1e-6, rtol_other=1e-15, what="sampled windows")
+    assert max_rel_err(res.rows[pick][ok, 0], rows[ok, 0]) < 1e-10
+
+
+def check_scaffold_background(eng, dg, s, kmax=8):
+    """Background of scaffold s alone (its own base range) vs the C oracle on its decoded bases."""
+    from oracle import c_oracle
+    g = dg.host
+    a = int(g.scaf_off[s])
+    b = (a + int(g.scaf_len[s]) + 1 + 127) & ~127           # next scaffold's start: the padding closes every word
+    d_fwd = eng.background(dg, kmax, first_base=a, last_base=b)
+    d_tables, _ = eng.finalize(d_fwd, kmax)
+    bases = decode(dg, a, int(g.scaf_len[s]))
+    tabs, _ = c_oracle.background(bases, np.array([0, len(bases)], np.uint64), 1, kmax, False, threads=8)
+    assert np.array_equal(d_tables.cpu().numpy().view(np.uint64), tabs)
+
+
+def test_c4_human_scale_3gbp():
+    """C4: 3 Gbp in 24 scaffolds of 50-250 Mbp (+2 small ones), AT-rich isochore blocks, one 3 Mbp N
+    run per long scaffold; default k = 1..8, w = 5000, step = 2500: ~1.2 M windows on one B200."""
+    import torch
+    from frisk_b200 import engine as eng
+    rng = np.random.Generator(np.random.PCG64(4004))
+    lens = rng.uniform(50e6, 250e6, 24)
+    lens = (lens * (3.0e9 / lens.sum())).astype(np.int64)
+    lens = np.concatenate([lens, [3_000_017, 1_234_567]])
+    runs = (list(range(24)) + [24, 25], [int(lens[s] // 3) for s in range(24)] + [1_000_000, 5], [3_000_000] * 24 + [517, 2500])
+    dg = build_device_genome(eng, lens, runs, seed=44, at_rich_block=300_000 // 16)
+    g = dg.host
+    assert g.padded_len > 2 ** 31
+    pipe = eng.Pipeline(dg)
+    pipe.enqueue()
+    res = pipe.result()
+    wins = pipe.wins
+    assert len(wins) > 1_150_000
+    assert len(res.rows) == int((pipe.d_status.cpu().numpy().view(np.uint32) & 8 == 0).sum())
+    check_books(res, g)
+    assert np.all(np.isfinite(res.rows[res.status == 0, 0])) and np.all(res.rows[res.status == 0, 0] >= 0)
+    # the N runs remove windows: every candidate fully inside a 3 Mbp run is excluded (F:238)
+    assert len(wins) - len(res.rows) >= 24 * (3_000_000 // 2500 - 3)
+    check_additivity(eng, dg)
+    pick = np.sort(rng.choice(len(res.rows), 260, replace=False))
+    near_runs = np.nonzero(res.rows[:, 1] != res.rows[:, 1])[0][:10]         # GC undefined: none expected
+    assert near_runs.size == 0
+    # windows that straddle an N-run edge (partly unresolved but kept) are the interesting ones
+    st = pipe.d_status.cpu().numpy().view(np.uint32)
+    kept = np.nonzero((st & 8) == 0)[0]
+    edge = np.nonzero(np.diff(kept) > 1)[0][:40]                              # rows just before an excluded stretch
+    pick = np.unique(np.concatenate([pick, edge, np.arange(len(res.rows) - 20, len(res.rows))]))
+    check_sampled_windows(eng, dg, res, wins, pick)
+    check_scaffold_background(eng, dg, 25)
+    check_scaffold_background(eng, dg, 24)
+    del pipe, dg
+    torch.cuda.empty_cache()
+
+
+def test_c5_wheat_scale_14gbp_fragmented():
+    """C5: 14 Gbp in 1,000,000 scaffolds (lognormal, median ~9 kbp, min 500), 30 % with 1-3 N runs of
+    10-2,000 bp; --scaffoldsAll so that short scaffolds become variable-length windows (F:211-221)."""
+    import torch
+    from frisk_b200 import engine as eng
+    rng = np.random.Generator(np.random.PCG64(5005))
+    n = 1_000_000
+    lens = np.exp(rng.normal(np.log(9000.0), 1.0, n))
+    lens = np.maximum((lens * (14.0e9 / lens.sum())).astype(np.int64), 500)
+    has = np.nonzero(rng.random(n) < 0.30)[0]
+    cnt = rng.integers(1, 4, len(has))
+    run_s = np.repeat(has, cnt)
+    j = np.arange(len(run_s)) - np.repeat(np.cumsum(cnt) - cnt, cnt)            # 0..cnt-1 inside each scaffold
+    third = lens[run_s] // 3                                                      # one run per third: no overlaps
+    run_l = np.minimum(rng.integers(10, 2001, len(run_s)), np.maximum(third // 2, 1))
+    run_o = j * third + (rng.random(len(run_s)) * np.maximum(third - run_l, 1)).astype(np.int64)
+    runs = (run_s, run_o, run_l)
+    dg = build_device_genome(eng, lens, runs, seed=55)
+    g = dg.host
+    assert g.padded_len > 14_000_000_000
+    pipe = eng.Pipeline(dg, scaffolds_all=True)
+    pipe.enqueue()
+    res = pipe.result()
+    wins = pipe.wins
+    assert len(wins) > 4_500_000 and wins.max_len <= 6250
+    check_books(res, g)
+    good = res.status == 0
+    assert good.mean() > 0.999
+    assert np.all(np.isfinite(res.rows[good, 0])) and np.all(res.rows[good, 0] >= 0)
+    check_additivity(eng, dg)
+    # sample: random rows, rows of the shortest scaffolds, and rows far beyond 2^32 bases
+    short = np.nonzero(wins.length[res.win_index] < 1500)[0][:60]
+    far = np.nonzero(wins.off[res.win_index] > np.uint64(2 ** 33))[0][-60:]
+    pick = np.unique(np.concatenate([rng.choice(len(res.rows), 200, replace=False), short, far]))
+    check_sampled_windows(eng, dg, res, wins, pick)
+    check_scaffold_background(eng, dg, int(np.argmax(lens)))
+    check_scaffold_background(eng, dg, n - 1)
+    del pipe, dg
+    torch.cuda.empty_cache()
