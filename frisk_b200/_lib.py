@@ -15,8 +15,8 @@ SO_PATH = os.path.join(HERE, "libfrisk_b200.so")
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NO_DEVICE, E_CAPACITY, E_FORMAT = 0, -1, -2, -3, -4, -5, -6
 ROW_KLD_ZERODIV, ROW_GC_ZERODIV, ROW_LOG_DOMAIN, ROW_EXCLUDED = 1, 2, 4, 8
-MAX_K = 8
-MAX_WINDOW = 65535
+MAX_K = 12
+MAX_WINDOW = 0x7FFFFFFF
 
 _p = C.c_void_p
 _u64 = C.c_uint64
@@ -65,7 +65,7 @@ class FriskError(RuntimeError):
 def build(force: bool = False) -> str:
     """Compile the shared library in-tree (nvcc, sm_100a).  Cross-compiles without a GPU."""
     src_dir = os.path.join(HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("frisk_kernels.cu", "frisk_ingest.cu", "frisk_host.cpp", "frisk_internal.h", "Makefile")]
+    srcs = [os.path.join(src_dir, f) for f in ("frisk_kernels.cu", "frisk_general.cu", "frisk_ingest.cu", "frisk_host.cpp", "frisk_internal.h", "Makefile")]
     srcs.append(os.path.join(os.path.dirname(HERE), "include", "frisk_b200.h"))
     stale = not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:

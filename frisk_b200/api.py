@@ -279,8 +279,10 @@ def makePicklePath(args, **kwargs) -> str:
 def score_genome(args, device="cuda:0") -> engine.HotPathResult:
     """The whole hot path in one call: background tables of ``args.hostSeq`` + every window row of
     ``args.querySeq or args.hostSeq`` (F:1442, F:1478-1494)."""
-    host = engine.PackedGenome.from_fasta(args.hostSeq, pinned=True)
-    query = host if not args.querySeq or args.querySeq == args.hostSeq else engine.PackedGenome.from_fasta(args.querySeq, pinned=True)
+    # device-side ingest: the FASTA text is copied to the GPU once and tokenised / packed there
+    # (the reference reads each file three times in Python: F:170, F:203, F:297)
+    host = engine.DeviceGenome.from_fasta(args.hostSeq, device)
+    query = host if not args.querySeq or args.querySeq == args.hostSeq else engine.DeviceGenome.from_fasta(args.querySeq, device)
     res = engine.run(query, host if query is not host else None, kmin=args.minWordSize, kmax=args.maxWordSize,
                      w=args.windowlen, step=args.increment, mask_host=args.maskHost, scaffolds_all=args.scaffoldsAll,
                      rip=bool(args.RIP), device=device)

@@ -18,6 +18,15 @@ int ws_get(int slot, size_t bytes, void** out);
 // The line starts at `line_start`; returns false for an empty name (the reference raises IndexError).
 bool parse_header_name(const unsigned char* t, uint64_t n, uint64_t line_start, uint64_t* name_off, uint32_t* name_len);
 
+// general path (frisk_general.cu): run-time K up to FRISK_B200_MAX_K, windows of any length
+int general_background(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, uint64_t w_lo, uint64_t w_hi, int K,
+                       int mask_host, uint64_t* fwd, cudaStream_t st);
+int general_finalize(const uint64_t* fwd, int K, int symmetric, uint64_t* tables, uint64_t* valid, cudaStream_t st);
+int general_genome_ivom(const uint64_t* tables, int kmin, int K, int64_t space, double* ig, cudaStream_t st);
+int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                  const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
+                  double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st);
+
 }  // namespace frisk_internal
 
 #define FRISK_CK(call)                                                        \

@@ -1148,6 +1148,7 @@ __global__ void __launch_bounds__(kThreads, 1) smem_atomic_bench_kernel(int iter
 
 thread_local char g_cuda_err[512] = "";
 int g_force_dense = 0;      // tests: force the dense-table kernel (frisk_b200_set_option)
+int g_force_general = 0;    // tests: force the general (global-memory) score kernel
 }  // namespace
 
 int frisk_internal::cuda_fail(cudaError_t e, const char* what) {
@@ -1335,7 +1336,7 @@ const char* frisk_b200_strerror(int code) {
     switch (code) {
         case FRISK_OK: return "ok";
         case FRISK_E_INVALID: return "invalid argument";
-        case FRISK_E_UNSUPPORTED: return "unsupported: kmax > 8 or window longer than 65535 bases";
+        case FRISK_E_UNSUPPORTED: return "unsupported: kmax > 12, more than 2^32-1 windows, or a table dump of windows > 65535 bases";
         case FRISK_E_CUDA: return "CUDA error (see frisk_b200_last_cuda_error)";
         case FRISK_E_NO_DEVICE: return "no CUDA device (frisk_b200 has no CPU fallback)";
         case FRISK_E_CAPACITY: return "output capacity too small";
@@ -1361,6 +1362,8 @@ int frisk_b200_background(const uint32_t* d_codes, const uint32_t* d_inv, const 
     if (rc) return rc;
     if (last_base == first_base) return FRISK_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (kmax > FRISK_B200_FAST_K)
+        return frisk_internal::general_background(d_codes, d_inv, d_low, first_base >> 5, last_base >> 5, kmax, mask_host, d_fwd, st);
     DISPATCH_K(kmax, launch_background<K>(d_codes, d_inv, d_low, first_base >> 5, last_base >> 5, mask_host, d_fwd, st));
 }
 
@@ -1370,6 +1373,7 @@ int frisk_b200_finalize_tables(const uint64_t* d_fwd, int kmax, int symmetric, u
     int rc = check_k(1, kmax);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (kmax > FRISK_B200_FAST_K) return frisk_internal::general_finalize(d_fwd, kmax, symmetric, d_tables, d_valid_kmax, st);
     DISPATCH_K(kmax, launch_finalize<K>(d_fwd, symmetric, d_tables, d_valid_kmax, st));
 }
 
@@ -1378,6 +1382,7 @@ int frisk_b200_genome_ivom(const uint64_t* d_tables, int kmin, int kmax, int64_t
     int rc = check_k(kmin, kmax);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (kmax > FRISK_B200_FAST_K) return frisk_internal::general_genome_ivom(d_tables, kmin, kmax, genome_space, d_ig, st);
     DISPATCH_K(kmax, launch_genome_ivom<K>(d_tables, kmin, genome_space, d_ig, st));
 }
 
@@ -1391,6 +1396,9 @@ int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint3
     if (max_win_len > FRISK_B200_MAX_WINDOW || n_win > 0xffffffffull) return FRISK_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int rip = want_rip && kmin <= 2 && kmax >= 2;
+    if (kmax > FRISK_B200_FAST_K || max_win_len > 65535u || g_force_general)
+        return frisk_internal::general_score(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, kmax,
+                                             rip, d_rows, d_status, d_dump, st);
     // default path: bucketed kernel (4 CTAs/SM); the dense-table kernel covers K < 4 and long windows
     if (kmax >= 4 && max_win_len <= kBuf3 - 6u && !g_force_dense) {
         switch (kmax) {
@@ -1409,6 +1417,7 @@ int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint3
 int frisk_b200_set_option(const char* name, int value) {
     if (!name) return FRISK_E_INVALID;
     if (strcmp(name, "force_dense_kernel") == 0) { g_force_dense = value; return FRISK_OK; }
+    if (strcmp(name, "force_general_kernel") == 0) { g_force_general = value; return FRISK_OK; }
     return FRISK_E_INVALID;
 }
 

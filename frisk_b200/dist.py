@@ -1,4 +1,12 @@
-"""Multi-GPU: one process per GPU, scaffolds sharded across ranks, ONE collective.
+"""Multi-GPU: one process per GPU, ONE collective.  Two ways to cut the work:
+
+* ``score_sharded``   -- scaffolds are dealt to ranks (LPT by bases); a rank only ever holds its own
+  scaffolds.  Right for fragmented assemblies (C5) and when the host side is the bottleneck.
+* ``score_balanced``  -- every rank ingests the whole FASTA on its own GPU (device-side ingest, one PCIe
+  link per GPU; 14 Gbp packed is 5 GB of 180 GB), counts an equal slice of the BASE RANGE and scores an
+  equal slice of the WINDOW LIST (by bases covered): exact balance even when 24 chromosomes meet 8 GPUs
+  (C4), no halo logic because every word's owner is the rank whose slice holds its first base, rows come
+  back already in reference order.
 
 The path shards naturally: every rank counts the forward-strand k-mers of
 its own scaffolds, the 87,380-counter tables (+ the genome-space scalar) are summed with a single
@@ -106,3 +114,61 @@ def gather_rows(res, mine, group=None, dst: int = 0):
     status = np.concatenate([o[4] for o in out])
     order = np.argsort(key, kind="stable")
     return [names[i] for i in order], coords[order], rows[order], status[order]
+
+
+# ---------------------------------------------------------------------- balanced slices of one replicated genome
+def split_base_range(padded_len: int, world: int) -> List[Tuple[int, int]]:
+    """[first_base, last_base) per rank: contiguous, multiples of 32, together exactly the range the
+    single-GPU background pass covers ([0, padded_len - 32): the last word is look-ahead padding)."""
+    words = padded_len // 32 - 1
+    cuts = [(words * r) // world for r in range(world + 1)]
+    return [(32 * cuts[r], 32 * cuts[r + 1]) for r in range(world)]
+
+
+def split_windows(lengths: np.ndarray, world: int) -> List[Tuple[int, int]]:
+    """[a, b) window-index ranges per rank, contiguous, balanced by the bases the windows cover
+    (--scaffoldsAll windows vary in length)."""
+    n = len(lengths)
+    if n == 0:
+        return [(0, 0)] * world
+    csum = np.cumsum(np.asarray(lengths, dtype=np.int64))
+    total = int(csum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(csum, (total * r) // world, side="left")))
+    cuts.append(n)
+    cuts = [min(max(c, cuts[i - 1] if i else 0), n) for i, c in enumerate(cuts)]
+    return [(cuts[r], max(cuts[r], cuts[r + 1])) for r in range(world)]
+
+
+def score_balanced(fasta_text, group=None, device=None, host_text=None, **params):
+    """Multi-GPU hot path on one replicated genome (see the module docstring).  Returns this rank's
+    HotPathResult (global tables and meta, this rank's slice of the rows) and its window range."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    dq = engine.DeviceGenome.from_fasta_bytes(fasta_text, device)
+    dh = engine.DeviceGenome.from_fasta_bytes(host_text, device) if host_text is not None else dq
+    wins_all = dq.host.windows(params.get("w", 5000), params.get("step", 2500), params.get("scaffolds_all", False))
+    a, b = split_windows(wins_all.length, world)[rank]
+    pipe = engine.Pipeline(dq, dh if dh is not dq else None, device=device, allreduce=make_allreduce(group),
+                           genome_space=dh.host.genome_space, wins=wins_all.slice(a, b),
+                           bg_range=split_base_range(dh.host.padded_len, world)[rank], **params)
+    pipe.enqueue()
+    return pipe.result(), (a, b)
+
+
+def gather_rows_in_order(res, group=None, dst: int = 0):
+    """Rows of ``score_balanced``: the ranks hold consecutive slices of the window list, so rank order
+    is reference order.  Returns (names, coords, rows, status) on ``dst``, None elsewhere."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    out = [None] * world if rank == dst else None
+    dist.gather_object((res.names, res.coords, res.rows, res.status), out, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return ([n for o in out for n in o[0]], np.concatenate([o[1].reshape(-1, 2) for o in out]),
+            np.concatenate([o[2].reshape(-1, 5) for o in out]), np.concatenate([o[3] for o in out]))

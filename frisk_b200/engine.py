@@ -372,7 +372,8 @@ class Pipeline:
     def __init__(self, query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1, kmax: int = 8,
                  w: int = 5000, step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False,
                  rip: bool = True, device="cuda:0", dump: bool = False, allreduce=None,
-                 genome_space: Optional[int] = None, wins: Optional[WindowList] = None):
+                 genome_space: Optional[int] = None, wins: Optional[WindowList] = None,
+                 bg_range: Optional[Tuple[int, int]] = None):
         import torch
         _lib.require_device()
         rc = 0 if 1 <= kmin <= kmax else _lib.E_INVALID
@@ -389,6 +390,9 @@ class Pipeline:
         self.allreduce = allreduce
         self.genome_space = self.host.genome_space if genome_space is None else int(genome_space)
         self.wins = wins if wins is not None else query.windows(w, step, scaffolds_all)
+        # base range of the host planes this pipeline counts (multi-GPU: a rank's slice; the last
+        # 32-base word is padding, only ever read as look-ahead)
+        self.bg_range = (0, host.padded_len - 32) if bg_range is None else (int(bg_range[0]), int(bg_range[1]))
         dev = self.dq.device
         self.device = dev
         n = len(self.wins)
@@ -422,7 +426,7 @@ class Pipeline:
             self.d_fwd.zero_()
             mark()
             dh = self.dh
-            _lib.check(L.frisk_b200_background(_ptr(dh.codes), _ptr(dh.inv), _ptr(dh.low), 0, dh.host.padded_len - 32,
+            _lib.check(L.frisk_b200_background(_ptr(dh.codes), _ptr(dh.inv), _ptr(dh.low), self.bg_range[0], self.bg_range[1],
                                                self.kmax, int(self.mask_host), _ptr(self.d_fwd), st), "frisk_b200_background")
             mark()
             space = self.genome_space

@@ -34,13 +34,14 @@ extern "C" {
 #endif
 
 #define FRISK_B200_ABI_VERSION 1
-#define FRISK_B200_MAX_K 8          /* largest supported --maxWordSize (4^8 u16 bins live in one SM's smem) */
-#define FRISK_B200_MAX_WINDOW 65535 /* largest window length (u16 window counters) */
+#define FRISK_B200_MAX_K 12              /* largest supported --maxWordSize (K <= 8: shared-memory kernels; 9..12: general path) */
+#define FRISK_B200_FAST_K 8              /* ... served by the tuned shared-memory kernels */
+#define FRISK_B200_MAX_WINDOW 0x7fffffff /* largest window length (<= 65,535: shared-memory kernels; longer: general path) */
 
 enum {
     FRISK_OK = 0,
     FRISK_E_INVALID = -1,     /* bad argument (null pointer, kmin > kmax, ...) */
-    FRISK_E_UNSUPPORTED = -2, /* kmax > FRISK_B200_MAX_K or window longer than FRISK_B200_MAX_WINDOW */
+    FRISK_E_UNSUPPORTED = -2, /* kmax > FRISK_B200_MAX_K, window longer than FRISK_B200_MAX_WINDOW, > 2^32-1 windows */
     FRISK_E_CUDA = -3,        /* a CUDA call failed; see frisk_b200_last_cuda_error() */
     FRISK_E_NO_DEVICE = -4,   /* no CUDA device: there is deliberately no CPU fallback */
     FRISK_E_CAPACITY = -5,    /* an output array is too small; the required count is still reported */
@@ -145,7 +146,8 @@ int frisk_b200_genome_ivom(const uint64_t *d_tables, int kmin, int kmax, int64_t
  * d_rows: n_win x 5 doubles {windowKLD, GC, PI, SI, CRI} (PI/SI/CRI NaN unless want_rip and
  * kmin <= 2 <= kmax).  d_status: n_win FRISK_ROW_* words.  d_dump (nullable, tests only):
  * n_win x frisk_b200_table_size(1,kmax) uint16 window tables, orders 1..kmax.
- * max_win_len: the largest win_len (<= FRISK_B200_MAX_WINDOW).
+ * max_win_len: the largest win_len (<= FRISK_B200_MAX_WINDOW).  kmax <= 8 and windows <= 65,535 bases
+ * run in the shared-memory kernels; anything else in the general kernel (frisk_general.cu), same results.
  */
 int frisk_b200_score(const uint32_t *d_codes, const uint32_t *d_inv, const uint32_t *d_low,
                      const uint64_t *d_win_off, const uint32_t *d_win_len, uint64_t n_win, uint32_t max_win_len,

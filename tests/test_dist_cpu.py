@@ -23,6 +23,25 @@ def test_shard_scaffolds_balanced_and_complete():
         assert max(loads) - min(loads) <= max(lens)
 
 
+def test_balanced_slices_cover_everything_once():
+    rng = np.random.default_rng(4)
+    for world in (1, 2, 3, 8):
+        for padded in (128, 4096, 128 * 77777, 128 * 1_000_003):
+            parts = fdist.split_base_range(padded, world)
+            assert parts[0][0] == 0 and parts[-1][1] == padded - 32
+            assert all(a % 32 == 0 and b % 32 == 0 and a <= b for a, b in parts)
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 32
+        for lengths in (np.full(1000, 5000), rng.integers(1, 6251, 100_000), np.array([5000]), np.zeros(0, np.int64)):
+            parts = fdist.split_windows(lengths, world)
+            assert parts[0][0] == 0 and parts[-1][1] == len(lengths)
+            assert all(a <= b for a, b in parts) and all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            if len(lengths) >= 100 * world:
+                loads = [int(lengths[a:b].sum()) for a, b in parts]
+                assert max(loads) - min(loads) <= 2 * int(lengths.max())
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -49,7 +49,7 @@ def test_staged_path_matches_reference_golden(eng, case):
 
 
 @pytest.mark.parametrize("case", ["edge_default", "edge_scaffoldsAll", "edge_maskHost", "c2_small_query_vs_c1_host",
-                                  "edge_k2_5_w1000_i250"])
+                                  "edge_k2_5_w1000_i250", "edge_k9_10_w2500_i2500"])
 def test_host_buffer_path_matches_reference_golden(eng, case):
     g = Golden(case)
     res = _run_case(eng, g, host_path=True)
@@ -58,7 +58,7 @@ def test_host_buffer_path_matches_reference_golden(eng, case):
     assert np.array_equal(res.rows, staged.rows, equal_nan=True), "both entry paths run the same kernels"
 
 
-@pytest.mark.parametrize("case", ["edge_default", "edge_k2_5_w1000_i250", "edge_scaffoldsAll", "edge_k1_1"])
+@pytest.mark.parametrize("case", ["edge_default", "edge_k2_5_w1000_i250", "edge_scaffoldsAll", "edge_k1_1", "edge_k1_9"])
 def test_window_tables_bit_exact(eng, case):
     """Window k-mer tables (debug dump of the shared-memory histograms) vs the reference's."""
     from oracle import c_oracle
@@ -93,6 +93,76 @@ def test_dense_table_kernel_matches_reference_golden(eng, case):
     default = _run_case(eng, g, dump=True)
     assert np.array_equal(res.win_tables, default.win_tables)
     assert max_rel_err(res.rows[:, 0], default.rows[:, 0]) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["edge_default", "edge_scaffoldsAll", "edge_maskHost", "edge_k2_5_w1000_i250", "edge_k1_1",
+                                  "c2_small_query_vs_c1_host"])
+def test_general_kernel_matches_reference_golden(eng, case):
+    """The general (global-memory, run-time K) score kernel serves kmax 9..12 and windows longer than
+    65,535 bases; forced here on the default-range cases it must agree with the reference and with the
+    shared-memory kernels, and be bit-reproducible."""
+    from frisk_b200 import _lib
+    g = Golden(case)
+    _lib.check(_lib.lib().frisk_b200_set_option(b"force_general_kernel", 1), "set_option")
+    try:
+        res = _run_case(eng, g, dump=True)
+        again = _run_case(eng, g)
+    finally:
+        _lib.lib().frisk_b200_set_option(b"force_general_kernel", 0)
+    _check_against_golden(res, g, case + "[general]")
+    assert np.array_equal(res.rows, again.rows, equal_nan=True)
+    default = _run_case(eng, g, dump=True)
+    assert np.array_equal(res.win_tables, default.win_tables)
+    assert np.array_equal(res.status, default.status)
+    ok = res.status == 0
+    assert max_rel_err(res.rows[ok, 0], default.rows[ok, 0]) < 1e-12
+
+
+@pytest.mark.parametrize("kw", [dict(kmin=1, kmax=10), dict(kmin=3, kmax=12, w=3000, step=1500, scaffolds_all=True),
+                                dict(kmin=11, kmax=11, mask_host=True)])
+def test_word_sizes_beyond_8_against_c_oracle(eng, kw):
+    """--maxWordSize 9..12 (the reference takes any; its default is 8): background, finalise, genome IVOM
+    and scoring all run in the general path.  Tables bit-exact, rows to 1e-10."""
+    from frisk_b200 import synth
+    from oracle import c_oracle
+    sc = synth.make("edge") + synth.make("C2", 0.004, seed=9)
+    full = dict(kmin=1, kmax=8, w=5000, step=2500, mask_host=False, scaffolds_all=False, rip=True)
+    full.update(kw)
+    ref = c_oracle.run(sc, threads=8, **full)
+    g = eng.PackedGenome.from_scaffolds(sc, pinned=True)
+    for res in (eng.run(g, **full), eng.run_host(g, **full)):
+        assert np.array_equal(res.tables, ref["tables"])
+        assert list(res.meta) == [int(x) for x in ref["meta"]]
+        assert res.names == ref["names"] and np.array_equal(res.coords, ref["coords"])
+        assert np.array_equal(res.status & 7, ref["status"] & 7)
+        ok = ref["status"] == 0
+        assert_rows_close(res.rows[ok], ref["rows"][ok], rtol_kld=1e-6, rtol_other=1e-15, what=str(kw))
+        assert max_rel_err(res.rows[ok, 0], ref["rows"][ok, 0]) < 1e-10
+
+
+def test_windows_longer_than_65535_bases(eng):
+    """--windowlen beyond the 16-bit counters of the shared-memory kernels, default k = 1..8 and a
+    narrow k = 2..5 (tables entirely in shared memory), with N runs and soft-masked bases inside."""
+    from frisk_b200 import synth
+    from oracle import c_oracle
+    sc = synth.make("C1", 0.2, seed=31) + synth.make("edge")
+    name, seq = sc[0]
+    seq = seq.copy()
+    seq[200_000:230_000] = ord("N")
+    seq[400_000:420_000] |= 0x20                       # lower case
+    sc[0] = (name, seq)
+    for kw in (dict(kmin=1, kmax=8, w=100_000, step=40_000), dict(kmin=2, kmax=5, w=70_001, step=70_001, scaffolds_all=True)):
+        full = dict(mask_host=False, scaffolds_all=False, rip=True)
+        full.update(kw)
+        ref = c_oracle.run(sc, threads=8, **full)
+        res = eng.run(eng.PackedGenome.from_scaffolds(sc), **full)
+        assert len(res.rows) == len(ref["rows"]) > 0
+        assert np.array_equal(res.tables, ref["tables"])
+        assert np.array_equal(res.coords, ref["coords"])
+        assert np.array_equal(res.status & 7, ref["status"] & 7)
+        ok = ref["status"] == 0
+        assert_rows_close(res.rows[ok], ref["rows"][ok], rtol_kld=1e-6, rtol_other=1e-15, what="long windows " + str(kw))
+        assert max_rel_err(res.rows[ok, 0], ref["rows"][ok, 0]) < 1e-10
 
 
 def test_long_windows_use_segments(eng):

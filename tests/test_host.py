@@ -132,8 +132,9 @@ def test_window_rows_match_reference_golden_coords():
     assert a[-2:] == [(15001, 20000), (15000, 20000)]
 
 
-def test_too_long_window_is_refused():
+def test_long_windows_are_enumerated():
+    """Windows beyond the shared-memory kernels' 65,535 bases are legal (general kernel)."""
     g = engine.PackedGenome.from_scaffolds([("big", synth.iid_bases(np.random.default_rng(1), 300_000, 0.5))])
-    with pytest.raises(_lib.FriskError) as ei:
-        g.windows(70_000, 35_000)
-    assert ei.value.code == _lib.E_UNSUPPORTED
+    wins = g.windows(70_000, 35_000)
+    assert wins.max_len == 70_000 and len(wins) == 8          # j = 0, 35k, ..., 245k (F:228): the last two jump back
+    assert _lib.MAX_K == 12 and _lib.MAX_WINDOW == 0x7FFFFFFF

@@ -31,7 +31,23 @@ def main():
         err = np.abs(rows[good, 0] - ref["rows"][good, 0]) / np.maximum(np.abs(ref["rows"][good, 0]), 1e-300)
         assert err.max() < 1e-10, err.max()
         assert np.array_equal(rows[good, 1:], ref["rows"][good, 1:], equal_nan=True)
-        print("dist_check ok: world=%d rows=%d max KLD rel err %.2e" % (dist.get_world_size(), len(names), err.max()))
+        print("sharded ok: world=%d rows=%d max KLD rel err %.2e" % (dist.get_world_size(), len(names), err.max()))
+    # second scheme: one replicated genome (device-side ingest of the FASTA text on every rank), equal
+    # slices of the base range and of the window list
+    text = np.frombuffer(synth.fasta_bytes(scaffolds), dtype=np.uint8)
+    res2, (a, b) = fdist.score_balanced(text, **params)
+    gathered2 = fdist.gather_rows_in_order(res2)
+    if dist.get_rank() == 0:
+        names, coords, rows, status = gathered2
+        assert np.array_equal(res2.tables, ref["tables"]), "balanced: all-reduced tables differ"
+        assert list(res2.meta) == [int(x) for x in ref["meta"]], (res2.meta, ref["meta"])
+        assert names == ref["names"] and np.array_equal(coords, ref["coords"])
+        err2 = np.abs(rows[good, 0] - ref["rows"][good, 0]) / np.maximum(np.abs(ref["rows"][good, 0]), 1e-300)
+        assert err2.max() < 1e-10, err2.max()
+        assert np.array_equal(rows[good, 1:], ref["rows"][good, 1:], equal_nan=True)
+        assert np.array_equal(rows, gathered[2], equal_nan=True), "both schemes run the same kernels on the same windows"
+        print("balanced ok: rank 0 scored windows [%d, %d) of %d" % (a, b, len(names)))
+        print("dist_check ok: world=%d rows=%d max KLD rel err %.2e" % (dist.get_world_size(), len(names), max(err.max(), err2.max())))
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
