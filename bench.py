@@ -263,7 +263,8 @@ def run_gpu(args):
         # N = 1: exactly one C-ABI call (frisk_b200_run_host) from pinned host buffers to pinned host results
         if world == 1:
             return engine.run_host(genome, wins=wins, out=out, assemble_result=False, **PARAMS)
-        return engine.run(genome, device=dev, allreduce=allreduce, genome_space=space, wins=wins, **PARAMS)
+        # N > 1: the same traffic through the resident pipeline (the all-reduce sits between its kernels)
+        return pipe.step_from_host(out)
 
     if args.profile:
         e2e_steps = 0
@@ -348,7 +349,7 @@ def run_gpu(args):
                                     "marginalisation, K-1 and K from a counting sort)"},
             "e2e": {"value": (all_bases / (e2e_step_ms * 1e-3) / 1e9) if e2e_steps else None, "unit": "Gbp/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_step_ms, "steps": e2e_steps,
-                    "api": "frisk_b200_run_host (C ABI, pinned host planes)" if world == 1 else "engine.run + NCCL all-reduce"},
+                    "api": "frisk_b200_run_host (C ABI, pinned host planes)" if world == 1 else "engine.Pipeline.step_from_host (pinned host planes, NCCL all-reduce between kernels)"},
             "e2e_fasta": ({"value": all_bases / (fasta_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": fasta_ms,
                            "h2d_bytes_per_step": fasta_bytes_n + wins.off.nbytes + wins.length.nbytes, "d2h_bytes_per_step": d2h,
                            "api": "frisk_b200_fasta_open/_pack (device-side FASTA ingest) + frisk_b200_run_resident, from pinned FASTA text"}

@@ -344,11 +344,9 @@ int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* lo
     const uint64_t slab_words = K > kSmemOrders ? (loff(K + 1) - loff(kSmemOrders + 1)) + p4(K) : 0;
     uint32_t* slab = nullptr;
     if (slab_words) {
-        void* p = nullptr;
         const uint64_t count_words = loff(K + 1) - loff(kSmemOrders + 1);
-        int rc = ws_get(14, (size_t)(grid * slab_words * 4), &p);
-        if (rc) return rc;
-        slab = (uint32_t*)p;
+        // stream-ordered: up to 156 MB per CTA at K = 12, handed back as soon as the kernel is done
+        FRISK_CK(cudaMallocAsync((void**)&slab, (size_t)(grid * slab_words * 4), st));
         for (uint64_t c = 0; c < grid; ++c) {                          // counts = 0, first = "none"
             FRISK_CK(cudaMemsetAsync(slab + c * slab_words, 0, count_words * 4, st));
             FRISK_CK(cudaMemsetAsync(slab + c * slab_words + count_words, 0xff, p4(K) * 4, st));
@@ -362,6 +360,7 @@ int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* lo
                                                        win_len, (uint32_t)n_win, reinterpret_cast<const double2*>(ig), kmin, K,
                                                        want_rip, slab, slab_words, rows, status, dump);
     FRISK_CK(cudaGetLastError());
+    if (slab) FRISK_CK(cudaFreeAsync(slab, st));
     return FRISK_OK;
 }
 

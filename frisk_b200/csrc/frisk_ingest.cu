@@ -360,8 +360,8 @@ int pool_ready(int dev) {
     if (!done[dev & 63]) {
         cudaMemPool_t pool;
         FRISK_CK(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = ~0ull;                      // keep freed blocks cached: repeated ingests do not hit the allocator
-        FRISK_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        uint64_t keep = 1ull << 30;                 // up to 1 GiB of freed blocks stays cached: repeated ingests of
+        FRISK_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));   // ordinary genomes skip the allocator
         done[dev & 63] = true;
     }
     return FRISK_OK;

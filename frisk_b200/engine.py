@@ -446,6 +446,32 @@ class Pipeline:
                            "frisk_b200_score")
             mark()
 
+    def step_from_host(self, out: "HostOutputs") -> "HostOutputs":
+        """One end-to-end pass without any allocation: H2D of the (pinned) host planes into the
+        resident device buffers, every kernel (with the all-reduce when one is set), D2H of rows,
+        status, tables and the valid-word count into ``out`` (pinned).  Returns after the stream is
+        idle.  This is the multi-GPU counterpart of the single C call frisk_b200_run_host."""
+        import torch
+        dev = self.device
+        with torch.cuda.device(dev):
+            for dg in ((self.dh,) if self.dh is self.dq else (self.dh, self.dq)):
+                g = dg.host
+                dg.codes.copy_(torch.from_numpy(g.codes.view(np.int32)), non_blocking=True)
+                dg.inv.copy_(torch.from_numpy(g.inv.view(np.int32)), non_blocking=True)
+                if dg.low is not None:
+                    dg.low.copy_(torch.from_numpy(g.low.view(np.int32)), non_blocking=True)
+            self.d_off.copy_(torch.from_numpy(self.wins.off.view(np.int64)), non_blocking=True)
+            self.d_len.copy_(torch.from_numpy(self.wins.length.view(np.int32)), non_blocking=True)
+            self.enqueue()
+            n = len(self.wins)
+            if n:
+                torch.from_numpy(out.rows[:n]).copy_(self.d_rows, non_blocking=True)
+                torch.from_numpy(out.status[:n].view(np.int32)).copy_(self.d_status, non_blocking=True)
+            torch.from_numpy(out.tables.view(np.int64)).copy_(self.d_tables, non_blocking=True)
+            torch.from_numpy(out.valid.view(np.int64)).copy_(self.d_valid, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        return out
+
     def result(self) -> HotPathResult:
         import torch
         torch.cuda.synchronize(self.device)
@@ -469,6 +495,34 @@ def run(query, host=None, kmin: int = 1, kmax: int = 8, w: int = 5000,
                     genome_space, wins)
     pipe.enqueue()
     return pipe.result()
+
+
+def run_sweep(query, kmaxes: Sequence[int] = tuple(range(1, 9)), kmin: int = 1, w: int = 5000, step: int = 2500,
+              mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True, device="cuda:0"):
+    """Scores for several --maxWordSize values in one go (BASELINE config C3: the k sweep 1..8, i.e. eight
+    reference runs ``-m kmin -k k'``).  The count of x-words does not depend on kmax (F:338-351 counts every
+    order independently), so ONE background pass at max(kmaxes) serves every k'; per k' only the genome
+    IVOM table and the window kernel run.  Returns {k': HotPathResult}."""
+    import torch
+    _lib.require_device()
+    dq = query if isinstance(query, DeviceGenome) else DeviceGenome(query, device)
+    g = dq.host
+    top = max(kmaxes)
+    d_tables, _ = finalize(background(dq, top, mask_host), top)
+    wins = g.windows(w, step, scaffolds_all)
+    out = {}
+    for k in sorted(set(int(x) for x in kmaxes)):
+        if k < kmin:
+            continue
+        tsz = _lib.table_size(1, k)
+        d_tab_k = d_tables[:tsz]
+        d_ig = genome_ivom(d_tab_k, kmin, k, g.genome_space)
+        d_rows, d_status, _ = score(dq, wins, d_ig, kmin, k, rip)
+        torch.cuda.synchronize(dq.device)
+        tables = d_tab_k.cpu().numpy().view(np.uint64)
+        valid = int(tables[_lib.table_size(1, k - 1) if k > 1 else 0:].sum()) // 2      # both strands were added
+        out[k] = assemble(g, g, wins, tables, valid, d_rows.cpu().numpy(), d_status.cpu().numpy().view(np.uint32), kmin, k)
+    return out
 
 
 def run_host(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1, kmax: int = 8, w: int = 5000,

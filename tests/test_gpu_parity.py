@@ -365,6 +365,25 @@ def test_background_16bit_counter_wraps_are_exact(eng):
     assert g.ex_max(8, int(d_valid.item())) == int(meta[1])
 
 
+def test_kmax_sweep_shares_one_background_pass(eng):
+    """BASELINE config C3 (k sweep 1..8, here at 1 % scale with its TE-like repeats): every k' of the sweep
+    equals a separate reference-style run with --maxWordSize k' (C oracle)."""
+    from frisk_b200 import synth
+    from oracle import c_oracle
+    sc = synth.make("C3", 0.01)
+    sweep = eng.run_sweep(eng.PackedGenome.from_scaffolds(sc), kmaxes=range(1, 9))
+    assert sorted(sweep) == list(range(1, 9))
+    for k, res in sweep.items():
+        ref = c_oracle.run(sc, threads=8, kmin=1, kmax=k)
+        assert np.array_equal(res.tables, ref["tables"]), k
+        assert list(res.meta) == [int(x) for x in ref["meta"]], k
+        assert np.array_equal(res.coords, ref["coords"])
+        ok = ref["status"] == 0
+        assert np.array_equal(res.status & 7, ref["status"] & 7)
+        assert_rows_close(res.rows[ok], ref["rows"][ok], rtol_kld=1e-6, rtol_other=1e-15, what="sweep k=%d" % k)
+        assert max_rel_err(res.rows[ok, 0], ref["rows"][ok, 0]) < 1e-10
+
+
 def test_no_silent_fallback_symbols_loaded(eng):
     """The product library is the thing that ran: it is loaded in this process and reports a GPU."""
     from frisk_b200 import _lib
