@@ -748,7 +748,8 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
     uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem);
     uint16_t* mask16 = reinterpret_cast<uint16_t*>(smem + L::OFF_MASK);
     uint32_t* mask32 = reinterpret_cast<uint32_t*>(smem + L::OFF_MASK);
-    // per bucket: bits 0-14 start of its K-mers in its list, bit 15 dirty, bits 16-31 start of a dirty bucket's entries in buf
+    // per bucket: clean: bits 0-12 start of its K-mers in the list, bit 15 = 0, bits 16-31 its presence mask;
+    //             dirty: bits 0-14 start in the dirty list, bit 15 = 1, bits 16-31 start of its entries in buf
     uint32_t* dst32 = reinterpret_cast<uint32_t*>(smem + L::OFF_CUR);
     double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);       // .x = num, .y = den (u32 bit pattern)
     double2* logtab = reinterpret_cast<double2*>(smem + L::OFF_LOG);
@@ -934,8 +935,8 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                             outv[j] = 0x8000u | (runA >> 16) | (runB << 16);
                             runA += pc << 16;
                             runB += nbs[j];
-                        } else {
-                            outv[j] = runA & 0xffffu;
+                        } else {                                           // clean: list start | presence mask << 16 (all P3/P4 need)
+                            outv[j] = (runA & 0x1fffu) | (mks[j] << 16);
                             runA += pc;
                         }
                     }
@@ -960,10 +961,15 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 const uint32_t b = pl >> 18, rank = (pl >> 5) & 0x1fffu;
                 const uint32_t d = dst32[b];
                 if (c5 < 16u) {
-                    const uint32_t slot = (d & 0x7fffu) + __popc((uint32_t)mask16[b] & ((1u << c5) - 1u));
                     const uint16_t kappa = (uint16_t)((b << 4) | c5);
-                    if (d & 0x8000u) { list[cap - 1u - slot] = kappa; buf[(d >> 16) + rank] = (uint8_t)c5; }
-                    else list[slot] = kappa;
+                    const uint32_t below = (1u << c5) - 1u;
+                    // clean bucket: cursor and mask come in the one word; a dirty one (rare) reads its mask too
+                    uint32_t slot = (d & 0x1fffu) + __popc((d >> 16) & below);
+                    if (d & 0x8000u) {
+                        slot = cap - 1u - ((d & 0x7fffu) + __popc((uint32_t)mask16[b] & below));
+                        buf[(d >> 16) + rank] = (uint8_t)c5;
+                    }
+                    list[slot] = kappa;
                 } else {
                     buf[(d >> 16) + rank] = (uint8_t)c5;                   // a short word makes its bucket dirty
                 }
@@ -1046,7 +1052,8 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         for (uint32_t e = tid; e < n_clean; e += kT3) {
             const uint32_t kappa = list[e];
             const uint32_t b = kappa >> 4, j = (kappa >> 2) & 3u;
-            score_one(kappa, b, tabB[b], __popc(((uint32_t)mask16[b] >> (4 * j)) & 15u), 1u);
+            const uint32_t msk = dst32[b] >> 16;                               // clean bucket: count = popc(mask)
+            score_one(kappa, b, __popc(msk), __popc((msk >> (4 * j)) & 15u), 1u);
         }
         for (uint32_t e = tid; e < n_dirty; e += kT3) {
             const uint32_t kappa = list[cap - 1u - e];
