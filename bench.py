@@ -72,6 +72,26 @@ def committed_traffic():
         return None
 
 
+def committed_pipe_utilisation():
+    """What actually limits the dominant kernel, from the committed `ncu --set full` capture of the same
+    command (profiles/r01_ncu_raw_metrics.json): LSU data-pipe and issue-slot utilisation.  Static evidence
+    (a run under ncu is never timed); the live numbers beside it are the CUDA-event times."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_raw_metrics.json")) as fh:
+            d = json.load(fh)
+        key = [k for k in d if k.startswith("score_windows_bucket_kernel<8,5,0,1>")][-1]
+        m = d[key]
+        num = lambda name: float(m[name].split()[0])
+        return {"kernel": key, "lsu_data_pipe_pct_of_peak": num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                "issue_slots_pct_of_peak": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "fp64_pipe_pct_of_peak": num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                "warp_instructions": num("smsp__inst_executed.sum"),
+                "shared_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+                "source": "profiles/r01_ncu_raw_metrics.json (ncu --set full, same command, not timed)"}
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -339,14 +359,15 @@ def run_gpu(args):
                          "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "not the binding bound: window tables never leave shared memory, so the kernel reads each "
-                                 "packed base once (traffic ~= algorithmic bytes) and is limited by instruction issue and "
-                                 "shared-memory atomics; see smem_atomic and DESIGN.md"},
+                                 "packed base once (traffic ~= algorithmic bytes); it is limited by the LSU data pipe "
+                                 "(shared-memory wavefronts + divergent L2 gathers) and issue slots: see limiter, smem_atomic, DESIGN.md"},
             "smem_atomic": {"algorithmic_updates_per_s": alg_updates / (score_ms * 1e-3),
                             "peak_updates_per_s": atomic_peak, "peak_source": "measured live: frisk_b200_bench_smem_atomics, random bins",
                             "frac": (alg_updates / (score_ms * 1e-3) / atomic_peak) if atomic_peak else None,
                             "note": "SURVEY 8(d) bound: algorithmic = one histogram update per (order, valid position) = 39,972 per "
                                     "5 kb window; the kernel issues ~2.5 atomics per position (orders below K-2 come from "
                                     "marginalisation, K-1 and K from a counting sort)"},
+            "limiter": committed_pipe_utilisation(),
             "e2e": {"value": (all_bases / (e2e_step_ms * 1e-3) / 1e9) if e2e_steps else None, "unit": "Gbp/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_step_ms, "steps": e2e_steps,
                     "api": "frisk_b200_run_host (C ABI, pinned host planes)" if world == 1 else "engine.Pipeline.step_from_host (pinned host planes, NCCL all-reduce between kernels)"},

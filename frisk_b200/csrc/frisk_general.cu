@@ -345,6 +345,7 @@ int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* lo
     uint32_t* slab = nullptr;
     if (slab_words) {
         const uint64_t count_words = loff(K + 1) - loff(kSmemOrders + 1);
+        { const int rc = pool_ready(); if (rc) return rc; }
         // stream-ordered: up to 156 MB per CTA at K = 12, handed back as soon as the kernel is done
         FRISK_CK(cudaMallocAsync((void**)&slab, (size_t)(grid * slab_words * 4), st));
         for (uint64_t c = 0; c < grid; ++c) {                          // counts = 0, first = "none"

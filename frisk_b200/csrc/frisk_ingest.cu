@@ -355,18 +355,6 @@ fasta_padding_kernel(const unsigned long long* __restrict__ scaf_off, const unsi
     for (; a < b; a += 32) inv[a >> 5] = 0xffffffffu;
 }
 
-int pool_ready(int dev) {
-    static bool done[64] = {};
-    if (!done[dev & 63]) {
-        cudaMemPool_t pool;
-        FRISK_CK(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = 1ull << 30;                 // up to 1 GiB of freed blocks stays cached: repeated ingests of
-        FRISK_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));   // ordinary genomes skip the allocator
-        done[dev & 63] = true;
-    }
-    return FRISK_OK;
-}
-
 }  // namespace
 
 struct frisk_b200_fasta {
@@ -392,9 +380,7 @@ int free_all(frisk_b200_fasta* h, cudaStream_t st) {
 }
 
 int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st) {
-    int dev = 0;
-    FRISK_CK(cudaGetDevice(&dev));
-    int rc = pool_ready(dev);
+    int rc = frisk_internal::pool_ready();
     if (rc) return rc;
     h->n = n;
     h->n_tiles = n ? (n + kTile - 1) / kTile : 0;

@@ -14,6 +14,9 @@ int cuda_fail(cudaError_t e, const char* what);
 // cached per-device workspace (grown on demand, freed by frisk_b200_release_workspace)
 int ws_get(int slot, size_t bytes, void** out);
 
+// once per device: let the default memory pool keep up to 1 GiB of freed cudaMallocAsync scratch
+int pool_ready();
+
 // FASTA header rule of the reference (F:156): name = line.strip().strip('>').split()[0].
 // The line starts at `line_start`; returns false for an empty name (the reference raises IndexError).
 bool parse_header_name(const unsigned char* t, uint64_t n, uint64_t line_start, uint64_t* name_off, uint32_t* name_len);

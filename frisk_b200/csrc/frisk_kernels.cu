@@ -16,6 +16,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/frisk_b200.h"
 #include "frisk_internal.h"
 
@@ -187,9 +189,27 @@ bg_reduce_kernel(const uint32_t* __restrict__ partial, int n_parts, unsigned lon
 //   forward_totals_kernel   one CTA per order-R subtree (R = K-4): F_x for x = R..K
 //   forward_low_kernel      one CTA: F_x for x = R-1..1 (<= 84 bins)
 //   symmetrise_kernel       one thread per table entry, each {kmer, revcomp} pair handled once
-template <int K>
+// Where the forward counters come from: this GPU's buffer, or -- multi-GPU, fused all-reduce -- the sum
+// over every rank's buffer read directly through NVLink peer mappings (no separate collective, no
+// staging copy: the reduction happens in the registers of the kernel that needs the sums).
+struct LocalFwd {
+    const unsigned long long* p;
+    __device__ __forceinline__ unsigned long long operator()(uint32_t i) const { return p[i]; }
+};
+constexpr int kMaxPeers = 16;
+struct PeerFwd {
+    const unsigned long long* p[kMaxPeers];
+    int n;
+    __device__ __forceinline__ unsigned long long operator()(uint32_t i) const {
+        unsigned long long s = 0;
+        for (int q = 0; q < n; ++q) s += __ldcv(p[q] + i);       // peers wrote these before the cross-GPU barrier
+        return s;
+    }
+};
+
+template <int K, typename Fwd>
 __global__ void __launch_bounds__(256)
-forward_totals_kernel(const unsigned long long* __restrict__ fwd, unsigned long long* __restrict__ tables,
+forward_totals_kernel(const Fwd fwd, unsigned long long* __restrict__ tables,
                       unsigned long long* __restrict__ valid_kmax) {
     constexpr int R = K > 4 ? K - 4 : 0;
     __shared__ unsigned long long lvl[2][256];
@@ -198,7 +218,7 @@ forward_totals_kernel(const unsigned long long* __restrict__ fwd, unsigned long 
     uint32_t n = pow4(K - R);                         // subtree nodes at the current order
     unsigned long long v = 0;
     if (t < n) {
-        v = fwd[lvl_off(K) + root * n + t];
+        v = fwd(lvl_off(K) + root * n + t);
         tables[lvl_off(K) + root * n + t] = v;
         lvl[0][t] = v;
     }
@@ -216,7 +236,7 @@ forward_totals_kernel(const unsigned long long* __restrict__ fwd, unsigned long 
         n >>= 2;
         if (t < n) {
             const unsigned long long* ch = &lvl[cur][4 * t];
-            const unsigned long long f = fwd[lvl_off(x) + root * n + t] + ch[0] + ch[1] + ch[2] + ch[3];
+            const unsigned long long f = fwd(lvl_off(x) + root * n + t) + ch[0] + ch[1] + ch[2] + ch[3];
             tables[lvl_off(x) + root * n + t] = f;
             lvl[cur ^ 1][t] = f;
         }
@@ -225,15 +245,15 @@ forward_totals_kernel(const unsigned long long* __restrict__ fwd, unsigned long 
     }
 }
 
-template <int K>
+template <int K, typename Fwd>
 __global__ void __launch_bounds__(64)
-forward_low_kernel(const unsigned long long* __restrict__ fwd, unsigned long long* __restrict__ tables) {
+forward_low_kernel(const Fwd fwd, unsigned long long* __restrict__ tables) {
     constexpr int R = K > 4 ? K - 4 : 0;
     for (int x = R - 1; x >= 1; --x) {
         const uint32_t t = threadIdx.x;
         if (t < pow4(x)) {
             const unsigned long long* ch = tables + lvl_off(x + 1) + 4 * t;
-            tables[lvl_off(x) + t] = fwd[lvl_off(x) + t] + ch[0] + ch[1] + ch[2] + ch[3];
+            tables[lvl_off(x) + t] = fwd(lvl_off(x) + t) + ch[0] + ch[1] + ch[2] + ch[3];
         }
         __syncthreads();
     }
@@ -1187,30 +1207,32 @@ int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t
     // at least ~2 rounds of 1024 words per CTA, otherwise fewer CTAs
     const uint64_t want = (n_words + 2047) / 2048;
     if ((uint64_t)grid > want) grid = want ? (int)want : 1;
-    // large tables: per-CTA partial tables + one reduction instead of ~65 k global atomics per CTA
+    // large tables: per-CTA partial tables + one reduction instead of ~65 k global atomics per CTA.
+    // Stream-ordered scratch (cached by the device's memory pool): concurrent calls on different
+    // streams never share it.
     uint32_t* partial = nullptr;
     if (NB >= 4096u && grid > 1) {
-        void* p = nullptr;
-        int rc = ws_get(13, (size_t)grid * NW * sizeof(uint32_t), &p);
+        int rc = frisk_internal::pool_ready();
         if (rc) return rc;
-        partial = (uint32_t*)p;
+        CK(cudaMallocAsync((void**)&partial, (size_t)grid * NW * sizeof(uint32_t), st));
     }
     bg_count_kernel<K><<<grid, kThreads, smem, st>>>(codes, inv, low, w_lo, w_hi, mask_host,
                                                       reinterpret_cast<unsigned long long*>(fwd), partial);
-    if (partial)
+    if (partial) {
         bg_reduce_kernel<K><<<(NW + 31) / 32, 256, 0, st>>>(partial, grid, reinterpret_cast<unsigned long long*>(fwd));
+        CK(cudaFreeAsync(partial, st));
+    }
     CK(cudaGetLastError());
     return FRISK_OK;
 }
 
-template <int K>
-int launch_finalize(const uint64_t* fwd, int symmetric, uint64_t* tables, uint64_t* valid, cudaStream_t st) {
+template <int K, typename Fwd>
+int launch_finalize(const Fwd f, int symmetric, uint64_t* tables, uint64_t* valid, cudaStream_t st) {
     constexpr int R = K > 4 ? K - 4 : 0;
-    auto f = reinterpret_cast<const unsigned long long*>(fwd);
     auto t = reinterpret_cast<unsigned long long*>(tables);
     if (valid) CK(cudaMemsetAsync(valid, 0, sizeof(uint64_t), st));
-    forward_totals_kernel<K><<<pow4(R), 256, 0, st>>>(f, t, reinterpret_cast<unsigned long long*>(valid));
-    if (R > 1) forward_low_kernel<K><<<1, 64, 0, st>>>(f, t);
+    forward_totals_kernel<K, Fwd><<<pow4(R), 256, 0, st>>>(f, t, reinterpret_cast<unsigned long long*>(valid));
+    if (R > 1) forward_low_kernel<K, Fwd><<<1, 64, 0, st>>>(f, t);
     if (symmetric) symmetrise_kernel<K><<<(lvl_off(K + 1) + 255) / 256, 256, 0, st>>>(t);
     CK(cudaGetLastError());
     return FRISK_OK;
@@ -1319,8 +1341,23 @@ struct Workspace {
     size_t cap[32] = {};
 };
 Workspace g_ws[64];
+std::mutex g_run_mu[64];     // frisk_b200_run_host / _run_resident share the workspace: one call at a time per device
 
 }  // namespace
+
+int frisk_internal::pool_ready() {
+    static bool done[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (!done[dev & 63]) {
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = 1ull << 30;     // up to 1 GiB of freed stream-ordered scratch stays cached in the pool
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        done[dev & 63] = true;
+    }
+    return FRISK_OK;
+}
 
 int frisk_internal::ws_get(int slot, size_t bytes, void** out) {
     int dev = 0;
@@ -1381,7 +1418,25 @@ int frisk_b200_finalize_tables(const uint64_t* d_fwd, int kmax, int symmetric, u
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (kmax > FRISK_B200_FAST_K) return frisk_internal::general_finalize(d_fwd, kmax, symmetric, d_tables, d_valid_kmax, st);
-    DISPATCH_K(kmax, launch_finalize<K>(d_fwd, symmetric, d_tables, d_valid_kmax, st));
+    const LocalFwd f{reinterpret_cast<const unsigned long long*>(d_fwd)};
+    DISPATCH_K(kmax, (launch_finalize<K, LocalFwd>(f, symmetric, d_tables, d_valid_kmax, st)));
+}
+
+int frisk_b200_finalize_tables_peers(const uint64_t* const* d_fwd_peers, int world, int kmax, int symmetric,
+                                     uint64_t* d_tables, uint64_t* d_valid_kmax, void* stream) {
+    if (!d_fwd_peers || !d_tables || world < 1) return FRISK_E_INVALID;
+    int rc = check_k(1, kmax);
+    if (rc) return rc;
+    if (world > kMaxPeers || kmax > FRISK_B200_FAST_K) return FRISK_E_UNSUPPORTED;
+    PeerFwd f;
+    f.n = world;
+    for (int q = 0; q < kMaxPeers; ++q) f.p[q] = nullptr;
+    for (int q = 0; q < world; ++q) {
+        if (!d_fwd_peers[q]) return FRISK_E_INVALID;
+        f.p[q] = reinterpret_cast<const unsigned long long*>(d_fwd_peers[q]);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_K(kmax, (launch_finalize<K, PeerFwd>(f, symmetric, d_tables, d_valid_kmax, st)));
 }
 
 int frisk_b200_genome_ivom(const uint64_t* d_tables, int kmin, int kmax, int64_t genome_space, double* d_ig, void* stream) {
@@ -1516,6 +1571,9 @@ int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const ui
     int rc = check_k(kmin, kmax);
     if (rc) return rc;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    int dev_ = 0;
+    CK(cudaGetDevice(&dev_));
+    std::lock_guard<std::mutex> lock(g_run_mu[dev_ & 63]);
     cudaStream_t st = (cudaStream_t)stream;
     CopyCtx* cc = nullptr;
     if ((rc = copy_ctx(&cc))) return rc;
@@ -1580,6 +1638,9 @@ int frisk_b200_run_resident(const uint32_t* d_h_codes, const uint32_t* d_h_inv, 
     int rc = check_k(kmin, kmax);
     if (rc) return rc;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    int dev_ = 0;
+    CK(cudaGetDevice(&dev_));
+    std::lock_guard<std::mutex> lock(g_run_mu[dev_ & 63]);
     void* dfwd;
     if ((rc = ws_get(6, ((size_t)frisk_b200_table_size(1, kmax) + 1) * 8, &dfwd))) return rc;
     return run_tail(d_h_codes, d_h_inv, d_h_low, h_padded_len, false, d_q_codes, d_q_inv, d_q_low, win_off, win_len, n_win,

@@ -67,15 +67,17 @@ def read_fasta_file(path: str) -> np.ndarray:
 
 
 def _decode_names(buf: np.ndarray, name_off: np.ndarray, name_len: np.ndarray) -> List[str]:
-    if len(name_off) == 0:
+    """Header tokens -> str.  All name bytes are gathered with one fancy-index (a 1 M-scaffold
+    assembly must not pay a numpy slice of a multi-GB buffer per record), then cut up."""
+    n = len(name_off)
+    if n == 0:
         return []
-    if len(name_off) > 4096:
-        # one pass over the headers only: a 1 M-scaffold assembly must not pay a Python slice of a
-        # multi-GB buffer per record
-        ends = name_off.astype(np.int64) + name_len.astype(np.int64)
-        return [buf[int(a):int(b)].tobytes().decode() for a, b in zip(name_off.astype(np.int64), ends)]
-    raw = memoryview(buf)
-    return [bytes(raw[int(a):int(a) + int(l)]).decode() for a, l in zip(name_off, name_len)]
+    lens = name_len.astype(np.int64)
+    ends = np.cumsum(lens)
+    starts = ends - lens
+    idx = np.repeat(name_off.astype(np.int64) - starts, lens) + np.arange(int(ends[-1]), dtype=np.int64)
+    flat = buf[idx].tobytes().decode()
+    return [flat[a:b] for a, b in zip(starts.tolist(), ends.tolist())]
 
 
 @dataclass

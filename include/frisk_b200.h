@@ -130,6 +130,19 @@ int frisk_b200_finalize_tables(const uint64_t *d_fwd, int kmax, int symmetric, u
                                uint64_t *d_valid_kmax, void *stream);
 
 /*
+ * frisk_b200_finalize_tables_peers: multi-GPU frisk_b200_finalize_tables with the all-reduce of the
+ * counters FUSED in: d_fwd_peers is a HOST array of `world` device pointers, the counter buffer of
+ * every rank as mapped into this process (NVLink peer mappings, e.g. the buffer_ptrs of a torch
+ * symmetric-memory allocation); the kernels read and sum them directly, so no collective and no
+ * staging copy sits between the background count and the finalised tables.  The caller must have
+ * put a cross-GPU barrier on `stream` after its frisk_b200_background calls (every rank's counters
+ * complete and visible) and must not overwrite a buffer before the following barrier (double-buffer
+ * the counters).  kmax <= 8, world <= 16; FRISK_E_UNSUPPORTED otherwise (use an all-reduce then).
+ */
+int frisk_b200_finalize_tables_peers(const uint64_t *const *d_fwd_peers, int world, int kmax, int symmetric,
+                                     uint64_t *d_tables, uint64_t *d_valid_kmax, void *stream);
+
+/*
  * frisk_b200_genome_ivom: for every kmax-mer, the un-normalised genome IVOM value of
  * IvomBuild(isGenomeIVOM=True) (F:411-450) and its log2, as pairs of doubles (4^kmax pairs).
  * It depends only on the genome tables, so it is computed once instead of once per window.
