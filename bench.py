@@ -240,10 +240,21 @@ def run_gpu(args):
     t_pack = time.perf_counter() - t0
     bases = genome.total_len
     allreduce, space = None, genome.genome_space
+    peers = None
     if world > 1:
         space = fdist.global_genome_space(space, dev)
         allreduce = fdist.make_allreduce()
-    pipe = engine.Pipeline(genome, device=dev, allreduce=allreduce, genome_space=space, **PARAMS)
+        if not args.nccl:
+            peers = fdist.PeerExchange(PARAMS["kmax"], dev)
+            ok = torch.tensor([int(peers.available)], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)                     # all ranks or none
+            if not int(ok.item()):
+                if rank == 0:
+                    print("fused peer exchange unavailable (%s): NCCL all-reduce" % peers.reason, file=sys.stderr)
+                peers = None
+    pipe = engine.Pipeline(genome, device=dev, allreduce=allreduce, genome_space=space, peers=peers, **PARAMS)
+    collective = "none" if world == 1 else ("counters summed inside the finalise kernels over NVLink peer memory" if pipe.peers is not None
+                                            else "1 NCCL all-reduce")
     n_win = len(pipe.wins)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -351,7 +362,7 @@ def run_gpu(args):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16/u64 counts + f64 scores", "data": "synthetic",
             "config": {"workload": WORKLOAD, "bases_per_gpu": bases, "windows_per_gpu": n_win,
-                       "l2": "flushed between timed steps (512 MiB write)", "parallelism": "scaffold shards x%d, 1 all-reduce" % world},
+                       "l2": "flushed between timed steps (512 MiB write)", "parallelism": "scaffold shards x%d, %s" % (world, collective)},
             "windows_per_s": all_win * args.steps / (total_ms * 1e-3),
             "stage_ms": {"background": float(stage[:, 0].mean()), "tables+ivom(+allreduce)": float(stage[:, 1].mean()),
                          "score": score_ms},
@@ -402,6 +413,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="frisk_b200", choices=["frisk_b200", "reference"])
+    ap.add_argument("--nccl", action="store_true", help="N > 1: combine the counters with an NCCL all-reduce instead of the fused peer sum")
     ap.add_argument("--profile", action="store_true", help="kernels only: skip the e2e and CPU-baseline legs (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -35,7 +35,7 @@ PROTOTYPES = {
     "frisk_b200_windows": (_i, [_p, _p, _u64, _i, _i, _i, _u64, _p, _p, _p, _p, _p, _p]),
     "frisk_b200_background": (_i, [_p, _p, _p, _u64, _u64, _i, _i, _p, _p]),
     "frisk_b200_finalize_tables": (_i, [_p, _i, _i, _p, _p, _p]),
-    "frisk_b200_finalize_tables_peers": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "frisk_b200_finalize_tables_peers": (_i, [_p, _p, _i, _i, _u64, _i, _i, _p, _p, _p]),
     "frisk_b200_kld": (_i, [_p, _p, _u64, _p, _p]),
     "frisk_b200_set_option": (_i, [C.c_char_p, _i]),
     "frisk_b200_genome_ivom": (_i, [_p, _i, _i, C.c_int64, _p, _p]),

@@ -195,15 +195,40 @@ bg_reduce_kernel(const uint32_t* __restrict__ partial, int n_parts, unsigned lon
 struct LocalFwd {
     const unsigned long long* p;
     __device__ __forceinline__ unsigned long long operator()(uint32_t i) const { return p[i]; }
+    __device__ __forceinline__ void arrive_and_wait() const {}
 };
 constexpr int kMaxPeers = 16;
 struct PeerFwd {
     const unsigned long long* p[kMaxPeers];
-    int n;
+    unsigned long long* flags[kMaxPeers];     // flags[q][r]: "rank r's counters of epoch >= value are complete", in rank q's memory
+    int n, rank;
+    unsigned long long epoch;                 // 0: the caller already synchronised the GPUs
     __device__ __forceinline__ unsigned long long operator()(uint32_t i) const {
         unsigned long long s = 0;
-        for (int q = 0; q < n; ++q) s += __ldcv(p[q] + i);       // peers wrote these before the cross-GPU barrier
+        for (int q = 0; q < n; ++q) s += __ldcv(p[q] + i);       // written before the peers' arrival below
         return s;
+    }
+    // Cross-GPU barrier folded into the first kernel that needs the peers' counters: this rank's count
+    // kernels are complete (stream order), so CTA 0 posts the epoch into every peer's flag array; every
+    // CTA then waits until all ranks have posted into ours.  A peer that never arrives (a rank died) traps
+    // after ~10 s instead of hanging the GPU.
+    __device__ __forceinline__ void arrive_and_wait() const {
+        if (epoch == 0) return;
+        if (blockIdx.x == 0 && (int)threadIdx.x < n) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[threadIdx.x] + rank), "l"(epoch) : "memory");
+        }
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            for (int q = 0; q < n; ++q) {
+                unsigned long long seen;
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags[rank] + q) : "memory");
+                    if (seen < epoch && clock64() - t0 > 20000000000ll) __trap();
+                } while (seen < epoch);
+            }
+        }
+        __syncthreads();
     }
 };
 
@@ -216,9 +241,22 @@ forward_totals_kernel(const Fwd fwd, unsigned long long* __restrict__ tables,
     __shared__ unsigned long long red[8];
     const uint32_t root = blockIdx.x, t = threadIdx.x;
     uint32_t n = pow4(K - R);                         // subtree nodes at the current order
+    // every counter this thread will need is requested up front (with peer buffers each is a round
+    // trip over NVLink: one exposed latency instead of one per level)
+    constexpr int LV = K - (R > 1 ? R : 1);           // levels below the top handled here
+    unsigned long long own[LV > 0 ? LV : 1];
     unsigned long long v = 0;
+    fwd.arrive_and_wait();
+    if (t < n) v = fwd(lvl_off(K) + root * n + t);
+    {
+        uint32_t m = n;
+#pragma unroll
+        for (int i = 0; i < LV; ++i) {
+            m >>= 2;
+            own[i] = (t < m) ? fwd(lvl_off(K - 1 - i) + root * m + t) : 0ull;
+        }
+    }
     if (t < n) {
-        v = fwd(lvl_off(K) + root * n + t);
         tables[lvl_off(K) + root * n + t] = v;
         lvl[0][t] = v;
     }
@@ -232,11 +270,13 @@ forward_totals_kernel(const Fwd fwd, unsigned long long* __restrict__ tables,
         if (sum) atomicAdd(valid_kmax, sum);
     }
     int cur = 0;
-    for (int x = K - 1; x >= (R > 1 ? R : 1); --x) {
+#pragma unroll
+    for (int i = 0; i < LV; ++i) {
+        const int x = K - 1 - i;
         n >>= 2;
         if (t < n) {
             const unsigned long long* ch = &lvl[cur][4 * t];
-            const unsigned long long f = fwd(lvl_off(x) + root * n + t) + ch[0] + ch[1] + ch[2] + ch[3];
+            const unsigned long long f = own[i] + ch[0] + ch[1] + ch[2] + ch[3];
             tables[lvl_off(x) + root * n + t] = f;
             lvl[cur ^ 1][t] = f;
         }
@@ -249,11 +289,15 @@ template <int K, typename Fwd>
 __global__ void __launch_bounds__(64)
 forward_low_kernel(const Fwd fwd, unsigned long long* __restrict__ tables) {
     constexpr int R = K > 4 ? K - 4 : 0;
+    const uint32_t t = threadIdx.x;
+    unsigned long long own[R > 1 ? R - 1 : 1];         // this thread's counter of every level, requested up front
+#pragma unroll
+    for (int x = R - 1; x >= 1; --x) own[x - 1] = (t < pow4(x)) ? fwd(lvl_off(x) + t) : 0ull;
+#pragma unroll
     for (int x = R - 1; x >= 1; --x) {
-        const uint32_t t = threadIdx.x;
         if (t < pow4(x)) {
             const unsigned long long* ch = tables + lvl_off(x + 1) + 4 * t;
-            tables[lvl_off(x) + t] = fwd(lvl_off(x) + t) + ch[0] + ch[1] + ch[2] + ch[3];
+            tables[lvl_off(x) + t] = own[x - 1] + ch[0] + ch[1] + ch[2] + ch[3];
         }
         __syncthreads();
     }
@@ -1422,18 +1466,23 @@ int frisk_b200_finalize_tables(const uint64_t* d_fwd, int kmax, int symmetric, u
     DISPATCH_K(kmax, (launch_finalize<K, LocalFwd>(f, symmetric, d_tables, d_valid_kmax, st)));
 }
 
-int frisk_b200_finalize_tables_peers(const uint64_t* const* d_fwd_peers, int world, int kmax, int symmetric,
-                                     uint64_t* d_tables, uint64_t* d_valid_kmax, void* stream) {
-    if (!d_fwd_peers || !d_tables || world < 1) return FRISK_E_INVALID;
+int frisk_b200_finalize_tables_peers(const uint64_t* const* d_fwd_peers, uint64_t* const* d_flag_peers, int rank, int world,
+                                     uint64_t epoch, int kmax, int symmetric, uint64_t* d_tables, uint64_t* d_valid_kmax,
+                                     void* stream) {
+    if (!d_fwd_peers || !d_tables || world < 1 || rank < 0 || rank >= world) return FRISK_E_INVALID;
+    if (d_flag_peers && epoch == 0) return FRISK_E_INVALID;
     int rc = check_k(1, kmax);
     if (rc) return rc;
     if (world > kMaxPeers || kmax > FRISK_B200_FAST_K) return FRISK_E_UNSUPPORTED;
     PeerFwd f;
     f.n = world;
-    for (int q = 0; q < kMaxPeers; ++q) f.p[q] = nullptr;
+    f.rank = rank;
+    f.epoch = d_flag_peers ? epoch : 0;
+    for (int q = 0; q < kMaxPeers; ++q) { f.p[q] = nullptr; f.flags[q] = nullptr; }
     for (int q = 0; q < world; ++q) {
-        if (!d_fwd_peers[q]) return FRISK_E_INVALID;
+        if (!d_fwd_peers[q] || (d_flag_peers && !d_flag_peers[q])) return FRISK_E_INVALID;
         f.p[q] = reinterpret_cast<const unsigned long long*>(d_fwd_peers[q]);
+        if (d_flag_peers) f.flags[q] = reinterpret_cast<unsigned long long*>(d_flag_peers[q]);
     }
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_K(kmax, (launch_finalize<K, PeerFwd>(f, symmetric, d_tables, d_valid_kmax, st)));

@@ -15,6 +15,7 @@ tables redundantly and scores its own windows.  No other exchange exists on the 
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -56,6 +57,66 @@ def make_allreduce(group=None):
     return hook
 
 
+class PeerExchange:
+    """The all-reduce of the counters FUSED into the finalise kernels (frisk_b200_finalize_tables_peers):
+    every rank's counter buffer lives in torch symmetric memory (CUDA IPC peer mappings over NVLink /
+    NVSwitch -- torch is the plumbing: allocation, handle exchange, the cross-GPU stream barrier), and
+    the kernels that marginalise the counters read and sum all ranks' buffers directly.  Two buffers
+    alternate so that a rank may start counting the next genome while a slower peer still reads the
+    previous one.  Falls back (``available`` False) when symmetric memory cannot be set up; callers
+    then use ``make_allreduce``."""
+
+    def __init__(self, kmax: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self.available = False
+        self.reason = ""
+        self.parity = 0
+        self.world = dist.get_world_size(group)
+        self.tsz = _lib.table_size(1, kmax)
+        self.stride = (self.tsz + 15) // 16 * 16          # int64 elements per buffer (128-byte aligned)
+        if kmax > 8 or self.world > 16:
+            self.reason = "kmax > 8 or world > 16"
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm
+            pg = group if group is not None else dist.group.WORLD
+            self.rank = dist.get_rank(group)
+            self.epoch = 0
+            # [counters, even epochs | counters, odd epochs | one arrival flag per rank]
+            self.buf = symm.empty(2 * self.stride + 16, dtype=torch.int64, device=device)
+            self.hdl = symm.rendezvous(self.buf, pg)
+            ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+            assert len(ptrs) == self.world and all(ptrs)
+            self.ptr_arrays = []
+            for par in (0, 1):
+                arr = (C.c_void_p * self.world)(*[C.c_void_p(p + par * self.stride * 8) for p in ptrs])
+                self.ptr_arrays.append(arr)
+            self.flag_array = (C.c_void_p * self.world)(*[C.c_void_p(p + 2 * self.stride * 8) for p in ptrs])
+            self.buf.zero_()
+            torch.cuda.synchronize(device)
+            dist.barrier(group)                         # every rank's flags are zero before anyone posts
+            self.available = True
+        except Exception as e:      # no P2P / no symmetric-memory backend in this build
+            self.reason = "%s: %s" % (type(e).__name__, e)
+
+    def local(self):
+        """This rank's counter buffer for the current step (a view of the symmetric allocation)."""
+        a = self.parity * self.stride
+        return self.buf[a:a + self.tsz]
+
+    def finalize(self, kmax: int, d_tables, d_valid, stream_ptr):
+        """The fused barrier + sum + finalise (the GPUs synchronise inside the first kernel).  Flips the buffer."""
+        from . import _lib
+        self.epoch += 1
+        rc = _lib.lib().frisk_b200_finalize_tables_peers(self.ptr_arrays[self.parity], self.flag_array, self.rank, self.world,
+                                                         self.epoch, kmax, 1, C.c_void_p(int(d_tables.data_ptr())),
+                                                         C.c_void_p(int(d_valid.data_ptr())), stream_ptr)
+        _lib.check(rc, "frisk_b200_finalize_tables_peers")
+        self.parity ^= 1
+
+
 def reduce_counts_cpu(tables: np.ndarray, genome_space: int, group=None) -> Tuple[np.ndarray, int]:
     """Same reduction on host arrays (gloo); used by the CPU world_size-2 tests of the sharding logic."""
     import torch
@@ -66,7 +127,7 @@ def reduce_counts_cpu(tables: np.ndarray, genome_space: int, group=None) -> Tupl
     return out[:-1].astype(np.uint64), int(out[-1])
 
 
-def score_sharded(scaffolds, group=None, device=None, **params):
+def score_sharded(scaffolds, group=None, device=None, fused: bool = True, **params):
     """Multi-GPU hot path, one call per rank: this rank packs and scores its own scaffolds against
     the background of ALL ranks' scaffolds (one NCCL all-reduce inside the pipeline).
 
@@ -81,9 +142,11 @@ def score_sharded(scaffolds, group=None, device=None, **params):
     mine = shard_scaffolds([len(s) for _, s in scaffolds], world)[rank]
     genome = engine.PackedGenome.from_scaffolds([scaffolds[i] for i in mine], pinned=True)
     space = global_genome_space(genome.genome_space, device, group)
-    pipe = engine.Pipeline(genome, device=device, allreduce=make_allreduce(group), genome_space=space, **params)
+    peers = PeerExchange(params.get("kmax", 8), device, group) if fused else None
+    pipe = engine.Pipeline(genome, device=device, allreduce=make_allreduce(group), genome_space=space, peers=peers, **params)
     pipe.enqueue()
     res = pipe.result()
+    res.collective = "fused peer sum (NVLink)" if pipe.peers is not None else "NCCL all-reduce"
     # totalLen and nnTotal are sums over scaffolds; exMax = (all kmax-word start positions) - (valid
     # kmax-words), where the valid count finalised from the all-reduced counters is already global
     kmax = pipe.kmax
@@ -141,7 +204,7 @@ def split_windows(lengths: np.ndarray, world: int) -> List[Tuple[int, int]]:
     return [(cuts[r], max(cuts[r], cuts[r + 1])) for r in range(world)]
 
 
-def score_balanced(fasta_text, group=None, device=None, host_text=None, **params):
+def score_balanced(fasta_text, group=None, device=None, host_text=None, fused: bool = True, **params):
     """Multi-GPU hot path on one replicated genome (see the module docstring).  Returns this rank's
     HotPathResult (global tables and meta, this rank's slice of the rows) and its window range."""
     import torch
@@ -154,11 +217,14 @@ def score_balanced(fasta_text, group=None, device=None, host_text=None, **params
     dh = engine.DeviceGenome.from_fasta_bytes(host_text, device) if host_text is not None else dq
     wins_all = dq.host.windows(params.get("w", 5000), params.get("step", 2500), params.get("scaffolds_all", False))
     a, b = split_windows(wins_all.length, world)[rank]
+    peers = PeerExchange(params.get("kmax", 8), device, group) if fused else None
     pipe = engine.Pipeline(dq, dh if dh is not dq else None, device=device, allreduce=make_allreduce(group),
                            genome_space=dh.host.genome_space, wins=wins_all.slice(a, b),
-                           bg_range=split_base_range(dh.host.padded_len, world)[rank], **params)
+                           bg_range=split_base_range(dh.host.padded_len, world)[rank], peers=peers, **params)
     pipe.enqueue()
-    return pipe.result(), (a, b)
+    res = pipe.result()
+    res.collective = "fused peer sum (NVLink)" if pipe.peers is not None else "NCCL all-reduce"
+    return res, (a, b)
 
 
 def gather_rows_in_order(res, group=None, dst: int = 0):

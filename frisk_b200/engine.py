@@ -334,6 +334,7 @@ class HotPathResult:
     win_index: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # candidate index of each row
     row_scaf: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))   # scaffold index (in the query) of each row
     win_tables: Optional[np.ndarray] = None   # uint16 [n, table_size(kmin,kmax)] when dump=True
+    collective: str = ""                      # multi-GPU: how the counters were combined
 
     def raise_reference_errors(self) -> None:
         """The reference aborts on the first window that raises; mirror that when asked."""
@@ -375,7 +376,7 @@ class Pipeline:
                  w: int = 5000, step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False,
                  rip: bool = True, device="cuda:0", dump: bool = False, allreduce=None,
                  genome_space: Optional[int] = None, wins: Optional[WindowList] = None,
-                 bg_range: Optional[Tuple[int, int]] = None):
+                 bg_range: Optional[Tuple[int, int]] = None, peers=None):
         import torch
         _lib.require_device()
         rc = 0 if 1 <= kmin <= kmax else _lib.E_INVALID
@@ -390,6 +391,9 @@ class Pipeline:
         self.query, self.host = query, host
         self.kmin, self.kmax, self.mask_host, self.rip = kmin, kmax, mask_host, rip
         self.allreduce = allreduce
+        # dist.PeerExchange: the all-reduce fused into the finalise kernels (counters summed straight
+        # out of every rank's buffer over NVLink); `allreduce` is then unused
+        self.peers = peers if (peers is not None and peers.available) else None
         self.genome_space = self.host.genome_space if genome_space is None else int(genome_space)
         self.wins = wins if wins is not None else query.windows(w, step, scaffolds_all)
         # base range of the host planes this pipeline counts (multi-GPU: a rank's slice; the last
@@ -425,17 +429,21 @@ class Pipeline:
 
         with torch.cuda.device(dev):
             st = _stream_ptr(dev)
-            self.d_fwd.zero_()
+            d_fwd = self.peers.local() if self.peers is not None else self.d_fwd
+            d_fwd.zero_()
             mark()
             dh = self.dh
             _lib.check(L.frisk_b200_background(_ptr(dh.codes), _ptr(dh.inv), _ptr(dh.low), self.bg_range[0], self.bg_range[1],
-                                               self.kmax, int(self.mask_host), _ptr(self.d_fwd), st), "frisk_b200_background")
+                                               self.kmax, int(self.mask_host), _ptr(d_fwd), st), "frisk_b200_background")
             mark()
             space = self.genome_space
-            if self.allreduce is not None:
-                space = self.allreduce(self.d_fwd, space)
-            _lib.check(L.frisk_b200_finalize_tables(_ptr(self.d_fwd), self.kmax, 1, _ptr(self.d_tables), _ptr(self.d_valid), st),
-                       "frisk_b200_finalize_tables")
+            if self.peers is not None:
+                self.peers.finalize(self.kmax, self.d_tables, self.d_valid, st)
+            else:
+                if self.allreduce is not None:
+                    space = self.allreduce(self.d_fwd, space)
+                _lib.check(L.frisk_b200_finalize_tables(_ptr(self.d_fwd), self.kmax, 1, _ptr(self.d_tables), _ptr(self.d_valid), st),
+                           "frisk_b200_finalize_tables")
             _lib.check(L.frisk_b200_genome_ivom(_ptr(self.d_tables), self.kmin, self.kmax, int(space), _ptr(self.d_ig), st),
                        "frisk_b200_genome_ivom")
             mark()

@@ -134,13 +134,20 @@ int frisk_b200_finalize_tables(const uint64_t *d_fwd, int kmax, int symmetric, u
  * counters FUSED in: d_fwd_peers is a HOST array of `world` device pointers, the counter buffer of
  * every rank as mapped into this process (NVLink peer mappings, e.g. the buffer_ptrs of a torch
  * symmetric-memory allocation); the kernels read and sum them directly, so no collective and no
- * staging copy sits between the background count and the finalised tables.  The caller must have
- * put a cross-GPU barrier on `stream` after its frisk_b200_background calls (every rank's counters
- * complete and visible) and must not overwrite a buffer before the following barrier (double-buffer
- * the counters).  kmax <= 8, world <= 16; FRISK_E_UNSUPPORTED otherwise (use an all-reduce then).
+ * staging copy sits between the background count and the finalised tables.
+ * Synchronisation between the GPUs is folded into the first kernel: d_flag_peers (host array of
+ * `world` device pointers, NULLable) names, per rank, an array of `world` uint64 flags in that rank's
+ * peer-mapped memory, zero before the first call; `epoch` must be 1, 2, 3, ... on successive calls (the
+ * same sequence on every rank).  Rank r posts `epoch` into flags[q][r] of every peer q and waits for
+ * flags[r][*] >= epoch (a peer that never arrives traps the kernel after ~10 s instead of hanging).
+ * With d_flag_peers == NULL the caller must have put its own cross-GPU barrier on `stream` after its
+ * frisk_b200_background calls.  Either way a counter buffer must not be rewritten before the call after
+ * next (alternate between two buffers).  kmax <= 8, world <= 16; FRISK_E_UNSUPPORTED otherwise (use an
+ * all-reduce then).
  */
-int frisk_b200_finalize_tables_peers(const uint64_t *const *d_fwd_peers, int world, int kmax, int symmetric,
-                                     uint64_t *d_tables, uint64_t *d_valid_kmax, void *stream);
+int frisk_b200_finalize_tables_peers(const uint64_t *const *d_fwd_peers, uint64_t *const *d_flag_peers, int rank,
+                                     int world, uint64_t epoch, int kmax, int symmetric, uint64_t *d_tables,
+                                     uint64_t *d_valid_kmax, void *stream);
 
 /*
  * frisk_b200_genome_ivom: for every kmax-mer, the un-normalised genome IVOM value of

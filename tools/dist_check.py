@@ -17,8 +17,21 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     scaffolds = synth.make("C2", 0.02, seed=5) + synth.make("edge")
     params = dict(kmin=1, kmax=8, w=5000, step=2500, mask_host=False, scaffolds_all=True, rip=True)
-    res, mine = fdist.score_sharded(scaffolds, **params)
+    res, mine = fdist.score_sharded(scaffolds, fused=False, **params)          # NCCL all-reduce
     gathered = fdist.gather_rows(res, mine)
+    res_f, mine_f = fdist.score_sharded(scaffolds, fused=True, **params)       # all-reduce fused into the finalise kernels
+    gathered_f = fdist.gather_rows(res_f, mine_f)
+    if dist.get_rank() == 0:
+        print("collectives:", res.collective, "|", res_f.collective)
+        assert np.array_equal(res_f.tables, res.tables), "fused peer sum != NCCL all-reduce"
+        assert res_f.meta == res.meta
+        assert np.array_equal(gathered_f[2], gathered[2], equal_nan=True)
+        for _ in range(3):                                                     # buffer parity flips every pass
+            again, _m = fdist.score_sharded(scaffolds, fused=True, **params)
+            assert np.array_equal(again.tables, res.tables)
+    else:
+        for _ in range(3):
+            fdist.score_sharded(scaffolds, fused=True, **params)
     ok = True
     if dist.get_rank() == 0:
         from oracle import c_oracle
