@@ -207,6 +207,27 @@ int frisk_b200_pack(const char* src, const uint64_t* src_off, const uint64_t* sr
     return FRISK_OK;
 }
 
+int frisk_b200_plane_sparse(const uint32_t* plane, uint64_t n_words, uint64_t cap, uint32_t* idx, uint32_t* val,
+                            uint64_t* n_nonzero) {
+    if (!n_nonzero || (!plane && n_words) || n_words > 0xffffffffull) return FRISK_E_INVALID;
+    uint64_t n = 0;
+    const uint64_t* p64 = reinterpret_cast<const uint64_t*>(plane);     // planes are 16-byte aligned (padded_len % 128 == 0)
+    for (uint64_t w = 0; w + 1 < n_words; w += 2) {
+        if (p64[w >> 1] == 0) continue;                                  // two words at a time: most of the plane is zero
+        for (uint64_t k = w; k < w + 2; ++k) {
+            if (!plane[k]) continue;
+            if (n < cap && idx && val) { idx[n] = (uint32_t)k; val[n] = plane[k]; }
+            ++n;
+        }
+    }
+    if ((n_words & 1) && plane[n_words - 1]) {
+        if (n < cap && idx && val) { idx[n] = (uint32_t)(n_words - 1); val[n] = plane[n_words - 1]; }
+        ++n;
+    }
+    *n_nonzero = n;
+    return (n > cap && idx && val) ? FRISK_E_CAPACITY : FRISK_OK;
+}
+
 int frisk_b200_windows(const uint64_t* scaf_len, const uint64_t* scaf_off, uint64_t n_scaf, int w, int step,
                        int scaffolds_all, uint64_t cap, uint64_t* win_off, uint32_t* win_len, uint32_t* win_scaf,
                        int64_t* win_start, int64_t* win_stop, uint64_t* n_windows) {

@@ -1608,13 +1608,48 @@ int copy_ctx(CopyCtx** out) {
 }
 }  // namespace
 
-int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const uint32_t* h_low, uint64_t h_padded_len,
-                        const uint32_t* q_codes, const uint32_t* q_inv, const uint32_t* q_low, uint64_t q_padded_len,
-                        const uint64_t* win_off, const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len,
-                        int kmin, int kmax, int mask_host, int want_rip, int64_t genome_space, double* rows_out,
-                        uint32_t* status_out, uint64_t* tables_out, uint64_t* valid_kmax_out, void* stream) {
-    if (!h_codes || !h_inv || !q_codes || !q_inv || (h_padded_len & 127) || (q_padded_len & 127) || h_padded_len < 128 ||
-        q_padded_len < 128)
+// One genome's planes in host memory; the invalid plane either dense or as its non-zero words.
+struct HostPlanes {
+    const uint32_t* codes;
+    const uint32_t* inv;            // dense (padded_len / 32 words) or nullptr
+    const uint32_t* inv_idx;        // sparse: word indices ...
+    const uint32_t* inv_val;        // ... and the words
+    uint64_t inv_n;
+    const uint32_t* low;            // nullable
+    uint64_t padded_len;
+};
+
+__global__ void __launch_bounds__(256)
+plane_scatter_kernel(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ val, uint64_t n, uint32_t* __restrict__ plane) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    if (i < n) plane[idx[i]] = val[i];
+}
+
+// invalid plane of `hp` -> d_inv on the copy stream (sparse: zero fill + pairs + scatter)
+static int upload_inv(const HostPlanes& hp, void* d_inv, int slot_idx, int slot_val, cudaStream_t copy) {
+    if (hp.inv) return FRISK_OK;                      // dense: goes up with the code chunks
+    CK(cudaMemsetAsync(d_inv, 0, hp.padded_len / 8, copy));
+    if (hp.inv_n) {
+        void *di, *dv;
+        int rc;
+        if ((rc = ws_get(slot_idx, hp.inv_n * 4, &di))) return rc;
+        if ((rc = ws_get(slot_val, hp.inv_n * 4, &dv))) return rc;
+        CK(cudaMemcpyAsync(di, hp.inv_idx, hp.inv_n * 4, cudaMemcpyHostToDevice, copy));
+        CK(cudaMemcpyAsync(dv, hp.inv_val, hp.inv_n * 4, cudaMemcpyHostToDevice, copy));
+        plane_scatter_kernel<<<(unsigned)((hp.inv_n + 255) / 256), 256, 0, copy>>>((const uint32_t*)di, (const uint32_t*)dv,
+                                                                                  hp.inv_n, (uint32_t*)d_inv);
+        CK(cudaGetLastError());
+    }
+    return FRISK_OK;
+}
+
+static int run_host_impl(const HostPlanes& h, const HostPlanes& q, bool same, const uint64_t* win_off, const uint32_t* win_len,
+                         uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host, int want_rip,
+                         int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
+                         uint64_t* valid_kmax_out, void* stream) {
+    const uint64_t h_padded_len = h.padded_len, q_padded_len = q.padded_len;
+    if (!h.codes || !q.codes || (!h.inv && !h.inv_idx && h.inv_n) || (!q.inv && !q.inv_idx && q.inv_n) ||
+        (h_padded_len & 127) || (q_padded_len & 127) || h_padded_len < 128 || q_padded_len < 128)
         return FRISK_E_INVALID;
     if (n_win && (!win_off || !win_len || !rows_out || !status_out)) return FRISK_E_INVALID;
     int rc = check_k(kmin, kmax);
@@ -1626,12 +1661,11 @@ int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const ui
     cudaStream_t st = (cudaStream_t)stream;
     CopyCtx* cc = nullptr;
     if ((rc = copy_ctx(&cc))) return rc;
-    const bool same = (h_codes == q_codes) && (h_inv == q_inv) && (h_padded_len == q_padded_len);
     const size_t tsz = (size_t)frisk_b200_table_size(1, kmax);
     void *dhc, *dhi, *dhl = nullptr, *dqc, *dqi, *dql = nullptr, *dfwd;
     if ((rc = ws_get(0, h_padded_len / 4, &dhc))) return rc;
     if ((rc = ws_get(1, h_padded_len / 8, &dhi))) return rc;
-    if (h_low && (rc = ws_get(2, h_padded_len / 8, &dhl))) return rc;
+    if (h.low && (rc = ws_get(2, h_padded_len / 8, &dhl))) return rc;
     if ((rc = ws_get(6, (tsz + 1) * 8, &dfwd))) return rc;
     CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, st));
     // The planes go up in chunks on the copy stream; the background count of a chunk starts as soon
@@ -1639,6 +1673,7 @@ int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const ui
     // so only the last chunk's count is not hidden behind PCIe.
     CK(cudaEventRecord(cc->ev[kMaxChunks], st));
     CK(cudaStreamWaitEvent(cc->copy, cc->ev[kMaxChunks], 0));          // order behind earlier work on `stream`
+    if ((rc = upload_inv(h, dhi, 15, 16, cc->copy))) return rc;
     uint64_t n_chunks = (h_padded_len + (8ull << 20) - 1) / (8ull << 20);
     if (n_chunks > (uint64_t)kMaxChunks) n_chunks = kMaxChunks;
     const uint64_t chunk = ((h_padded_len + n_chunks - 1) / n_chunks + 127) & ~127ull;
@@ -1646,9 +1681,9 @@ int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const ui
     for (uint64_t c = 0; c < n_chunks; ++c) {
         const uint64_t b0 = c * chunk, b1 = (b0 + chunk < h_padded_len) ? b0 + chunk : h_padded_len;
         if (b0 >= b1) break;
-        CK(cudaMemcpyAsync((char*)dhc + b0 / 4, (const char*)h_codes + b0 / 4, (b1 - b0) / 4, cudaMemcpyHostToDevice, cc->copy));
-        CK(cudaMemcpyAsync((char*)dhi + b0 / 8, (const char*)h_inv + b0 / 8, (b1 - b0) / 8, cudaMemcpyHostToDevice, cc->copy));
-        if (h_low) CK(cudaMemcpyAsync((char*)dhl + b0 / 8, (const char*)h_low + b0 / 8, (b1 - b0) / 8, cudaMemcpyHostToDevice, cc->copy));
+        CK(cudaMemcpyAsync((char*)dhc + b0 / 4, (const char*)h.codes + b0 / 4, (b1 - b0) / 4, cudaMemcpyHostToDevice, cc->copy));
+        if (h.inv) CK(cudaMemcpyAsync((char*)dhi + b0 / 8, (const char*)h.inv + b0 / 8, (b1 - b0) / 8, cudaMemcpyHostToDevice, cc->copy));
+        if (h.low) CK(cudaMemcpyAsync((char*)dhl + b0 / 8, (const char*)h.low + b0 / 8, (b1 - b0) / 8, cudaMemcpyHostToDevice, cc->copy));
         CK(cudaEventRecord(cc->ev[c], cc->copy));
         CK(cudaStreamWaitEvent(st, cc->ev[c], 0));
         const uint64_t upto = (b1 == h_padded_len) ? h_padded_len - 32 : b1 - 128;
@@ -1663,15 +1698,45 @@ int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const ui
     else {
         if ((rc = ws_get(3, q_padded_len / 4, &dqc))) return rc;
         if ((rc = ws_get(4, q_padded_len / 8, &dqi))) return rc;
-        if (q_low && (rc = ws_get(5, q_padded_len / 8, &dql))) return rc;
-        CK(cudaMemcpyAsync(dqc, q_codes, q_padded_len / 4, cudaMemcpyHostToDevice, cc->copy));
-        CK(cudaMemcpyAsync(dqi, q_inv, q_padded_len / 8, cudaMemcpyHostToDevice, cc->copy));
-        if (q_low) CK(cudaMemcpyAsync(dql, q_low, q_padded_len / 8, cudaMemcpyHostToDevice, cc->copy));
+        if (q.low && (rc = ws_get(5, q_padded_len / 8, &dql))) return rc;
+        CK(cudaMemcpyAsync(dqc, q.codes, q_padded_len / 4, cudaMemcpyHostToDevice, cc->copy));
+        if (q.inv) CK(cudaMemcpyAsync(dqi, q.inv, q_padded_len / 8, cudaMemcpyHostToDevice, cc->copy));
+        else if ((rc = upload_inv(q, dqi, 17, 18, cc->copy))) return rc;
+        if (q.low) CK(cudaMemcpyAsync(dql, q.low, q_padded_len / 8, cudaMemcpyHostToDevice, cc->copy));
     }
     return run_tail((const uint32_t*)dhc, (const uint32_t*)dhi, (const uint32_t*)dhl, h_padded_len, true,
                     (const uint32_t*)dqc, (const uint32_t*)dqi, (const uint32_t*)dql, win_off, win_len, n_win, max_win_len,
                     kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out, valid_kmax_out, dfwd, st,
                     cc->copy, cc->ev[kMaxChunks + 1]);
+}
+
+int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const uint32_t* h_low, uint64_t h_padded_len,
+                        const uint32_t* q_codes, const uint32_t* q_inv, const uint32_t* q_low, uint64_t q_padded_len,
+                        const uint64_t* win_off, const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len,
+                        int kmin, int kmax, int mask_host, int want_rip, int64_t genome_space, double* rows_out,
+                        uint32_t* status_out, uint64_t* tables_out, uint64_t* valid_kmax_out, void* stream) {
+    if (!h_inv || !q_inv) return FRISK_E_INVALID;
+    const HostPlanes h{h_codes, h_inv, nullptr, nullptr, 0, h_low, h_padded_len};
+    const HostPlanes q{q_codes, q_inv, nullptr, nullptr, 0, q_low, q_padded_len};
+    const bool same = (h_codes == q_codes) && (h_inv == q_inv) && (h_padded_len == q_padded_len);
+    return run_host_impl(h, q, same, win_off, win_len, n_win, max_win_len, kmin, kmax, mask_host, want_rip, genome_space,
+                         rows_out, status_out, tables_out, valid_kmax_out, stream);
+}
+
+int frisk_b200_run_host_sparse(const uint32_t* h_codes, const uint32_t* h_inv_idx, const uint32_t* h_inv_val, uint64_t h_inv_n,
+                               const uint32_t* h_low, uint64_t h_padded_len, const uint32_t* q_codes,
+                               const uint32_t* q_inv_idx, const uint32_t* q_inv_val, uint64_t q_inv_n, const uint32_t* q_low,
+                               uint64_t q_padded_len, const uint64_t* win_off, const uint32_t* win_len, uint64_t n_win,
+                               uint32_t max_win_len, int kmin, int kmax, int mask_host, int want_rip, int64_t genome_space,
+                               double* rows_out, uint32_t* status_out, uint64_t* tables_out, uint64_t* valid_kmax_out,
+                               void* stream) {
+    if ((h_inv_n && (!h_inv_idx || !h_inv_val)) || (q_inv_n && (!q_inv_idx || !q_inv_val))) return FRISK_E_INVALID;
+    if (h_padded_len / 32 > 0xffffffffull || q_padded_len / 32 > 0xffffffffull) return FRISK_E_UNSUPPORTED;   // 32-bit word indices
+    const HostPlanes h{h_codes, nullptr, h_inv_idx, h_inv_val, h_inv_n, h_low, h_padded_len};
+    const HostPlanes q{q_codes, nullptr, q_inv_idx, q_inv_val, q_inv_n, q_low, q_padded_len};
+    const bool same = (h_codes == q_codes) && (h_inv_idx == q_inv_idx) && (h_inv_n == q_inv_n) && (h_padded_len == q_padded_len);
+    return run_host_impl(h, q, same, win_off, win_len, n_win, max_win_len, kmin, kmax, mask_host, want_rip, genome_space,
+                         rows_out, status_out, tables_out, valid_kmax_out, stream);
 }
 
 int frisk_b200_run_resident(const uint32_t* d_h_codes, const uint32_t* d_h_inv, const uint32_t* d_h_low,

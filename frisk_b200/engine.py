@@ -183,6 +183,22 @@ class PackedGenome:
                    "frisk_b200_windows")
         return WindowList(off, ln, sc, st, sp)
 
+    def inv_sparse(self) -> Tuple[np.ndarray, np.ndarray]:
+        """The invalid plane's non-zero words as (word index, word) arrays (frisk_b200_plane_sparse),
+        page-locked when the planes are; computed once."""
+        if getattr(self, "_inv_sparse", None) is None:
+            L = _lib.lib()
+            n = C.c_uint64(0)
+            nw = self.inv.shape[0]
+            _lib.check(L.frisk_b200_plane_sparse(_ptr(self.inv), nw, 0, None, None, C.byref(n)), "frisk_b200_plane_sparse")
+            cap = int(n.value)
+            idx = _alloc(max(cap, 1), np.uint32, self.pinned)
+            val = _alloc(max(cap, 1), np.uint32, self.pinned)
+            _lib.check(L.frisk_b200_plane_sparse(_ptr(self.inv), nw, cap, _ptr(idx), _ptr(val), C.byref(n)),
+                       "frisk_b200_plane_sparse")
+            self._inv_sparse = (idx[:cap], val[:cap])
+        return self._inv_sparse
+
     def ex_max(self, kmax: int, valid_kmax: int) -> int:
         """exMax (F:344): kmax-words that contain an invalid character."""
         possible = np.maximum(self.scaf_len.astype(np.int64) - kmax + 1, 0).sum()
@@ -537,7 +553,8 @@ def run_sweep(query, kmaxes: Sequence[int] = tuple(range(1, 9)), kmin: int = 1, 
 
 def run_host(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1, kmax: int = 8, w: int = 5000,
              step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True,
-             wins: Optional[WindowList] = None, out=None, stream: int = 0, assemble_result: bool = True):
+             wins: Optional[WindowList] = None, out=None, stream: int = 0, assemble_result: bool = True,
+             sparse: Optional[bool] = None):
     """Same path as ``run`` but as ONE C call from host buffers (frisk_b200_run_host): H2D of the
     planes and window list, all kernels, D2H of rows/status/tables.  Used for end-to-end timing;
     ``assemble_result=False`` returns the raw HostOutputs (rows of every candidate window, status
@@ -549,12 +566,25 @@ def run_host(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int
     n = len(wins)
     if out is None:
         out = HostOutputs(n, kmax)
-    rc = _lib.lib().frisk_b200_run_host(
-        _ptr(host.codes), _ptr(host.inv), _ptr(host.low), host.padded_len,
-        _ptr(query.codes), _ptr(query.inv), _ptr(query.low), query.padded_len,
-        _ptr(wins.off), _ptr(wins.length), n, wins.max_len, kmin, kmax, int(mask_host), int(rip),
-        int(host.genome_space), _ptr(out.rows), _ptr(out.status), _ptr(out.tables), _ptr(out.valid), C.c_void_p(stream))
-    _lib.check(rc, "frisk_b200_run_host")
+    # ``sparse``: upload the (nearly empty) invalid planes as their non-zero words
+    # (frisk_b200_run_host_sparse); None = whenever that is at most a quarter of the dense plane
+    if sparse is None:
+        sparse = all(8 * len(g.inv_sparse()[0]) <= g.inv.nbytes // 4 and g.padded_len // 32 < 2 ** 32 for g in {id(host): host, id(query): query}.values())
+    if sparse:
+        (hi, hv), (qi, qv) = host.inv_sparse(), query.inv_sparse()
+        rc = _lib.lib().frisk_b200_run_host_sparse(
+            _ptr(host.codes), _ptr(hi), _ptr(hv), len(hi), _ptr(host.low), host.padded_len,
+            _ptr(query.codes), _ptr(qi), _ptr(qv), len(qi), _ptr(query.low), query.padded_len,
+            _ptr(wins.off), _ptr(wins.length), n, wins.max_len, kmin, kmax, int(mask_host), int(rip),
+            int(host.genome_space), _ptr(out.rows), _ptr(out.status), _ptr(out.tables), _ptr(out.valid), C.c_void_p(stream))
+        _lib.check(rc, "frisk_b200_run_host_sparse")
+    else:
+        rc = _lib.lib().frisk_b200_run_host(
+            _ptr(host.codes), _ptr(host.inv), _ptr(host.low), host.padded_len,
+            _ptr(query.codes), _ptr(query.inv), _ptr(query.low), query.padded_len,
+            _ptr(wins.off), _ptr(wins.length), n, wins.max_len, kmin, kmax, int(mask_host), int(rip),
+            int(host.genome_space), _ptr(out.rows), _ptr(out.status), _ptr(out.tables), _ptr(out.valid), C.c_void_p(stream))
+        _lib.check(rc, "frisk_b200_run_host")
     if not assemble_result:
         return out
     return assemble(query, host, wins, out.tables, int(out.valid[0]), out.rows[:n], out.status[:n], kmin, kmax)

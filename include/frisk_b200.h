@@ -200,6 +200,24 @@ int frisk_b200_run_host(const uint32_t *h_codes, const uint32_t *h_inv, const ui
                         uint32_t *status_out, uint64_t *tables_out, uint64_t *valid_kmax_out, void *stream);
 
 /*
+ * Sparse form of a 1-bit plane: its non-zero 32-base words as (word index, word) pairs.  Assemblies
+ * have few unresolved bases, so the invalid plane -- a third of the packed bytes -- is nearly all
+ * zeros; frisk_b200_run_host_sparse uploads the pairs instead and expands them on the device, which
+ * takes that third off the PCIe transfer.  frisk_b200_plane_sparse (host) extracts the pairs: arrays
+ * may be NULL to only count; *n_nonzero always receives the count; FRISK_E_CAPACITY if cap is too small.
+ * Planes of up to 2^32 words (137 Gbases).
+ */
+int frisk_b200_plane_sparse(const uint32_t *plane, uint64_t n_words, uint64_t cap, uint32_t *idx, uint32_t *val,
+                            uint64_t *n_nonzero);
+int frisk_b200_run_host_sparse(const uint32_t *h_codes, const uint32_t *h_inv_idx, const uint32_t *h_inv_val,
+                               uint64_t h_inv_n, const uint32_t *h_low, uint64_t h_padded_len, const uint32_t *q_codes,
+                               const uint32_t *q_inv_idx, const uint32_t *q_inv_val, uint64_t q_inv_n,
+                               const uint32_t *q_low, uint64_t q_padded_len, const uint64_t *win_off,
+                               const uint32_t *win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax,
+                               int mask_host, int want_rip, int64_t genome_space, double *rows_out, uint32_t *status_out,
+                               uint64_t *tables_out, uint64_t *valid_kmax_out, void *stream);
+
+/*
  * frisk_b200_run_resident: frisk_b200_run_host for planes that are already in device memory (e.g.
  * written by frisk_b200_fasta_pack): no plane upload; the window list still comes from, and the
  * results still go to, host memory.

@@ -56,6 +56,13 @@ def test_host_buffer_path_matches_reference_golden(eng, case):
     _check_against_golden(res, g, case + "[run_host]")
     staged = _run_case(eng, g)
     assert np.array_equal(res.rows, staged.rows, equal_nan=True), "both entry paths run the same kernels"
+    # the invalid plane uploaded dense / as its non-zero words: same bits
+    q = eng.PackedGenome.from_scaffolds(g.scaffolds(), pinned=True)
+    h = eng.PackedGenome.from_scaffolds(g.host(), pinned=True) if g.host() is not None else None
+    for sparse in (False, True):
+        alt = eng.run_host(q, h, sparse=sparse, **g.kwargs())
+        assert np.array_equal(alt.rows, res.rows, equal_nan=True) and np.array_equal(alt.tables, res.tables), sparse
+        assert alt.meta == res.meta and np.array_equal(alt.status, res.status)
 
 
 @pytest.mark.parametrize("case", ["edge_default", "edge_k2_5_w1000_i250", "edge_scaffoldsAll", "edge_k1_1", "edge_k1_9"])

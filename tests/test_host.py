@@ -138,3 +138,19 @@ def test_long_windows_are_enumerated():
     wins = g.windows(70_000, 35_000)
     assert wins.max_len == 70_000 and len(wins) == 8          # j = 0, 35k, ..., 245k (F:228): the last two jump back
     assert _lib.MAX_K == 12 and _lib.MAX_WINDOW == 0x7FFFFFFF
+
+
+def test_sparse_form_of_the_invalid_plane():
+    """frisk_b200_plane_sparse: the non-zero words of a plane, in order; rebuilding the plane from them is exact."""
+    for sc in (synth.make("edge"), synth.make("C2", 0.02), [("allN", np.full(1000, ord("N"), np.uint8))]):
+        g = engine.PackedGenome.from_scaffolds(sc)
+        idx, val = g.inv_sparse()
+        nz = np.nonzero(g.inv)[0]
+        assert np.array_equal(idx, nz.astype(np.uint32)) and np.array_equal(val, g.inv[nz])
+        rebuilt = np.zeros_like(g.inv)
+        rebuilt[idx] = val
+        assert np.array_equal(rebuilt, g.inv)
+    n = C.c_uint64(0)
+    rc = _lib.lib().frisk_b200_plane_sparse(engine._ptr(g.inv), g.inv.shape[0], 1, engine._ptr(np.zeros(1, np.uint32)),
+                                            engine._ptr(np.zeros(1, np.uint32)), C.byref(n))
+    assert rc == _lib.E_CAPACITY and n.value == len(idx)
