@@ -294,7 +294,10 @@ def run_gpu(args):
         # N = 1: exactly one C-ABI call (frisk_b200_run_host) from pinned host buffers to pinned host results
         if world == 1:
             return engine.run_host(genome, wins=wins, out=out, assemble_result=False, **PARAMS)
-        # N > 1: the same traffic through the resident pipeline (the all-reduce sits between its kernels)
+        # N > 1: this rank's share in one C call with the exchange fused in (frisk_b200_run_host_peers), or --
+        # NCCL fallback -- the same traffic through the resident pipeline (the all-reduce sits between its kernels)
+        if pipe.peers is not None:
+            return pipe.peers.run_host(genome, wins, out, space, stream_ptr=engine._stream_ptr(dev), **PARAMS)
         return pipe.step_from_host(out)
 
     if args.profile:
@@ -335,7 +338,7 @@ def run_gpu(args):
     clocks = sampler.finish(t_wall0, t_wall1)
 
     h2d = genome.plane_bytes + wins.off.nbytes + wins.length.nbytes
-    if world == 1:      # the C call uploads the invalid plane as (index, word) pairs
+    if world == 1 or pipe.peers is not None:      # the C call uploads the invalid plane as (index, word) pairs
         h2d += 8 * len(genome.inv_sparse()[0]) - genome.inv.nbytes
     d2h = n_win * 44 + _lib.table_size(1, PARAMS["kmax"]) * 8 + 8
 
@@ -383,7 +386,8 @@ def run_gpu(args):
             "limiter": committed_pipe_utilisation(),
             "e2e": {"value": (all_bases / (e2e_step_ms * 1e-3) / 1e9) if e2e_steps else None, "unit": "Gbp/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_step_ms, "steps": e2e_steps,
-                    "api": "frisk_b200_run_host_sparse (C ABI, one call; pinned host planes, invalid plane as its non-zero words)" if world == 1 else "engine.Pipeline.step_from_host (pinned host planes, NCCL all-reduce between kernels)"},
+                    "api": "frisk_b200_run_host_sparse (C ABI, one call; pinned host planes, invalid plane as its non-zero words)" if world == 1 else ("frisk_b200_run_host_peers (C ABI, one call per rank; pinned host planes, fused peer exchange)" if pipe.peers is not None
+                                else "engine.Pipeline.step_from_host (pinned host planes, NCCL all-reduce between kernels)")},
             "e2e_fasta": ({"value": all_bases / (fasta_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": fasta_ms,
                            "h2d_bytes_per_step": fasta_bytes_n + wins.off.nbytes + wins.length.nbytes, "d2h_bytes_per_step": d2h,
                            "api": "frisk_b200_fasta_open/_pack (device-side FASTA ingest) + frisk_b200_run_resident, from pinned FASTA text"}

@@ -45,6 +45,8 @@ PROTOTYPES = {
     "frisk_b200_plane_sparse": (_i, [_p, _u64, _u64, _p, _p, _p]),
     "frisk_b200_run_host_sparse": (_i, [_p, _p, _p, _u64, _p, _u64, _p, _p, _p, _u64, _p, _u64, _p, _p, _u64, C.c_uint32,
                                         _i, _i, _i, _i, C.c_int64, _p, _p, _p, _p, _p]),
+    "frisk_b200_run_host_peers": (_i, [_p, _p, _p, _u64, _p, _u64, _p, _p, _u64, C.c_uint32, _i, _i, _i, _i, C.c_int64,
+                                       _p, _p, _p, _i, _i, _u64, _p, _p, _p, _p, _p]),
     "frisk_b200_run_resident": (_i, [_p, _p, _p, _u64, _p, _p, _p, _u64, _p, _p, _u64, C.c_uint32, _i, _i, _i, _i,
                                      C.c_int64, _p, _p, _p, _p, _p]),
     "frisk_b200_fasta_open": (_i, [_p, _u64, _p, C.POINTER(C.c_void_p), C.POINTER(_u64), C.POINTER(_u64), _p]),

@@ -1541,7 +1541,16 @@ int frisk_b200_kld(const double* d_genome_ivom, const double* d_window_ivom, uin
 
 // Everything after the planes are on the device: [background], finalize, genome IVOM, window
 // upload, score, download.  `copy` (nullable) already carries the uploads this run must wait for.
-static int run_tail(const uint32_t* dhc, const uint32_t* dhi, const uint32_t* dhl, uint64_t h_padded_len, bool bg_enqueued,
+// multi-GPU: where the other ranks' counters are (frisk_b200_finalize_tables_peers); world == 0: single GPU
+struct PeerArgs {
+    uint64_t* d_fwd_local = nullptr;
+    const uint64_t* const* d_fwd_peers = nullptr;
+    uint64_t* const* d_flag_peers = nullptr;
+    int rank = 0, world = 0;
+    uint64_t epoch = 0;
+};
+
+static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* dhi, const uint32_t* dhl, uint64_t h_padded_len, bool bg_enqueued,
                     const uint32_t* dqc, const uint32_t* dqi, const uint32_t* dql, const uint64_t* win_off,
                     const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host,
                     int want_rip, int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
@@ -1568,7 +1577,9 @@ static int run_tail(const uint32_t* dhc, const uint32_t* dhi, const uint32_t* dh
         if (rc) return rc;
     }
     uint64_t* dvalid = (uint64_t*)dtab + tsz;
-    rc = frisk_b200_finalize_tables((const uint64_t*)dfwd, kmax, 1, (uint64_t*)dtab, dvalid, st);
+    rc = peers.world ? frisk_b200_finalize_tables_peers(peers.d_fwd_peers, peers.d_flag_peers, peers.rank, peers.world, peers.epoch,
+                                                        kmax, 1, (uint64_t*)dtab, dvalid, st)
+                     : frisk_b200_finalize_tables((const uint64_t*)dfwd, kmax, 1, (uint64_t*)dtab, dvalid, st);
     if (rc) return rc;
     rc = frisk_b200_genome_ivom((const uint64_t*)dtab, kmin, kmax, genome_space, (double*)dig, st);
     if (rc) return rc;
@@ -1643,7 +1654,7 @@ static int upload_inv(const HostPlanes& hp, void* d_inv, int slot_idx, int slot_
     return FRISK_OK;
 }
 
-static int run_host_impl(const HostPlanes& h, const HostPlanes& q, bool same, const uint64_t* win_off, const uint32_t* win_len,
+static int run_host_impl(const PeerArgs& peers, const HostPlanes& h, const HostPlanes& q, bool same, const uint64_t* win_off, const uint32_t* win_len,
                          uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host, int want_rip,
                          int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
                          uint64_t* valid_kmax_out, void* stream) {
@@ -1666,8 +1677,14 @@ static int run_host_impl(const HostPlanes& h, const HostPlanes& q, bool same, co
     if ((rc = ws_get(0, h_padded_len / 4, &dhc))) return rc;
     if ((rc = ws_get(1, h_padded_len / 8, &dhi))) return rc;
     if (h.low && (rc = ws_get(2, h_padded_len / 8, &dhl))) return rc;
-    if ((rc = ws_get(6, (tsz + 1) * 8, &dfwd))) return rc;
-    CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, st));
+    if (peers.world) {
+        if (!peers.d_fwd_local || !peers.d_fwd_peers) return FRISK_E_INVALID;
+        dfwd = peers.d_fwd_local;                     // this rank's counters live where the peers can read them
+        CK(cudaMemsetAsync(dfwd, 0, tsz * 8, st));
+    } else {
+        if ((rc = ws_get(6, (tsz + 1) * 8, &dfwd))) return rc;
+        CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, st));
+    }
     // The planes go up in chunks on the copy stream; the background count of a chunk starts as soon
     // as the chunk has landed (it stops 128 bases short of the chunk's end: the kernel looks ahead),
     // so only the last chunk's count is not hidden behind PCIe.
@@ -1704,7 +1721,7 @@ static int run_host_impl(const HostPlanes& h, const HostPlanes& q, bool same, co
         else if ((rc = upload_inv(q, dqi, 17, 18, cc->copy))) return rc;
         if (q.low) CK(cudaMemcpyAsync(dql, q.low, q_padded_len / 8, cudaMemcpyHostToDevice, cc->copy));
     }
-    return run_tail((const uint32_t*)dhc, (const uint32_t*)dhi, (const uint32_t*)dhl, h_padded_len, true,
+    return run_tail(peers, (const uint32_t*)dhc, (const uint32_t*)dhi, (const uint32_t*)dhl, h_padded_len, true,
                     (const uint32_t*)dqc, (const uint32_t*)dqi, (const uint32_t*)dql, win_off, win_len, n_win, max_win_len,
                     kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out, valid_kmax_out, dfwd, st,
                     cc->copy, cc->ev[kMaxChunks + 1]);
@@ -1719,7 +1736,7 @@ int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const ui
     const HostPlanes h{h_codes, h_inv, nullptr, nullptr, 0, h_low, h_padded_len};
     const HostPlanes q{q_codes, q_inv, nullptr, nullptr, 0, q_low, q_padded_len};
     const bool same = (h_codes == q_codes) && (h_inv == q_inv) && (h_padded_len == q_padded_len);
-    return run_host_impl(h, q, same, win_off, win_len, n_win, max_win_len, kmin, kmax, mask_host, want_rip, genome_space,
+    return run_host_impl(PeerArgs(), h, q, same, win_off, win_len, n_win, max_win_len, kmin, kmax, mask_host, want_rip, genome_space,
                          rows_out, status_out, tables_out, valid_kmax_out, stream);
 }
 
@@ -1735,7 +1752,25 @@ int frisk_b200_run_host_sparse(const uint32_t* h_codes, const uint32_t* h_inv_id
     const HostPlanes h{h_codes, nullptr, h_inv_idx, h_inv_val, h_inv_n, h_low, h_padded_len};
     const HostPlanes q{q_codes, nullptr, q_inv_idx, q_inv_val, q_inv_n, q_low, q_padded_len};
     const bool same = (h_codes == q_codes) && (h_inv_idx == q_inv_idx) && (h_inv_n == q_inv_n) && (h_padded_len == q_padded_len);
-    return run_host_impl(h, q, same, win_off, win_len, n_win, max_win_len, kmin, kmax, mask_host, want_rip, genome_space,
+    return run_host_impl(PeerArgs(), h, q, same, win_off, win_len, n_win, max_win_len, kmin, kmax, mask_host, want_rip, genome_space,
+                         rows_out, status_out, tables_out, valid_kmax_out, stream);
+}
+
+int frisk_b200_run_host_peers(const uint32_t* h_codes, const uint32_t* h_inv_idx, const uint32_t* h_inv_val, uint64_t h_inv_n,
+                              const uint32_t* h_low, uint64_t h_padded_len, const uint64_t* win_off, const uint32_t* win_len,
+                              uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host, int want_rip,
+                              int64_t genome_space, uint64_t* d_fwd_local, const uint64_t* const* d_fwd_peers,
+                              uint64_t* const* d_flag_peers, int rank, int world, uint64_t epoch, double* rows_out,
+                              uint32_t* status_out, uint64_t* tables_out, uint64_t* valid_kmax_out, void* stream) {
+    if ((h_inv_n && (!h_inv_idx || !h_inv_val)) || world < 1 || rank < 0 || rank >= world || !d_fwd_local || !d_fwd_peers ||
+        !d_flag_peers || epoch == 0)
+        return FRISK_E_INVALID;
+    if (h_padded_len / 32 > 0xffffffffull || kmax > FRISK_B200_FAST_K || world > kMaxPeers) return FRISK_E_UNSUPPORTED;
+    const HostPlanes h{h_codes, nullptr, h_inv_idx, h_inv_val, h_inv_n, h_low, h_padded_len};
+    PeerArgs peers;
+    peers.d_fwd_local = d_fwd_local; peers.d_fwd_peers = d_fwd_peers; peers.d_flag_peers = d_flag_peers;
+    peers.rank = rank; peers.world = world; peers.epoch = epoch;
+    return run_host_impl(peers, h, h, true, win_off, win_len, n_win, max_win_len, kmin, kmax, mask_host, want_rip, genome_space,
                          rows_out, status_out, tables_out, valid_kmax_out, stream);
 }
 
@@ -1757,7 +1792,7 @@ int frisk_b200_run_resident(const uint32_t* d_h_codes, const uint32_t* d_h_inv, 
     std::lock_guard<std::mutex> lock(g_run_mu[dev_ & 63]);
     void* dfwd;
     if ((rc = ws_get(6, ((size_t)frisk_b200_table_size(1, kmax) + 1) * 8, &dfwd))) return rc;
-    return run_tail(d_h_codes, d_h_inv, d_h_low, h_padded_len, false, d_q_codes, d_q_inv, d_q_low, win_off, win_len, n_win,
+    return run_tail(PeerArgs(), d_h_codes, d_h_inv, d_h_low, h_padded_len, false, d_q_codes, d_q_inv, d_q_low, win_off, win_len, n_win,
                     max_win_len, kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out,
                     valid_kmax_out, dfwd, (cudaStream_t)stream, nullptr, nullptr);
 }

@@ -2,6 +2,9 @@
 
 * ``score_sharded``   -- scaffolds are dealt to ranks (LPT by bases); a rank only ever holds its own
   scaffolds.  Right for fragmented assemblies (C5) and when the host side is the bottleneck.
+* ``score_fasta_sharded`` -- the FASTA TEXT is cut at record boundaries into ``world`` byte ranges of equal
+  size; a rank uploads and tokenises only its range (device-side ingest), so host memory and PCIe traffic
+  per GPU shrink with the number of GPUs (C5: 14 GB of text, 1 M scaffolds).  Rows come back in file order.
 * ``score_balanced``  -- every rank ingests the whole FASTA on its own GPU (device-side ingest, one PCIe
   link per GPU; 14 Gbp packed is 5 GB of 180 GB), counts an equal slice of the BASE RANGE and scores an
   equal slice of the WINDOW LIST (by bases covered): exact balance even when 24 chromosomes meet 8 GPUs
@@ -105,6 +108,23 @@ class PeerExchange:
         """This rank's counter buffer for the current step (a view of the symmetric allocation)."""
         a = self.parity * self.stride
         return self.buf[a:a + self.tsz]
+
+    def run_host(self, genome, wins, out, genome_space: int, kmin=1, kmax=8, mask_host=False, rip=True, stream_ptr=None, **_):
+        """This rank's share end to end in ONE C call (frisk_b200_run_host_peers): chunked upload of the
+        pinned host planes overlapped with the count, fused exchange, score, download into ``out``."""
+        from . import _lib, engine
+        self.epoch += 1
+        hi, hv = genome.inv_sparse()
+        n = len(wins)
+        rc = _lib.lib().frisk_b200_run_host_peers(
+            engine._ptr(genome.codes), engine._ptr(hi), engine._ptr(hv), len(hi), engine._ptr(genome.low), genome.padded_len,
+            engine._ptr(wins.off), engine._ptr(wins.length), n, wins.max_len, kmin, kmax, int(mask_host), int(rip),
+            int(genome_space), C.c_void_p(int(self.local().data_ptr())), self.ptr_arrays[self.parity], self.flag_array,
+            self.rank, self.world, self.epoch, engine._ptr(out.rows), engine._ptr(out.status), engine._ptr(out.tables),
+            engine._ptr(out.valid), stream_ptr)
+        _lib.check(rc, "frisk_b200_run_host_peers")
+        self.parity ^= 1
+        return out
 
     def finalize(self, kmax: int, d_tables, d_valid, stream_ptr):
         """The fused barrier + sum + finalise (the GPUs synchronise inside the first kernel).  Flips the buffer."""
@@ -238,3 +258,70 @@ def gather_rows_in_order(res, group=None, dst: int = 0):
         return None
     return ([n for o in out for n in o[0]], np.concatenate([o[1].reshape(-1, 2) for o in out]),
             np.concatenate([o[2].reshape(-1, 5) for o in out]), np.concatenate([o[3] for o in out]))
+
+
+# ---------------------------------------------------------------------- the FASTA text cut at record boundaries
+def split_fasta_text(text: np.ndarray, world: int) -> List[Tuple[int, int]]:
+    """Byte ranges [a, b) of FASTA text per rank: consecutive, covering the whole text, every range
+    starting at a header line (a '>' first on its line; the first range also keeps whatever precedes the
+    first header, which the reference ignores), sizes as equal as record boundaries allow."""
+    buf = np.ascontiguousarray(text, dtype=np.uint8)
+    n = int(buf.shape[0])
+
+    def next_header(pos: int) -> int:
+        """First offset >= pos at which a header line starts (n if none)."""
+        if pos <= 0:
+            return 0
+        if pos >= n:
+            return n
+        j = _find(buf, b"\n>", pos - 1, n)            # a header needs the newline before it
+        return n if j < 0 else j + 1
+
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(max(next_header((n * r) // world), cuts[-1]))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def _find(buf: np.ndarray, pat: bytes, lo: int, hi: int) -> int:
+    """bytes.find over a numpy buffer without copying more than a window at a time."""
+    step = 1 << 24
+    while lo < hi:
+        end = min(lo + step + len(pat), hi)
+        k = buf[lo:end].tobytes().find(pat)
+        if k >= 0:
+            return lo + k
+        lo += step
+    return -1
+
+
+def score_fasta_sharded(fasta_text, group=None, device=None, fused: bool = True, **params):
+    """Multi-GPU hot path from FASTA text with the INGEST sharded too: rank r uploads and tokenises only
+    its byte range (split_fasta_text), counts and scores its own records against the background of all
+    ranks (one exchange of the counters).  Returns this rank's HotPathResult with global tables/meta;
+    ``gather_rows_in_order`` puts the rows back in file order."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    buf = np.ascontiguousarray(fasta_text, dtype=np.uint8) if not isinstance(fasta_text, (bytes, bytearray)) else np.frombuffer(fasta_text, np.uint8)
+    a, b = split_fasta_text(buf, world)[rank]
+    dq = engine.DeviceGenome.from_fasta_bytes(buf[a:b], device)
+    g = dq.host
+    space = global_genome_space(g.genome_space, device, group)
+    peers = PeerExchange(params.get("kmax", 8), device, group) if fused else None
+    pipe = engine.Pipeline(dq, device=device, allreduce=make_allreduce(group), genome_space=space, peers=peers, **params)
+    pipe.enqueue()
+    res = pipe.result()
+    res.collective = "fused peer sum (NVLink)" if pipe.peers is not None else "NCCL all-reduce"
+    kmax = pipe.kmax
+    possible = int(np.maximum(g.scaf_len.astype(np.int64) - kmax + 1, 0).sum())
+    valid_global = possible - res.meta[1]              # finalised from the summed counters: already global
+    meta = torch.tensor([res.meta[0], possible, res.meta[2]], dtype=torch.int64, device=device)
+    dist.all_reduce(meta, op=dist.ReduceOp.SUM, group=group)
+    tot = [int(x) for x in meta.tolist()]
+    res.meta = (tot[0], tot[1] - valid_global, tot[2])
+    return res, (a, b)

@@ -218,6 +218,21 @@ int frisk_b200_run_host_sparse(const uint32_t *h_codes, const uint32_t *h_inv_id
                                uint64_t *tables_out, uint64_t *valid_kmax_out, void *stream);
 
 /*
+ * frisk_b200_run_host_peers: one rank's share of a multi-GPU run in one call -- frisk_b200_run_host_sparse
+ * for this rank's scaffolds (query == host shard) with the exchange of the counters fused in
+ * (frisk_b200_finalize_tables_peers: d_fwd_local is this rank's counter buffer for this call, one of the
+ * d_fwd_peers; flags / rank / world / epoch as there).  genome_space is the GLOBAL totalLen - nnTotal.
+ * tables_out / valid_kmax_out are global.  Every rank must make the call; kmax <= 8.
+ */
+int frisk_b200_run_host_peers(const uint32_t *h_codes, const uint32_t *h_inv_idx, const uint32_t *h_inv_val,
+                              uint64_t h_inv_n, const uint32_t *h_low, uint64_t h_padded_len, const uint64_t *win_off,
+                              const uint32_t *win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax,
+                              int mask_host, int want_rip, int64_t genome_space, uint64_t *d_fwd_local,
+                              const uint64_t *const *d_fwd_peers, uint64_t *const *d_flag_peers, int rank, int world,
+                              uint64_t epoch, double *rows_out, uint32_t *status_out, uint64_t *tables_out,
+                              uint64_t *valid_kmax_out, void *stream);
+
+/*
  * frisk_b200_run_resident: frisk_b200_run_host for planes that are already in device memory (e.g.
  * written by frisk_b200_fasta_pack): no plane upload; the window list still comes from, and the
  * results still go to, host memory.

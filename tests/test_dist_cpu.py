@@ -42,6 +42,27 @@ def test_balanced_slices_cover_everything_once():
                 assert max(loads) - min(loads) <= 2 * int(lengths.max())
 
 
+def test_fasta_text_is_cut_at_record_boundaries():
+    sc = synth.make("C5", 0.00005, seed=3) + synth.make("edge")
+    text = np.frombuffer(synth.fasta_bytes(sc) + b">tail_without_newline\nACGT", dtype=np.uint8)
+    whole = text.tobytes()
+    for world in (1, 2, 3, 8, 64):
+        parts = fdist.split_fasta_text(text, world)
+        assert parts[0][0] == 0 and parts[-1][1] == len(text)
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        for a, b in parts:
+            assert a == b or a == 0 or (whole[a:a + 1] == b">" and whole[a - 1:a] == b"\n")
+        # every record lands in exactly one part, in order
+        names = [n for a, b in parts for n in __import__("frisk_b200").engine.PackedGenome.from_fasta_bytes(whole[a:b]).names]
+        assert names == [n for n, _ in sc] + ["tail_without_newline"]
+        if world <= 8:
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) < 2 * max(len(s) for _, s in sc) + 4096
+    # a '>' inside a sequence line is not a record boundary
+    odd = np.frombuffer(b">a\nAC>GT\nACGT\n>b\nAC\n", dtype=np.uint8)
+    assert fdist.split_fasta_text(odd, 2) == [(0, 14), (14, 20)]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -45,6 +45,21 @@ def main():
         assert err.max() < 1e-10, err.max()
         assert np.array_equal(rows[good, 1:], ref["rows"][good, 1:], equal_nan=True)
         print("sharded ok: world=%d rows=%d max KLD rel err %.2e" % (dist.get_world_size(), len(names), err.max()))
+    # the same shard end to end through ONE C call per rank (frisk_b200_run_host_peers: upload overlapped with the
+    # count, fused exchange, score, download)
+    from frisk_b200 import engine
+    dev = torch.device("cuda", local)
+    shard = engine.PackedGenome.from_scaffolds([scaffolds[i] for i in mine_f], pinned=True)
+    space = fdist.global_genome_space(shard.genome_space, dev)
+    px = fdist.PeerExchange(8, dev)
+    assert px.available, px.reason
+    wins = shard.windows(params["w"], params["step"], params["scaffolds_all"])
+    out = engine.HostOutputs(len(wins), 8)
+    for _ in range(2):
+        px.run_host(shard, wins, out, space, stream_ptr=engine._stream_ptr(dev), **params)
+    one = engine.assemble(shard, shard, wins, out.tables, int(out.valid[0]), out.rows[:len(wins)], out.status[:len(wins)], 1, 8)
+    assert np.array_equal(one.tables, res_f.tables), "run_host_peers: tables differ from the staged path"
+    assert np.array_equal(one.rows, res_f.rows, equal_nan=True) and np.array_equal(one.status, res_f.status)
     # second scheme: one replicated genome (device-side ingest of the FASTA text on every rank), equal
     # slices of the base range and of the window list
     text = np.frombuffer(synth.fasta_bytes(scaffolds), dtype=np.uint8)
@@ -60,6 +75,16 @@ def main():
         assert np.array_equal(rows[good, 1:], ref["rows"][good, 1:], equal_nan=True)
         assert np.array_equal(rows, gathered[2], equal_nan=True), "both schemes run the same kernels on the same windows"
         print("balanced ok: rank 0 scored windows [%d, %d) of %d" % (a, b, len(names)))
+    # third scheme: the text itself cut at record boundaries, every rank ingests only its byte range
+    res3, (ta, tb) = fdist.score_fasta_sharded(text, **params)
+    gathered3 = fdist.gather_rows_in_order(res3)
+    if dist.get_rank() == 0:
+        names3, coords3, rows3, status3 = gathered3
+        assert np.array_equal(res3.tables, ref["tables"]), "fasta-sharded: tables differ"
+        assert list(res3.meta) == [int(x) for x in ref["meta"]], (res3.meta, ref["meta"])
+        assert names3 == ref["names"] and np.array_equal(coords3, ref["coords"])
+        assert np.array_equal(rows3, gathered[2], equal_nan=True)
+        print("fasta-sharded ok: rank 0 ingested bytes [%d, %d) of %d" % (ta, tb, len(text)))
         print("dist_check ok: world=%d rows=%d max KLD rel err %.2e" % (dist.get_world_size(), len(names), max(err.max(), err2.max())))
     dist.barrier()
     dist.destroy_process_group()
