@@ -37,6 +37,8 @@ PROTOTYPES = {
     "frisk_b200_finalize_tables": (_i, [_p, _i, _i, _p, _p, _p]),
     "frisk_b200_finalize_tables_peers": (_i, [_p, _p, _i, _i, _u64, _i, _i, _p, _p, _p]),
     "frisk_b200_kld": (_i, [_p, _p, _u64, _p, _p]),
+    "frisk_b200_feature_slots": (_i, [_i, _i, _p, _p]),
+    "frisk_b200_region_features": (_i, [_p, _p, _p, _p, _u64, _i, _i, _p, _u64, _p, _p]),
     "frisk_b200_set_option": (_i, [C.c_char_p, _i]),
     "frisk_b200_genome_ivom": (_i, [_p, _i, _i, C.c_int64, _p, _p]),
     "frisk_b200_score": (_i, [_p, _p, _p, _p, _p, _u64, C.c_uint32, _p, _i, _i, _i, _p, _p, _p, _p]),
@@ -71,7 +73,7 @@ class FriskError(RuntimeError):
 def build(force: bool = False) -> str:
     """Compile the shared library in-tree (nvcc, sm_100a).  Cross-compiles without a GPU."""
     src_dir = os.path.join(HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("frisk_kernels.cu", "frisk_general.cu", "frisk_ingest.cu", "frisk_host.cpp", "frisk_internal.h", "Makefile")]
+    srcs = [os.path.join(src_dir, f) for f in ("frisk_kernels.cu", "frisk_general.cu", "frisk_ingest.cu", "frisk_features.cu", "frisk_host.cpp", "frisk_internal.h", "Makefile")]
     srcs.append(os.path.join(os.path.dirname(HERE), "include", "frisk_b200.h"))
     stale = not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:

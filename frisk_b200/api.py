@@ -35,7 +35,7 @@ from . import _lib, engine
 
 __all__ = ["LETTERS", "tempPathCheck", "countN", "calcGC", "iterFasta", "crawlGenome", "prepareMaps", "rangeMaps",
            "revComplement", "computeKmers", "IvomBuild", "KLD", "calcRIP", "makePicklePath", "mainArgs", "main",
-           "score_genome", "FRISK_VERSION"]
+           "scrubMirrors", "flattenKmerMap", "pcaFeatures", "score_genome", "FRISK_VERSION"]
 
 FRISK_VERSION = "b200-0.1"
 LETTERS = ("A", "T", "G", "C")             # F:70 -- alphabet and table order
@@ -265,6 +265,47 @@ def calcRIP(windowKmers, args):
 
 
 # ------------------------------------------------------------------------------ batch path + CLI
+def scrubMirrors(kDicts):
+    """F:797-811: per order, drop the k-mers whose reverse complement was already seen (table order)."""
+    clean = []
+    for table in kDicts:
+        kept = {}
+        for key, value in table.items():
+            if key in kept or revComplement(key) in kept:
+                continue
+            kept[key] = value
+        clean.append(kept)
+    return clean
+
+
+def flattenKmerMap(kMap, window=1, seqLen=1, kmin=1, kmax=5, prop=False):
+    """F:813-831: the tables of orders kmin..kmax as one vector -- proportions within each order
+    (prop=True) or counts scaled to a standard window length."""
+    values = []
+    for table in kMap:
+        if not table or not (kmin <= len(next(iter(table))) <= kmax):
+            continue
+        if prop:
+            total = sum(table.values())
+            values.extend(float(v) / total for v in table.values())      # ZeroDivisionError like the reference
+        else:
+            values.extend(table.values())
+    arr = np.array(values)
+    return arr if prop else (float(window) / seqLen) * arr
+
+
+def pcaFeatures(args, regions, device="cuda:0"):
+    """The reference's loop F:1571-1591 for all regions at once: ``regions`` = [(name, sequence)];
+    returns (labels, float64[n, F]) = (anomLabels, anomCounts).  One GPU kernel (one CTA per region)."""
+    regions = list(regions)
+    g = engine.PackedGenome.from_scaffolds(regions)
+    dg = engine.DeviceGenome(g, device)
+    feats = engine.region_features(dg, g.scaf_off, g.scaf_len.astype(np.uint32), args.pcaMin, args.pcaMax)
+    if np.isnan(feats).any():
+        raise ZeroDivisionError("float division by zero (reference F:824: a region without a valid word of some order)")
+    return np.array([n for n, _ in regions]), feats
+
+
 def makePicklePath(args, **kwargs) -> str:
     """F:497-506."""
     base = os.path.basename(args.hostSeq)

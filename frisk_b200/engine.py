@@ -336,6 +336,42 @@ def score(dg: DeviceGenome, wins: WindowList, d_ig, kmin: int, kmax: int, rip: b
     return d_rows, d_status, d_dump
 
 
+_SLOT_CACHE = {}
+
+
+def feature_slots(kmin: int, kmax: int) -> Tuple[np.ndarray, int]:
+    """(slot int32[table_size(1,kmax)], n_features): position of every kept k-mer in the composition vector
+    of frisk_b200_region_features (scrubMirrors order, F:797-811), -1 for the dropped mirror images."""
+    key = (kmin, kmax)
+    if key not in _SLOT_CACHE:
+        slot = np.zeros(_lib.table_size(1, kmax), np.int32)
+        n = C.c_uint64(0)
+        _lib.check(_lib.lib().frisk_b200_feature_slots(kmin, kmax, _ptr(slot), C.byref(n)), "frisk_b200_feature_slots")
+        _SLOT_CACHE[key] = (slot, int(n.value))
+    return _SLOT_CACHE[key]
+
+
+def region_features(dg: DeviceGenome, off: np.ndarray, length: np.ndarray, kmin: int = 1, kmax: int = 6) -> np.ndarray:
+    """Strand-symmetric k-mer proportion vectors of the regions [off, off+length) of the packed planes, one
+    CTA per region (frisk_b200_region_features): the reference's per-anomaly computeKmers(pcaMode, sym) +
+    scrubMirrors + flattenKmerMap(prop=True), F:1571-1591, for every region at once.  -> float64 [n, F]."""
+    import torch
+    _lib.require_device()
+    slot, nf = feature_slots(kmin, kmax)
+    n = len(off)
+    dev = dg.device
+    d_out = torch.empty((n, nf), dtype=torch.float64, device=dev)
+    if n:
+        d_off = torch.from_numpy(np.ascontiguousarray(off, np.uint64).view(np.int64)).to(dev)
+        d_len = torch.from_numpy(np.ascontiguousarray(length, np.uint32).view(np.int32)).to(dev)
+        d_slot = torch.from_numpy(slot).to(dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().frisk_b200_region_features(_ptr(dg.codes), _ptr(dg.inv), _ptr(d_off), _ptr(d_len), n, kmin, kmax,
+                                                             _ptr(d_slot), nf, _ptr(d_out), _stream_ptr(dev)),
+                       "frisk_b200_region_features")
+    return d_out.cpu().numpy()
+
+
 @dataclass
 class HotPathResult:
     kmin: int

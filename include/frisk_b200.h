@@ -174,6 +174,22 @@ int frisk_b200_score(const uint32_t *d_codes, const uint32_t *d_inv, const uint3
                      const double *d_ig, int kmin, int kmax, int want_rip, double *d_rows, uint32_t *d_status,
                      uint16_t *d_dump, void *stream);
 
+/*
+ * Strand-symmetric composition vectors of sequence regions, in batch: what the reference builds per
+ * anomalous window for its PCA / t-SNE stage with computeKmers(pcaMode=True, sym=True) (F:1576-1578),
+ * scrubMirrors (F:797-811) and flattenKmerMap(prop=True) (F:813-831).  For every order k = kmin..kmax
+ * (<= 7; the reference's default is 1..6) and every k-mer that comes first of its {k-mer, reverse
+ * complement} pair in table order: (count + count of the reverse complement) / (sum of that over the
+ * kept k-mers of the order).  Regions are upper-cased like windows (soft-masked bases count).
+ * frisk_b200_feature_slots (host): slot[sum 4^k entries, orders 1..kmax] = position of the k-mer in
+ * the vector or -1; *n_features = vector length.  frisk_b200_region_features: d_out[n_regions][n_features];
+ * an order without any valid word gives NaN (the reference raises ZeroDivisionError, F:824).
+ */
+int frisk_b200_feature_slots(int kmin, int kmax, int32_t *slot, uint64_t *n_features);
+int frisk_b200_region_features(const uint32_t *d_codes, const uint32_t *d_inv, const uint64_t *d_reg_off,
+                               const uint32_t *d_reg_len, uint64_t n_regions, int kmin, int kmax, const int32_t *d_slot,
+                               uint64_t n_features, double *d_out, void *stream);
+
 /* Tuning/test switches.  "force_dense_kernel" = 1 makes frisk_b200_score use the dense-table
  * kernel (the general path for kmax < 4 or windows > 8192 bases) for every input. */
 int frisk_b200_set_option(const char *name, int value);

@@ -241,3 +241,32 @@ def score_windows(scaffolds: Sequence[Tuple[str, str]], kmin: int = 1, kmax: int
         pi, si, cri = calc_rip(win, kmin, kmax) if do_rip else (None, None, None)
         rows.append((name, start, stop, score, gc, pi, si, cri))
     return genome, rows
+
+
+# --------------------------------------------------------------------------- PCA features (F:797-831, F:1571-1591)
+def scrub_mirrors(k_dicts: list) -> list:
+    """F:797-811: keep, per order, the first of each {k-mer, reverse complement} pair in table order."""
+    out = []
+    for table in k_dicts:
+        kept: Dict[str, int] = {}
+        for key in table:
+            if key in kept or rev_complement(key) in kept:
+                continue
+            kept[key] = table[key]
+        out.append(kept)
+    return out
+
+
+def flatten_props(k_dicts: list) -> list:
+    """F:813-831 with prop=True: every order's values divided by the order's sum, concatenated."""
+    vec = []
+    for table in k_dicts:
+        total = sum(table.values())
+        vec.extend(float(v) / total for v in table.values())
+    return vec
+
+
+def region_features(seq: str, kmin: int, kmax: int) -> list:
+    """The reference's per-region feature vector (F:1576-1584): symmetric counts, mirrors scrubbed, proportions."""
+    maps = compute_kmers([("r", seq)], kmin, kmax, both_strands=True)[:kmax - kmin + 1]
+    return flatten_props(scrub_mirrors(maps))

@@ -100,3 +100,34 @@ def test_cli_main_writes_reference_products(tmp_path, case, flags, capsys):
     # second run re-uses both caches (default: --recalc / --recalcWin not given) and returns the frame
     frame2 = frisk.main(["-H", path, "-t", str(tmp), "--quiet"] + flags)
     assert frame2.equals(frame)
+
+
+def test_batch_pca_features_match_the_reference_formulation():
+    """frisk_b200_region_features (one CTA per region) vs the oracle's restatement of
+    computeKmers(pcaMode, sym) + scrubMirrors + flattenKmerMap(prop=True) (F:1571-1591), and vs this
+    package's own per-region dict path."""
+    import argparse
+    from frisk_b200 import api, engine, synth
+    from oracle import frisk_oracle as fo
+    rng = np.random.default_rng(8)
+    edge = synth.make("edge")
+    big = synth.make("C1", 0.02)[0][1]
+    regions = [("r%d" % i, big[a:a + int(l)]) for i, (a, l) in enumerate(zip(rng.integers(0, 90_000, 12), rng.integers(300, 9000, 12)))]
+    regions += [(n, s[:4000]) for n, s in edge[:3]]                       # lower case, N runs, IUPAC inside
+    regions.append(("long", big[:100_000]))
+    args = argparse.Namespace(pcaMin=1, pcaMax=6)
+    labels, feats = api.pcaFeatures(args, regions)
+    assert list(labels) == [n for n, _ in regions] and feats.shape == (len(regions), 2772)
+    for (name, seq), row in zip(regions, feats):
+        want = np.array(fo.region_features(seq.tobytes().decode(), 1, 6))
+        assert np.array_equal(row, want), name                           # one exact division per entry
+    # the dict-level API path (computeKmers on the GPU + host scrub/flatten) agrees
+    name, seq = regions[0]
+    args2 = argparse.Namespace(pcaMin=2, pcaMax=4, minWordSize=1, maxWordSize=8, maskHost=False, hostSeq="")
+    maps = api.computeKmers(args2, window=[(name, seq.tobytes().decode())], pcaMode=True, kmerMap=api.rangeMaps(2, 4),
+                            getMeta=False, sym=True)
+    vec = api.flattenKmerMap(api.scrubMirrors(maps), window=5000, seqLen=len(seq), kmin=2, kmax=4, prop=True)
+    _, f24 = api.pcaFeatures(argparse.Namespace(pcaMin=2, pcaMax=4), [regions[0]])
+    assert np.array_equal(vec, f24[0])
+    with pytest.raises(ZeroDivisionError):
+        api.pcaFeatures(args, [("tiny", np.frombuffer(b"ACG", np.uint8))])   # no 4-mer at all: F:824 divides by zero

@@ -72,3 +72,20 @@ def test_cli_parser_defaults_and_paths():
     assert frisk.makePicklePath(args, space="window") == "temp/q.fa_kmers_2_5_KLD_window_1000_increment_250.p"
     with pytest.raises(SystemExit):
         frisk.mainArgs(["-H", "h.fa", "-m", "5", "-k", "3"])
+
+
+def test_scrub_mirrors_and_flatten_match_oracle():
+    from frisk_b200 import _lib, api, engine
+    from oracle import frisk_oracle as fo
+    seq = synth.make("edge")[0][1][:3000].tobytes().decode().upper().replace("N", "A")
+    maps = fo.compute_kmers([("r", seq)], 1, 4, both_strands=True)[:4]
+    ours = api.flattenKmerMap(api.scrubMirrors(maps), kmin=1, kmax=4, prop=True)
+    assert np.array_equal(ours, np.array(fo.flatten_props(fo.scrub_mirrors(maps))))
+    counts = api.flattenKmerMap(maps, window=5000, seqLen=len(seq), kmin=2, kmax=3, prop=False)
+    assert len(counts) == 16 + 64 and np.isclose(counts.sum(), (5000.0 / len(seq)) * (2 * (len(seq) - 1) + 2 * (len(seq) - 2)))
+    slot, nf = engine.feature_slots(1, 6)
+    assert nf == 2 + 10 + 32 + 136 + 512 + 2080 and slot.shape[0] == _lib.table_size(1, 6)
+    # kept = first of each pair in table order
+    keys = api._kmer_keys(3)
+    kept = [k for k, sl in zip(keys, slot[20:84]) if sl >= 0]
+    assert kept == list(fo.scrub_mirrors([dict.fromkeys(keys, 0)])[0])

@@ -88,3 +88,17 @@ def test_live_reference_text_matches_golden_and_oracle():
     assert np.array_equal(_tables_array(genome, p["kmin"], p["kmax"]), g.tables)
     assert [r[0] for r in rows] == g.names
     assert np.array_equal(np.array([r[3] for r in rows], float), g.vals[:, 0])
+
+
+def test_pca_feature_restatement_known_answers():
+    """scrubMirrors / flattenKmerMap(prop=True) (F:797-831) on a sequence small enough to do by hand."""
+    from oracle import frisk_oracle as fo
+    # AACG: 1-mers fwd A2 C1 G1, + revcomp (CGTT) C1 G1 T2 -> A2 T2 G2 C2; kept A (T is its mirror), G (C its mirror)
+    v = fo.region_features("AACG", 1, 1)
+    assert v == [0.5, 0.5]
+    # 2-mers of AACG: AA AC CG; revcomps TT GT CG -> AA1 AC1 CG2 TT1 GT1; kept in table order (A,T,G,C digits):
+    # AA AT AG AC TA TG TC GG GC CG (10 of 16: GA is the mirror of TC, which comes first); counts AA1 AC1 CG2, others 0 -> total 4
+    maps = fo.scrub_mirrors(fo.compute_kmers([("r", "AACG")], 2, 2, both_strands=True)[:1])
+    assert list(maps[0]) == ["AA", "AT", "AG", "AC", "TA", "TG", "TC", "GG", "GC", "CG"]
+    assert fo.region_features("AACG", 2, 2) == [0.25, 0, 0, 0.25, 0, 0, 0, 0, 0, 0.5]
+    assert len(fo.region_features("ACGTTGCAACGT" * 5, 1, 6)) == 2 + 10 + 32 + 136 + 512 + 2080
