@@ -131,3 +131,25 @@ def test_large_single_line_record_and_many_small_records():
     tiny = [("t%d" % i, np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(rng.integers(0, 40)))])
             for i in range(5000)]                              # ... and 5,000 records shorter than a line
     assert_same_genome(fasta_text(small + tiny, width=60))
+
+
+def test_multi_gigabyte_text_beyond_2_pow_32_bytes():
+    """C4-scale input: 4.5 GB of FASTA text (55 k records, 4.4 Gbp) through the device ingest -- byte offsets,
+    record positions and packed positions beyond 2^32 -- against the host packer, plane for plane."""
+    import torch
+    block = np.frombuffer(synth.fasta_bytes(synth.make("C2", 1.0, seed=77)), dtype=np.uint8)
+    reps = (4_500_000_000 + len(block) - 1) // len(block)
+    text = np.tile(block, reps)
+    assert text.shape[0] > 2 ** 32
+    dg = engine.DeviceGenome.from_fasta_bytes(text)
+    host = engine.PackedGenome.from_fasta_bytes(text)
+    assert dg.host.names == host.names and len(host.names) == 500 * reps
+    assert np.array_equal(dg.host.scaf_len, host.scaf_len) and np.array_equal(dg.host.scaf_off, host.scaf_off)
+    assert dg.host.padded_len == host.padded_len > 2 ** 32
+    assert (dg.host.total_len, dg.host.nn_total, dg.host.n_lower) == (host.total_len, host.nn_total, host.n_lower)
+    dev = dg.device
+    assert torch.equal(dg.codes, torch.from_numpy(host.codes.view(np.int32)).to(dev))
+    assert torch.equal(dg.inv, torch.from_numpy(host.inv.view(np.int32)).to(dev))
+    assert (dg.low is None) == (host.low is None)
+    del dg, host, text
+    torch.cuda.empty_cache()
