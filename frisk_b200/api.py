@@ -459,12 +459,12 @@ def main(argv=None):
     else:
         allWindows = windows_frame(res, with_rip)
         outPath = os.path.join(args.tempDir, args.outfile)
+        body = res.tsv_body(with_rip).decode()                      # the rows exactly as str() prints them, formatted in C
         with open(outPath, "w") as handle:                          # F:1463-1497
             handle.write("\t".join(allWindows.columns.values) + "\n")
-            lines = ["\t".join(str(v) for v in row) for row in allWindows.itertuples(index=False, name=None)]
-            handle.write("\n".join(lines) + ("\n" if lines else ""))
+            handle.write(body)
         if not args.quiet:
-            sys.stdout.write("\n".join(lines) + ("\n" if lines else ""))   # F:1494
+            sys.stdout.write(body)                                  # F:1494
         logging.info("Saving calculated window KLD scores as: %s" % windowsPickle)
         allWindows.to_pickle(windowsPickle, protocol=2)             # F:1501
         if args.exitAfter == "WindowKLD":                           # F:1503-1505

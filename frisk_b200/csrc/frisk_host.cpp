@@ -3,6 +3,9 @@
 // Pure CPU; no CUDA calls here.
 #include <algorithm>
 #include <atomic>
+#include <charconv>
+#include <cmath>
+#include <string>
 #include <cstdint>
 #include <cstring>
 #include <thread>
@@ -204,6 +207,106 @@ int frisk_b200_pack(const char* src, const uint64_t* src_off, const uint64_t* sr
         for (int k = 0; k < 3; ++k) stats[k] += part[(size_t)t * 3 + k];
     if (err.load()) return err.load();
     if (!low && stats[2]) return FRISK_E_FORMAT;
+    return FRISK_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// str(float) of Python 3 / numpy (repr, shortest round-trip digits; exponent form when the decimal
+// point would sit before the 4th leading zero or after the 16th digit; integral values get ".0")
+inline void append_pyfloat(std::string& out, double x) {
+    if (std::isnan(x)) { out += "nan"; return; }
+    if (std::isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
+    char buf[40];
+    const auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);   // [-]d[.ddd]e[+-]XX, shortest
+    const char* p = buf;
+    if (*p == '-') { out += '-'; ++p; }
+    const char* e = p;
+    while (e < r.ptr && *e != 'e') ++e;
+    char digits[24];
+    int nd = 0;
+    for (const char* q = p; q < e; ++q)
+        if (*q != '.') digits[nd++] = *q;
+    int ex = 0;
+    {
+        const char* q = e + 1;
+        const bool neg = *q == '-';
+        if (*q == '-' || *q == '+') ++q;
+        for (; q < r.ptr; ++q) ex = ex * 10 + (*q - '0');
+        if (neg) ex = -ex;
+    }
+    const int decpt = ex + 1;                             // value = 0.d1d2... * 10^decpt
+    if (nd == 1 && digits[0] == '0') { out += "0.0"; return; }
+    if (decpt <= -4 || decpt > 16) {                      // exponent notation, at least two exponent digits
+        out += digits[0];
+        if (nd > 1) { out += '.'; out.append(digits + 1, nd - 1); }
+        out += 'e';
+        int x10 = decpt - 1;
+        out += x10 < 0 ? '-' : '+';
+        if (x10 < 0) x10 = -x10;
+        char eb[8];
+        int ne = 0;
+        do { eb[ne++] = (char)('0' + x10 % 10); x10 /= 10; } while (x10);
+        if (ne < 2) eb[ne++] = '0';
+        while (ne) out += eb[--ne];
+    } else if (decpt <= 0) {
+        out += "0.";
+        out.append((size_t)(-decpt), '0');
+        out.append(digits, nd);
+    } else if (decpt >= nd) {
+        out.append(digits, nd);
+        out.append((size_t)(decpt - nd), '0');
+        out += ".0";
+    } else {
+        out.append(digits, decpt);
+        out += '.';
+        out.append(digits + decpt, nd - decpt);
+    }
+}
+
+inline void append_int(std::string& out, int64_t v) {
+    char buf[24];
+    const auto r = std::to_chars(buf, buf + sizeof(buf), v);
+    out.append(buf, r.ptr - buf);
+}
+}  // namespace
+
+extern "C" {
+
+int frisk_b200_format_rows(const char* names, const uint64_t* name_off, const uint32_t* name_len, const uint32_t* row_name,
+                           const int64_t* start, const int64_t* stop, const double* rows, uint64_t n_rows, int n_values,
+                           char* out, uint64_t cap, uint64_t* n_bytes, int threads) {
+    if (!n_bytes || n_values < 0 || n_values > 5 || (n_rows && (!names || !name_off || !name_len || !row_name || !start || !stop || !rows)))
+        return FRISK_E_INVALID;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    if ((uint64_t)threads > n_rows / 4096 + 1) threads = (int)(n_rows / 4096 + 1);
+    std::vector<std::string> parts((size_t)threads);
+    auto work = [&](int t) {
+        const uint64_t a = n_rows * (uint64_t)t / (uint64_t)threads, b = n_rows * (uint64_t)(t + 1) / (uint64_t)threads;
+        std::string& o = parts[(size_t)t];
+        o.reserve((size_t)(b - a) * 96);
+        for (uint64_t i = a; i < b; ++i) {
+            const uint32_t s = row_name[i];
+            o.append(names + name_off[s], name_len[s]);
+            o += '\t'; append_int(o, start[i]);
+            o += '\t'; append_int(o, stop[i]);
+            for (int c = 0; c < n_values; ++c) { o += '\t'; append_pyfloat(o, rows[i * 5 + (uint64_t)c]); }
+            o += '\n';
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    uint64_t total = 0;
+    for (const auto& p : parts) total += p.size();
+    *n_bytes = total;
+    if (!out) return FRISK_OK;                            // size query
+    if (total > cap) return FRISK_E_CAPACITY;
+    uint64_t pos = 0;
+    for (const auto& p : parts) { memcpy(out + pos, p.data(), p.size()); pos += p.size(); }
     return FRISK_OK;
 }
 

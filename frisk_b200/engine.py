@@ -387,6 +387,27 @@ class HotPathResult:
     row_scaf: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))   # scaffold index (in the query) of each row
     win_tables: Optional[np.ndarray] = None   # uint16 [n, table_size(kmin,kmax)] when dump=True
     collective: str = ""                      # multi-GPU: how the counters were combined
+    scaf_names: List[str] = field(default_factory=list)    # the query's scaffold names (row_scaf indexes this)
+
+    def tsv_body(self, with_rip: bool) -> bytes:
+        """The rows as the reference writes them to raw_window_scores.bed (F:1493): tab-separated,
+        floats as str(float) -- formatted by frisk_b200_format_rows (threads) instead of a Python loop."""
+        n = len(self.rows)
+        enc = [s.encode() for s in self.scaf_names]
+        lens = np.array([len(b) for b in enc], dtype=np.uint32)
+        offs = (np.cumsum(lens, dtype=np.uint64) - lens).astype(np.uint64)
+        blob = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
+        row_name = np.ascontiguousarray(self.row_scaf, dtype=np.uint32)
+        start = np.ascontiguousarray(self.coords[:, 0], dtype=np.int64)
+        stop = np.ascontiguousarray(self.coords[:, 1], dtype=np.int64)
+        rows = np.ascontiguousarray(self.rows, dtype=np.float64)
+        nv = 5 if with_rip else 2
+        cap = int(lens[row_name].sum()) + n * (44 + 26 * nv) + 16 if n else 16
+        out = np.empty(cap, dtype=np.uint8)
+        nb = C.c_uint64(0)
+        _lib.check(_lib.lib().frisk_b200_format_rows(_ptr(blob), _ptr(offs), _ptr(lens), _ptr(row_name), _ptr(start), _ptr(stop),
+                                                     _ptr(rows), n, nv, _ptr(out), cap, C.byref(nb), 0), "frisk_b200_format_rows")
+        return out[:int(nb.value)].tobytes()
 
     def raise_reference_errors(self) -> None:
         """The reference aborts on the first window that raises; mirror that when asked."""
@@ -415,7 +436,8 @@ def assemble(query: PackedGenome, host: PackedGenome, wins: WindowList, tables_1
     if dump is not None:
         wt = _slice_orders(dump[idx], kmin, kmax)
     return HotPathResult(kmin, kmax, _slice_orders(tables_1k, kmin, kmax).copy(), meta, names, coords,
-                         rows[idx], status[idx].astype(np.uint32), len(wins), idx, wins.scaf[idx].astype(np.int64), wt)
+                         rows[idx], status[idx].astype(np.uint32), len(wins), idx, wins.scaf[idx].astype(np.int64), wt,
+                         scaf_names=list(query.names))
 
 
 class Pipeline:

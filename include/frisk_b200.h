@@ -104,6 +104,19 @@ int frisk_b200_windows(const uint64_t *scaf_len, const uint64_t *scaf_off, uint6
                        int scaffolds_all, uint64_t cap, uint64_t *win_off, uint32_t *win_len, uint32_t *win_scaf,
                        int64_t *win_start, int64_t *win_stop, uint64_t *n_windows);
 
+/*
+ * frisk_b200_format_rows (host, threads): the body of the reference's raw_window_scores.bed (F:1493):
+ * per row "name \t start \t stop \t v0 ... \n" with the first n_values (2: windowKLD, GC; 5: + PI, SI,
+ * CRI) of the row's five doubles, every float written exactly as Python 3's str(float) writes it
+ * (shortest round-trip digits, "1e-05"-style exponents, "nan"/"inf", ".0" on integral values).
+ * Row i's name is names[name_off[row_name[i]] ..+ name_len[row_name[i]]).  out == NULL only
+ * reports *n_bytes; FRISK_E_CAPACITY if cap is too small.  A 1.2 M-row table takes seconds in a
+ * Python loop and tens of milliseconds here.
+ */
+int frisk_b200_format_rows(const char *names, const uint64_t *name_off, const uint32_t *name_len,
+                           const uint32_t *row_name, const int64_t *start, const int64_t *stop, const double *rows,
+                           uint64_t n_rows, int n_values, char *out, uint64_t cap, uint64_t *n_bytes, int threads);
+
 /* ------------------------------------------------------------------ device side
  *
  * frisk_b200_background: forward-strand k-mer counts of the packed bases [first_base, last_base)

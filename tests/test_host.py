@@ -154,3 +154,27 @@ def test_sparse_form_of_the_invalid_plane():
     rc = _lib.lib().frisk_b200_plane_sparse(engine._ptr(g.inv), g.inv.shape[0], 1, engine._ptr(np.zeros(1, np.uint32)),
                                             engine._ptr(np.zeros(1, np.uint32)), C.byref(n))
     assert rc == _lib.E_CAPACITY and n.value == len(idx)
+
+
+def test_tsv_formatter_writes_floats_like_python():
+    """frisk_b200_format_rows vs "\\t".join(str(v) ...) (what the reference's handle.write does, F:1493)."""
+    rng = np.random.default_rng(12)
+    n = 20000
+    special = np.array([0.0, -0.0, 1.0, 100000.0, 1e15, 1e16, 1e17, 1.5e16, 123456789012345680000.0, 0.0001, 0.00001, 1e-5 * 1.5,
+                        5e-324, 1.7976931348623157e308, np.nan, np.inf, -np.inf, 0.1, 1 / 3, 2 / 3, 0.5, 2500 / 5000, 1e22, 1e23,
+                        9007199254740993.0, 0.30000000000000004, -2.5e-7, 12345.678, 4.35, 0.000123456789])
+    vals = np.concatenate([special, rng.random(n), rng.normal(size=n) * 10.0 ** rng.integers(-12, 12, n),
+                           rng.integers(0, 5001, n) / rng.integers(1, 5001, n)])
+    vals = np.resize(vals, (len(vals) // 5) * 5).reshape(-1, 5)
+    m = len(vals)
+    names = ["scaffold_%d" % i for i in range(7)] + ["x"]
+    res = engine.HotPathResult(1, 8, np.zeros(0, np.uint64), (0, 0, 0), [], np.stack([np.arange(m) * 2500 + 1, np.arange(m) * 2500 + 5000], 1),
+                               vals, np.zeros(m, np.uint32), m, np.arange(m), rng.integers(0, len(names), m), None, scaf_names=names)
+    for with_rip in (True, False):
+        nv = 5 if with_rip else 2
+        want = "".join("\t".join([names[int(s)], str(int(a)), str(int(b))] + [str(float(v)) for v in row[:nv]]) + "\n"
+                       for s, (a, b), row in zip(res.row_scaf, res.coords, vals))
+        assert res.tsv_body(with_rip).decode() == want
+    empty = engine.HotPathResult(1, 8, np.zeros(0, np.uint64), (0, 0, 0), [], np.zeros((0, 2), np.int64), np.zeros((0, 5)),
+                                 np.zeros(0, np.uint32), 0, np.zeros(0, np.int64), np.zeros(0, np.int64), None, scaf_names=names)
+    assert empty.tsv_body(True) == b""
