@@ -1341,7 +1341,10 @@ template <int K, bool DUMP, bool ALLK>
 int launch_score_bucket2(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                          const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
                          double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
-    // positions per thread = 4 * ROUNDS, held in registers: 5 rounds cover the default 5,000-base windows
+    // positions per thread = 4 * ROUNDS, held in registers: 5 rounds cover the default 5,000-base windows,
+    // 2 rounds short ones (-w 1000 / -w 2000) without dragging three idle rounds through every phase
+    if (max_len <= kT3 * 4u * 2u - 6u)
+        return launch_score_bucket3<K, 2, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
     if (max_len <= kT3 * 4u * 5u - 6u)
         return launch_score_bucket3<K, 5, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
     return launch_score_bucket3<K, 8, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);

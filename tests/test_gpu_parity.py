@@ -226,6 +226,8 @@ def test_bit_reproducible(eng):
     ("C3", 0.01, dict(kmin=1, kmax=6)),
     ("C5", 0.0002, dict(scaffolds_all=True)),
     ("C4", 0.0005, dict(w=2000, step=500)),
+    ("C2", 0.02, dict(w=1000, step=500, scaffolds_all=True)),          # short windows: the 2-round instantiation
+    ("C1", 0.05, dict(w=2040, step=1020, kmin=3)),
 ])
 def test_against_c_oracle_on_fresh_genomes(eng, config, scale, kw):
     from frisk_b200 import synth
