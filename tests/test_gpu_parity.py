@@ -228,6 +228,8 @@ def test_bit_reproducible(eng):
     ("C4", 0.0005, dict(w=2000, step=500)),
     ("C2", 0.02, dict(w=1000, step=500, scaffolds_all=True)),          # short windows: the 2-round instantiation
     ("C1", 0.05, dict(w=2040, step=1020, kmin=3)),
+    ("C1", 0.06, dict(w=8000, step=3000)),                              # the 8-round instantiation (5,115..8,186 bases)
+    ("C2", 0.03, dict(w=8186, step=8186, scaffolds_all=True, kmax=5)),
 ])
 def test_against_c_oracle_on_fresh_genomes(eng, config, scale, kw):
     from frisk_b200 import synth
