@@ -471,6 +471,14 @@ def main(argv=None):
             logging.info("Finished calculating window KLD scores. Exiting.")
             sys.exit(0)
         logging.info("Finished calculating window KLD scores.")
+    if args.hmmKLD:                                                 # F:1536-1548: 2-state HMM over the window scores
+        from . import downstream
+        model = downstream.fit_hmm(allWindows["windowKLD"].to_numpy(dtype=float))
+        hmmBED, allWindows = downstream.hmm2BED(allWindows, model, dataCol="windowKLD")
+        with open(os.path.join(args.tempDir, args.hmmOutfile), "w") as handle:
+            for line in downstream.hmmBED2GFF(hmmBED):
+                handle.write(line)
+        logging.info("Wrote %d HMM state intervals to %s" % (len(hmmBED), os.path.join(args.tempDir, args.hmmOutfile)))
     logging.info("frisk_b200 covers the hot path only; thresholding / HMM / projection / graphics (reference "
                  "F:1509-1851) read %s and %s" % (os.path.join(args.tempDir, args.outfile), windowsPickle))
     return allWindows

@@ -132,3 +132,27 @@ def run_hot_path(args, genomepickle="/dev/null", want_tables=False):
     if want_tables:
         return genome, rows, tables
     return genome, rows
+
+
+# threshold helpers of the downstream stage: runnable unmodified with the xrange shim
+_THRESH_RANGES = [
+    (508, 513),   # FDBins
+    (515, 543),   # otsu
+    (664, 690),   # setKLDThresh
+]
+
+
+def load_thresholds() -> types.SimpleNamespace:
+    """The reference's FDBins / otsu / setKLDThresh (F:508-543, F:664-690), executed from its source text."""
+    raw = open(REF_FILE, "rb").read()
+    if hashlib.sha256(raw).hexdigest() != REF_SHA256:
+        raise RuntimeError("reference file drifted")
+    lines = raw.decode().split("\n")
+    text = "from __future__ import division\n"
+    for a, b in _THRESH_RANGES:
+        text += "\n".join(lines[a - 1:b]) + "\n\n"
+    import logging, math
+    import numpy as np
+    glb = {"xrange": range, "np": np, "math": math, "logging": logging, "__name__": "frisk_reference_thresholds"}
+    exec(compile(text, REF_FILE + "<threshold slices>", "exec"), glb)
+    return types.SimpleNamespace(**{k: v for k, v in glb.items() if not k.startswith("__")})

@@ -102,6 +102,24 @@ def test_cli_main_writes_reference_products(tmp_path, case, flags, capsys):
     assert frame2.equals(frame)
 
 
+def test_cli_hmm_stage_writes_state_intervals(tmp_path):
+    """--hmmKLD (F:1536-1548): scores from the GPU -> 2-state HMM -> 2StateHmm.gff3; the state paths equal those
+    obtained from the reference's own scores (golden c1_small)."""
+    import frisk
+    from frisk_b200 import downstream, synth
+    g = Golden("c1_small")
+    path = str(tmp_path / "genome.fa")
+    synth.write_fasta(g.scaffolds(), path)
+    tmp = tmp_path / "temp"
+    frame = frisk.main(["-H", path, "-t", str(tmp), "--quiet", "--RIP", "--hmmKLD"])
+    lines = open(tmp / "2StateHmm.gff3").read().splitlines()
+    assert lines[0] == "##gff-version 3" and len(lines) >= 3
+    assert "hmmState" in frame.columns
+    ref_model = downstream.fit_hmm(g.vals[:, 0])
+    if isinstance(ref_model, downstream.GaussianHMM2):
+        assert np.array_equal(frame["hmmState"].to_numpy().astype(int), ref_model.predict(g.vals[:, 0]))
+
+
 def test_batch_pca_features_match_the_reference_formulation():
     """frisk_b200_region_features (one CTA per region) vs the oracle's restatement of
     computeKmers(pcaMode, sym) + scrubMirrors + flattenKmerMap(prop=True) (F:1571-1591), and vs this
