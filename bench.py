@@ -351,6 +351,14 @@ def run_gpu(args):
     total_ms, e2e_step_ms = float(tot[0]), float(tot[1])
     all_bases, all_win = int(cnt[0]), int(cnt[1])
 
+    occ = None
+    try:
+        import ctypes as C
+        a, b = C.c_int(0), C.c_int(0)
+        _lib.check(_lib.lib().frisk_b200_score_occupancy(PARAMS["kmax"], wins.max_len, C.byref(a), C.byref(b)), "score_occupancy")
+        occ = {"ctas_per_sm": a.value, "threads_per_cta": b.value}
+    except Exception:
+        pass
     if rank == 0:
         value = all_bases * args.steps / (total_ms * 1e-3) / 1e9
         peak, peak_kind = measured_peak_gbs()
@@ -367,7 +375,7 @@ def run_gpu(args):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16/u64 counts + f64 scores", "data": "synthetic",
             "config": {"workload": WORKLOAD, "bases_per_gpu": bases, "windows_per_gpu": n_win,
-                       "l2": "flushed between timed steps (512 MiB write)", "parallelism": "scaffold shards x%d, %s" % (world, collective)},
+                       "l2": "flushed between timed steps (512 MiB write)", "score_kernel_occupancy": occ, "parallelism": "scaffold shards x%d, %s" % (world, collective)},
             "windows_per_s": all_win * args.steps / (total_ms * 1e-3),
             "stage_ms": {"background": float(stage[:, 0].mean()), "tables+ivom(+allreduce)": float(stage[:, 1].mean()),
                          "score": score_ms},

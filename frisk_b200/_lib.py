@@ -40,6 +40,7 @@ PROTOTYPES = {
     "frisk_b200_kld": (_i, [_p, _p, _u64, _p, _p]),
     "frisk_b200_feature_slots": (_i, [_i, _i, _p, _p]),
     "frisk_b200_region_features": (_i, [_p, _p, _p, _p, _u64, _i, _i, _p, _u64, _p, _p]),
+    "frisk_b200_score_occupancy": (_i, [_i, C.c_uint32, C.POINTER(_i), C.POINTER(_i)]),
     "frisk_b200_set_option": (_i, [C.c_char_p, _i]),
     "frisk_b200_genome_ivom": (_i, [_p, _i, _i, C.c_int64, _p, _p]),
     "frisk_b200_score": (_i, [_p, _p, _p, _p, _p, _u64, C.c_uint32, _p, _i, _i, _i, _p, _p, _p, _p]),

@@ -1323,6 +1323,9 @@ int launch_score_bucket3(const uint32_t* codes, const uint32_t* inv, const uint3
     const size_t smem = L::total(cap);
     auto kern = score_windows_bucket_kernel<K, ROUNDS, DUMP, ALLK>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // four CTAs of 57 KB need the whole 228 KB carve-out: ask for it instead of leaving the L1/shared
+    // split to the driver's per-launch heuristic (a smaller split silently costs a CTA per SM: 0.73 -> 0.83 ms)
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT3, smem));
     if (per_sm < 1) per_sm = 1;
@@ -1528,6 +1531,35 @@ int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint3
                                      d_rows, d_status, d_dump, st));
 }
 
+int frisk_b200_score_occupancy(int kmax, uint32_t max_win_len, int* ctas_per_sm, int* threads_per_cta) {
+    if (!ctas_per_sm || !threads_per_cta) return FRISK_E_INVALID;
+    int rc = check_k(1, kmax);
+    if (rc) return rc;
+    *ctas_per_sm = 1;
+    *threads_per_cta = kThreads;
+    if (kmax > FRISK_B200_FAST_K || max_win_len > 65535u) { *threads_per_cta = 1024; return FRISK_OK; }   // general kernel
+    if (kmax < 4 || max_win_len > kBuf3 - 6u || g_force_dense) return FRISK_OK;                                // dense kernel
+    const uint32_t cap = (max_win_len + 15u) & ~15u;
+    *threads_per_cta = kT3;
+#define FRISK_OCC(KK)                                                                                                   \
+    case KK: {                                                                                                          \
+        auto kern = max_win_len <= kT3 * 4u * 2u - 6u ? score_windows_bucket_kernel<KK, 2, false, true>                 \
+                    : (max_win_len <= kT3 * 4u * 5u - 6u ? score_windows_bucket_kernel<KK, 5, false, true>              \
+                                                          : score_windows_bucket_kernel<KK, 8, false, true>);           \
+        const size_t smem = Score3Layout<KK>::total(cap);                                                               \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, kT3, smem));                                \
+        return FRISK_OK;                                                                                                \
+    }
+    switch (kmax) {
+        FRISK_OCC(4) FRISK_OCC(5) FRISK_OCC(6) FRISK_OCC(7) FRISK_OCC(8)
+        default: break;
+    }
+#undef FRISK_OCC
+    return FRISK_OK;
+}
+
 int frisk_b200_set_option(const char* name, int value) {
     if (!name) return FRISK_E_INVALID;
     if (strcmp(name, "force_dense_kernel") == 0) { g_force_dense = value; return FRISK_OK; }
@@ -1588,11 +1620,22 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
     if (rc) return rc;
     if (copy) CK(cudaStreamWaitEvent(st, copy_done, 0));
     if (n_win) {
+        // Pinned result buffers are written by the score kernel itself (40 + 4 bytes per window, posted
+        // PCIe writes while it runs): no download after the kernel.  Pageable ones get a copy.
+        cudaPointerAttributes pa_rows{}, pa_stat{};
+        const bool direct = cudaPointerGetAttributes(&pa_rows, rows_out) == cudaSuccess && pa_rows.type == cudaMemoryTypeHost &&
+                            cudaPointerGetAttributes(&pa_stat, status_out) == cudaSuccess && pa_stat.type == cudaMemoryTypeHost &&
+                            pa_rows.devicePointer && pa_stat.devicePointer;
+        cudaGetLastError();                             // a pageable pointer makes the query itself report an error
+        double* k_rows = direct ? (double*)pa_rows.devicePointer : (double*)drows;
+        uint32_t* k_stat = direct ? (uint32_t*)pa_stat.devicePointer : (uint32_t*)dstat;
         rc = frisk_b200_score(dqc, dqi, dql, (const uint64_t*)dwo, (const uint32_t*)dwl, n_win, max_win_len,
-                              (const double*)dig, kmin, kmax, want_rip, (double*)drows, (uint32_t*)dstat, nullptr, st);
+                              (const double*)dig, kmin, kmax, want_rip, k_rows, k_stat, nullptr, st);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(rows_out, drows, n_win * 40, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(status_out, dstat, n_win * 4, cudaMemcpyDeviceToHost, st));
+        if (!direct) {
+            CK(cudaMemcpyAsync(rows_out, drows, n_win * 40, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(status_out, dstat, n_win * 4, cudaMemcpyDeviceToHost, st));
+        }
     }
     if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, st));
     if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, st));

@@ -203,6 +203,10 @@ int frisk_b200_region_features(const uint32_t *d_codes, const uint32_t *d_inv, c
                                const uint32_t *d_reg_len, uint64_t n_regions, int kmin, int kmax, const int32_t *d_slot,
                                uint64_t n_features, double *d_out, void *stream);
 
+/* How frisk_b200_score would run the default (kmin = 1, no dump) configuration on the current device:
+ * resident CTAs per SM and threads per CTA of the window kernel it selects (diagnostic; bench.py reports it). */
+int frisk_b200_score_occupancy(int kmax, uint32_t max_win_len, int *ctas_per_sm, int *threads_per_cta);
+
 /* Tuning/test switches.  "force_dense_kernel" = 1 makes frisk_b200_score use the dense-table
  * kernel (the general path for kmax < 4 or windows > 8192 bases) for every input. */
 int frisk_b200_set_option(const char *name, int value);
