@@ -395,6 +395,44 @@ def test_kmax_sweep_shares_one_background_pass(eng):
         assert max_rel_err(res.rows[ok, 0], ref["rows"][ok, 0]) < 1e-10
 
 
+def test_concurrent_streams_and_threads_do_not_share_scratch(eng):
+    """Two host threads, each with its own CUDA stream, run different genomes at the same time through
+    the staged entry points, the one-call entry point and the device ingest; every result equals the
+    serial one bit for bit (scratch is stream-ordered, the cached workspace is locked per device)."""
+    import threading
+    import torch
+    from frisk_b200 import synth
+    genomes = [synth.make("C2", 0.02, seed=s) + synth.make("edge") for s in (101, 202)]
+    packed = [eng.PackedGenome.from_scaffolds(sc, pinned=True) for sc in genomes]
+    texts = [np.frombuffer(synth.fasta_bytes(sc), dtype=np.uint8) for sc in genomes]
+    serial = [eng.run(g, scaffolds_all=True) for g in packed]
+    results = [[None] * 3 for _ in genomes]
+    errors = []
+
+    def work(i):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for _ in range(5):
+                    results[i][0] = eng.run(packed[i], scaffolds_all=True)
+                    results[i][1] = eng.run_host(packed[i], scaffolds_all=True)
+                    results[i][2] = eng.run_fasta(texts[i], scaffolds_all=True)
+            stream.synchronize()
+        except Exception as e:            # surfaced below: a thread must not die silently
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(genomes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i, ref in enumerate(serial):
+        for res in results[i]:
+            assert np.array_equal(res.tables, ref.tables)
+            assert np.array_equal(res.rows, ref.rows, equal_nan=True) and np.array_equal(res.status, ref.status)
+
+
 def test_no_silent_fallback_symbols_loaded(eng):
     """The product library is the thing that ran: it is loaded in this process and reports a GPU."""
     from frisk_b200 import _lib
