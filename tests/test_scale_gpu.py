@@ -253,3 +253,37 @@ def test_c5_wheat_scale_14gbp_fragmented():
     check_scaffold_background(eng, dg, n - 1)
     del pipe, dg
     torch.cuda.empty_cache()
+
+
+def test_c3_plant_scale_k_sweep_120mbp():
+    """C3 at FULL size: 120 Mbp in 12 chromosomes with 30 % TE-like repeats, scored for every kmax' = 1..8
+    (eight reference runs) from ONE background pass.  Background bit-exact against the C oracle; per k' the
+    order-k' tables are the prefix of the kmax = 8 tables, the books close, and 150 sampled windows agree
+    with the oracle scoring them against the GPU's tables."""
+    from frisk_b200 import _lib, engine as eng, synth
+    from oracle import c_oracle
+    sc = synth.make("C3", 1.0)
+    g = eng.PackedGenome.from_scaffolds(sc)
+    assert g.total_len == 120_000_000
+    sweep = eng.run_sweep(g, kmaxes=range(1, 9))
+    seq, off = c_oracle.concat(sc)
+    tabs8, meta8 = c_oracle.background(seq, off, 1, 8, False, threads=16)
+    assert np.array_equal(sweep[8].tables, tabs8) and list(sweep[8].meta) == [int(x) for x in meta8]
+    _, woff, wlen, st, sp = c_oracle.crawl(seq, off)
+    rng = np.random.Generator(np.random.PCG64(33))
+    pick = np.sort(rng.choice(len(woff), 150, replace=False))
+    for k, res in sweep.items():
+        assert len(res.rows) == len(woff) == 48_000 and np.array_equal(res.coords, np.stack([st, sp], 1))
+        tsz = _lib.table_size(1, k)
+        assert np.array_equal(res.tables, tabs8[:tsz])                       # x-word counts do not depend on kmax
+        possible = int(np.maximum(g.scaf_len.astype(np.int64) - k + 1, 0).sum())
+        assert int(res.tables[_lib.table_size(1, k - 1) if k > 1 else 0:].sum()) // 2 + res.meta[1] == possible
+        meta = np.array(res.meta, dtype=np.uint64)
+        rows, status = c_oracle.score(seq, woff[pick], wlen[pick], np.ascontiguousarray(res.tables), meta, 1, k, True, threads=16)
+        assert np.all(status == 0) and np.all(res.status[pick] == 0)
+        assert_rows_close(res.rows[pick], rows, rtol_kld=1e-6, rtol_other=1e-15, what="C3 k=%d" % k)
+        assert max_rel_err(res.rows[pick, 0], rows[:, 0]) < 1e-10
+        assert np.all(np.isfinite(res.rows[:, 0])) and np.all(res.rows[:, 0] >= 0)
+    # more context can only sharpen the contrast on repeats: the mean score grows with k'
+    means = [float(sweep[k].rows[:, 0].mean()) for k in range(1, 9)]
+    assert all(a < b for a, b in zip(means, means[1:]))
