@@ -1172,6 +1172,183 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
     }
 }
 
+// ============================================================================================
+// Window scoring for small word sizes (K <= 6): no sorting at all.  The whole order-K table has at most
+// 4,096 bins, so every position does ONE u16 shared-memory atomic on order K (or on the order of its
+// longest valid word), lower orders follow by marginalisation, and the epilogue simply walks the bins
+// of order K in order (coalesced genome-IVOM reads, fixed summation order -> bit-reproducible).
+// 11 KB of shared memory: 6 CTAs of 256 threads per SM.  Windows up to 65,535 bases (16-bit counters).
+// ============================================================================================
+struct SmallSmem {
+    double q[8];
+    double red[3][kW3];
+    int n_non, n_gc, flags, pad;
+};
+
+template <int K>
+struct SmallLayout {
+    static constexpr uint32_t NTAB = lvl_off(K + 1);                       // u16 entries, orders 1..K
+    static constexpr uint32_t TAB_BYTES = (NTAB * 2u + 15u) & ~15u;
+    static constexpr uint32_t OFF_LOG = TAB_BYTES;
+    static constexpr uint32_t OFF_SS = OFF_LOG + 128u * 16u;
+    static constexpr uint32_t TOTAL = OFF_SS + (uint32_t)sizeof(SmallSmem);
+};
+
+template <int K, bool DUMP>
+__global__ void __launch_bounds__(kT3, 6)
+score_windows_small_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
+                           const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
+                           const double2* __restrict__ ig, int kmin, int want_rip,
+                           double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
+    using L = SmallLayout<K>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem);
+    uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem);
+    double2* logtab = reinterpret_cast<double2*>(smem + L::OFF_LOG);
+    SmallSmem& ss = *reinterpret_cast<SmallSmem*>(smem + L::OFF_SS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (uint32_t i = tid; i < L::TAB_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { ss.n_non = 0; ss.n_gc = 0; ss.flags = 0; }
+    if (tid < 128) {
+        const double c = 1.0 + ((double)tid + 0.5) / 128.0;
+        const double ic = 1.0 / c;
+        logtab[tid] = make_double2(ic, -log2(ic));
+    }
+    __syncthreads();
+
+    for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x) {
+        const uint64_t o = win_off[win];
+        const uint32_t len = win_len[win];
+        const uint32_t o_lo = (uint32_t)(o & 31);
+        const uint32_t* __restrict__ cw = codes + (o >> 5) * 2;
+        const uint32_t* __restrict__ mw = inv + (o >> 5);
+        const uint32_t* __restrict__ lw = low ? low + (o >> 5) : nullptr;
+        const uint32_t g0 = o_lo >> 2;
+        const uint32_t ngroups = ((o_lo + len + 3u) >> 2) - g0;
+
+        // ---- count: one atomic per position, on the order of its longest valid word (<= K) -----------
+        int non = 0, gc = 0;
+        for (uint32_t gi = tid; gi < ngroups; gi += kT3) {
+            const GroupWords gw = load_group(cw, mw, lw, (g0 + gi) << 2);
+            visit_group(gw, (g0 + gi) << 2, o_lo, len, [&](uint32_t, uint32_t p, uint32_t c32, uint32_t m, uint32_t lowbit) {
+                const uint32_t unres = (m >> 31) | lowbit;                       // not an upper-case ATGC (F:106-118)
+                non += unres;
+                gc += (1 - unres) & (c32 >> 31);
+                const uint32_t rest = len - p;
+                const int v = min(min(__clz(m), K), (int)(rest < (uint32_t)K ? rest : (uint32_t)K));
+                if (v > 0) {
+                    const uint32_t g = lvl_off(v) + (c32 >> (32 - 2 * v));
+                    atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
+                }
+            });
+        }
+        non = __reduce_add_sync(kFull, non);
+        gc = __reduce_add_sync(kFull, gc);
+        if (lane == 0 && (non | gc)) { atomicAdd(&ss.n_non, non); atomicAdd(&ss.n_gc, gc); }
+        __syncthreads();
+        // ---- lower orders: F_x = words that end at order x + marginal of F_{x+1} ----------------------
+#pragma unroll
+        for (int x = K - 1; x >= 1; --x) {
+            for (uint32_t t = tid; t < pow4(x); t += kT3) {
+                const uint2 ch = *reinterpret_cast<const uint2*>(tab16 + lvl_off(x + 1) + 4 * t);
+                tab16[lvl_off(x) + t] += (uint16_t)((ch.x & 0xffffu) + (ch.x >> 16) + (ch.y & 0xffffu) + (ch.y >> 16));
+            }
+            __syncthreads();
+        }
+        const int n_non = ss.n_non, n_gc = ss.n_gc, n_up = (int)len - n_non;
+        const bool excluded = (double)n_non >= 0.3 * (double)len;              // F:238 / F:213
+        if (tid < K) {
+            const int x = tid + 1;
+            const long long d = ((long long)n_up - (long long)(x - 1)) * 2;
+            ss.q[tid] = (double)pow4(x) / (double)d;
+        }
+        uint32_t n_at = 0, n_ta = 0, n_sub = 0, n_prod = 0;
+        if (K >= 2 && tid == 0 && want_rip) {
+            const uint16_t* di = tab16 + lvl_off(2);
+            n_at = di[1]; n_ta = di[4]; n_sub = (uint32_t)di[3] + di[9]; n_prod = (uint32_t)di[12] + di[6];
+        }
+        if (DUMP) {
+            uint16_t* d = dump + (size_t)win * lvl_off(K + 1);
+            for (uint32_t i = tid; i < lvl_off(K + 1); i += kT3) d[i] = excluded ? (uint16_t)0 : tab16[i];
+        }
+        __syncthreads();
+
+        // ---- epilogue: every occupied bin of order K, in table order ------------------------------------
+        double s_w = 0.0, s_g = 0.0, s_t = 0.0;
+        uint32_t any = 0;
+        if (!excluded) {
+            for (uint32_t kappa = tid; kappa < pow4(K); kappa += kT3) {
+                const uint32_t ck = tab16[lvl_off(K) + kappa];
+                if (ck == 0) continue;
+                double num = 0.0;
+                uint32_t den = 0;
+#pragma unroll
+                for (int x = 1; x <= K; ++x) {
+                    if (x >= kmin) {
+                        const uint32_t c = (x == K) ? ck : (uint32_t)tab16[lvl_off(x) + (kappa >> (2 * (K - x)))];
+                        den += c << (2 * x);
+                        num = fma(ss.q[x - 1], u32_to_double(c * c), num);
+                    }
+                }
+                const double iw = div_pos(num, (double)den);
+                const double2 g = __ldg(ig + kappa);
+                s_w += iw;
+                s_g += g.x;
+                s_t = fma(iw, log2_pos(iw, logtab) - g.y, s_t);
+                any = 1;
+            }
+        }
+#pragma unroll
+        for (int ofs = 16; ofs; ofs >>= 1) {
+            s_w += __shfl_xor_sync(kFull, s_w, ofs);
+            s_g += __shfl_xor_sync(kFull, s_g, ofs);
+            s_t += __shfl_xor_sync(kFull, s_t, ofs);
+        }
+        any = __any_sync(kFull, any);
+        if (lane == 0) {
+            ss.red[0][warp] = s_w; ss.red[1][warp] = s_g; ss.red[2][warp] = s_t;
+            if (any) atomicOr(&ss.flags, 1);
+        }
+        __syncthreads();                                                       // everyone is done with the tables
+        for (uint32_t i = tid; i < L::TAB_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) {
+            double* row = rows + (size_t)win * 5;
+            if (excluded) {
+                status[win] = FRISK_ROW_EXCLUDED;
+                for (int c = 0; c < 5; ++c) row[c] = CUDART_NAN;
+            } else {
+                double a = 0, bsum = 0, c = 0;
+                for (int w = 0; w < kW3; ++w) { a += ss.red[0][w]; bsum += ss.red[1][w]; c += ss.red[2][w]; }
+                uint32_t st = 0;
+                double kld = 0.0;                          // the reference returns 0 for a window without kmax-mers
+                if (ss.flags & 1) {
+                    bool zd = bsum != bsum;                // NaN genome IVOM entry: ZeroDivisionError at F:437
+                    for (int x = kmin; x <= K; ++x) zd |= ((long long)n_up - (long long)(x - 1)) == 0;
+                    if (zd) { st |= FRISK_ROW_KLD_ZERODIV; kld = CUDART_NAN; }
+                    else {
+                        kld = c / a + (log2(bsum) - log2(a));
+                        if (!(kld == kld) || isinf(kld)) st |= FRISK_ROW_LOG_DOMAIN;
+                    }
+                }
+                row[0] = kld;
+                if (n_up == 0) { st |= FRISK_ROW_GC_ZERODIV; row[1] = CUDART_NAN; }
+                else row[1] = (double)n_gc / (double)n_up;   // F:136
+                double pi = CUDART_NAN, si = CUDART_NAN, cri = CUDART_NAN;
+                if (K >= 2 && want_rip) {
+                    if (n_at > 0) pi = (double)n_ta / (double)n_at;        // F:480-483
+                    if (n_sub > 0) si = (double)n_prod / (double)n_sub;    // F:485-489
+                    if (pi != 0.0 && si != 0.0) cri = pi - si;             // F:491: 0.0 falsy, NaN truthy
+                }
+                row[2] = pi; row[3] = si; row[4] = cri;
+                status[win] = st;
+            }
+            ss.n_non = 0; ss.n_gc = 0; ss.flags = 0;
+        }
+        __syncthreads();
+    }
+}
+
 // KLD of two already-normalised IVOM vectors (F:459-472): sum w*log2(w/G), G == 0 skipped.
 // One CTA, fixed reduction tree.  Only used by the dict-level compatibility API; the batch path
 // computes the same quantity inside score_windows_kernel.
@@ -1220,6 +1397,7 @@ __global__ void __launch_bounds__(kThreads, 1) smem_atomic_bench_kernel(int iter
 thread_local char g_cuda_err[512] = "";
 int g_force_dense = 0;      // tests: force the dense-table kernel (frisk_b200_set_option)
 int g_force_general = 0;    // tests: force the general (global-memory) score kernel
+int g_force_bucket = 0;     // tests: keep kmax 4..6 on the bucketed kernel instead of the small-K kernel
 }  // namespace
 
 int frisk_internal::cuda_fail(cudaError_t e, const char* what) {
@@ -1363,6 +1541,29 @@ int launch_score_bucket(const uint32_t* codes, const uint32_t* inv, const uint32
         return dump ? launch_score_bucket2<K, true, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st)
                     : launch_score_bucket2<K, false, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
     return launch_score_bucket2<K, false, true>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
+}
+
+template <int K>
+int launch_score_small(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                       const uint32_t* win_len, uint64_t n_win, const double* ig, int kmin, int want_rip,
+                       double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+    using L = SmallLayout<K>;
+    auto launch = [&](auto kern) -> int {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT3, L::TOTAL));
+        if (per_sm < 1) per_sm = 1;
+        const int sms = sm_count();
+        if (sms <= 0) return FRISK_E_NO_DEVICE;
+        uint64_t grid = (uint64_t)sms * (uint64_t)per_sm;
+        if (grid > n_win) grid = n_win;
+        kern<<<(unsigned)grid, kT3, L::TOTAL, st>>>(codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len,
+                                                    (uint32_t)n_win, reinterpret_cast<const double2*>(ig), kmin, want_rip, rows,
+                                                    status, dump);
+        CK(cudaGetLastError());
+        return FRISK_OK;
+    };
+    return dump ? launch(score_windows_small_kernel<K, true>) : launch(score_windows_small_kernel<K, false>);
 }
 
 #define DISPATCH_K(kmax, expr)                      \
@@ -1516,7 +1717,19 @@ int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint3
     if (kmax > FRISK_B200_FAST_K || max_win_len > 65535u || g_force_general)
         return frisk_internal::general_score(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, kmax,
                                              rip, d_rows, d_status, d_dump, st);
-    // default path: bucketed kernel (4 CTAs/SM); the dense-table kernel covers K < 4 and long windows
+    // word sizes up to 6: the whole order-K table is small -- no sorting, 6 CTAs/SM, any window up to 65,535 bases
+    if (kmax <= 6 && !g_force_dense && !g_force_bucket) {
+        switch (kmax) {
+            case 1: return launch_score_small<1>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
+            case 2: return launch_score_small<2>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
+            case 3: return launch_score_small<3>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
+            case 4: return launch_score_small<4>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
+            case 5: return launch_score_small<5>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
+            case 6: return launch_score_small<6>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
+            default: break;
+        }
+    }
+    // kmax 7 and 8 (and 4..6 when forced): bucketed kernel (4 CTAs/SM); the dense-table kernel covers long windows
     if (kmax >= 4 && max_win_len <= kBuf3 - 6u && !g_force_dense) {
         switch (kmax) {
             case 4: return launch_score_bucket<4>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
@@ -1538,6 +1751,21 @@ int frisk_b200_score_occupancy(int kmax, uint32_t max_win_len, int* ctas_per_sm,
     *ctas_per_sm = 1;
     *threads_per_cta = kThreads;
     if (kmax > FRISK_B200_FAST_K || max_win_len > 65535u) { *threads_per_cta = 1024; return FRISK_OK; }   // general kernel
+    if (kmax <= 6 && !g_force_dense && !g_force_bucket) {                                                       // small-K kernel
+        *threads_per_cta = kT3;
+        switch (kmax) {
+#define FRISK_OCC_S(KK)                                                                                                         \
+    case KK:                                                                                                                    \
+        CK(cudaFuncSetAttribute(score_windows_small_kernel<KK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                (int)SmallLayout<KK>::TOTAL));                                                                  \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, score_windows_small_kernel<KK, false>, kT3,               \
+                                                         SmallLayout<KK>::TOTAL));                                              \
+        return FRISK_OK;
+            FRISK_OCC_S(1) FRISK_OCC_S(2) FRISK_OCC_S(3) FRISK_OCC_S(4) FRISK_OCC_S(5) FRISK_OCC_S(6)
+#undef FRISK_OCC_S
+            default: break;
+        }
+    }
     if (kmax < 4 || max_win_len > kBuf3 - 6u || g_force_dense) return FRISK_OK;                                // dense kernel
     const uint32_t cap = (max_win_len + 15u) & ~15u;
     *threads_per_cta = kT3;
@@ -1564,6 +1792,7 @@ int frisk_b200_set_option(const char* name, int value) {
     if (!name) return FRISK_E_INVALID;
     if (strcmp(name, "force_dense_kernel") == 0) { g_force_dense = value; return FRISK_OK; }
     if (strcmp(name, "force_general_kernel") == 0) { g_force_general = value; return FRISK_OK; }
+    if (strcmp(name, "force_bucket_kernel") == 0) { g_force_bucket = value; return FRISK_OK; }
     return FRISK_E_INVALID;
 }
 

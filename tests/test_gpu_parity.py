@@ -172,6 +172,29 @@ def test_windows_longer_than_65535_bases(eng):
         assert max_rel_err(res.rows[ok, 0], ref["rows"][ok, 0]) < 1e-10
 
 
+@pytest.mark.parametrize("case", ["edge_k2_5_w1000_i250", "edge_k1_3_w3000_i1000", "edge_k1_1"])
+def test_small_word_sizes_three_kernels_agree(eng, case):
+    """kmax <= 6 is served by the small-K kernel (no sorting); the bucketed kernel (kmax 4..6, forced) and
+    the dense-table kernel (forced) must give the same window tables and the same rows to 1e-12."""
+    from frisk_b200 import _lib
+    g = Golden(case)
+    default = _run_case(eng, g, dump=True)
+    _check_against_golden(default, g, case + "[small-K]")
+    again = _run_case(eng, g)
+    assert np.array_equal(default.rows, again.rows, equal_nan=True)             # bit-reproducible
+    for opt in (b"force_bucket_kernel", b"force_dense_kernel"):
+        _lib.check(_lib.lib().frisk_b200_set_option(opt, 1), "set_option")
+        try:
+            other = _run_case(eng, g, dump=True)
+        finally:
+            _lib.lib().frisk_b200_set_option(opt, 0)
+        _check_against_golden(other, g, case + "[%s]" % opt.decode())
+        assert np.array_equal(other.win_tables, default.win_tables)
+        ok = default.status == 0
+        assert np.array_equal(other.status, default.status)
+        assert max_rel_err(other.rows[ok, 0], default.rows[ok, 0]) < 1e-12
+
+
 def test_long_windows_use_segments(eng):
     """Windows longer than the bucketed kernel's 8192-base buffer (and longer than the dense
     kernel's 8192-entry k-mer list) against the C oracle."""
@@ -230,6 +253,9 @@ def test_bit_reproducible(eng):
     ("C1", 0.05, dict(w=2040, step=1020, kmin=3)),
     ("C1", 0.06, dict(w=8000, step=3000)),                              # the 8-round instantiation (5,115..8,186 bases)
     ("C2", 0.03, dict(w=8186, step=8186, scaffolds_all=True, kmax=5)),
+    ("C2", 0.02, dict(kmax=6, w=60000, step=20000)),                    # small-K kernel, windows near its 65,535 limit
+    ("C2", 0.02, dict(kmax=4, kmin=2)),
+    ("C2", 0.02, dict(kmax=2)),
 ])
 def test_against_c_oracle_on_fresh_genomes(eng, config, scale, kw):
     from frisk_b200 import synth
