@@ -178,3 +178,33 @@ def test_tsv_formatter_writes_floats_like_python():
     empty = engine.HotPathResult(1, 8, np.zeros(0, np.uint64), (0, 0, 0), [], np.zeros((0, 2), np.int64), np.zeros((0, 5)),
                                  np.zeros(0, np.uint32), 0, np.zeros(0, np.int64), np.zeros(0, np.int64), None, scaf_names=names)
     assert empty.tsv_body(True) == b""
+
+
+def test_argument_checks_answer_before_any_device_work():
+    """Bad arguments are refused with FRISK_E_INVALID / FRISK_E_UNSUPPORTED by every entry point, without a GPU
+    (nothing is dereferenced or launched before the checks)."""
+    L = _lib.lib()
+    dummy = np.zeros(64, np.uint64)
+    p = engine._ptr(dummy)
+    null = C.c_void_p(0)
+    n = C.c_uint64(0)
+    assert L.frisk_b200_background(null, p, null, 0, 64, 8, 0, p, null) == _lib.E_INVALID
+    assert L.frisk_b200_background(p, p, null, 16, 64, 8, 0, p, null) == _lib.E_INVALID            # not a multiple of 32
+    assert L.frisk_b200_background(p, p, null, 0, 64, 13, 0, p, null) == _lib.E_UNSUPPORTED
+    assert L.frisk_b200_background(p, p, null, 64, 64, 8, 0, p, null) == _lib.OK                    # empty range: nothing to do
+    assert L.frisk_b200_finalize_tables(null, 8, 1, p, null, null) == _lib.E_INVALID
+    assert L.frisk_b200_genome_ivom(p, 3, 2, 1000, p, null) == _lib.E_INVALID                       # kmin > kmax
+    assert L.frisk_b200_genome_ivom(p, 1, 13, 1000, p, null) == _lib.E_UNSUPPORTED
+    assert L.frisk_b200_score(p, p, null, p, p, 0, 5000, p, 1, 8, 1, p, p, null, null) == _lib.OK   # no windows
+    assert L.frisk_b200_score(p, p, null, p, p, 10, 5000, null, 1, 8, 1, p, p, null, null) == _lib.E_INVALID
+    assert L.frisk_b200_windows(p, p, 1, 0, 2500, 0, 0, null, null, null, null, null, C.byref(n)) == _lib.E_INVALID
+    assert L.frisk_b200_feature_slots(1, 8, null, C.byref(n)) == _lib.E_UNSUPPORTED
+    assert L.frisk_b200_feature_slots(3, 2, null, C.byref(n)) == _lib.E_INVALID
+    assert L.frisk_b200_format_rows(null, null, null, null, null, null, null, 0, 6, null, 0, C.byref(n), 1) == _lib.E_INVALID
+    assert L.frisk_b200_finalize_tables_peers(null, null, 0, 2, 1, 8, 1, p, null, null) == _lib.E_INVALID
+    assert L.frisk_b200_run_host(p, null, null, 128, p, p, null, 128, null, null, 0, 0, 1, 8, 0, 1, 100, null, null, null, null,
+                                 null) == _lib.E_INVALID
+    assert L.frisk_b200_run_resident(p, p, null, 100, p, p, null, 128, null, null, 0, 0, 1, 8, 0, 1, 100, null, null, null, null,
+                                     null) == _lib.E_INVALID                                         # padded_len % 128
+    assert b"unsupported" in L.frisk_b200_strerror(_lib.E_UNSUPPORTED) and L.frisk_b200_strerror(-99) == b"unknown error"
+    assert L.frisk_b200_set_option(b"no_such_option", 1) == _lib.E_INVALID
