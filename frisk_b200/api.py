@@ -35,7 +35,7 @@ from . import _lib, engine
 
 __all__ = ["LETTERS", "tempPathCheck", "countN", "calcGC", "iterFasta", "crawlGenome", "prepareMaps", "rangeMaps",
            "revComplement", "computeKmers", "IvomBuild", "KLD", "calcRIP", "makePicklePath", "mainArgs", "main",
-           "scrubMirrors", "flattenKmerMap", "pcaFeatures", "score_genome", "FRISK_VERSION"]
+           "scrubMirrors", "flattenKmerMap", "pcaFeatures", "pcaFeaturesFromIntervals", "score_genome", "FRISK_VERSION"]
 
 FRISK_VERSION = "b200-0.1"
 LETTERS = ("A", "T", "G", "C")             # F:70 -- alphabet and table order
@@ -304,6 +304,34 @@ def pcaFeatures(args, regions, device="cuda:0"):
     if np.isnan(feats).any():
         raise ZeroDivisionError("float division by zero (reference F:824: a region without a valid word of some order)")
     return np.array([n for n, _ in regions]), feats
+
+
+def pcaFeaturesFromIntervals(args, genome, intervals):
+    """The same vectors straight from the packed planes: ``genome`` is an engine.DeviceGenome (e.g. the one the
+    scores were computed from), ``intervals`` the (chrom, start, stop, ...) records of thresholdKLD / hmm2BED.
+    Replaces getFasta + getBEDSeq (F:166-192: sequence = scaffold[start-1:stop], label "chrom:start:stop", records
+    on unknown scaffolds or of zero length are skipped) + the per-region loop F:1571-1591 without ever
+    materialising a sequence string."""
+    g = genome.host
+    index = {name: i for i, name in enumerate(g.names)}
+    labels, off, length = [], [], []
+    for rec in intervals:
+        i = index.get(str(rec[0]))
+        if i is None:
+            logging.error("Scaffold %s not found in reference." % str(rec[0]))
+            continue
+        a, b = int(rec[1]) - 1, min(int(rec[2]), int(g.scaf_len[i]))
+        name = ":".join([str(rec[0]), str(rec[1]), str(rec[2])])
+        if b <= a or a < 0:
+            logging.error("Error: Retrieved zero len sequence for %s" % name)
+            continue
+        labels.append(name)
+        off.append(int(g.scaf_off[i]) + a)
+        length.append(b - a)
+    feats = engine.region_features(genome, np.array(off, np.uint64), np.array(length, np.uint32), args.pcaMin, args.pcaMax)
+    if np.isnan(feats).any():
+        raise ZeroDivisionError("float division by zero (reference F:824: a region without a valid word of some order)")
+    return np.array(labels), feats
 
 
 def makePicklePath(args, **kwargs) -> str:

@@ -149,3 +149,27 @@ def test_batch_pca_features_match_the_reference_formulation():
     assert np.array_equal(vec, f24[0])
     with pytest.raises(ZeroDivisionError):
         api.pcaFeatures(args, [("tiny", np.frombuffer(b"ACG", np.uint8))])   # no 4-mer at all: F:824 divides by zero
+
+
+def test_pca_features_straight_from_the_planes(tmp_path):
+    """thresholdKLD intervals -> composition vectors read from the resident planes (no getFasta / getBEDSeq
+    strings) == the vectors of the extracted sequences (reference slicing rule seq[start-1:stop])."""
+    import argparse
+    from frisk_b200 import api, downstream, engine, synth
+    sc = synth.make("C1", 0.04) + synth.make("edge")[:2]
+    text = synth.fasta_bytes(sc)
+    dg = engine.DeviceGenome.from_fasta_bytes(text)
+    res = engine.run(dg, scaffolds_all=True)
+    frame = api.windows_frame(res, with_rip=True)
+    targs = argparse.Namespace(findSelf=False, mergeDist=0, dimReduce="features")
+    thr = np.percentile(np.log10(frame["windowKLD"][frame["windowKLD"] > 0]), 80.0)
+    merged, _ = downstream.thresholdKLD(frame, thr, targs, merge=True)
+    assert len(merged) >= 5
+    merged = merged + [("no_such_scaffold", 1, 100, 0.1, 0.1, 0.1)]
+    args = argparse.Namespace(pcaMin=1, pcaMax=6)
+    labels, feats = api.pcaFeaturesFromIntervals(args, dg, merged)
+    assert len(labels) == len(merged) - 1 and labels[0] == "%s:%d:%d" % merged[0][:3]
+    seqs = dict(sc)
+    regions = [(lab, seqs[rec[0]][int(rec[1]) - 1:int(rec[2])]) for lab, rec in zip(labels, merged)]
+    labels2, feats2 = api.pcaFeatures(args, regions)
+    assert list(labels2) == list(labels) and np.array_equal(feats, feats2)
