@@ -58,6 +58,9 @@ PROTOTYPES = {
     "frisk_b200_fasta_pack": (_i, [_p, _p, _p, _p, _p]),
     "frisk_b200_fasta_close": (_i, [_p, _p]),
     "frisk_b200_release_workspace": (_i, []),
+    "frisk_b200_device_alloc": (_i, [C.POINTER(C.c_void_p), _u64]),
+    "frisk_b200_device_free": (_i, [_p]),
+    "frisk_b200_set_device": (_i, [_i]),
     "frisk_b200_host_alloc": (_i, [C.POINTER(C.c_void_p), _u64]),
     "frisk_b200_host_free": (_i, [_p]),
     "frisk_b200_bench_smem_atomics": (_i, [_i, _i, _i, C.POINTER(C.c_float), _p]),

@@ -350,11 +350,14 @@ def score_genome(args, device="cuda:0") -> engine.HotPathResult:
     ``args.querySeq or args.hostSeq`` (F:1442, F:1478-1494)."""
     # device-side ingest: the FASTA text is copied to the GPU once and tokenised / packed there
     # (the reference reads each file three times in Python: F:170, F:203, F:297)
-    host = engine.DeviceGenome.from_fasta(args.hostSeq, device)
-    query = host if not args.querySeq or args.querySeq == args.hostSeq else engine.DeviceGenome.from_fasta(args.querySeq, device)
-    res = engine.run(query, host if query is not host else None, kmin=args.minWordSize, kmax=args.maxWordSize,
-                     w=args.windowlen, step=args.increment, mask_host=args.maskHost, scaffolds_all=args.scaffoldsAll,
-                     rip=bool(args.RIP), device=device)
+    # ... and everything goes through the C ABI alone (DevBuf planes, one frisk_b200_run_resident call): PyTorch is
+    # never imported on this path -- its import takes several seconds, the run itself milliseconds
+    ingest = lambda path: engine.DeviceGenome.from_fasta_bytes_native(engine.read_fasta_file(path), device)
+    host = ingest(args.hostSeq)
+    query = host if not args.querySeq or args.querySeq == args.hostSeq else ingest(args.querySeq)
+    res = engine.run_resident(query, host if query is not host else None, kmin=args.minWordSize, kmax=args.maxWordSize,
+                              w=args.windowlen, step=args.increment, mask_host=args.maskHost,
+                              scaffolds_all=args.scaffoldsAll, rip=bool(args.RIP))
     res.raise_reference_errors()                 # the reference aborts on ZeroDivisionError (F:437, F:136)
     return res
 

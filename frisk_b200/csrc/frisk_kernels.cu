@@ -2083,6 +2083,24 @@ int frisk_b200_release_workspace(void) {
     return FRISK_OK;
 }
 
+int frisk_b200_device_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return FRISK_E_INVALID;
+    if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    CK(cudaMalloc(ptr, bytes ? bytes : 1));
+    return FRISK_OK;
+}
+
+int frisk_b200_device_free(void* ptr) {
+    if (ptr) CK(cudaFree(ptr));
+    return FRISK_OK;
+}
+
+int frisk_b200_set_device(int index) {
+    if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    CK(cudaSetDevice(index));
+    return FRISK_OK;
+}
+
 int frisk_b200_host_alloc(void** ptr, uint64_t bytes) {
     if (!ptr) return FRISK_E_INVALID;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;

@@ -12,6 +12,7 @@ C call from pinned host buffers used for end-to-end timing.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -20,6 +21,38 @@ import numpy as np
 from . import _lib
 
 SeqLike = Union[np.ndarray, bytes, str]
+
+
+def _torch_loaded() -> bool:
+    return "torch" in sys.modules
+
+
+class DevBuf:
+    """Device memory owned through the C ABI (frisk_b200_device_alloc): what holds the planes when PyTorch is
+    not in the process (the CLI path never imports it: the import alone takes longer than the run)."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        _lib.check(_lib.lib().frisk_b200_device_alloc(C.byref(p), int(nbytes)), "frisk_b200_device_alloc")
+        self._p, self.nbytes = p, int(nbytes)
+
+    def data_ptr(self) -> int:
+        return int(self._p.value or 0)
+
+    def __del__(self):
+        try:
+            if self._p:
+                _lib.lib().frisk_b200_device_free(self._p)
+                self._p = C.c_void_p()
+        except Exception:
+            pass
+
+
+def _device_index(device) -> int:
+    if isinstance(device, int):
+        return device
+    text = str(device)
+    return int(text.split(":")[1]) if ":" in text else 0
 
 
 def _ptr(a) -> C.c_void_p:
@@ -220,9 +253,13 @@ class DeviceGenome:
     """The packed planes resident in HBM (torch tensors used purely as device buffers)."""
 
     def __init__(self, g: PackedGenome, device="cuda:0", stream=None, planes=None):
-        import torch
         _lib.require_device()
         self.host = g
+        if planes is not None and isinstance(planes[0], DevBuf):
+            self.device = device                      # native planes: torch is not needed (and may not be loaded)
+            self.codes, self.inv, self.low = planes
+            return
+        import torch
         self.device = torch.device(device)
         if planes is not None:
             self.codes, self.inv, self.low = planes
@@ -231,6 +268,34 @@ class DeviceGenome:
             self.codes = torch.from_numpy(g.codes.view(np.int32)).to(self.device, non_blocking=True)
             self.inv = torch.from_numpy(g.inv.view(np.int32)).to(self.device, non_blocking=True)
             self.low = torch.from_numpy(g.low.view(np.int32)).to(self.device, non_blocking=True) if g.low is not None else None
+
+    @classmethod
+    def from_fasta_bytes_native(cls, text: Union[bytes, np.ndarray], device="cuda:0") -> "DeviceGenome":
+        """``from_fasta_bytes`` without PyTorch: the planes are DevBuf allocations (cudaMalloc through the C
+        ABI), work goes to the default stream.  Used by the CLI."""
+        _lib.require_device()
+        L = _lib.lib()
+        buf = _as_u8(text)
+        _lib.check(L.frisk_b200_set_device(_device_index(device)), "frisk_b200_set_device")
+        h = C.c_void_p()
+        nrec, padded = C.c_uint64(0), C.c_uint64(0)
+        stats = np.zeros(3, np.uint64)
+        _lib.check(L.frisk_b200_fasta_open(_ptr(buf), buf.shape[0], None, C.byref(h), C.byref(nrec), C.byref(padded), _ptr(stats)),
+                   "frisk_b200_fasta_open")
+        try:
+            R, P = int(nrec.value), int(padded.value)
+            name_off = np.zeros(R, np.uint64); name_len = np.zeros(R, np.uint32)
+            seq_len = np.zeros(R, np.uint64); scaf_off = np.zeros(R, np.uint64)
+            _lib.check(L.frisk_b200_fasta_records(h, _ptr(name_off), _ptr(name_len), _ptr(seq_len), _ptr(scaf_off)),
+                       "frisk_b200_fasta_records")
+            codes, inv = DevBuf(P // 4), DevBuf(P // 8)
+            low = DevBuf(P // 8) if int(stats[2]) else None
+            _lib.check(L.frisk_b200_fasta_pack(h, _ptr(codes), _ptr(inv), _ptr(low), None), "frisk_b200_fasta_pack")
+        finally:
+            L.frisk_b200_fasta_close(h, None)
+        names = _decode_names(buf, name_off, name_len)
+        g = PackedGenome(names, seq_len, scaf_off, P, None, None, None, int(stats[0]), int(stats[1]), int(stats[2]), False)
+        return cls(g, str(device), planes=(codes, inv, low))
 
     @classmethod
     def from_fasta_bytes(cls, text: Union[bytes, np.ndarray], device="cuda:0") -> "DeviceGenome":
@@ -278,6 +343,8 @@ class DeviceGenome:
 
 
 def _stream_ptr(device) -> C.c_void_p:
+    if not _torch_loaded():
+        return C.c_void_p(0)                 # no torch in the process: the default stream
     import torch
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -654,21 +721,30 @@ def run_resident(dq: DeviceGenome, dh: Optional[DeviceGenome] = None, kmin: int 
     """``run_host`` for planes that are already on the device (frisk_b200_run_resident): one C call
     that uploads the window list, runs every kernel and downloads rows/status/tables."""
     _lib.require_device()
-    import torch
     dh = dh or dq
     query, host = dq.host, dh.host
     if wins is None:
         wins = query.windows(w, step, scaffolds_all)
     n = len(wins)
+    native = isinstance(dq.codes, DevBuf)
     if out is None:
-        out = HostOutputs(n, kmax)
-    with torch.cuda.device(dq.device):
-        rc = _lib.lib().frisk_b200_run_resident(
+        out = HostOutputs(n, kmax, pinned=not native)
+
+    def call():
+        return _lib.lib().frisk_b200_run_resident(
             _ptr(dh.codes), _ptr(dh.inv), _ptr(dh.low), host.padded_len,
             _ptr(dq.codes), _ptr(dq.inv), _ptr(dq.low), query.padded_len,
             _ptr(wins.off), _ptr(wins.length), n, wins.max_len, kmin, kmax, int(mask_host), int(rip),
             int(host.genome_space), _ptr(out.rows), _ptr(out.status), _ptr(out.tables), _ptr(out.valid),
             _stream_ptr(dq.device))
+
+    if native:
+        _lib.check(_lib.lib().frisk_b200_set_device(_device_index(dq.device)), "frisk_b200_set_device")
+        rc = call()
+    else:
+        import torch
+        with torch.cuda.device(dq.device):
+            rc = call()
     _lib.check(rc, "frisk_b200_run_resident")
     if not assemble_result:
         return out

@@ -304,6 +304,12 @@ int frisk_b200_fasta_close(frisk_b200_fasta *h, void *stream);
 /* Free the cached device workspace of frisk_b200_run_host on the current device. */
 int frisk_b200_release_workspace(void);
 
+/* Plain device memory (cudaMalloc / cudaFree) and device selection, so that a caller without a GPU array
+ * library of its own -- the CLI: importing PyTorch costs more than the whole run -- can own its planes. */
+int frisk_b200_device_alloc(void **ptr, uint64_t bytes);
+int frisk_b200_device_free(void *ptr);
+int frisk_b200_set_device(int index);
+
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so Python can build pinned planes. */
 int frisk_b200_host_alloc(void **ptr, uint64_t bytes);
 int frisk_b200_host_free(void *ptr);

@@ -2,6 +2,8 @@
 import pickle
 import types
 
+import os
+
 import numpy as np
 import pytest
 
@@ -173,3 +175,25 @@ def test_pca_features_straight_from_the_planes(tmp_path):
     regions = [(lab, seqs[rec[0]][int(rec[1]) - 1:int(rec[2])]) for lab, rec in zip(labels, merged)]
     labels2, feats2 = api.pcaFeatures(args, regions)
     assert list(labels2) == list(labels) and np.array_equal(feats, feats2)
+
+
+def test_cli_runs_without_importing_torch(tmp_path):
+    """The CLI path goes through the C ABI alone (native device buffers, one frisk_b200_run_resident call):
+    PyTorch -- whose import alone takes seconds -- must not be loaded, and the products equal the golden ones."""
+    import subprocess
+    import sys
+    import pandas as pd
+    from frisk_b200 import synth
+    g = Golden("c2_small")
+    path = str(tmp_path / "genome.fa")
+    synth.write_fasta(g.scaffolds(), path)
+    tmp = tmp_path / "temp"
+    code = ("import sys, frisk; frisk.main(['-H', %r, '-t', %r, '--quiet', '--RIP']); "
+            "assert 'torch' not in sys.modules, 'torch was imported'; print('no torch')" % (path, str(tmp)))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=600)
+    assert out.returncode == 0 and "no torch" in out.stdout, out.stdout[-1000:] + out.stderr[-3000:]
+    tsv = pd.read_csv(tmp / "raw_window_scores.bed", sep="\t", float_precision="round_trip")
+    assert list(tsv["name"]) == g.names and np.array_equal(tsv[["start", "stop"]].to_numpy(), g.coords)
+    assert_rows_close(tsv[["windowKLD", "GC", "PI", "SI", "CRI"]].to_numpy(float), g.vals, rtol_kld=1e-6, rtol_other=1e-15,
+                      what="c2_small[CLI, native buffers]")
