@@ -37,6 +37,7 @@ PROTOTYPES = {
     "frisk_b200_background": (_i, [_p, _p, _p, _u64, _u64, _i, _i, _p, _p]),
     "frisk_b200_finalize_tables": (_i, [_p, _i, _i, _p, _p, _p]),
     "frisk_b200_finalize_tables_peers": (_i, [_p, _p, _i, _i, _u64, _i, _i, _p, _p, _p]),
+    "frisk_b200_finalize_ivom": (_i, [_p, _p, _p, _i, _i, _u64, _i, _i, C.c_int64, _p, _p, _p, _p]),
     "frisk_b200_kld": (_i, [_p, _p, _u64, _p, _p]),
     "frisk_b200_feature_slots": (_i, [_i, _i, _p, _p]),
     "frisk_b200_region_features": (_i, [_p, _p, _p, _p, _u64, _i, _i, _p, _u64, _p, _p]),

@@ -10,6 +10,7 @@
 //
 // Table index convention everywhere: base-4 number, digits A=0 T=1 G=2 C=3, first base most
 // significant (the reference's dict key order, F:70/F:253-274); complement = digit ^ 1.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -103,7 +104,7 @@ bg_count_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__
         uint32_t m0 = __ldg(inv + wd), m1 = __ldg(inv + wd + 1);
         if (use_low) { m0 |= __ldg(low + wd); m1 |= __ldg(low + wd + 1); }
         const uint32_t c0 = __ldg(codes + 2 * wd), c1 = __ldg(codes + 2 * wd + 1), c2 = __ldg(codes + 2 * wd + 2);
-        const bool all_valid = (m0 == 0u) && (K == 1 || (m1 >> (33 - K)) == 0u);
+        const bool all_valid = (m0 == 0u) && (K == 1 || (m1 >> ((33 - K) & 31)) == 0u);
         if (all_valid) {                                   // the common word: 32 full K-words, no per-position checks
             // all 32 atomics are issued before any of their results is looked at; a wrap (rare) is
             // detected through one running minimum and handled after the fact
@@ -233,20 +234,17 @@ struct PeerFwd {
 };
 
 template <int K, typename Fwd>
-__global__ void __launch_bounds__(256)
-forward_totals_kernel(const Fwd fwd, unsigned long long* __restrict__ tables,
-                      unsigned long long* __restrict__ valid_kmax) {
+__device__ __forceinline__ void forward_totals_body(const Fwd& fwd, unsigned long long* __restrict__ tables,
+                                                    unsigned long long* __restrict__ valid_kmax, uint32_t root,
+                                                    unsigned long long (*lvl)[256], unsigned long long* red) {
     constexpr int R = K > 4 ? K - 4 : 0;
-    __shared__ unsigned long long lvl[2][256];
-    __shared__ unsigned long long red[8];
-    const uint32_t root = blockIdx.x, t = threadIdx.x;
+    const uint32_t t = threadIdx.x;
     uint32_t n = pow4(K - R);                         // subtree nodes at the current order
     // every counter this thread will need is requested up front (with peer buffers each is a round
     // trip over NVLink: one exposed latency instead of one per level)
     constexpr int LV = K - (R > 1 ? R : 1);           // levels below the top handled here
     unsigned long long own[LV > 0 ? LV : 1];
     unsigned long long v = 0;
-    fwd.arrive_and_wait();
     if (t < n) v = fwd(lvl_off(K) + root * n + t);
     {
         uint32_t m = n;
@@ -286,8 +284,17 @@ forward_totals_kernel(const Fwd fwd, unsigned long long* __restrict__ tables,
 }
 
 template <int K, typename Fwd>
-__global__ void __launch_bounds__(64)
-forward_low_kernel(const Fwd fwd, unsigned long long* __restrict__ tables) {
+__global__ void __launch_bounds__(256)
+forward_totals_kernel(const Fwd fwd, unsigned long long* __restrict__ tables,
+                      unsigned long long* __restrict__ valid_kmax) {
+    __shared__ unsigned long long lvl[2][256];
+    __shared__ unsigned long long red[8];
+    fwd.arrive_and_wait();
+    forward_totals_body<K, Fwd>(fwd, tables, valid_kmax, blockIdx.x, lvl, red);
+}
+
+template <int K, typename Fwd>
+__device__ __forceinline__ void forward_low_body(const Fwd& fwd, unsigned long long* __restrict__ tables) {
     constexpr int R = K > 4 ? K - 4 : 0;
     const uint32_t t = threadIdx.x;
     unsigned long long own[R > 1 ? R - 1 : 1];         // this thread's counter of every level, requested up front
@@ -303,11 +310,14 @@ forward_low_kernel(const Fwd fwd, unsigned long long* __restrict__ tables) {
     }
 }
 
+template <int K, typename Fwd>
+__global__ void __launch_bounds__(64)
+forward_low_kernel(const Fwd fwd, unsigned long long* __restrict__ tables) {
+    forward_low_body<K, Fwd>(fwd, tables);
+}
+
 template <int K>
-__global__ void __launch_bounds__(256)
-symmetrise_kernel(unsigned long long* __restrict__ tables) {
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= lvl_off(K + 1)) return;
+__device__ __forceinline__ void symmetrise_entry(unsigned long long* __restrict__ tables, uint32_t i) {
     int x = 1;
 #pragma unroll
     for (int y = 2; y <= K; ++y) x += (i >= lvl_off(y));
@@ -322,16 +332,21 @@ symmetrise_kernel(unsigned long long* __restrict__ tables) {
     }
 }
 
+template <int K>
+__global__ void __launch_bounds__(256)
+symmetrise_kernel(unsigned long long* __restrict__ tables) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < lvl_off(K + 1)) symmetrise_entry<K>(tables, i);
+}
+
 // Genome-side IVOM of every K-mer.  The reference's recurrence (F:426-446)
 //     a_x = w_x / W_x,  I_x = a_x p_x + (1 - a_x) I_{x-1},  W_x = sum_{y<=x} w_y
 // telescopes (multiply by W_x):  W_x I_x = w_x p_x + W_{x-1} I_{x-1}, hence
 //     I_K = sum_x w_x p_x / sum_x w_x,   w_x = C_x 4^x,  p_x = C_x / ((S-(x-1)) 2).
 // One division per k-mer instead of sixteen; agreement with the sequential form ~1e-15 relative.
 template <int K>
-__global__ void genome_ivom_kernel(const unsigned long long* __restrict__ tables, int kmin, long long space,
-                                   double2* __restrict__ ig) {
-    const uint32_t kappa = blockIdx.x * blockDim.x + threadIdx.x;
-    if (kappa >= pow4(K)) return;
+__device__ __forceinline__ void genome_ivom_entry(const unsigned long long* __restrict__ tables, int kmin, long long space,
+                                                  double2* __restrict__ ig, uint32_t kappa) {
     double num = 0.0;
     unsigned long long den = 0;
     bool bad = false;
@@ -349,6 +364,40 @@ __global__ void genome_ivom_kernel(const unsigned long long* __restrict__ tables
     }
     double v = bad ? CUDART_NAN : num / (double)den;
     ig[kappa] = make_double2(v, log2(v));
+}
+
+template <int K>
+__global__ void genome_ivom_kernel(const unsigned long long* __restrict__ tables, int kmin, long long space,
+                                   double2* __restrict__ ig) {
+    const uint32_t kappa = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kappa < pow4(K)) genome_ivom_entry<K>(tables, kmin, space, ig, kappa);
+}
+
+// The four finalising steps + the genome IVOM table as ONE cooperative launch (grid-wide barriers instead
+// of five launch boundaries: 23 us -> ~10 us).  With peer counters the cross-GPU arrival happens first.
+template <int K, typename Fwd>
+__global__ void __launch_bounds__(256)
+finalize_ivom_kernel(const Fwd fwd, unsigned long long* __restrict__ tables, unsigned long long* __restrict__ valid_kmax,
+                     int kmin, long long space, double2* __restrict__ ig) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    constexpr int R = K > 4 ? K - 4 : 0;
+    __shared__ unsigned long long lvl[2][256];
+    __shared__ unsigned long long red[8];
+    fwd.arrive_and_wait();
+    for (uint32_t root = blockIdx.x; root < pow4(R); root += gridDim.x) {
+        forward_totals_body<K, Fwd>(fwd, tables, valid_kmax, root, lvl, red);
+        __syncthreads();
+    }
+    grid.sync();
+    if (R > 1) {
+        if (blockIdx.x == 0) forward_low_body<K, Fwd>(fwd, tables);
+        grid.sync();
+    }
+    const uint32_t gtid = blockIdx.x * 256 + threadIdx.x, gstride = gridDim.x * 256;
+    for (uint32_t i = gtid; i < lvl_off(K + 1); i += gstride) symmetrise_entry<K>(tables, i);
+    grid.sync();
+    for (uint32_t kappa = gtid; kappa < pow4(K); kappa += gstride) genome_ivom_entry<K>(tables, kmin, space, ig, kappa);
 }
 
 // ============================================================================================
@@ -1460,6 +1509,25 @@ int launch_finalize(const Fwd f, int symmetric, uint64_t* tables, uint64_t* vali
     return FRISK_OK;
 }
 
+template <int K, typename Fwd>
+int launch_finalize_ivom(Fwd f, int kmin, int64_t space, uint64_t* tables, uint64_t* valid, double* ig, cudaStream_t st) {
+    auto kern = finalize_ivom_kernel<K, Fwd>;
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+    const int sms = sm_count();
+    if (sms <= 0) return FRISK_E_NO_DEVICE;
+    if (per_sm < 1) return FRISK_E_UNSUPPORTED;
+    int grid = sms * (per_sm > 2 ? 2 : per_sm);                          // every CTA resident (grid-wide barriers); 2 per SM measured best
+    if (valid) CK(cudaMemsetAsync(valid, 0, sizeof(uint64_t), st));
+    unsigned long long* t = reinterpret_cast<unsigned long long*>(tables);
+    unsigned long long* v = reinterpret_cast<unsigned long long*>(valid);
+    long long sp = (long long)space;
+    double2* g = reinterpret_cast<double2*>(ig);
+    void* args[] = {(void*)&f, (void*)&t, (void*)&v, (void*)&kmin, (void*)&sp, (void*)&g};
+    CK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(256), args, 0, st));
+    return FRISK_OK;
+}
+
 template <int K>
 int launch_genome_ivom(const uint64_t* tables, int kmin, int64_t space, double* ig, cudaStream_t st) {
     const uint32_t n = pow4(K);
@@ -1695,6 +1763,36 @@ int frisk_b200_finalize_tables_peers(const uint64_t* const* d_fwd_peers, uint64_
     DISPATCH_K(kmax, (launch_finalize<K, PeerFwd>(f, symmetric, d_tables, d_valid_kmax, st)));
 }
 
+int frisk_b200_finalize_ivom(const uint64_t* d_fwd, const uint64_t* const* d_fwd_peers, uint64_t* const* d_flag_peers, int rank,
+                             int world, uint64_t epoch, int kmin, int kmax, int64_t genome_space, uint64_t* d_tables,
+                             uint64_t* d_valid_kmax, double* d_ig, void* stream) {
+    if (!d_tables || !d_ig || (world == 0 && !d_fwd) || (world > 0 && (!d_fwd_peers || rank < 0 || rank >= world)))
+        return FRISK_E_INVALID;
+    if (world > 0 && d_flag_peers && epoch == 0) return FRISK_E_INVALID;
+    int rc = check_k(kmin, kmax);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kmax > FRISK_B200_FAST_K) {                                   // general path: separate launches
+        if (world > 0) return FRISK_E_UNSUPPORTED;
+        if ((rc = frisk_internal::general_finalize(d_fwd, kmax, 1, d_tables, d_valid_kmax, st))) return rc;
+        return frisk_internal::general_genome_ivom(d_tables, kmin, kmax, genome_space, d_ig, st);
+    }
+    if (world == 0) {
+        const LocalFwd f{reinterpret_cast<const unsigned long long*>(d_fwd)};
+        DISPATCH_K(kmax, (launch_finalize_ivom<K, LocalFwd>(f, kmin, genome_space, d_tables, d_valid_kmax, d_ig, st)));
+    }
+    if (world > kMaxPeers) return FRISK_E_UNSUPPORTED;
+    PeerFwd f;
+    f.n = world; f.rank = rank; f.epoch = d_flag_peers ? epoch : 0;
+    for (int q = 0; q < kMaxPeers; ++q) { f.p[q] = nullptr; f.flags[q] = nullptr; }
+    for (int q = 0; q < world; ++q) {
+        if (!d_fwd_peers[q] || (d_flag_peers && !d_flag_peers[q])) return FRISK_E_INVALID;
+        f.p[q] = reinterpret_cast<const unsigned long long*>(d_fwd_peers[q]);
+        if (d_flag_peers) f.flags[q] = reinterpret_cast<unsigned long long*>(d_flag_peers[q]);
+    }
+    DISPATCH_K(kmax, (launch_finalize_ivom<K, PeerFwd>(f, kmin, genome_space, d_tables, d_valid_kmax, d_ig, st)));
+}
+
 int frisk_b200_genome_ivom(const uint64_t* d_tables, int kmin, int kmax, int64_t genome_space, double* d_ig, void* stream) {
     if (!d_tables || !d_ig) return FRISK_E_INVALID;
     int rc = check_k(kmin, kmax);
@@ -1841,11 +1939,8 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
         if (rc) return rc;
     }
     uint64_t* dvalid = (uint64_t*)dtab + tsz;
-    rc = peers.world ? frisk_b200_finalize_tables_peers(peers.d_fwd_peers, peers.d_flag_peers, peers.rank, peers.world, peers.epoch,
-                                                        kmax, 1, (uint64_t*)dtab, dvalid, st)
-                     : frisk_b200_finalize_tables((const uint64_t*)dfwd, kmax, 1, (uint64_t*)dtab, dvalid, st);
-    if (rc) return rc;
-    rc = frisk_b200_genome_ivom((const uint64_t*)dtab, kmin, kmax, genome_space, (double*)dig, st);
+    rc = frisk_b200_finalize_ivom((const uint64_t*)dfwd, peers.d_fwd_peers, peers.d_flag_peers, peers.rank, peers.world, peers.epoch,
+                                  kmin, kmax, genome_space, (uint64_t*)dtab, dvalid, (double*)dig, st);
     if (rc) return rc;
     if (copy) CK(cudaStreamWaitEvent(st, copy_done, 0));
     if (n_win) {

@@ -126,6 +126,16 @@ class PeerExchange:
         self.parity ^= 1
         return out
 
+    def finalize_ivom(self, kmin: int, kmax: int, genome_space: int, d_tables, d_valid, d_ig, stream_ptr):
+        """The fused barrier + sum + finalise + genome IVOM table, one cooperative launch.  Flips the buffer."""
+        from . import _lib
+        self.epoch += 1
+        rc = _lib.lib().frisk_b200_finalize_ivom(None, self.ptr_arrays[self.parity], self.flag_array, self.rank, self.world,
+                                                 self.epoch, kmin, kmax, int(genome_space), C.c_void_p(int(d_tables.data_ptr())),
+                                                 C.c_void_p(int(d_valid.data_ptr())), C.c_void_p(int(d_ig.data_ptr())), stream_ptr)
+        _lib.check(rc, "frisk_b200_finalize_ivom")
+        self.parity ^= 1
+
     def finalize(self, kmax: int, d_tables, d_valid, stream_ptr):
         """The fused barrier + sum + finalise (the GPUs synchronise inside the first kernel).  Flips the buffer."""
         from . import _lib

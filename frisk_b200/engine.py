@@ -553,7 +553,7 @@ class Pipeline:
         self.d_dump = torch.empty((n, tsz), dtype=torch.int16, device=dev) if dump else None
         self.d_off = torch.from_numpy(self.wins.off.view(np.int64)).to(dev, non_blocking=True)
         self.d_len = torch.from_numpy(self.wins.length.view(np.int32)).to(dev, non_blocking=True)
-        self.launches_per_step = 7          # bg_count, bg_reduce, forward_totals, forward_low, symmetrise, genome_ivom, score_windows
+        self.launches_per_step = 4          # bg_count, bg_reduce, finalize_ivom (cooperative), score_windows
 
     def enqueue(self, marks=None) -> None:
         """Launch one pass.  ``marks`` (optional list) receives a CUDA event after each stage:
@@ -578,15 +578,14 @@ class Pipeline:
                                                self.kmax, int(self.mask_host), _ptr(d_fwd), st), "frisk_b200_background")
             mark()
             space = self.genome_space
-            if self.peers is not None:
-                self.peers.finalize(self.kmax, self.d_tables, self.d_valid, st)
+            if self.peers is not None:      # counters summed from every rank's buffer inside the (one) finalising launch
+                self.peers.finalize_ivom(self.kmin, self.kmax, int(space), self.d_tables, self.d_valid, self.d_ig, st)
             else:
                 if self.allreduce is not None:
                     space = self.allreduce(self.d_fwd, space)
-                _lib.check(L.frisk_b200_finalize_tables(_ptr(self.d_fwd), self.kmax, 1, _ptr(self.d_tables), _ptr(self.d_valid), st),
-                           "frisk_b200_finalize_tables")
-            _lib.check(L.frisk_b200_genome_ivom(_ptr(self.d_tables), self.kmin, self.kmax, int(space), _ptr(self.d_ig), st),
-                       "frisk_b200_genome_ivom")
+                _lib.check(L.frisk_b200_finalize_ivom(_ptr(self.d_fwd), None, None, 0, 0, 0, self.kmin, self.kmax, int(space),
+                                                      _ptr(self.d_tables), _ptr(self.d_valid), _ptr(self.d_ig), st),
+                           "frisk_b200_finalize_ivom")
             mark()
             n = len(self.wins)
             if n:

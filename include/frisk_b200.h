@@ -163,6 +163,17 @@ int frisk_b200_finalize_tables_peers(const uint64_t *const *d_fwd_peers, uint64_
                                      uint64_t *d_valid_kmax, void *stream);
 
 /*
+ * frisk_b200_finalize_ivom: frisk_b200_finalize_tables (symmetric) + frisk_b200_genome_ivom as ONE
+ * cooperative launch (grid-wide barriers instead of five launch boundaries).  world == 0: the counters
+ * are d_fwd; world > 0: they are summed from d_fwd_peers exactly as frisk_b200_finalize_tables_peers does
+ * (flags / rank / epoch as there).  kmax 9..12: falls back to the separate general-path launches
+ * (single GPU only).
+ */
+int frisk_b200_finalize_ivom(const uint64_t *d_fwd, const uint64_t *const *d_fwd_peers, uint64_t *const *d_flag_peers,
+                             int rank, int world, uint64_t epoch, int kmin, int kmax, int64_t genome_space,
+                             uint64_t *d_tables, uint64_t *d_valid_kmax, double *d_ig, void *stream);
+
+/*
  * frisk_b200_genome_ivom: for every kmax-mer, the un-normalised genome IVOM value of
  * IvomBuild(isGenomeIVOM=True) (F:411-450) and its log2, as pairs of doubles (4^kmax pairs).
  * It depends only on the genome tables, so it is computed once instead of once per window.
