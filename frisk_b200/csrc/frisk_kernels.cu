@@ -303,8 +303,9 @@ __device__ __forceinline__ void forward_low_body(const Fwd& fwd, unsigned long l
 #pragma unroll
     for (int x = R - 1; x >= 1; --x) {
         if (t < pow4(x)) {
+            // (L2 loads: in the fused kernel these entries were written by other CTAs earlier in the same launch)
             const unsigned long long* ch = tables + lvl_off(x + 1) + 4 * t;
-            tables[lvl_off(x) + t] = own[x - 1] + ch[0] + ch[1] + ch[2] + ch[3];
+            tables[lvl_off(x) + t] = own[x - 1] + __ldcg(ch) + __ldcg(ch + 1) + __ldcg(ch + 2) + __ldcg(ch + 3);
         }
         __syncthreads();
     }
@@ -324,11 +325,11 @@ __device__ __forceinline__ void symmetrise_entry(unsigned long long* __restrict_
     const uint32_t b = i - lvl_off(x);
     const uint32_t r = revcomp_idx(b, x);
     if (b < r) {
-        const unsigned long long sum = tables[i] + tables[lvl_off(x) + r];
+        const unsigned long long sum = __ldcg(tables + i) + __ldcg(tables + lvl_off(x) + r);
         tables[i] = sum;
         tables[lvl_off(x) + r] = sum;
     } else if (b == r) {
-        tables[i] *= 2ull;                          // palindrome: +1 word, +1 its own reverse complement
+        tables[i] = 2ull * __ldcg(tables + i);      // palindrome: +1 word, +1 its own reverse complement
     }
 }
 
@@ -353,7 +354,7 @@ __device__ __forceinline__ void genome_ivom_entry(const unsigned long long* __re
 #pragma unroll
     for (int x = 1; x <= K; ++x) {
         if (x < kmin) continue;
-        const unsigned long long c = tables[lvl_off(x) + (kappa >> (2 * (K - x)))];
+        const unsigned long long c = __ldcg(tables + lvl_off(x) + (kappa >> (2 * (K - x))));
         const long long d = (space - (long long)(x - 1)) * 2;
         if (d == 0) bad = true;
         const double q = (double)pow4(x) / (double)d;

@@ -459,6 +459,27 @@ def test_concurrent_streams_and_threads_do_not_share_scratch(eng):
             assert np.array_equal(res.rows, ref.rows, equal_nan=True) and np.array_equal(res.status, ref.status)
 
 
+def test_fused_finalise_launch_is_stable_and_equals_the_staged_kernels(eng):
+    """The cooperative finalise + genome-IVOM launch (grid-wide barriers between its phases) against the five
+    separate kernels of the staged entry points, and against itself over 300 back-to-back launches."""
+    import torch
+    from frisk_b200 import synth
+    g = eng.PackedGenome.from_scaffolds(synth.make("C2", 0.05, seed=3) + synth.make("edge"))
+    pipe = eng.Pipeline(g, scaffolds_all=True)
+    pipe.enqueue()
+    torch.cuda.synchronize()
+    t0, ig0, rows0 = pipe.d_tables.clone(), pipe.d_ig.clone(), pipe.d_rows.clone()
+    d_tables, d_valid = eng.finalize(eng.background(pipe.dq, 8), 8)          # staged: forward_totals/low/symmetrise kernels
+    d_ig = eng.genome_ivom(d_tables, 1, 8, g.genome_space)
+    assert torch.equal(d_tables, t0) and int(d_valid.item()) == int(pipe.d_valid.item())
+    assert torch.equal(d_ig.view(torch.int64), ig0.view(torch.int64))        # same bits, NaN entries included
+    for _ in range(300):
+        pipe.enqueue()
+    torch.cuda.synchronize()
+    assert torch.equal(pipe.d_tables, t0) and torch.equal(pipe.d_ig.view(torch.int64), ig0.view(torch.int64))
+    assert torch.equal(pipe.d_rows.view(torch.int64), rows0.view(torch.int64))
+
+
 def test_no_silent_fallback_symbols_loaded(eng):
     """The product library is the thing that ran: it is loaded in this process and reports a GPU."""
     from frisk_b200 import _lib
