@@ -34,6 +34,8 @@ PROTOTYPES = {
     "frisk_b200_pack": (_i, [_p, _p, _p, _p, _p, _u64, _u64, _p, _p, _p, _p, _i]),
     "frisk_b200_windows": (_i, [_p, _p, _u64, _i, _i, _i, _u64, _p, _p, _p, _p, _p, _p]),
     "frisk_b200_format_rows": (_i, [_p, _p, _p, _p, _p, _p, _p, _u64, _i, _p, _u64, _p, _i]),
+    "frisk_b200_hmm2_fit": (_i, [_p, _u64, _i, C.c_double, C.c_double, _p, _p, _p, _p]),
+    "frisk_b200_hmm2_viterbi": (_i, [_p, _u64, _p, _p, _p, _p, _p]),
     "frisk_b200_background": (_i, [_p, _p, _p, _u64, _u64, _i, _i, _p, _p]),
     "frisk_b200_finalize_tables": (_i, [_p, _i, _i, _p, _p, _p]),
     "frisk_b200_finalize_tables_peers": (_i, [_p, _p, _i, _i, _u64, _i, _i, _p, _p, _p]),

@@ -310,6 +310,113 @@ int frisk_b200_format_rows(const char* names, const uint64_t* name_off, const ui
     return FRISK_OK;
 }
 
+// ---- 2-state 1-D Gaussian HMM (the fallback of downstream.fit_hmm when hmmlearn is absent) -------------
+// Same algorithm and the same order of operations as downstream.GaussianHMM2 (log-space forward/backward,
+// Baum-Welch updates, Viterbi), in C so that a million window scores take a fraction of a second.
+}  // extern "C"
+
+namespace {
+inline double logaddexp2(double a, double b) {
+    if (a == b) return a + 0.6931471805599453;                  // numpy: log(2) added when equal (also inf handling)
+    const double d = a - b;
+    return d > 0 ? a + std::log1p(std::exp(-d)) : b + std::log1p(std::exp(d));
+}
+inline void log_gauss(const double* x, uint64_t n, const double mean[2], const double var[2], double* logb) {
+    const double c0 = std::log(2 * M_PI * var[0]), c1 = std::log(2 * M_PI * var[1]);
+    for (uint64_t t = 0; t < n; ++t) {
+        const double d0 = x[t] - mean[0], d1 = x[t] - mean[1];
+        logb[2 * t] = -0.5 * (c0 + d0 * d0 / var[0]);
+        logb[2 * t + 1] = -0.5 * (c1 + d1 * d1 / var[1]);
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int frisk_b200_hmm2_fit(const double* x, uint64_t n, int n_iter, double tol, double min_covar, double start[2],
+                        double trans[4], double mean[2], double var[2]) {
+    if (!x || n < 2 || !start || !trans || !mean || !var || n_iter < 1) return FRISK_E_INVALID;
+    std::vector<double> sorted(x, x + n), logb(2 * n), la(2 * n), lb(2 * n);
+    std::sort(sorted.begin(), sorted.end());
+    const uint64_t half = n / 2;
+    double m0 = 0, m1 = 0, mu = 0;
+    for (uint64_t i = 0; i < half; ++i) m0 += sorted[i];
+    for (uint64_t i = half; i < n; ++i) m1 += sorted[i];
+    mean[0] = m0 / (double)half; mean[1] = m1 / (double)(n - half);
+    for (uint64_t i = 0; i < n; ++i) mu += x[i];
+    mu /= (double)n;
+    double v = 0;
+    for (uint64_t i = 0; i < n; ++i) v += (x[i] - mu) * (x[i] - mu);
+    var[0] = var[1] = v / (double)n + min_covar;
+    start[0] = start[1] = 0.5;
+    trans[0] = trans[1] = trans[2] = trans[3] = 0.5;
+    double prev = -INFINITY;
+    for (int it = 0; it < n_iter; ++it) {
+        log_gauss(x, n, mean, var, logb.data());
+        const double lt[4] = {std::log(trans[0]), std::log(trans[1]), std::log(trans[2]), std::log(trans[3])};
+        la[0] = std::log(start[0]) + logb[0]; la[1] = std::log(start[1]) + logb[1];
+        for (uint64_t t = 1; t < n; ++t) {
+            la[2 * t] = logb[2 * t] + logaddexp2(la[2 * t - 2] + lt[0], la[2 * t - 1] + lt[2]);
+            la[2 * t + 1] = logb[2 * t + 1] + logaddexp2(la[2 * t - 2] + lt[1], la[2 * t - 1] + lt[3]);
+        }
+        lb[2 * n - 2] = lb[2 * n - 1] = 0.0;
+        for (uint64_t t = n - 1; t-- > 0;) {
+            const double b0 = logb[2 * t + 2] + lb[2 * t + 2], b1 = logb[2 * t + 3] + lb[2 * t + 3];
+            lb[2 * t] = logaddexp2(lt[0] + b0, lt[1] + b1);
+            lb[2 * t + 1] = logaddexp2(lt[2] + b0, lt[3] + b1);
+        }
+        const double ll = logaddexp2(la[2 * n - 2], la[2 * n - 1]);
+        double w[2] = {0, 0}, sx[2] = {0, 0}, xi[4] = {0, 0, 0, 0};
+        for (uint64_t t = 0; t < n; ++t) {
+            const double g0 = std::exp(la[2 * t] + lb[2 * t] - ll), g1 = std::exp(la[2 * t + 1] + lb[2 * t + 1] - ll);
+            w[0] += g0; w[1] += g1; sx[0] += g0 * x[t]; sx[1] += g1 * x[t];
+            if (t + 1 < n) {
+                const double b0 = logb[2 * t + 2] + lb[2 * t + 2], b1 = logb[2 * t + 3] + lb[2 * t + 3];
+                xi[0] += std::exp(la[2 * t] + lt[0] + b0 - ll); xi[1] += std::exp(la[2 * t] + lt[1] + b1 - ll);
+                xi[2] += std::exp(la[2 * t + 1] + lt[2] + b0 - ll); xi[3] += std::exp(la[2 * t + 1] + lt[3] + b1 - ll);
+            }
+        }
+        const double g00 = std::exp(la[0] + lb[0] - ll), g01 = std::exp(la[1] + lb[1] - ll);
+        start[0] = g00 / (g00 + g01); start[1] = g01 / (g00 + g01);
+        trans[0] = xi[0] / (xi[0] + xi[1]); trans[1] = xi[1] / (xi[0] + xi[1]);
+        trans[2] = xi[2] / (xi[2] + xi[3]); trans[3] = xi[3] / (xi[2] + xi[3]);
+        mean[0] = sx[0] / w[0]; mean[1] = sx[1] / w[1];
+        double sv[2] = {0, 0};
+        for (uint64_t t = 0; t < n; ++t) {
+            const double g0 = std::exp(la[2 * t] + lb[2 * t] - ll), g1 = std::exp(la[2 * t + 1] + lb[2 * t + 1] - ll);
+            sv[0] += g0 * (x[t] - mean[0]) * (x[t] - mean[0]); sv[1] += g1 * (x[t] - mean[1]) * (x[t] - mean[1]);
+        }
+        var[0] = sv[0] / w[0] + min_covar; var[1] = sv[1] / w[1] + min_covar;
+        if (ll - prev < tol) break;
+        prev = ll;
+    }
+    return FRISK_OK;
+}
+
+int frisk_b200_hmm2_viterbi(const double* x, uint64_t n, const double start[2], const double trans[4], const double mean[2],
+                            const double var[2], int32_t* path) {
+    if (!x || !n || !start || !trans || !mean || !var || !path) return FRISK_E_INVALID;
+    std::vector<double> logb(2 * n);
+    std::vector<uint8_t> back(2 * n);
+    log_gauss(x, n, mean, var, logb.data());
+    const double lt[4] = {std::log(trans[0]), std::log(trans[1]), std::log(trans[2]), std::log(trans[3])};
+    double d0 = std::log(start[0]) + logb[0], d1 = std::log(start[1]) + logb[1];
+    for (uint64_t t = 1; t < n; ++t) {
+        const double a0 = d0 + lt[0], a1 = d1 + lt[2], b0 = d0 + lt[1], b1 = d1 + lt[3];
+        back[2 * t] = a1 > a0;          // argmax keeps the first maximum, like numpy
+        back[2 * t + 1] = b1 > b0;
+        d0 = (a1 > a0 ? a1 : a0) + logb[2 * t];
+        d1 = (b1 > b0 ? b1 : b0) + logb[2 * t + 1];
+    }
+    int s = d1 > d0;
+    path[n - 1] = s;
+    for (uint64_t t = n - 1; t > 0; --t) {
+        s = back[2 * t + (uint64_t)s];
+        path[t - 1] = s;
+    }
+    return FRISK_OK;
+}
+
 int frisk_b200_plane_sparse(const uint32_t* plane, uint64_t n_words, uint64_t cap, uint32_t* idx, uint32_t* val,
                             uint64_t* n_nonzero) {
     if (!n_nonzero || (!plane && n_words) || n_words > 0xffffffffull) return FRISK_E_INVALID;

@@ -205,6 +205,34 @@ class GaussianHMM2:
         return -0.5 * (np.log(2 * np.pi * var)[None, :] + (x[:, None] - mean[None, :]) ** 2 / var[None, :])
 
     def fit(self, X):
+        """Baum-Welch in C (frisk_b200_hmm2_fit; a million observations in a fraction of a second)."""
+        import ctypes as C
+        from . import _lib
+        x = np.ascontiguousarray(np.asarray(X, float).reshape(-1))
+        start, trans, mean, var = np.zeros(2), np.zeros(4), np.zeros(2), np.zeros(2)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        _lib.check(_lib.lib().frisk_b200_hmm2_fit(p(x), len(x), self.n_iter, self.tol, self.min_covar, p(start), p(trans), p(mean),
+                                                  p(var)), "frisk_b200_hmm2_fit")
+        self.startprob_, self.transmat_, self.means_, self.vars_ = start, trans.reshape(2, 2), mean, var
+        return self
+
+    def predict(self, X):
+        """Viterbi path in C (frisk_b200_hmm2_viterbi)."""
+        import ctypes as C
+        from . import _lib
+        x = np.ascontiguousarray(np.asarray(X, float).reshape(-1))
+        path = np.zeros(len(x), np.int32)
+        if len(x) == 0:
+            return path.astype(int)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        tr = np.ascontiguousarray(self.transmat_, float).reshape(-1)
+        _lib.check(_lib.lib().frisk_b200_hmm2_viterbi(p(x), len(x), p(np.ascontiguousarray(self.startprob_, float)), p(tr),
+                                                      p(np.ascontiguousarray(self.means_, float)),
+                                                      p(np.ascontiguousarray(self.vars_, float)), p(path)), "frisk_b200_hmm2_viterbi")
+        return path.astype(int)
+
+    def fit_numpy(self, X):
+        """The same algorithm in numpy (the cross-check of the C routine in tests/test_downstream.py)."""
         x = np.asarray(X, float).reshape(-1)
         order = np.sort(x)
         half = len(x) // 2
@@ -238,7 +266,7 @@ class GaussianHMM2:
         self.startprob_, self.transmat_, self.means_, self.vars_ = start, trans, mean, var
         return self
 
-    def predict(self, X):
+    def predict_numpy(self, X):
         x = np.asarray(X, float).reshape(-1)
         logb = self._log_gauss(x, self.means_, self.vars_)
         lt = np.log(self.transmat_)

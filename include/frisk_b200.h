@@ -117,6 +117,18 @@ int frisk_b200_format_rows(const char *names, const uint64_t *name_off, const ui
                            const uint32_t *row_name, const int64_t *start, const int64_t *stop, const double *rows,
                            uint64_t n_rows, int n_values, char *out, uint64_t cap, uint64_t *n_bytes, int threads);
 
+/*
+ * Host helpers of the 2-state HMM segmentation (F:1536-1548) for installations without hmmlearn: a
+ * deterministic 1-D, 2-state Gaussian HMM.  frisk_b200_hmm2_fit: Baum-Welch from uniform start/transition
+ * probabilities, means = means of the lower/upper half of the sorted data, variances = data variance +
+ * min_covar; at most n_iter iterations, stops when the log-likelihood gains less than tol.  trans is
+ * row-major [from][to].  frisk_b200_hmm2_viterbi: the most likely state path (0/1 per observation).
+ */
+int frisk_b200_hmm2_fit(const double *x, uint64_t n, int n_iter, double tol, double min_covar, double start[2],
+                        double trans[4], double mean[2], double var[2]);
+int frisk_b200_hmm2_viterbi(const double *x, uint64_t n, const double start[2], const double trans[4],
+                            const double mean[2], const double var[2], int32_t *path);
+
 /* ------------------------------------------------------------------ device side
  *
  * frisk_b200_background: forward-strand k-mer counts of the packed bases [first_base, last_base)

@@ -96,3 +96,24 @@ def test_hmm_glue_on_planted_islands():
     assert f[1] == "frisk_" + ds.FRISK_VERSION and f[2] in ("State1", "State2") and f[8].startswith("ID=" + f[2] + "_")
     minority = min(("State1", "State2"), key=lambda s: sum(int(r[2]) - int(r[1]) for r in bed if r[3] == s))
     assert 10 <= sum(1 for r in bed if r[3] == minority) <= 60          # ~25 planted islands
+
+
+def test_c_hmm_equals_the_numpy_formulation():
+    """frisk_b200_hmm2_fit / _viterbi (C) against the numpy statement of the same algorithm: parameters to 1e-9,
+    state paths identical, on the reference's own C1 scores and on a harder two-regime series."""
+    import time
+    rng = np.random.default_rng(4)
+    series = [np.load(os.path.join(HERE, "golden", "c1_full.npz"))["row_vals"][:, 0],
+              np.concatenate([rng.normal(0.2, 0.05, 700), rng.normal(0.5, 0.2, 90), rng.normal(0.2, 0.05, 1300),
+                              rng.normal(0.6, 0.1, 40), rng.normal(0.25, 0.05, 500)])]
+    for x in series:
+        a, b = ds.GaussianHMM2().fit(x), ds.GaussianHMM2().fit_numpy(x)
+        for name in ("startprob_", "transmat_", "means_", "vars_"):
+            assert np.allclose(getattr(a, name), getattr(b, name), rtol=1e-9, atol=1e-12), name
+        assert np.array_equal(a.predict(x), b.predict_numpy(x))
+        assert np.array_equal(a.predict(x), hmm_ref.predict(hmm_ref.fit(x), x))
+    big = np.abs(rng.normal(0.3, 0.1, 1_200_000)) + 1e-3
+    t = time.time()
+    m = ds.GaussianHMM2().fit(big)
+    path = m.predict(big)
+    assert time.time() - t < 20 and len(path) == len(big)           # a C4-sized table of window scores
