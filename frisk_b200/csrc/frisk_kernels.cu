@@ -850,8 +850,8 @@ template <int K, int ROUNDS, bool DUMP, bool ALLK>
 __global__ void __launch_bounds__(kT3, 4)
 score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                             const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
-                            const double2* __restrict__ ig, int kmin_arg, int want_rip, uint32_t cap,
-                            double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
+                            const double2* __restrict__ ig, int kmin_arg, int want_rip, uint32_t cap, uint32_t len_min,
+                            uint32_t len_max, double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
     using L = Score3Layout<K>;
     constexpr int B = L::B, LP = L::LP;
     constexpr uint32_t NBK = L::NBK, PER = L::PER;
@@ -882,10 +882,12 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
     }
     __syncthreads();
 
-    int par = 0;
-    for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x, par ^= 1) {
-        const uint64_t o = win_off[win];
+    int par = 1;                                         // flipped by every window this launch processes
+    for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x) {
         const uint32_t len = win_len[win];
+        if (len < len_min || len > len_max) continue;    // another launch (other buffer size) takes this one
+        par ^= 1;
+        const uint64_t o = win_off[win];
         // 32-bit addressing relative to the window's first mask word
         const uint32_t o_lo = (uint32_t)(o & 31);
         const uint32_t* __restrict__ cw = codes + (o >> 5) * 2;
@@ -1564,7 +1566,8 @@ int launch_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* low
 template <int K, int ROUNDS, bool DUMP, bool ALLK>
 int launch_score_bucket3(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                          const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
-                         double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+                         double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, uint32_t len_min = 0,
+                         uint32_t len_max = 0xffffffffu) {
     using L = Score3Layout<K>;
     const uint32_t cap = (max_len + 15u) & ~15u;
     const size_t smem = L::total(cap);
@@ -1582,7 +1585,7 @@ int launch_score_bucket3(const uint32_t* codes, const uint32_t* inv, const uint3
     if (grid > n_win) grid = n_win;
     kern<<<(unsigned)grid, kT3, smem, st>>>(
         codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len, (uint32_t)n_win,
-        reinterpret_cast<const double2*>(ig), kmin, want_rip, cap, rows, status, dump);
+        reinterpret_cast<const double2*>(ig), kmin, want_rip, cap, len_min, len_max, rows, status, dump);
     CK(cudaGetLastError());
     return FRISK_OK;
 }
@@ -1597,6 +1600,17 @@ int launch_score_bucket2(const uint32_t* codes, const uint32_t* inv, const uint3
         return launch_score_bucket3<K, 2, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
     if (max_len <= kT3 * 4u * 5u - 6u)
         return launch_score_bucket3<K, 5, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
+    // Longer windows need a bigger buffer, which costs a CTA per SM.  With --scaffoldsAll nearly all windows are
+    // still the standard length and only whole short scaffolds (up to 1.25 w) are longer: two launches, each
+    // taking the windows of its length class, keep the standard ones at four CTAs per SM.
+    constexpr uint32_t kStd = 5104u;                   // largest buffer that still fits four CTAs
+    if (n_win >= 4096) {
+        int rc = launch_score_bucket3<K, 5, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, kStd, ig, kmin, want_rip, rows, status,
+                                                       dump, st, 0u, kStd);
+        if (rc) return rc;
+        return launch_score_bucket3<K, 8, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status,
+                                                      dump, st, kStd + 1u, 0xffffffffu);
+    }
     return launch_score_bucket3<K, 8, DUMP, ALLK>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
 }
 

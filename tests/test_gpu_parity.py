@@ -256,6 +256,7 @@ def test_bit_reproducible(eng):
     ("C2", 0.02, dict(kmax=6, w=60000, step=20000)),                    # small-K kernel, windows near its 65,535 limit
     ("C2", 0.02, dict(kmax=4, kmin=2)),
     ("C2", 0.02, dict(kmax=2)),
+    ("C5", 0.002, dict(scaffolds_all=True)),                            # > 4,096 windows of mixed length: two length-class launches
 ])
 def test_against_c_oracle_on_fresh_genomes(eng, config, scale, kw):
     from frisk_b200 import synth
