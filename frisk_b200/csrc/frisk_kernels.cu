@@ -884,10 +884,10 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
 
     int par = 1;                                         // flipped by every window this launch processes
     for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x) {
+        const uint64_t o = win_off[win];                 // (both descriptor loads are in flight before the length test)
         const uint32_t len = win_len[win];
         if (len < len_min || len > len_max) continue;    // another launch (other buffer size) takes this one
         par ^= 1;
-        const uint64_t o = win_off[win];
         // 32-bit addressing relative to the window's first mask word
         const uint32_t o_lo = (uint32_t)(o & 31);
         const uint32_t* __restrict__ cw = codes + (o >> 5) * 2;
