@@ -86,6 +86,8 @@ def committed_pipe_utilisation():
                 "issue_slots_pct_of_peak": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                 "fp64_pipe_pct_of_peak": num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
                 "warp_instructions": num("smsp__inst_executed.sum"),
+                "note": "issue_slots_pct_of_peak is the kernel's fraction of its own instruction-issue roofline (warp-instructions / "
+                        "(SMs x 4 schedulers x clock x time)); the HBM roofline above is not binding for this path",
                 "shared_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
                 "source": "profiles/r01_ncu_raw_metrics.json (ncu --set full, same command, not timed)"}
     except Exception:
