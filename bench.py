@@ -230,6 +230,9 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     _lib.require_device()
+    for item in args.option or []:           # A/B of kernel choices: frisk_b200_set_option (e.g. force_bucket_kernel=1)
+        name, _, val = item.partition("=")
+        _lib.check(_lib.lib().frisk_b200_set_option(name.encode(), int(val or 1)), "set_option " + item)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -442,6 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="frisk_b200", choices=["frisk_b200", "reference"])
     ap.add_argument("--nccl", action="store_true", help="N > 1: combine the counters with an NCCL all-reduce instead of the fused peer sum")
+    ap.add_argument("--option", action="append", help="library option name=value (frisk_b200_set_option), repeatable")
     ap.add_argument("--profile", action="store_true", help="kernels only: skip the e2e and CPU-baseline legs (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

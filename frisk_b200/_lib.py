@@ -11,7 +11,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libfrisk_b200.so")
+SO_PATH = os.environ.get("FRISK_B200_LIB") or os.path.join(HERE, "libfrisk_b200.so")   # override: kernel A/B builds (tools/)
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NO_DEVICE, E_CAPACITY, E_FORMAT = 0, -1, -2, -3, -4, -5, -6
 ROW_KLD_ZERODIV, ROW_GC_ZERODIV, ROW_LOG_DOMAIN, ROW_EXCLUDED = 1, 2, 4, 8
@@ -81,7 +81,7 @@ class FriskError(RuntimeError):
 def build(force: bool = False) -> str:
     """Compile the shared library in-tree (nvcc, sm_100a).  Cross-compiles without a GPU."""
     src_dir = os.path.join(HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("frisk_kernels.cu", "frisk_general.cu", "frisk_ingest.cu", "frisk_features.cu", "frisk_host.cpp", "frisk_internal.h", "Makefile")]
+    srcs = [os.path.join(src_dir, f) for f in ("frisk_kernels.cu", "frisk_direct.cu", "frisk_device.cuh", "frisk_general.cu", "frisk_ingest.cu", "frisk_features.cu", "frisk_host.cpp", "frisk_internal.h", "Makefile")]
     srcs.append(os.path.join(os.path.dirname(HERE), "include", "frisk_b200.h"))
     stale = not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:

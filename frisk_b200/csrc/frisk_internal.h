@@ -30,6 +30,20 @@ int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* lo
                   const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
                   double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st);
 
+
+// direct score kernel (frisk_direct.cu): kmax 7, 8 and windows <= 8,186 bases.  Windows it cannot finish exactly
+// (a K-mer seen 256+ times, more than 64 N-boundary words) are marked kRowRedo in `status` and re-done by the
+// bucketed kernel (frisk_kernels.cu), launched behind it on the same stream.
+constexpr uint32_t kRowRedo = 0x80000000u;
+int score_direct(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                 const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
+                 double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st);
+int score_direct_occupancy(int K, uint32_t max_len, int* ctas_per_sm, int* threads_per_cta);
+int score_bucket_redo(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                      const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
+                      double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st);
+int sm_count_cached();
+
 }  // namespace frisk_internal
 
 #define FRISK_CK(call)                                                        \

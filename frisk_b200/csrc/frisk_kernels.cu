@@ -21,6 +21,14 @@
 
 #include "../../include/frisk_b200.h"
 #include "frisk_internal.h"
+#include "frisk_device.cuh"
+
+// log2 in the window-kernel epilogues: table-driven (log2_pos) or table-free series (log2_series)
+#ifdef FRISK_SERIES_LOG2
+#define FRISK_LOG2(x, tab) log2_series(x)
+#else
+#define FRISK_LOG2(x, tab) log2_pos(x, tab)
+#endif
 
 namespace {
 
@@ -28,16 +36,6 @@ constexpr int kThreads = 1024;          // one CTA per SM: the 4^8 u16 window ta
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kListCap = 8192;     // compacted (kmer, count) entries per segment
 constexpr int kMaxSeg = 8;
-constexpr uint32_t kFull = 0xffffffffu;
-
-__host__ __device__ constexpr uint32_t pow4(int k) { return 1u << (2 * k); }
-// offset (in entries) of order x inside a concatenation of orders 1..: sum_{y<x} 4^y
-__host__ __device__ constexpr uint32_t lvl_off(int x) { return (pow4(x) - 4u) / 3u; }
-
-__device__ __forceinline__ double u32_to_double(uint32_t v) {
-    // exact: 2^52 + v has v in the low mantissa bits
-    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
-}
 
 // reverse complement of the x-mer with index idx (F:276-278): reverse the digits, xor each with 1
 __device__ __forceinline__ uint32_t revcomp_idx(uint32_t idx, int x) {
@@ -448,33 +446,6 @@ struct ScoreLayout {
     static constexpr uint32_t TOTAL = OFF_SS + (uint32_t)sizeof(ScoreSmem);
 };
 
-// log2 of a positive normal double: x = 2^e * m, m in [1,2); m = c (1 + r) with c the midpoint of
-// one of 128 mantissa intervals, |r| <= 2^-8; log2(1+r) by a degree-6 Taylor polynomial
-// (truncation < 3e-18).  tab[i] = {1/c_i rounded, -log2 of that rounded value}.  ~20 instructions
-// against ~75 for the library log2 (which also handles zero, denormals, inf, NaN).
-__device__ __forceinline__ double log2_pos(double x, const double2* __restrict__ tab) {
-    const int hi = __double2hiint(x);
-    const double2 t = tab[(hi >> 13) & 127];
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-    const double r = fma(m, t.x, -1.0);
-    double p = fma(r, -0.24044917348149390, 0.28853900817779268);
-    p = fma(r, p, -0.36067376022224085);
-    p = fma(r, p, 0.48089834696298783);
-    p = fma(r, p, -0.72134752044448170);
-    p = fma(r, p, 1.4426950408889634);
-    return fma(r, p, (double)((hi >> 20) - 1023) + t.y);
-}
-
-// n / d for a positive normal d: hardware reciprocal seed + two Newton steps + one residual step
-__device__ __forceinline__ double div_pos(double n, double d) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    r = fma(r, fma(-d, r, 1.0), r);
-    r = fma(r, fma(-d, r, 1.0), r);
-    const double q = n * r;
-    return fma(fma(-d, q, n), r, q);
-}
-
 template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
 score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
@@ -693,7 +664,7 @@ score_windows_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restr
                 const double2 g = __ldg(ig + kappa);
                 s_w += iw;
                 s_g += g.x;
-                s_t = fma(iw, log2_pos(iw, logtab) - g.y, s_t);
+                s_t = fma(iw, FRISK_LOG2(iw, logtab) - g.y, s_t);
                 bad |= (g.x != g.x);
             }
             __syncthreads();                               // list is reused by the next segment
@@ -817,32 +788,6 @@ __device__ __forceinline__ void load_u16s(const uint16_t* p, uint32_t (&out)[PER
     }
 }
 
-// One round of the position walk: the four absolute-aligned bases of group `gi` (see below), with
-// the words they need loaded once.  f(j, p, c32, m, low_bit) for the positions inside the window:
-// j = 0..3, p = position in the window, c32 = the 16 bases from p (2 bits each, first base on top),
-// m = unresolved mask of the 32 bases from p (bit 31 = p), low_bit = 1 when base p is lower case.
-struct GroupWords { uint32_t chi, clo, mhi, mlo, lhi; };
-
-__device__ __forceinline__ GroupWords load_group(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ mw,
-                                                 const uint32_t* __restrict__ lw, uint32_t a0) {
-    GroupWords g;
-    g.chi = __ldg(cw + (a0 >> 4)); g.clo = __ldg(cw + (a0 >> 4) + 1);
-    g.mhi = __ldg(mw + (a0 >> 5)); g.mlo = __ldg(mw + (a0 >> 5) + 1);
-    g.lhi = lw ? __ldg(lw + (a0 >> 5)) : 0u;
-    return g;
-}
-
-template <typename F>
-__device__ __forceinline__ void visit_group(const GroupWords& g, uint32_t a0, uint32_t o_lo, uint32_t len, F f) {
-    const uint32_t cs = (a0 & 15u) * 2u, ms = a0 & 31u;               // cs <= 24, ms <= 28
-#pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) {
-        const uint32_t p = a0 + j - o_lo;                              // wraps for bases before the window
-        if (p < len)
-            f(j, p, __funnelshift_l(g.clo, g.chi, cs + 2u * j), __funnelshift_l(g.mlo, g.mhi, ms + j), (g.lhi << (ms + j)) >> 31);
-    }
-}
-
 // ROUNDS rounds of 4 positions per thread cover a window of up to 4*NT*ROUNDS - 3 bases; what a
 // position contributes (bucket, suffix code, arrival rank in its bucket) stays in registers
 // between the counting pass and the placement pass, so the sequence is read and decoded once.
@@ -851,7 +796,8 @@ __global__ void __launch_bounds__(kT3, 4)
 score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                             const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
                             const double2* __restrict__ ig, int kmin_arg, int want_rip, uint32_t cap, uint32_t len_min,
-                            uint32_t len_max, double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
+                            uint32_t len_max, double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump,
+                            uint32_t redo_only) {
     using L = Score3Layout<K>;
     constexpr int B = L::B, LP = L::LP;
     constexpr uint32_t NBK = L::NBK, PER = L::PER;
@@ -887,6 +833,8 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         const uint64_t o = win_off[win];                 // (both descriptor loads are in flight before the length test)
         const uint32_t len = win_len[win];
         if (len < len_min || len > len_max) continue;    // another launch (other buffer size) takes this one
+        // second launch behind the direct kernel (frisk_direct.cu): only the windows it handed over
+        if (redo_only && !(status[win] & frisk_internal::kRowRedo)) continue;
         par ^= 1;
         // 32-bit addressing relative to the window's first mask word
         const uint32_t o_lo = (uint32_t)(o & 31);
@@ -1163,7 +1111,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             const double2 g = __ldg(ig + kappa);
             s_w += iw;
             s_g += g.x;                                    // a NaN entry (reference: ZeroDivisionError) poisons the sum
-            s_t = fma(iw, log2_pos(iw, logtab) - g.y, s_t);
+            s_t = fma(iw, FRISK_LOG2(iw, logtab) - g.y, s_t);
         };
         for (uint32_t e = tid; e < n_clean; e += kT3) {
             const uint32_t kappa = list[e];
@@ -1347,7 +1295,7 @@ score_windows_small_kernel(const uint32_t* __restrict__ codes, const uint32_t* _
                 const double2 g = __ldg(ig + kappa);
                 s_w += iw;
                 s_g += g.x;
-                s_t = fma(iw, log2_pos(iw, logtab) - g.y, s_t);
+                s_t = fma(iw, FRISK_LOG2(iw, logtab) - g.y, s_t);
                 any = 1;
             }
         }
@@ -1449,13 +1397,18 @@ __global__ void __launch_bounds__(kThreads, 1) smem_atomic_bench_kernel(int iter
 thread_local char g_cuda_err[512] = "";
 int g_force_dense = 0;      // tests: force the dense-table kernel (frisk_b200_set_option)
 int g_force_general = 0;    // tests: force the general (global-memory) score kernel
-int g_force_bucket = 0;     // tests: keep kmax 4..6 on the bucketed kernel instead of the small-K kernel
+int g_force_direct = 0;     // tests / A-B: kmax 7, 8 on the direct kernel wherever it can run
+int g_force_bucket = 0;     // tests: keep kmax 4..8 on the bucketed kernel instead of the small-K / direct kernel
 }  // namespace
 
 int frisk_internal::cuda_fail(cudaError_t e, const char* what) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
     return FRISK_E_CUDA;
 }
+
+#ifndef FRISK_DIRECT_DEFAULT
+#define FRISK_DIRECT_DEFAULT(kmax, len) ((kmax) == 7 && (len) > 2042u)
+#endif
 
 namespace {
 using frisk_internal::ws_get;
@@ -1567,7 +1520,7 @@ template <int K, int ROUNDS, bool DUMP, bool ALLK>
 int launch_score_bucket3(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                          const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
                          double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, uint32_t len_min = 0,
-                         uint32_t len_max = 0xffffffffu) {
+                         uint32_t len_max = 0xffffffffu, uint32_t redo_only = 0) {
     using L = Score3Layout<K>;
     const uint32_t cap = (max_len + 15u) & ~15u;
     const size_t smem = L::total(cap);
@@ -1585,7 +1538,7 @@ int launch_score_bucket3(const uint32_t* codes, const uint32_t* inv, const uint3
     if (grid > n_win) grid = n_win;
     kern<<<(unsigned)grid, kT3, smem, st>>>(
         codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len, (uint32_t)n_win,
-        reinterpret_cast<const double2*>(ig), kmin, want_rip, cap, len_min, len_max, rows, status, dump);
+        reinterpret_cast<const double2*>(ig), kmin, want_rip, cap, len_min, len_max, rows, status, dump, redo_only);
     CK(cudaGetLastError());
     return FRISK_OK;
 }
@@ -1626,6 +1579,22 @@ int launch_score_bucket(const uint32_t* codes, const uint32_t* inv, const uint32
     return launch_score_bucket2<K, false, true>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
 }
 
+// the windows the direct kernel marked kRowRedo (generic instantiation: any kmin, optional dump)
+template <int K>
+int launch_score_bucket_redo(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                             const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
+                             double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+#define FRISK_REDO(R)                                                                                                          \
+    (dump ? launch_score_bucket3<K, R, true, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, \
+                                                    status, dump, st, 0u, 0xffffffffu, 1u)                                     \
+          : launch_score_bucket3<K, R, false, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, \
+                                                     status, dump, st, 0u, 0xffffffffu, 1u))
+    if (max_len <= kT3 * 4u * 2u - 6u) return FRISK_REDO(2);
+    if (max_len <= kT3 * 4u * 5u - 6u) return FRISK_REDO(5);
+    return FRISK_REDO(8);
+#undef FRISK_REDO
+}
+
 template <int K>
 int launch_score_small(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                        const uint32_t* win_len, uint64_t n_win, const double* ig, int kmin, int want_rip,
@@ -1662,6 +1631,15 @@ int launch_score_small(const uint32_t* codes, const uint32_t* inv, const uint32_
         default: return FRISK_E_UNSUPPORTED;        \
     }
 
+// Which window kernel serves kmax 7 and 8 (windows <= 8,186 bases)?  Measured on C2 (tools/direct_vs_bucket.py):
+// the direct kernel wins where the buckets of the bucketed kernel run full (kmax 7: 1,024 buckets) and windows
+// are long; the bucketed kernel keeps kmax 8 and short windows.
+bool use_direct_kernel(int kmax, uint32_t max_win_len) {
+    if (kmax < 7 || kmax > 8 || max_win_len > kBuf3 - 6u || g_force_dense || g_force_bucket) return false;
+    if (g_force_direct) return true;
+    return FRISK_DIRECT_DEFAULT(kmax, max_win_len);
+}
+
 int check_k(int kmin, int kmax) {
     if (kmin < 1 || kmin > kmax) return FRISK_E_INVALID;
     if (kmax > FRISK_B200_MAX_K) return FRISK_E_UNSUPPORTED;
@@ -1678,6 +1656,17 @@ Workspace g_ws[64];
 std::mutex g_run_mu[64];     // frisk_b200_run_host / _run_resident share the workspace: one call at a time per device
 
 }  // namespace
+
+int frisk_internal::sm_count_cached() { return sm_count(); }
+
+int frisk_internal::score_bucket_redo(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                                      const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K,
+                                      int want_rip, double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+    if (max_len > kBuf3 - 6u) return FRISK_E_UNSUPPORTED;
+    if (K == 8) return launch_score_bucket_redo<8>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
+    if (K == 7) return launch_score_bucket_redo<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
+    return FRISK_E_UNSUPPORTED;
+}
 
 int frisk_internal::pool_ready() {
     static bool done[64] = {};
@@ -1842,7 +1831,11 @@ int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint3
             default: break;
         }
     }
-    // kmax 7 and 8 (and 4..6 when forced): bucketed kernel (4 CTAs/SM); the dense-table kernel covers long windows
+    // kmax 7 and 8: the direct kernel (byte table, no sorting; 3 CTAs/SM), then the bucketed one over whatever it handed back
+    if (use_direct_kernel(kmax, max_win_len))
+        return frisk_internal::score_direct(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, kmax, rip,
+                                            d_rows, d_status, d_dump, st);
+    // kmax 4..8 when forced: bucketed kernel (4 CTAs/SM); the dense-table kernel covers long windows
     if (kmax >= 4 && max_win_len <= kBuf3 - 6u && !g_force_dense) {
         switch (kmax) {
             case 4: return launch_score_bucket<4>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, rip, d_rows, d_status, d_dump, st);
@@ -1880,6 +1873,7 @@ int frisk_b200_score_occupancy(int kmax, uint32_t max_win_len, int* ctas_per_sm,
         }
     }
     if (kmax < 4 || max_win_len > kBuf3 - 6u || g_force_dense) return FRISK_OK;                                // dense kernel
+    if (use_direct_kernel(kmax, max_win_len)) return frisk_internal::score_direct_occupancy(kmax, max_win_len, ctas_per_sm, threads_per_cta);
     const uint32_t cap = (max_win_len + 15u) & ~15u;
     *threads_per_cta = kT3;
 #define FRISK_OCC(KK)                                                                                                   \
@@ -1906,6 +1900,7 @@ int frisk_b200_set_option(const char* name, int value) {
     if (strcmp(name, "force_dense_kernel") == 0) { g_force_dense = value; return FRISK_OK; }
     if (strcmp(name, "force_general_kernel") == 0) { g_force_general = value; return FRISK_OK; }
     if (strcmp(name, "force_bucket_kernel") == 0) { g_force_bucket = value; return FRISK_OK; }
+    if (strcmp(name, "force_direct_kernel") == 0) { g_force_direct = value; return FRISK_OK; }
     return FRISK_E_INVALID;
 }
 

@@ -195,6 +195,109 @@ def test_small_word_sizes_three_kernels_agree(eng, case):
         assert max_rel_err(other.rows[ok, 0], default.rows[ok, 0]) < 1e-12
 
 
+def _with_option(opt, value, fn):
+    from frisk_b200 import _lib
+    _lib.check(_lib.lib().frisk_b200_set_option(opt, value), "set_option")
+    try:
+        return fn()
+    finally:
+        _lib.lib().frisk_b200_set_option(opt, 0)
+
+
+@pytest.mark.parametrize("case", ["edge_default", "edge_scaffoldsAll", "edge_maskHost", "edge_k4_8", "c1_small",
+                                  "c2_small_query_vs_c1_host"])
+def test_direct_kernel_agrees_with_bucket_and_dense_kernels(eng, case):
+    """kmax 7 and 8 run on the direct kernel (byte table, every position scores its own K-mer with weight
+    1/count; frisk_direct.cu).  It must reproduce the reference goldens, be bit-reproducible, and agree with the
+    bucketed and the dense-table kernels (forced): identical window tables and status, rows to 1e-12; the
+    384-thread instantiation gives the same."""
+    g = Golden(case)
+    default = _run_case(eng, g, dump=True)
+    err = _check_against_golden(default, g, case + "[direct]")
+    assert err < 1e-10
+    again = _run_case(eng, g)
+    assert np.array_equal(default.rows, again.rows, equal_nan=True)
+    ok = default.status == 0
+    for opt, val in ((b"force_bucket_kernel", 1), (b"force_dense_kernel", 1), (b"force_direct_kernel", 1)):
+        other = _with_option(opt, val, lambda: _run_case(eng, g, dump=True))
+        _check_against_golden(other, g, case + "[%s]" % opt.decode())
+        assert np.array_equal(other.win_tables, default.win_tables), opt
+        assert np.array_equal(other.status, default.status), opt
+        assert np.array_equal(np.isnan(other.rows), np.isnan(default.rows)), opt
+        assert max_rel_err(other.rows[ok, 0], default.rows[ok, 0]) < 1e-12, opt
+        assert np.array_equal(other.rows[:, 1:], default.rows[:, 1:], equal_nan=True), opt
+
+
+@pytest.mark.parametrize("kw", [dict(kmax=7), dict(kmax=7, kmin=3, w=2000, step=700, scaffolds_all=True),
+                                dict(kmax=8, kmin=6), dict(kmax=8, kmin=8, w=7000, step=3000), dict(kmax=7, kmin=7, mask_host=True)])
+def test_direct_kernel_word_ranges_against_c_oracle(eng, kw):
+    """kmax 7 (16 KiB byte table, order-4 atomics) and kmin > 1 on the direct kernel: window tables bit-exact
+    against the C oracle for every window, rows to 1e-10, bucketed kernel (forced) to 1e-12."""
+    from frisk_b200 import synth
+    from oracle import c_oracle
+    sc = synth.make("edge") + synth.make("C2", 0.004, seed=5)
+    full = dict(kmin=1, kmax=8, w=5000, step=2500, mask_host=False, scaffolds_all=False, rip=True)
+    full.update(kw)
+    ref = c_oracle.run(sc, threads=8, **full)
+    g = eng.PackedGenome.from_scaffolds(sc)
+    res = eng.run(g, dump=True, **full)
+    assert np.array_equal(res.tables, ref["tables"])
+    assert np.array_equal(res.coords, ref["coords"])
+    assert np.array_equal(res.status & 7, ref["status"] & 7)
+    ok = ref["status"] == 0
+    assert_rows_close(res.rows[ok], ref["rows"][ok], rtol_kld=1e-6, rtol_other=1e-15, what=str(kw))
+    assert max_rel_err(res.rows[ok, 0], ref["rows"][ok, 0]) < 1e-10
+    seq, off = c_oracle.concat(sc)
+    for i in range(len(ref["rows"])):
+        if ref["status"][i] & 8:
+            continue
+        win = seq[int(ref["win_off"][i]):int(ref["win_off"][i]) + int(ref["win_len"][i])]
+        _, _, wt, _ = c_oracle.window_tables(win, ref["tables"], ref["meta"], full["kmin"], full["kmax"])
+        assert np.array_equal(res.win_tables[i].astype(np.uint64), wt), (kw, i)
+    other = _with_option(b"force_bucket_kernel", 1, lambda: eng.run(g, dump=True, **full))
+    assert np.array_equal(other.win_tables, res.win_tables)
+    assert np.array_equal(other.status, res.status)
+    assert max_rel_err(other.rows[ok, 0], res.rows[ok, 0]) < 1e-12
+
+
+def test_direct_kernel_hands_over_what_a_byte_cannot_hold(eng):
+    """Windows with a K-mer seen 256+ times (byte wrap) or with more than 64 words cut short at K-1 / K-2 bases
+    (many N boundaries) are marked for the bucketed kernel and re-done there: rows and tables still exact, and
+    no internal marker survives in the status words."""
+    from frisk_b200 import synth
+    from oracle import c_oracle
+    rng = np.random.Generator(np.random.PCG64(8))
+    a = synth.iid_bases(rng, 60_000, 0.45)
+    a[2_000:2_300] = ord("A")                                  # 293 x AAAAAAAA: just over a byte
+    a[7_600:7_860] = ord("C")                                  # 253 x CCCCCCCC: just under
+    a[12_000:12_600] = np.tile(np.frombuffer(b"ACG", dtype=np.uint8), 200)
+    for p in range(20_000, 24_000, 40):                        # an N every 40 bases: 100 boundaries per window
+        a[p] = ord("N")
+    for p in range(30_000, 32_400, 80):                        # 30 boundaries: stays on the direct kernel (60 side words)
+        a[p] = ord("N")
+    a[40_000:40_255 + 7] = ord("T")                            # exactly 255 x TTTTTTTT
+    a[45_000:45_256 + 7] = ord("G")                            # exactly 256 x GGGGGGGG
+    sc = [("handover", a)]
+    for kw in (dict(), dict(kmax=7), dict(w=3000, step=1000, kmin=2)):
+        full = dict(kmin=1, kmax=8, w=5000, step=2500, mask_host=False, scaffolds_all=False, rip=True)
+        full.update(kw)
+        ref = c_oracle.run(sc, threads=4, **full)
+        res = eng.run(eng.PackedGenome.from_scaffolds(sc), dump=True, **full)
+        assert np.array_equal(res.tables, ref["tables"])
+        assert np.array_equal(res.status & 7, ref["status"] & 7)
+        assert not np.any(res.status & 0x80000000), "internal redo marker must not survive"
+        ok = ref["status"] == 0
+        assert_rows_close(res.rows[ok], ref["rows"][ok], rtol_kld=1e-6, rtol_other=1e-15, what="handover")
+        assert max_rel_err(res.rows[ok, 0], ref["rows"][ok, 0]) < 1e-10
+        seq, off = c_oracle.concat(sc)
+        for i in range(len(ref["rows"])):
+            win = seq[int(ref["win_off"][i]):int(ref["win_off"][i]) + int(ref["win_len"][i])]
+            _, _, wt, _ = c_oracle.window_tables(win, ref["tables"], ref["meta"], full["kmin"], full["kmax"])
+            assert np.array_equal(res.win_tables[i].astype(np.uint64), wt), (kw, i)
+        nodump = eng.run(eng.PackedGenome.from_scaffolds(sc), **full)
+        assert np.array_equal(nodump.rows, res.rows, equal_nan=True)
+
+
 def test_long_windows_use_segments(eng):
     """Windows longer than the bucketed kernel's 8192-base buffer (and longer than the dense
     kernel's 8192-entry k-mer list) against the C oracle."""
