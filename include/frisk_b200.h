@@ -230,8 +230,11 @@ int frisk_b200_region_features(const uint32_t *d_codes, const uint32_t *d_inv, c
  * resident CTAs per SM and threads per CTA of the window kernel it selects (diagnostic; bench.py reports it). */
 int frisk_b200_score_occupancy(int kmax, uint32_t max_win_len, int *ctas_per_sm, int *threads_per_cta);
 
-/* Tuning/test switches.  "force_dense_kernel" = 1 makes frisk_b200_score use the dense-table
- * kernel (the general path for kmax < 4 or windows > 8192 bases) for every input. */
+/* Tuning/test switches (0 = default behaviour).  "force_dense_kernel" = 1 makes frisk_b200_score use the
+ * dense-table kernel (the path for windows of 8,187..65,535 bases) for every input; "force_bucket_kernel" = 1 keeps
+ * kmax 4..8 on the bucketed kernel (default for kmax 8); "force_direct_kernel" = 1 runs kmax 7 and 8 on the direct
+ * kernel (default for kmax 7) wherever windows are <= 8,186 bases; "force_general_kernel" = 1 selects the general
+ * (global-memory, run-time K) path.  All of them produce the same rows (tests/test_gpu_parity.py). */
 int frisk_b200_set_option(const char *name, int value);
 
 /*
