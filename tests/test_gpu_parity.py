@@ -254,13 +254,15 @@ def test_direct_kernel_word_ranges_against_c_oracle(eng, kw):
         win = seq[int(ref["win_off"][i]):int(ref["win_off"][i]) + int(ref["win_len"][i])]
         _, _, wt, _ = c_oracle.window_tables(win, ref["tables"], ref["meta"], full["kmin"], full["kmax"])
         assert np.array_equal(res.win_tables[i].astype(np.uint64), wt), (kw, i)
-    other = _with_option(b"force_bucket_kernel", 1, lambda: eng.run(g, dump=True, **full))
-    assert np.array_equal(other.win_tables, res.win_tables)
-    assert np.array_equal(other.status, res.status)
-    assert max_rel_err(other.rows[ok, 0], res.rows[ok, 0]) < 1e-12
+    for opt in (b"force_bucket_kernel", b"force_direct_kernel"):
+        other = _with_option(opt, 1, lambda: eng.run(g, dump=True, **full))
+        assert np.array_equal(other.win_tables, res.win_tables), opt
+        assert np.array_equal(other.status, res.status), opt
+        assert max_rel_err(other.rows[ok, 0], res.rows[ok, 0]) < 1e-12, opt
 
 
-def test_direct_kernel_hands_over_what_a_byte_cannot_hold(eng):
+@pytest.mark.parametrize("opt", [None, b"force_direct_kernel"])
+def test_direct_kernel_hands_over_what_a_byte_cannot_hold(eng, opt):
     """Windows with a K-mer seen 256+ times (byte wrap) or with more than 64 words cut short at K-1 / K-2 bases
     (many N boundaries) are marked for the bucketed kernel and re-done there: rows and tables still exact, and
     no internal marker survives in the status words."""
@@ -282,7 +284,8 @@ def test_direct_kernel_hands_over_what_a_byte_cannot_hold(eng):
         full = dict(kmin=1, kmax=8, w=5000, step=2500, mask_host=False, scaffolds_all=False, rip=True)
         full.update(kw)
         ref = c_oracle.run(sc, threads=4, **full)
-        res = eng.run(eng.PackedGenome.from_scaffolds(sc), dump=True, **full)
+        run = lambda **k: eng.run(eng.PackedGenome.from_scaffolds(sc), **k, **full)
+        res = run(dump=True) if opt is None else _with_option(opt, 1, lambda: run(dump=True))
         assert np.array_equal(res.tables, ref["tables"])
         assert np.array_equal(res.status & 7, ref["status"] & 7)
         assert not np.any(res.status & 0x80000000), "internal redo marker must not survive"
@@ -294,7 +297,7 @@ def test_direct_kernel_hands_over_what_a_byte_cannot_hold(eng):
             win = seq[int(ref["win_off"][i]):int(ref["win_off"][i]) + int(ref["win_len"][i])]
             _, _, wt, _ = c_oracle.window_tables(win, ref["tables"], ref["meta"], full["kmin"], full["kmax"])
             assert np.array_equal(res.win_tables[i].astype(np.uint64), wt), (kw, i)
-        nodump = eng.run(eng.PackedGenome.from_scaffolds(sc), **full)
+        nodump = run() if opt is None else _with_option(opt, 1, run)
         assert np.array_equal(nodump.rows, res.rows, equal_nan=True)
 
 
