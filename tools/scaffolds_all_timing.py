@@ -2,9 +2,11 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from frisk_b200 import engine, synth
+from frisk_b200 import engine, synth, _lib
 g = engine.PackedGenome.from_scaffolds(synth.make("C5", 0.01))
-for sa in (False, True):
+for sa, opt in ((False, None), (True, None), (False, b"force_direct_kernel"), (True, b"force_direct_kernel")):
+    if opt:
+        _lib.check(_lib.lib().frisk_b200_set_option(opt, 1), "option")
     pipe = engine.Pipeline(g, scaffolds_all=sa)
     for _ in range(3):
         pipe.enqueue()
@@ -16,5 +18,7 @@ for sa in (False, True):
         torch.cuda.synchronize()
         ms.append(marks[2].elapsed_time(marks[3]))
     ms.sort()
-    print("scaffolds_all=%s: %d windows (max %d bases, %d longer than 5104), score %.3f ms, %.1f M windows/s" % (
-        sa, len(pipe.wins), pipe.wins.max_len, int((pipe.wins.length > 5104).sum()), ms[3], len(pipe.wins) / ms[3] / 1e3))
+    if opt:
+        _lib.lib().frisk_b200_set_option(opt, 0)
+    print("%s scaffolds_all=%s: %d windows (max %d bases, %d longer than 5104), score %.3f ms, %.1f M windows/s" % (
+        (opt or b"default").decode(), sa, len(pipe.wins), pipe.wins.max_len, int((pipe.wins.length > 5104).sum()), ms[3], len(pipe.wins) / ms[3] / 1e3))
