@@ -1189,8 +1189,11 @@ template <int K>
 struct SmallLayout {
     static constexpr uint32_t NTAB = lvl_off(K + 1);                       // u16 entries, orders 1..K
     static constexpr uint32_t TAB_BYTES = (NTAB * 2u + 15u) & ~15u;
+    static constexpr int P = K >= 3 ? (K - 1 < 4 ? K - 1 : 4) : 0;          // orders <= P are folded into one pair per order-P prefix
+    static constexpr uint32_t NPRE = P ? pow4(P) : 0u;
     static constexpr uint32_t OFF_LOG = TAB_BYTES;
-    static constexpr uint32_t OFF_SS = OFF_LOG + 128u * 16u;
+    static constexpr uint32_t OFF_PRE = OFF_LOG + 128u * 16u;
+    static constexpr uint32_t OFF_SS = OFF_PRE + NPRE * 16u;
     static constexpr uint32_t TOTAL = OFF_SS + (uint32_t)sizeof(SmallSmem);
 };
 
@@ -1205,7 +1208,10 @@ score_windows_small_kernel(const uint32_t* __restrict__ codes, const uint32_t* _
     uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem);
     uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem);
     double2* logtab = reinterpret_cast<double2*>(smem + L::OFF_LOG);
+    double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);          // .x = num, .y = den (low word) of the orders <= P
     SmallSmem& ss = *reinterpret_cast<SmallSmem*>(smem + L::OFF_SS);
+    constexpr int P = L::P;
+    (void)pre;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (uint32_t i = tid; i < L::TAB_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -1282,6 +1288,24 @@ score_windows_small_kernel(const uint32_t* __restrict__ codes, const uint32_t* _
             for (uint32_t i = tid; i < lvl_off(K + 1); i += kT3) d[i] = excluded ? (uint16_t)0 : tab16[i];
         }
         __syncthreads();
+        if constexpr (P > 0) {           // the low orders' share of numerator and denominator, once per order-P prefix
+            if (!excluded) {
+                for (uint32_t node = tid; node < pow4(P); node += kT3) {
+                    double num = 0.0;
+                    uint32_t den = 0;
+#pragma unroll
+                    for (int x = 1; x <= P; ++x) {
+                        if (x >= kmin) {
+                            const uint32_t c = tab16[lvl_off(x) + (node >> (2 * (P - x)))];
+                            den += c << (2 * x);
+                            num = fma(ss.q[x - 1], u32_to_double(c * c), num);
+                        }
+                    }
+                    pre[node] = make_double2(num, __hiloint2double(0, (int)den));
+                }
+            }
+            __syncthreads();
+        }
 
         // ---- epilogue: every occupied bin of order K, in table order ------------------------------------
         double s_w = 0.0, s_g = 0.0, s_t = 0.0;
@@ -1292,8 +1316,13 @@ score_windows_small_kernel(const uint32_t* __restrict__ codes, const uint32_t* _
                 if (ck == 0) continue;
                 double num = 0.0;
                 uint32_t den = 0;
+                if constexpr (P > 0) {
+                    const double2 pp = pre[kappa >> (2 * (K - P))];
+                    num = pp.x;
+                    den = (uint32_t)__double2loint(pp.y);
+                }
 #pragma unroll
-                for (int x = 1; x <= K; ++x) {
+                for (int x = P + 1; x <= K; ++x) {
                     if (x >= kmin) {
                         const uint32_t c = (x == K) ? ck : (uint32_t)tab16[lvl_off(x) + (kappa >> (2 * (K - x)))];
                         den += c << (2 * x);
