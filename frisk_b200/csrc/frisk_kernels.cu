@@ -1964,7 +1964,8 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
                     const uint32_t* dqc, const uint32_t* dqi, const uint32_t* dql, const uint64_t* win_off,
                     const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host,
                     int want_rip, int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
-                    uint64_t* valid_kmax_out, void* dfwd, cudaStream_t st, cudaStream_t copy, cudaEvent_t copy_done) {
+                    uint64_t* valid_kmax_out, void* dfwd, cudaStream_t st, cudaStream_t copy, cudaEvent_t copy_done,
+                    cudaEvent_t tables_ready) {
     const size_t tsz = (size_t)frisk_b200_table_size(1, kmax);
     void *dtab, *dig, *dwo = nullptr, *dwl = nullptr, *drows = nullptr, *dstat = nullptr;
     int rc;
@@ -1990,6 +1991,14 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
     rc = frisk_b200_finalize_ivom((const uint64_t*)dfwd, peers.d_fwd_peers, peers.d_flag_peers, peers.rank, peers.world, peers.epoch,
                                   kmin, kmax, genome_space, (uint64_t*)dtab, dvalid, (double*)dig, st);
     if (rc) return rc;
+    // the genome tables (0.7 MB) go back on the copy stream while the window kernel runs, not behind it
+    const bool tables_aside = copy && tables_ready && (tables_out || valid_kmax_out);
+    if (tables_aside) {
+        CK(cudaEventRecord(tables_ready, st));
+        CK(cudaStreamWaitEvent(copy, tables_ready, 0));
+        if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, copy));
+        if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, copy));
+    }
     if (copy) CK(cudaStreamWaitEvent(st, copy_done, 0));
     if (n_win) {
         // Pinned result buffers are written by the score kernel itself (40 + 4 bytes per window, posted
@@ -2009,9 +2018,12 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
             CK(cudaMemcpyAsync(status_out, dstat, n_win * 4, cudaMemcpyDeviceToHost, st));
         }
     }
-    if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, st));
-    if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, st));
+    if (!tables_aside) {
+        if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, st));
+        if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
+    if (tables_aside) CK(cudaStreamSynchronize(copy));
     return FRISK_OK;
 }
 
@@ -2020,7 +2032,7 @@ namespace {
 constexpr int kMaxChunks = 16;
 struct CopyCtx {
     cudaStream_t copy = nullptr;
-    cudaEvent_t ev[kMaxChunks + 2] = {};
+    cudaEvent_t ev[kMaxChunks + 3] = {};
 };
 CopyCtx g_copy[64];
 
@@ -2108,7 +2120,9 @@ static int run_host_impl(const PeerArgs& peers, const HostPlanes& h, const HostP
     // so only the last chunk's count is not hidden behind PCIe.
     CK(cudaEventRecord(cc->ev[kMaxChunks], st));
     CK(cudaStreamWaitEvent(cc->copy, cc->ev[kMaxChunks], 0));          // order behind earlier work on `stream`
-    if ((rc = upload_inv(h, dhi, 15, 16, cc->copy))) return rc;
+    // sparse invalid plane: zero fill + pairs + scatter on the COMPUTE stream, behind the first code chunk's transfer
+    // (on the copy stream they would delay that chunk by four small operations); the counts on `st` follow in order
+    if ((rc = upload_inv(h, dhi, 15, 16, st))) return rc;
     uint64_t n_chunks = (h_padded_len + (8ull << 20) - 1) / (8ull << 20);
     if (n_chunks > (uint64_t)kMaxChunks) n_chunks = kMaxChunks;
     const uint64_t chunk = ((h_padded_len + n_chunks - 1) / n_chunks + 127) & ~127ull;
@@ -2142,7 +2156,7 @@ static int run_host_impl(const PeerArgs& peers, const HostPlanes& h, const HostP
     return run_tail(peers, (const uint32_t*)dhc, (const uint32_t*)dhi, (const uint32_t*)dhl, h_padded_len, true,
                     (const uint32_t*)dqc, (const uint32_t*)dqi, (const uint32_t*)dql, win_off, win_len, n_win, max_win_len,
                     kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out, valid_kmax_out, dfwd, st,
-                    cc->copy, cc->ev[kMaxChunks + 1]);
+                    cc->copy, cc->ev[kMaxChunks + 1], cc->ev[kMaxChunks + 2]);
 }
 
 int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const uint32_t* h_low, uint64_t h_padded_len,
@@ -2212,7 +2226,7 @@ int frisk_b200_run_resident(const uint32_t* d_h_codes, const uint32_t* d_h_inv, 
     if ((rc = ws_get(6, ((size_t)frisk_b200_table_size(1, kmax) + 1) * 8, &dfwd))) return rc;
     return run_tail(PeerArgs(), d_h_codes, d_h_inv, d_h_low, h_padded_len, false, d_q_codes, d_q_inv, d_q_low, win_off, win_len, n_win,
                     max_win_len, kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out,
-                    valid_kmax_out, dfwd, (cudaStream_t)stream, nullptr, nullptr);
+                    valid_kmax_out, dfwd, (cudaStream_t)stream, nullptr, nullptr, nullptr);
 }
 
 int frisk_b200_release_workspace(void) {
