@@ -208,3 +208,6 @@ def test_argument_checks_answer_before_any_device_work():
                                      null) == _lib.E_INVALID                                         # padded_len % 128
     assert b"unsupported" in L.frisk_b200_strerror(_lib.E_UNSUPPORTED) and L.frisk_b200_strerror(-99) == b"unknown error"
     assert L.frisk_b200_set_option(b"no_such_option", 1) == _lib.E_INVALID
+    assert L.frisk_b200_set_option(None, 1) == _lib.E_INVALID
+    for opt in (b"force_dense_kernel", b"force_general_kernel", b"force_bucket_kernel", b"force_direct_kernel"):
+        assert L.frisk_b200_set_option(opt, 1) == 0 and L.frisk_b200_set_option(opt, 0) == 0, opt   # the switches in the header
