@@ -69,9 +69,6 @@ __device__ __forceinline__ uint32_t bytes_sum(uint32_t w, uint32_t acc) { return
 #ifndef FRISK_DIRECT_TABLOG
 #define FRISK_DIRECT_TABLOG 0
 #endif
-#ifndef FRISK_DIRECT_BATCH
-#define FRISK_DIRECT_BATCH 0
-#endif
 constexpr bool TABLOG = FRISK_DIRECT_TABLOG;      // log2 by series: no shared-memory table read in the epilogue
 
 template <int K, int NT, int ROUNDS, bool DUMP, bool ALLK>
@@ -313,36 +310,16 @@ score_windows_direct_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             s_g = fma(g.x, om, s_g);                       // a NaN entry (reference: ZeroDivisionError) poisons the sum
             s_t = fma(a, (TABLOG ? log2_pos(iw, logtab) : log2_series(iw)) - g.y, s_t);
         };
-#if FRISK_DIRECT_BATCH == 2
-        double2 gcur = __ldg(ig + (kk[0] & 0xffffu));
-#endif
 #pragma unroll 1
         for (int r = 0; r < ROUNDS; ++r) {
             uint32_t kp[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) kp[j] = (kk[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-#if FRISK_DIRECT_BATCH == 2
-            // the genome-IVOM gather of the NEXT K-mer is issued before this one is scored (one ahead: four at once
-            // -- FRISK_DIRECT_BATCH 1 -- clog the LSU queue and cost 12 %)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t nk = j < 3 ? kp[j + 1] : (kk[2 < 2 * ROUNDS ? 2 : 0] & 0xffffu);
-                const double2 gnext = __ldg(ig + nk);                       // (an empty slot reads entry 0: harmless)
-                if (vm & (1u << j)) score_one(kp[j], gcur);
-                gcur = gnext;
-            }
-#elif FRISK_DIRECT_BATCH == 1
-            double2 g4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) g4[j] = __ldg(ig + kp[j]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (vm & (1u << j)) score_one(kp[j], g4[j]);
-#else
+            // the gather is issued where it is used: four at the top of the round cost 12 % (0.771 -> 0.886 ms), one
+            // K-mer ahead 4 % -- they queue in front of the other warps' shared-memory traffic
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (vm & (1u << j)) score_one(kp[j], __ldg(ig + kp[j]));
-#endif
             vm >>= 4;
 #pragma unroll
             for (int i = 0; i + 2 < 2 * ROUNDS; ++i) kk[i] = kk[i + 2];     // rotate: the loop body stays one round long
