@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(NT, FRISK_DIRECT_MIN_CTAS(K))
 score_windows_direct_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                             const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
                             const double2* __restrict__ ig, int kmin_arg, int want_rip,
-                            double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
+                            double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump,
+                            uint32_t* redo_dst) {
     using L = DirectLayout<K, NT>;
     constexpr int A = L::A, LP = L::LP, NW = NT / 32;
     const int kmin = ALLK ? 1 : kmin_arg;                                // ALLK: the default --minWordSize 1
@@ -177,8 +178,9 @@ score_windows_direct_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 if (excluded) {
                     status[win] = FRISK_ROW_EXCLUDED;
                     for (int c = 0; c < 5; ++c) rows[(size_t)win * 5 + c] = CUDART_NAN;
+                    if (redo_dst != status) redo_dst[win] = 0;
                 } else {
-                    status[win] = kRowRedo;                                // the bucketed kernel takes this window
+                    redo_dst[win] = kRowRedo;                              // the bucketed kernel takes this window
                 }
             }
             if (DUMP && excluded) for (uint32_t i = tid; i < lvl_off(K + 1); i += NT) dmp[i] = 0;
@@ -359,6 +361,7 @@ score_windows_direct_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             }
             row[2] = pi; row[3] = si; row[4] = cri;
             status[win] = st;
+            if (redo_dst != status) redo_dst[win] = 0;
         }
         __syncthreads();                                                   // (5) tables zeroed, ss.red consumed
     }
@@ -367,7 +370,7 @@ score_windows_direct_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
 template <int K, int NT, int ROUNDS, bool DUMP, bool ALLK>
 int launch_direct4(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                    const uint32_t* win_len, uint64_t n_win, const double* ig, int kmin, int want_rip,
-                   double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, int* occ_only) {
+                   double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only) {
     using L = DirectLayout<K, NT>;
     auto kern = score_windows_direct_kernel<K, NT, ROUNDS, DUMP, ALLK>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
@@ -383,7 +386,7 @@ int launch_direct4(const uint32_t* codes, const uint32_t* inv, const uint32_t* l
     if (grid > n_win) grid = n_win;
     kern<<<(unsigned)grid, NT, L::TOTAL, st>>>(codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len,
                                                (uint32_t)n_win, reinterpret_cast<const double2*>(ig), kmin, want_rip, rows,
-                                               status, dump);
+                                               status, dump, redo_dst);
     CK(cudaGetLastError());
     return FRISK_OK;
 }
@@ -391,22 +394,22 @@ int launch_direct4(const uint32_t* codes, const uint32_t* inv, const uint32_t* l
 template <int K, int NT, int ROUNDS>
 int launch_direct3(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                    const uint32_t* win_len, uint64_t n_win, const double* ig, int kmin, int want_rip,
-                   double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, int* occ_only) {
-    if (dump) return launch_direct4<K, NT, ROUNDS, true, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, st, occ_only);
-    if (kmin != 1) return launch_direct4<K, NT, ROUNDS, false, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, st, occ_only);
-    return launch_direct4<K, NT, ROUNDS, false, true>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, st, occ_only);
+                   double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only) {
+    if (dump) return launch_direct4<K, NT, ROUNDS, true, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+    if (kmin != 1) return launch_direct4<K, NT, ROUNDS, false, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+    return launch_direct4<K, NT, ROUNDS, false, true>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
 }
 
 // positions per thread = 4 * ROUNDS (K-mer codes held in registers between the two passes)
 template <int K>
 int launch_direct(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                   const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
-                  double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, int* occ_only, int* threads) {
+                  double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only, int* threads) {
 #define FRISK_DIRECT(NT, R)                                                                                              \
     do {                                                                                                                 \
         if (threads) *threads = NT;                                                                                      \
-        return launch_direct3<K, NT, R>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, st, \
-                                        occ_only);                                                                       \
+        return launch_direct3<K, NT, R>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, \
+                                        st, occ_only);                                                                   \
     } while (0)
     if (max_len <= 256u * 4u * 2u - 6u) FRISK_DIRECT(256, 2);
     if (max_len <= 256u * 4u * 5u - 6u) FRISK_DIRECT(256, 5);
@@ -419,17 +422,30 @@ int launch_direct(const uint32_t* codes, const uint32_t* inv, const uint32_t* lo
 int frisk_internal::score_direct(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                                  const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K,
                                  int want_rip, double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+    if (K != 7 && K != 8) return FRISK_E_UNSUPPORTED;
+    // where the hand-over marks go: `status` itself when it is device memory, device scratch when it is pinned host
+    // memory (the second launch would otherwise read its marks across PCIe, one round trip per window)
+    uint32_t* redo = status;
+    uint32_t* scratch = nullptr;
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, status) != cudaSuccess || pa.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        int rc = pool_ready();
+        if (rc) return rc;
+        CK(cudaMallocAsync((void**)&scratch, n_win * sizeof(uint32_t), st));
+        redo = scratch;
+    }
     int rc;
-    if (K == 8) rc = launch_direct<8>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st, nullptr, nullptr);
-    else if (K == 7) rc = launch_direct<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st, nullptr, nullptr);
-    else return FRISK_E_UNSUPPORTED;
-    if (rc) return rc;
+    if (K == 8) rc = launch_direct<8>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo, st, nullptr, nullptr);
+    else rc = launch_direct<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo, st, nullptr, nullptr);
     // windows the byte table could not hold (marked kRowRedo): exact re-run on the bucketed kernel
-    return score_bucket_redo(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, K, want_rip, rows, status, dump, st);
+    if (!rc) rc = score_bucket_redo(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, K, want_rip, rows, status, dump, redo, st);
+    if (scratch) CK(cudaFreeAsync(scratch, st));
+    return rc;
 }
 
 int frisk_internal::score_direct_occupancy(int K, uint32_t max_len, int* ctas_per_sm, int* threads_per_cta) {
-    if (K == 8) return launch_direct<8>(nullptr, nullptr, nullptr, nullptr, nullptr, 1, max_len, nullptr, 1, 0, nullptr, nullptr, nullptr, 0, ctas_per_sm, threads_per_cta);
-    if (K == 7) return launch_direct<7>(nullptr, nullptr, nullptr, nullptr, nullptr, 1, max_len, nullptr, 1, 0, nullptr, nullptr, nullptr, 0, ctas_per_sm, threads_per_cta);
+    if (K == 8) return launch_direct<8>(nullptr, nullptr, nullptr, nullptr, nullptr, 1, max_len, nullptr, 1, 0, nullptr, nullptr, nullptr, nullptr, 0, ctas_per_sm, threads_per_cta);
+    if (K == 7) return launch_direct<7>(nullptr, nullptr, nullptr, nullptr, nullptr, 1, max_len, nullptr, 1, 0, nullptr, nullptr, nullptr, nullptr, 0, ctas_per_sm, threads_per_cta);
     return FRISK_E_UNSUPPORTED;
 }

@@ -32,8 +32,10 @@ int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* lo
 
 
 // direct score kernel (frisk_direct.cu): kmax 7, 8 and windows <= 8,186 bases.  Windows it cannot finish exactly
-// (a K-mer seen 256+ times, more than 64 N-boundary words) are marked kRowRedo in `status` and re-done by the
-// bucketed kernel (frisk_kernels.cu), launched behind it on the same stream.
+// (a K-mer seen 256+ times, more than 64 N-boundary words) are marked kRowRedo and re-done by the bucketed kernel
+// (frisk_kernels.cu), launched behind it on the same stream.  The marks live in `status` when that is device memory,
+// in stream-ordered device scratch when `status` is a pinned host buffer written over PCIe (frisk_b200_run_host):
+// the second launch must not read its marks back across the bus one window at a time.
 constexpr uint32_t kRowRedo = 0x80000000u;
 int score_direct(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                  const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
@@ -41,7 +43,7 @@ int score_direct(const uint32_t* codes, const uint32_t* inv, const uint32_t* low
 int score_direct_occupancy(int K, uint32_t max_len, int* ctas_per_sm, int* threads_per_cta);
 int score_bucket_redo(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                       const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
-                      double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st);
+                      double* rows, uint32_t* status, uint16_t* dump, const uint32_t* redo_src, cudaStream_t st);
 int sm_count_cached();
 
 }  // namespace frisk_internal

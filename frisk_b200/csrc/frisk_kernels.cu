@@ -797,7 +797,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                             const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
                             const double2* __restrict__ ig, int kmin_arg, int want_rip, uint32_t cap, uint32_t len_min,
                             uint32_t len_max, double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump,
-                            uint32_t redo_only) {
+                            const uint32_t* __restrict__ redo_src) {
     using L = Score3Layout<K>;
     constexpr int B = L::B, LP = L::LP;
     constexpr uint32_t NBK = L::NBK, PER = L::PER;
@@ -834,7 +834,7 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         const uint32_t len = win_len[win];
         if (len < len_min || len > len_max) continue;    // another launch (other buffer size) takes this one
         // second launch behind the direct kernel (frisk_direct.cu): only the windows it handed over
-        if (redo_only && !(status[win] & frisk_internal::kRowRedo)) continue;
+        if (redo_src && !(redo_src[win] & frisk_internal::kRowRedo)) continue;
         par ^= 1;
         // 32-bit addressing relative to the window's first mask word
         const uint32_t o_lo = (uint32_t)(o & 31);
@@ -1558,7 +1558,7 @@ template <int K, int ROUNDS, bool DUMP, bool ALLK>
 int launch_score_bucket3(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                          const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
                          double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, uint32_t len_min = 0,
-                         uint32_t len_max = 0xffffffffu, uint32_t redo_only = 0) {
+                         uint32_t len_max = 0xffffffffu, const uint32_t* redo_src = nullptr) {
     using L = Score3Layout<K>;
     const uint32_t cap = (max_len + 15u) & ~15u;
     const size_t smem = L::total(cap);
@@ -1576,7 +1576,7 @@ int launch_score_bucket3(const uint32_t* codes, const uint32_t* inv, const uint3
     if (grid > n_win) grid = n_win;
     kern<<<(unsigned)grid, kT3, smem, st>>>(
         codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len, (uint32_t)n_win,
-        reinterpret_cast<const double2*>(ig), kmin, want_rip, cap, len_min, len_max, rows, status, dump, redo_only);
+        reinterpret_cast<const double2*>(ig), kmin, want_rip, cap, len_min, len_max, rows, status, dump, redo_src);
     CK(cudaGetLastError());
     return FRISK_OK;
 }
@@ -1621,12 +1621,12 @@ int launch_score_bucket(const uint32_t* codes, const uint32_t* inv, const uint32
 template <int K>
 int launch_score_bucket_redo(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                              const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
-                             double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+                             double* rows, uint32_t* status, uint16_t* dump, const uint32_t* redo_src, cudaStream_t st) {
 #define FRISK_REDO(R)                                                                                                          \
     (dump ? launch_score_bucket3<K, R, true, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, \
-                                                    status, dump, st, 0u, 0xffffffffu, 1u)                                     \
+                                                    status, dump, st, 0u, 0xffffffffu, redo_src)                               \
           : launch_score_bucket3<K, R, false, false>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, \
-                                                     status, dump, st, 0u, 0xffffffffu, 1u))
+                                                     status, dump, st, 0u, 0xffffffffu, redo_src))
     if (max_len <= kT3 * 4u * 2u - 6u) return FRISK_REDO(2);
     if (max_len <= kT3 * 4u * 5u - 6u) return FRISK_REDO(5);
     return FRISK_REDO(8);
@@ -1699,10 +1699,11 @@ int frisk_internal::sm_count_cached() { return sm_count(); }
 
 int frisk_internal::score_bucket_redo(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                                       const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K,
-                                      int want_rip, double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
-    if (max_len > kBuf3 - 6u) return FRISK_E_UNSUPPORTED;
-    if (K == 8) return launch_score_bucket_redo<8>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
-    if (K == 7) return launch_score_bucket_redo<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, st);
+                                      int want_rip, double* rows, uint32_t* status, uint16_t* dump, const uint32_t* redo_src,
+                                      cudaStream_t st) {
+    if (max_len > kBuf3 - 6u || !redo_src) return FRISK_E_UNSUPPORTED;
+    if (K == 8) return launch_score_bucket_redo<8>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo_src, st);
+    if (K == 7) return launch_score_bucket_redo<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo_src, st);
     return FRISK_E_UNSUPPORTED;
 }
 

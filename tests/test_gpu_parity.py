@@ -299,6 +299,10 @@ def test_direct_kernel_hands_over_what_a_byte_cannot_hold(eng, opt):
             assert np.array_equal(res.win_tables[i].astype(np.uint64), wt), (kw, i)
         nodump = run() if opt is None else _with_option(opt, 1, run)
         assert np.array_equal(nodump.rows, res.rows, equal_nan=True)
+        # one C call from pinned host buffers: rows and status are written over PCIe, the hand-over marks stay on the device
+        hostrun = lambda: eng.run_host(eng.PackedGenome.from_scaffolds(sc, pinned=True), **full)
+        viahost = hostrun() if opt is None else _with_option(opt, 1, hostrun)
+        assert np.array_equal(viahost.rows, res.rows, equal_nan=True) and np.array_equal(viahost.status, res.status)
 
 
 def test_long_windows_use_segments(eng):
