@@ -466,8 +466,18 @@ int frisk_b200_windows(const uint64_t* scaf_len, const uint64_t* scaf_off, uint6
         // Once j + w overshoots it does so for every later j too, so the reference's never-cleared
         // `jumpback` flag (F:232) just means: every remaining j re-emits the last w bases (F:243).
         for (uint64_t j = 0; j + (uint64_t)step <= size; j += (uint64_t)step) {  // xrange(0, size - i + 1, i)
-            if (j + (uint64_t)w > size) put(s, size - w, w, (int64_t)(size - w), (int64_t)size);   // F:230-232, F:243
-            else put(s, j, w, (int64_t)j + 1, (int64_t)(j + w));                                  // F:245
+            if (j + (uint64_t)w > size) {                                                          // F:230-232, F:243
+                // size < w (possible when 0.75 w < step): seq[size - w : size] has a NEGATIVE start, which Python
+                // counts from the end -- the slice is the last min(w - size, size) bases; the coordinates stay
+                // (size - w, size).  Signed arithmetic throughout.
+                const int64_t lead = (int64_t)size - (int64_t)w;
+                if (lead >= 0) put(s, (uint64_t)lead, (uint64_t)w, lead, (int64_t)size);
+                else {
+                    const uint64_t d = (uint64_t)(-lead);
+                    if (d <= size) { if (d > 0) put(s, size - d, d, lead, (int64_t)size); }
+                    else put(s, 0, size, lead, (int64_t)size);
+                }
+            } else put(s, j, w, (int64_t)j + 1, (int64_t)(j + w));                                  // F:245
         }
     }
     *n_windows = n;

@@ -199,12 +199,36 @@ def config_edge(seed: int = 7) -> List[Scaffold]:
     return out
 
 
+def config_edge_short(seed: int = 17) -> List[Scaffold]:
+    """Scaffolds around one window length for runs with 0.75 w < step < w (meant for -w 1000 -i 800: minimum
+    size 950): a scaffold with 950 < size < w is windowed, its one window overshoots at j = 0, and the
+    reference's ``seq[size - w:size]`` (F:231) has a NEGATIVE start -- the last ``w - size`` bases, reported with
+    coordinates (size - w, size) (F:243)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for n, gc in [(975, 0.5), (999, 0.4), (951, 0.6), (950, 0.5), (1000, 0.5), (1001, 0.45), (1600, 0.55), (1799, 0.5),
+                  (1800, 0.5), (2400, 0.35), (4000, 0.5), (960, 0.3)]:
+        out.append(("short_%d" % n, iid_bases(rng, n, gc)))
+    a = iid_bases(rng, 970, 0.5)
+    a[945:960] = ord("N")                                  # 15 of the last 30 bases unresolved: the short window is excluded
+    out.append(("short_970_N", a))
+    b = iid_bases(rng, 990, 0.5)
+    b[985:988] = ord("n")                                  # 3 of the last 10: exactly 30 % -> excluded (>=, F:238)
+    out.append(("short_990_n", b))
+    c = iid_bases(rng, 980, 0.5)
+    c[962:967] = np.char.lower(c[962:967].view("S1")).view(np.uint8)   # 5 of the last 20 lower case: 25 %, kept
+    out.append(("short_980_low", c))
+    return out
+
+
 CONFIGS = {"C1": config_c1, "C2": config_c2, "C3": config_c3, "C4": config_c4, "C5": config_c5}
 
 
 def make(config: str, scale: float = 1.0, seed: int | None = None) -> List[Scaffold]:
     if config == "edge":
         return config_edge() if seed is None else config_edge(seed)
+    if config == "edge_short":
+        return config_edge_short() if seed is None else config_edge_short(seed)
     fn = CONFIGS[config]
     return fn(scale) if seed is None else fn(scale, seed)
 

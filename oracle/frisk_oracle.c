@@ -235,12 +235,16 @@ size_t frisk_oracle_crawl(const unsigned char *seq, size_t size, int w, int step
     if (small) return 0;
     for (size_t j = 0; j + step <= size; j += step) { /* xrange(0, size - i + 1, i), F:228 */
         size_t o, l = (size_t)w;
-        if (j + w > size) { o = size - w; jumped = 1; } /* F:230-232 */
-        else o = j;
+        if (j + w > size) { /* F:230-232; size < w: Python's negative slice start counts from the end */
+            jumped = 1;
+            if (size >= (size_t)w) o = size - w;
+            else if ((size_t)w - size <= size) { l = (size_t)w - size; o = size - l; }
+            else { o = 0; l = size; }
+        } else o = j;
         if ((double)count_non_atgc(seq + o, l) >= 0.3 * (double)l) continue; /* F:237-241 */
         if (n < cap) {
             off[n] = o; len[n] = (uint32_t)l;
-            if (jumped) { start[n] = (int64_t)(size - w); stop[n] = (int64_t)size; } /* F:243 */
+            if (jumped) { start[n] = (int64_t)size - (int64_t)w; stop[n] = (int64_t)size; } /* F:243 */
             else { start[n] = (int64_t)j + 1; stop[n] = (int64_t)(j + w); }        /* F:245 */
         }
         ++n;

@@ -41,6 +41,9 @@ CASES = {
     # beyond the default --maxWordSize 8: served by the general (global-memory) kernels
     "edge_k1_9": dict(genome=("edge", 1.0), params=dict(kmin=1, kmax=9)),
     "edge_k9_10_w2500_i2500": dict(genome=("edge", 1.0), params=dict(kmin=9, kmax=10, w=2500, i=2500, scaffoldsAll=True)),
+    # 0.75 w < step < w: scaffolds shorter than the window are windowed through a negative slice start (F:231)
+    "short_w1000_i800": dict(genome=("edge_short", 1.0), params=dict(w=1000, i=800)),
+    "short_w1000_i800_all": dict(genome=("edge_short", 1.0), params=dict(w=1000, i=800, scaffoldsAll=True, kmin=2, kmax=6)),
     "c1_small": dict(genome=("C1", 0.04), params={}),
     "c2_small": dict(genome=("C2", 0.01), params={}),
     "c2_small_query_vs_c1_host": dict(genome=("C2", 0.005), host=("C1", 0.02), params={}),

@@ -12,7 +12,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 SMALL_CASES = ["edge_default", "edge_scaffoldsAll", "edge_maskHost", "edge_k2_5_w1000_i250",
                "edge_k1_3_w3000_i1000", "edge_k4_8", "edge_k1_1", "edge_k1_9", "edge_k9_10_w2500_i2500", "c1_small", "c2_small",
-               "c2_small_query_vs_c1_host"]
+               "c2_small_query_vs_c1_host", "short_w1000_i800", "short_w1000_i800_all"]
 
 
 class Golden:

@@ -100,10 +100,15 @@ def test_fasta_scan_matches_reference_rules(tmp_path):
 
 
 @pytest.mark.parametrize("w,step,sa", [(5000, 2500, False), (5000, 2500, True), (1000, 250, False), (3000, 1000, True),
-                                       (4000, 1000, False), (5000, 5000, False), (700, 900, True)])
+                                       (4000, 1000, False), (5000, 5000, False), (700, 900, True),
+                                       # 0.75 w < step < w: scaffolds SHORTER than the window are windowed (F:231 negative slice)
+                                       (5000, 4000, False), (1000, 800, False), (1000, 800, True), (100, 80, False), (1000, 999, True)])
 def test_window_enumeration_matches_oracle(w, step, sa):
     """Candidates minus the 30 % rule (applied on the device) == crawlGenome (oracle)."""
-    sc = synth.make("edge") + synth.make("C5", 0.00002, seed=3)
+    sc = synth.make("edge") + synth.make("C5", 0.00002, seed=3) + synth.make("edge_short")
+    rng = np.random.default_rng(w * 7 + step)
+    sc += [("near_w_%d" % k, synth.iid_bases(rng, int(n), 0.5)) for k, n in
+           enumerate(rng.integers(max(min(int(1.75 * w - step), w) - 3, 1), w + 4, 12))]
     g = engine.PackedGenome.from_scaffolds(sc)
     wins = g.windows(w, step, sa)
     seq, off = c_oracle.concat(sc)
@@ -121,6 +126,14 @@ def test_window_enumeration_matches_oracle(w, step, sa):
     assert np.array_equal(wins.length[keep], wlen)
     rel = wins.off[keep] - g.scaf_off[wins.scaf[keep]]
     assert np.array_equal(rel, woff - off[sidx])
+    # ... and == the Python oracle, which keeps the reference's own slicing expression (F:231: a negative
+    # start when size < w); the C oracle above restates it with explicit arithmetic
+    from oracle import frisk_oracle
+    py = list(frisk_oracle.crawl_genome([(n, s.tobytes().decode()) for n, s in sc], w, step, sa))
+    assert [(a, b) for _, _, a, b in py] == list(zip(st.tolist(), sp.tolist()))
+    assert [len(x[0]) for x in py] == wlen.tolist()
+    assert all(x[0] == sc[int(s)][1][int(o - off[s]):int(o - off[s]) + int(l)].tobytes().decode()
+               for x, s, o, l in zip(py, sidx, woff, wlen))
 
 
 def test_window_rows_match_reference_golden_coords():
