@@ -156,3 +156,62 @@ def load_thresholds() -> types.SimpleNamespace:
     glb = {"xrange": range, "np": np, "math": math, "logging": logging, "__name__": "frisk_reference_thresholds"}
     exec(compile(text, REF_FILE + "<threshold slices>", "exec"), glb)
     return types.SimpleNamespace(**{k: v for k, v in glb.items() if not k.startswith("__")})
+
+
+# PCA features of anomalous regions: F:797-811 scrubMirrors runs unmodified; F:813-831
+# flattenKmerMap needs py2's list-returning dict.keys() (``d.keys()[0]`` at F:819) and ``itertools``
+_PCA_RANGES = [
+    (797, 811),   # scrubMirrors
+    (813, 831),   # flattenKmerMap
+]
+
+
+class _PyTwoListKeysDict(dict):
+    """dict whose ``keys()`` returns a list, as in py2 (F:819 indexes it); ``itervalues`` as above."""
+
+    def keys(self):
+        return list(dict.keys(self))
+
+    def itervalues(self):
+        return iter(self.values())
+
+
+def load_pca() -> types.SimpleNamespace:
+    """The hot-path namespace of ``load()`` plus the reference's scrubMirrors / flattenKmerMap, executed from
+    its source text.  Inside those two functions the name ``dict`` resolves to the py2-style subclass, so the
+    ``dict()`` that scrubMirrors builds (F:806) answers ``keys()[0]`` in flattenKmerMap."""
+    ns = load()
+    raw = open(REF_FILE, "rb").read()
+    lines = raw.decode().split("\n")
+    text = "from __future__ import division\n"
+    for a, b in _PCA_RANGES:
+        text += "\n".join(lines[a - 1:b]) + "\n\n"
+    import itertools
+    import numpy as np
+    glb = {"np": np, "itertools": itertools, "dict": _PyTwoListKeysDict, "revComplement": ns.revComplement,
+           "__name__": "frisk_reference_pca_features"}
+    exec(compile(text, REF_FILE + "<pca slices>", "exec"), glb)
+    ns.scrubMirrors = glb["scrubMirrors"]
+    ns.flattenKmerMap = glb["flattenKmerMap"]
+    return ns
+
+
+def run_pca_features(regions, pcaMin=1, pcaMax=6, windowlen=5000):
+    """The reference's loop F:1571-1591 over ``regions`` = [(name, sequence str)]: per region
+    computeKmers(pcaMode=True, sym=True, getMeta=False) -> scrubMirrors -> flattenKmerMap(prop=True).
+    Returns a list of 1-D float arrays; a region on which the reference raises ZeroDivisionError (F:824, no
+    valid word of some order) yields the string 'ZeroDivisionError'."""
+    ref = load_pca()
+    args = make_args(None, pcaMin=pcaMin, pcaMax=pcaMax, w=windowlen)
+    blank = ref.rangeMaps(pcaMin, pcaMax)
+    blank[0] = _PyTwoDict(blank[0])
+    out = []
+    for name, target in regions:
+        count_map = ref.computeKmers(args, genomepickle=None, window=[(name, target)], genomeMode=False, pcaMode=True,
+                                     kmerMap=blank, getMeta=False, sym=True)
+        uniq = ref.scrubMirrors(count_map)
+        try:
+            out.append(ref.flattenKmerMap(uniq, window=windowlen, seqLen=len(target), kmin=pcaMin, kmax=pcaMax, prop=True))
+        except ZeroDivisionError:
+            out.append("ZeroDivisionError")
+    return out

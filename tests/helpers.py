@@ -84,3 +84,18 @@ def max_rel_err(a, b, atol=KLD_ATOL):
         return 0.0
     diff = np.maximum(np.abs(a[ok] - b[ok]) - atol, 0.0)
     return float((diff / np.maximum(np.abs(b[ok]), 1e-300)).max())
+
+
+def pca_golden():
+    """tests/golden/pca_features.npz (make_pca_golden.py: the reference's own scrubMirrors / flattenKmerMap text):
+    returns (regions [(name, uint8 array)], {(pcaMin, pcaMax): float64[n, F]}); NaN rows = ZeroDivisionError."""
+    z = np.load(os.path.join(GOLDEN, "pca_features.npz"))
+    meta = json.loads(str(z["meta"]))
+    cache = {}
+    regions = []
+    for cfg, scale, s, a, l in meta["defs"]:
+        if (cfg, scale) not in cache:
+            cache[(cfg, scale)] = synth.make(cfg, scale)
+            assert synth.digest(cache[(cfg, scale)]) == meta["digests"]["%s@%s" % (cfg, scale)], "synthetic genome drifted"
+        regions.append(("%s_%d_%d_%d" % (cfg, s, a, l), cache[(cfg, scale)][s][1][a:a + l]))
+    return regions, {(lo, hi): z["feat_%d_%d" % (lo, hi)] for lo, hi in meta["ranges"]}

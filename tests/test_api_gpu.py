@@ -153,6 +153,25 @@ def test_batch_pca_features_match_the_reference_formulation():
         api.pcaFeatures(args, [("tiny", np.frombuffer(b"ACG", np.uint8))])   # no 4-mer at all: F:824 divides by zero
 
 
+def test_batch_pca_features_match_reference_text_golden():
+    """Row f3 pin on the device: frisk_b200_region_features == tests/golden/pca_features.npz, the vectors the
+    reference's OWN text (computeKmers(pcaMode, sym) F:280-367, scrubMirrors F:797-811, flattenKmerMap F:813-831)
+    produced for these regions, bit for bit; regions on which the reference raises ZeroDivisionError raise here."""
+    import argparse
+    from frisk_b200 import api
+    from tests.helpers import pca_golden
+    regions, gold = pca_golden()
+    for (lo, hi), want in gold.items():
+        ok = ~np.isnan(want).all(axis=1)
+        args = argparse.Namespace(pcaMin=lo, pcaMax=hi)
+        labels, feats = api.pcaFeatures(args, [r for r, k in zip(regions, ok) if k])
+        assert feats.shape == want[ok].shape and np.array_equal(feats, want[ok]), (lo, hi)
+        for r, k in zip(regions, ok):
+            if not k:
+                with pytest.raises(ZeroDivisionError):
+                    api.pcaFeatures(args, [r])
+
+
 def test_pca_features_straight_from_the_planes(tmp_path):
     """thresholdKLD intervals -> composition vectors read from the resident planes (no getFasta / getBEDSeq
     strings) == the vectors of the extracted sequences (reference slicing rule seq[start-1:stop])."""

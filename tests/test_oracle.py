@@ -102,3 +102,31 @@ def test_pca_feature_restatement_known_answers():
     assert list(maps[0]) == ["AA", "AT", "AG", "AC", "TA", "TG", "TC", "GG", "GC", "CG"]
     assert fo.region_features("AACG", 2, 2) == [0.25, 0, 0, 0.25, 0, 0, 0, 0, 0, 0.5]
     assert len(fo.region_features("ACGTTGCAACGT" * 5, 1, 6)) == 2 + 10 + 32 + 136 + 512 + 2080
+
+
+def test_pca_feature_restatement_matches_reference_text_golden():
+    """Row f3 pin: oracle.region_features == the vectors the reference's OWN computeKmers(pcaMode, sym) +
+    scrubMirrors + flattenKmerMap(prop=True) text produced (tests/golden/pca_features.npz), bit for bit."""
+    from oracle import frisk_oracle as fo
+    from tests.helpers import pca_golden
+    regions, gold = pca_golden()
+    for (lo, hi), want in gold.items():
+        for (name, seq), row in zip(regions, want):
+            if np.isnan(row).all():
+                with pytest.raises(ZeroDivisionError):
+                    fo.region_features(seq.tobytes().decode(), lo, hi)
+                continue
+            if len(seq) > 20_000 and (lo, hi) != (1, 6):
+                continue                                           # the long region once is enough for the Python loops
+            assert np.array_equal(np.array(fo.region_features(seq.tobytes().decode(), lo, hi)), row), (name, lo, hi)
+
+
+@pytest.mark.skipif(not ref_exec.available(), reason="reference tree not present (GPU box)")
+def test_pca_golden_is_what_the_reference_text_produces():
+    """Container-only: re-execute the reference's text on two regions and compare with the committed golden."""
+    from tests.helpers import pca_golden
+    regions, gold = pca_golden()
+    pick = [0, 9, 12]
+    vecs = ref_exec.run_pca_features([(regions[i][0], regions[i][1].tobytes().decode()) for i in pick], 2, 4)
+    for i, v in zip(pick, vecs):
+        assert np.array_equal(v, gold[(2, 4)][i])
