@@ -67,6 +67,8 @@ PROTOTYPES = {
     "frisk_b200_host_alloc": (_i, [C.POINTER(C.c_void_p), _u64]),
     "frisk_b200_host_free": (_i, [_p]),
     "frisk_b200_bench_smem_atomics": (_i, [_i, _i, _i, C.POINTER(C.c_float), _p]),
+    "frisk_b200_bench_l2_gather": (_i, [_i, _i, _u64, _i, C.POINTER(C.c_float), _p]),
+    "frisk_b200_bench_smem_loads": (_i, [_i, _i, _i, C.POINTER(C.c_float), _p]),
 }
 
 _LIB = None

@@ -1,0 +1,116 @@
+// frisk_b200: micro-benchmarks that measure the roofline denominators of the window kernels on the GPU at hand
+// (bench.py calls them live; SURVEY.md section 8d asks for measured, not assumed, rates):
+//   frisk_b200_bench_l2_gather   random 16-byte gathers from an L2-resident table (the genome-IVOM lookup: one
+//                                {I_g, log2 I_g} pair per distinct K-mer out of a 1 MiB table)
+//   frisk_b200_bench_smem_loads  random 4/8/16-byte loads from a 32 KiB shared-memory table (bank-conflicted reads:
+//                                what a position-ordered epilogue does to its count tables)
+// (the shared-memory ATOMIC rate is frisk_b200_bench_smem_atomics in frisk_kernels.cu)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/frisk_b200.h"
+#include "frisk_internal.h"
+
+namespace {
+#define CK(call) FRISK_CK(call)
+
+__device__ __forceinline__ uint32_t lcg(uint32_t& x) { x = x * 1664525u + 1013904223u; return x >> 8; }
+
+// mode 0: every lane an independent uniformly random entry (position-ordered epilogue)
+// mode 1: a warp's lanes read increasing entries with random gaps of mean `gap` (sorted epilogue: 4,794 of 65,536)
+__global__ void __launch_bounds__(256, 4)
+l2_gather_kernel(const double2* __restrict__ tab, uint32_t n_mask, int iters, int mode, uint32_t gap, double* sink) {
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    const uint32_t lane = threadIdx.x & 31u;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int it = 0; it < iters; it += 4) {
+        uint32_t i0, i1, i2, i3;
+        if (mode == 0) { i0 = lcg(x); i1 = lcg(x); i2 = lcg(x); i3 = lcg(x); }
+        else {
+            // inclusive scan of random gaps over the lanes -> increasing indices inside the warp
+            uint32_t g = 1u + lcg(x) % (2u * gap - 1u);
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, g, o); if ((int)lane >= o) g += y; }
+            const uint32_t base = __shfl_sync(0xffffffffu, lcg(x), 0);
+            i0 = base + g; i1 = i0 + 32u * gap; i2 = i1 + 32u * gap; i3 = i2 + 32u * gap;
+        }
+        const double2 v0 = __ldg(tab + (i0 & n_mask)), v1 = __ldg(tab + (i1 & n_mask));
+        const double2 v2 = __ldg(tab + (i2 & n_mask)), v3 = __ldg(tab + (i3 & n_mask));
+        a0 += v0.x + v0.y; a1 += v1.x + v1.y; a2 += v2.x + v2.y; a3 += v3.x + v3.y;
+    }
+    const double s = a0 + a1 + a2 + a3;
+    if (s == 1.2345e-300) sink[0] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+smem_load_kernel(int iters, T* sink) {
+    __shared__ __align__(16) unsigned char raw[32768];
+    T* tab = reinterpret_cast<T*>(raw);
+    constexpr uint32_t N = 32768u / sizeof(T);
+    for (uint32_t i = threadIdx.x; i < 32768u / 4u; i += 256) reinterpret_cast<uint32_t*>(raw)[i] = i;
+    __syncthreads();
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 777u;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; it += 4) {
+        const uint32_t i0 = lcg(x) & (N - 1), i1 = lcg(x) & (N - 1), i2 = lcg(x) & (N - 1), i3 = lcg(x) & (N - 1);
+        const T v0 = tab[i0], v1 = tab[i1], v2 = tab[i2], v3 = tab[i3];
+        acc += *reinterpret_cast<const uint32_t*>(&v0) + *reinterpret_cast<const uint32_t*>(&v1) +
+               *reinterpret_cast<const uint32_t*>(&v2) + *reinterpret_cast<const uint32_t*>(&v3);
+    }
+    if (acc == 0xdeadbeefu) *reinterpret_cast<uint32_t*>(sink) = acc;
+}
+
+template <typename F>
+int time_twice(F launch, cudaStream_t st, float* ms) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    launch();                                            // warm-up
+    CK(cudaEventRecord(a, st));
+    launch();
+    CK(cudaEventRecord(b, st));
+    CK(cudaEventSynchronize(b));
+    CK(cudaEventElapsedTime(ms, a, b));
+    CK(cudaEventDestroy(a));
+    CK(cudaEventDestroy(b));
+    CK(cudaGetLastError());
+    return FRISK_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int mode, float* ms, void* stream) {
+    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms || table_bytes < 4096 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 1)
+        return FRISK_E_INVALID;
+    if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    double2* tab = nullptr;
+    double* sink = nullptr;
+    CK(cudaMalloc(&tab, table_bytes));
+    CK(cudaMalloc(&sink, 8));
+    CK(cudaMemsetAsync(tab, 0, table_bytes, st));
+    const uint32_t n_mask = (uint32_t)(table_bytes / 16u) - 1u;
+    const uint32_t gap = 14u;                            // 65,536 entries / ~4,794 distinct K-mers of a 5 kb window
+    const int rc = time_twice([&] { l2_gather_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, mode, gap, sink); }, st, ms);
+    cudaFree(tab);
+    cudaFree(sink);
+    return rc;
+}
+
+int frisk_b200_bench_smem_loads(int blocks, int iters, int elem_bytes, float* ms, void* stream) {
+    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms) return FRISK_E_INVALID;
+    if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    void* sink = nullptr;
+    CK(cudaMalloc(&sink, 16));
+    int rc;
+    if (elem_bytes == 4) rc = time_twice([&] { smem_load_kernel<uint32_t><<<blocks, 256, 0, st>>>(iters, (uint32_t*)sink); }, st, ms);
+    else if (elem_bytes == 8) rc = time_twice([&] { smem_load_kernel<uint2><<<blocks, 256, 0, st>>>(iters, (uint2*)sink); }, st, ms);
+    else if (elem_bytes == 16) rc = time_twice([&] { smem_load_kernel<uint4><<<blocks, 256, 0, st>>>(iters, (uint4*)sink); }, st, ms);
+    else rc = FRISK_E_INVALID;
+    cudaFree(sink);
+    return rc;
+}
+
+}  // extern "C"

@@ -39,6 +39,11 @@ __device__ __forceinline__ double log2_pos(double x, const double2* __restrict__
 // read: ~10 wavefronts per warp; the kernels that use it are bound by the LSU data pipe, not by issue slots).
 // x = 2^e * m with m in [sqrt(1/2), sqrt(2)); t = (m - 1) / (m + 1), |t| <= 0.1716;
 // log2(m) = (2 / ln 2) * atanh(t) = t * sum_k c_k t^(2k), k = 0..7 (first dropped term < 1.7e-14 absolute).
+// coefficients (2 / ln 2) / (2k + 1), k = 7 .. 0, in constant memory: a DFMA takes them straight from the constant bank
+// (as immediates each costs two moves into uniform registers per use)
+__constant__ double kLog2Series[8] = {0.19235933878519512, 0.22195308321368667, 0.2623081892525388, 0.3205988979753252,
+                                      0.4121985831111324,  0.5770780163555853,  0.9617966939259756, 2.8853900817779268};
+
 __device__ __forceinline__ double log2_series(double x) {
     int hi = __double2hiint(x);
     const int big = ((hi & 0x000fffff) >= 0x6a09f) ? 1 : 0;           // mantissa above sqrt(2): halve it, e + 1
@@ -53,13 +58,13 @@ __device__ __forceinline__ double log2_series(double x) {
     double t = n * r;
     t = fma(fma(-d, t, n), r, t);
     const double s = t * t;
-    double p = fma(s, 0.19235933878519512, 0.22195308321368667);      // (2/ln2)/15, (2/ln2)/13
-    p = fma(s, p, 0.2623081892525388);                               // /11
-    p = fma(s, p, 0.3205988979753252);                               // /9
-    p = fma(s, p, 0.4121985831111324);                               // /7
-    p = fma(s, p, 0.5770780163555853);                               // /5
-    p = fma(s, p, 0.9617966939259756);                               // /3
-    p = fma(s, p, 2.8853900817779268);                                // 2/ln2
+    double p = fma(s, kLog2Series[0], kLog2Series[1]);                // (2/ln2)/15, (2/ln2)/13
+    p = fma(s, p, kLog2Series[2]);                                   // /11
+    p = fma(s, p, kLog2Series[3]);                                   // /9
+    p = fma(s, p, kLog2Series[4]);                                   // /7
+    p = fma(s, p, kLog2Series[5]);                                   // /5
+    p = fma(s, p, kLog2Series[6]);                                   // /3
+    p = fma(s, p, kLog2Series[7]);                                   // 2/ln2
     return fma(t, p, (double)e);
 }
 

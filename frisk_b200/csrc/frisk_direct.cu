@@ -440,7 +440,10 @@ int frisk_internal::score_direct(const uint32_t* codes, const uint32_t* inv, con
     else rc = launch_direct<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo, st, nullptr, nullptr);
     // windows the byte table could not hold (marked kRowRedo): exact re-run on the bucketed kernel
     if (!rc) rc = score_bucket_redo(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, K, want_rip, rows, status, dump, redo, st);
-    if (scratch) CK(cudaFreeAsync(scratch, st));
+    if (scratch) {                                         // freed on every path (stream-ordered: behind the launches above)
+        const cudaError_t e = cudaFreeAsync(scratch, st);
+        if (!rc && e != cudaSuccess) return frisk_internal::cuda_fail(e, "cudaFreeAsync(scratch)");
+    }
     return rc;
 }
 

@@ -46,6 +46,14 @@ int score_bucket_redo(const uint32_t* codes, const uint32_t* inv, const uint32_t
                       double* rows, uint32_t* status, uint16_t* dump, const uint32_t* redo_src, cudaStream_t st);
 int sm_count_cached();
 
+// nibble score kernel (frisk_nibble.cu): kmax 7, 8 and windows <= 8,186 bases; one 4-bit counter per K-mer, one atomic per
+// position, the first occurrence of a K-mer scores it.  Windows with a K-mer seen 16+ times (or more than 64 N-boundary
+// words) are marked kRowRedo and re-done by the bucketed kernel, exactly like the direct kernel's hand-over.
+int score_nibble(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                 const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
+                 double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st);
+int score_nibble_occupancy(int K, uint32_t max_len, int* ctas_per_sm, int* threads_per_cta);
+
 }  // namespace frisk_internal
 
 #define FRISK_CK(call)                                                        \

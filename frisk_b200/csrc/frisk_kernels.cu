@@ -1437,6 +1437,7 @@ int g_force_dense = 0;      // tests: force the dense-table kernel (frisk_b200_s
 int g_force_general = 0;    // tests: force the general (global-memory) score kernel
 int g_force_direct = 0;     // tests / A-B: kmax 7, 8 on the direct kernel wherever it can run
 int g_force_bucket = 0;     // tests: keep kmax 4..8 on the bucketed kernel instead of the small-K / direct kernel
+int g_force_nibble = 0;     // tests / A-B: kmax 7, 8 on the nibble kernel wherever it can run
 }  // namespace
 
 int frisk_internal::cuda_fail(cudaError_t e, const char* what) {
@@ -1446,6 +1447,9 @@ int frisk_internal::cuda_fail(cudaError_t e, const char* what) {
 
 #ifndef FRISK_DIRECT_DEFAULT
 #define FRISK_DIRECT_DEFAULT(kmax, len) ((kmax) == 7 && (len) > 2042u)
+#endif
+#ifndef FRISK_NIBBLE_DEFAULT
+#define FRISK_NIBBLE_DEFAULT(kmax, len) (0 && (kmax) == 8)   // off until measured faster (tools/k8_ab.py)
 #endif
 
 namespace {
@@ -1672,8 +1676,14 @@ int launch_score_small(const uint32_t* codes, const uint32_t* inv, const uint32_
 // Which window kernel serves kmax 7 and 8 (windows <= 8,186 bases)?  Measured on C2 (tools/direct_vs_bucket.py):
 // the direct kernel wins where the buckets of the bucketed kernel run full (kmax 7: 1,024 buckets) and windows
 // are long; the bucketed kernel keeps kmax 8 and short windows.
+bool use_nibble_kernel(int kmax, uint32_t max_win_len) {
+    if (kmax < 7 || kmax > 8 || max_win_len > kBuf3 - 6u || g_force_dense || g_force_bucket || g_force_direct) return false;
+    if (g_force_nibble) return true;
+    return FRISK_NIBBLE_DEFAULT(kmax, max_win_len);
+}
+
 bool use_direct_kernel(int kmax, uint32_t max_win_len) {
-    if (kmax < 7 || kmax > 8 || max_win_len > kBuf3 - 6u || g_force_dense || g_force_bucket) return false;
+    if (kmax < 7 || kmax > 8 || max_win_len > kBuf3 - 6u || g_force_dense || g_force_bucket || g_force_nibble) return false;
     if (g_force_direct) return true;
     return FRISK_DIRECT_DEFAULT(kmax, max_win_len);
 }
@@ -1870,7 +1880,11 @@ int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint3
             default: break;
         }
     }
-    // kmax 7 and 8: the direct kernel (byte table, no sorting; 3 CTAs/SM), then the bucketed one over whatever it handed back
+    // kmax 7 and 8: the nibble kernel (4-bit counters, one atomic per position) or the direct kernel (byte table), then the
+    // bucketed one over whatever they handed back
+    if (use_nibble_kernel(kmax, max_win_len))
+        return frisk_internal::score_nibble(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, kmax, rip,
+                                            d_rows, d_status, d_dump, st);
     if (use_direct_kernel(kmax, max_win_len))
         return frisk_internal::score_direct(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, kmax, rip,
                                             d_rows, d_status, d_dump, st);
@@ -1912,6 +1926,7 @@ int frisk_b200_score_occupancy(int kmax, uint32_t max_win_len, int* ctas_per_sm,
         }
     }
     if (kmax < 4 || max_win_len > kBuf3 - 6u || g_force_dense) return FRISK_OK;                                // dense kernel
+    if (use_nibble_kernel(kmax, max_win_len)) return frisk_internal::score_nibble_occupancy(kmax, max_win_len, ctas_per_sm, threads_per_cta);
     if (use_direct_kernel(kmax, max_win_len)) return frisk_internal::score_direct_occupancy(kmax, max_win_len, ctas_per_sm, threads_per_cta);
     const uint32_t cap = (max_win_len + 15u) & ~15u;
     *threads_per_cta = kT3;
@@ -1940,6 +1955,7 @@ int frisk_b200_set_option(const char* name, int value) {
     if (strcmp(name, "force_general_kernel") == 0) { g_force_general = value; return FRISK_OK; }
     if (strcmp(name, "force_bucket_kernel") == 0) { g_force_bucket = value; return FRISK_OK; }
     if (strcmp(name, "force_direct_kernel") == 0) { g_force_direct = value; return FRISK_OK; }
+    if (strcmp(name, "force_nibble_kernel") == 0) { g_force_nibble = value; return FRISK_OK; }
     return FRISK_E_INVALID;
 }
 

@@ -1,0 +1,562 @@
+// frisk_b200: the "nibble" window-score kernel for kmax 7 and 8 (windows <= 8,186 bases).
+//
+// Replaces, per window, the reference's computeKmers(window) + IvomBuild x2 + KLD + calcGC + calcRIP
+// (/root/reference/frisk/__init__.py F:1478-1494, F:280-367, F:369-472, F:120-137, F:474-495).
+//
+// ONE shared-memory atomic per position and no sorting.  The order-K code space is one 4-BIT counter per K-mer:
+// the 16 K-mers below an order-(K-2) prefix ("bucket") share one 64-bit word (4^6 buckets x 8 B = 32 KiB at K = 8).
+//   * a position adds 1 to its K-mer's nibble; afterwards every POSITION scores its own K-mer with weight 1/c_K
+//     (c_K = its count in the window), so the sum over positions equals the sum over distinct K-mers (F:448-472
+//     iterate the distinct keys) without enumerating or sorting them.  (Letting only the first arrival at a nibble
+//     score it would save the weights, but which occurrence arrives first is a race: the rows would no longer be
+//     bit-reproducible.)
+//   * one 64-bit load gives the three highest orders of a K-mer: its nibble (order K), the sum of the 4 nibbles of
+//     its 16-bit quarter (order K-1) and the sum of all 16 (order K-2);
+//   * order A = K-3 is the sum of four buckets' nibble sums (one pass over the table, coalesced, warp shuffles), the
+//     orders below follow by marginalisation, orders <= 4 are folded into one {numerator, denominator} pair per
+//     order-4 prefix (`pre`);
+//   * a thread's positions are fixed and so is the reduction tree -> bit-reproducible rows.
+// 40 KB of shared memory per CTA (K = 8).
+//
+// What a nibble cannot hold is handed to the bucketed kernel (frisk_kernels.cu), exactly: a window in which some
+// K-mer occurs 16+ times (the thread whose increment wraps the nibble sees 15 in the word it got back), or with
+// more than kSideCap words cut short by an N / the window end at K-1 or K-2 bases, is marked kRowRedo and re-done
+// by the launch that follows on the same stream.  Short words of K-1 / K-2 bases (every window has two at its
+// end) are not in the nibble table: they go to a small side list, and bit 15 of their order-A bin sends the (few)
+// K-mers below that bin through the list.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/frisk_b200.h"
+#include "frisk_internal.h"
+#include "frisk_device.cuh"
+
+namespace {
+using frisk_internal::kRowRedo;
+#define CK(call) FRISK_CK(call)
+
+constexpr uint32_t kSideCap = 64;
+constexpr int kNT = 256;
+
+struct NibSmem {
+    double q[8];
+    double red[3][kNT / 32];
+    int cnt[2][6];                    // [window parity][n_non, n_gc, full K-words counted, n_side, sum of all nibbles, -]
+    uint32_t c2[16];                  // final dinucleotide counts (RIP, and the way up to order 1)
+    uint32_t side[kSideCap];          // v << 16 | code of a word valid for v = K-1 or K-2 bases only
+};
+
+#ifndef FRISK_NIBBLE_TABLOG
+#define FRISK_NIBBLE_TABLOG 0
+#endif
+constexpr bool NIB_TABLOG = FRISK_NIBBLE_TABLOG;   // 0: log2 by series, no shared-memory table read in the epilogue
+
+template <int K>
+struct NibLayout {
+    static_assert(K == 7 || K == 8, "nibble kernel: K = 7 or 8");
+    static constexpr int B = K - 2;                                      // bucket order: 16 K-mers per bucket
+    static constexpr int A = K - 3;                                      // highest order kept as u16 counts
+    static constexpr int LP = 4;                                         // orders <= LP live in `pre`
+    static constexpr uint32_t NBK = pow4(B);
+    static constexpr uint32_t NPRE = pow4(LP);
+    static constexpr uint32_t NIB_BYTES = NBK * 8u;                      // 16 nibbles per bucket
+    static constexpr uint32_t LOW_BYTES = (lvl_off(A + 1) * 2u + 15u) & ~15u;   // orders 1..A, u16
+    static constexpr uint32_t ZERO_BYTES = NIB_BYTES + LOW_BYTES;
+    static constexpr uint32_t OFF_LOW = NIB_BYTES;
+    static constexpr uint32_t OFF_PRE = ZERO_BYTES;
+    static constexpr uint32_t OFF_LOG = OFF_PRE + NPRE * 16u;
+    static constexpr uint32_t OFF_SS = OFF_LOG + (NIB_TABLOG ? 128u * 16u : 0u);
+    static constexpr uint32_t TOTAL = OFF_SS + (uint32_t)sizeof(NibSmem);
+};
+
+// bytes of the result = sums of the two nibbles of each byte of w (<= 30)
+__device__ __forceinline__ uint32_t nib_pairs(uint32_t w) { return (w & 0x0f0f0f0fu) + ((w >> 4) & 0x0f0f0f0fu); }
+
+// gather bit1 of each of the 16 2-bit codes of a word into 16 contiguous bits (order kept)
+__device__ __forceinline__ uint32_t nib_high_bits16(uint32_t w) {
+    uint32_t x = (w >> 1) & 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    x = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+
+// Per-thread position masks: position i of the thread's chunk is bit (MB - 1 - i).  32 bits when the chunk and the
+// K - 1 bases of look-ahead fit (PP + K - 1 <= 32), 64 bits otherwise.
+template <bool WIDE> struct MaskT { using type = uint32_t; };
+template <> struct MaskT<true> { using type = unsigned long long; };
+__device__ __forceinline__ int popc_m(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int popc_m(unsigned long long x) { return __popcll(x); }
+__device__ __forceinline__ int clz_m(uint32_t x) { return __clz((int)x); }
+__device__ __forceinline__ int clz_m(unsigned long long x) { return __clzll((long long)x); }
+template <typename MT> __device__ __forceinline__ MT top_bits(int n) {       // the n leading bits set, 0 <= n
+    constexpr int MB = (int)sizeof(MT) * 8;
+    return n >= MB ? ~MT(0) : ~(~MT(0) >> n);
+}
+
+#ifndef FRISK_NIBBLE_CTAS
+#define FRISK_NIBBLE_CTAS 4
+#endif
+
+// PP = positions per thread: a thread owns ONE chunk of cs <= PP consecutive positions of the window
+// (cs = the window length spread over the CTA, a multiple of 4), reads the three or four code words and two or three
+// mask words that cover it once, and issues the atomics of its full K-words back to back from registers.
+template <int K, int PP, bool DUMP, bool ALLK>
+__global__ void __launch_bounds__(kNT, FRISK_NIBBLE_CTAS)
+score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
+                            const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
+                            const double2* __restrict__ ig, int kmin_arg, int want_rip,
+                            double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump,
+                            uint32_t* redo_dst) {
+    using L = NibLayout<K>;
+    static_assert(PP % 4 == 0 && PP >= 4 && PP + K - 1 <= 64, "chunk size");
+    constexpr int A = L::A, LP = L::LP, NT = kNT, NW = NT / 32;
+    constexpr bool WIDE = PP + K - 1 > 32;
+    using MT = typename MaskT<WIDE>::type;
+    constexpr int MB = (int)sizeof(MT) * 8;
+    constexpr int NA = ((PP - 1) * 2 + 2 * K + 31) / 32;                 // aligned code words a chunk's K-mers touch
+    constexpr int NM = WIDE ? 3 : 2;                                     // raw mask words
+    const int kmin = ALLK ? 1 : kmin_arg;                                // ALLK: the default --minWordSize 1
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* nib32 = reinterpret_cast<uint32_t*>(smem);                // word kappa >> 3, nibble kappa & 7
+    const uint2* nib64 = reinterpret_cast<const uint2*>(smem);          // bucket kappa >> 4
+    uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem + L::OFF_LOW);    // orders 1..A at lvl_off(x)
+    uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem + L::OFF_LOW);
+    double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);       // .x = num, .y = {flag, den} as two u32
+    double2* logtab = reinterpret_cast<double2*>(smem + L::OFF_LOG);
+    NibSmem& ss = *reinterpret_cast<NibSmem*>(smem + L::OFF_SS);
+    (void)logtab;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 12) ss.cnt[tid / 6][tid % 6] = 0;
+    if (NIB_TABLOG && tid < 128) {
+        const double c = 1.0 + ((double)tid + 0.5) / 128.0;
+        const double ic = 1.0 / c;
+        logtab[tid] = make_double2(ic, -log2(ic));
+    }
+    __syncthreads();
+
+    int par = 1;
+    for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x) {
+        const uint64_t o = win_off[win];
+        const uint32_t len = win_len[win];
+        par ^= 1;
+        // 32-bit addressing relative to the window's first mask word
+        const uint32_t o_lo = (uint32_t)(o & 31);
+        const uint32_t* __restrict__ cw = codes + (o >> 5) * 2;
+        const uint32_t* __restrict__ mw = inv + (o >> 5);
+        const uint32_t* __restrict__ lw = low ? low + (o >> 5) : nullptr;
+        const uint32_t cs = max(4u, ((len + NT - 1) / NT + 3u) & ~3u);    // positions per thread (<= PP: checked by the launcher)
+        const uint32_t p0 = (uint32_t)tid * cs;                          // this thread's first position
+
+        // ---- P1: composition + ONE atomic per full K-word, all from registers ----------------------------
+        uint32_t kk[PP / 2];                                             // two K-mer codes per register
+        MT vm = 0;                                                       // position i (bit MB-1-i) holds a full K-word
+        {
+            int non = 0, gc = 0, nfull = 0;
+#pragma unroll
+            for (int i = 0; i < PP / 2; ++i) kk[i] = 0;
+            if (p0 < len) {
+                const uint32_t r0 = o_lo + p0;
+                uint32_t raw[NA + 1], mraw[NM], lraw[NM];
+#pragma unroll
+                for (int j = 0; j <= NA; ++j) raw[j] = __ldg(cw + (r0 >> 4) + j);
+#pragma unroll
+                for (int j = 0; j < NM; ++j) mraw[j] = __ldg(mw + (r0 >> 5) + j);
+#pragma unroll
+                for (int j = 0; j < NM; ++j) lraw[j] = lw ? __ldg(lw + (r0 >> 5) + j) : 0u;
+                uint32_t W[NA];                                          // W[j]: the 16 bases from position 16 j
+                const uint32_t sc = (r0 & 15u) * 2u, ms = r0 & 31u;
+#pragma unroll
+                for (int j = 0; j < NA; ++j) W[j] = __funnelshift_l(raw[j + 1], raw[j], sc);
+                MT M, Lm;
+                if constexpr (WIDE) {
+                    M = ((MT)__funnelshift_l(mraw[1], mraw[0], ms) << 32) | (MT)__funnelshift_l(mraw[2], mraw[1], ms);
+                    Lm = ((MT)__funnelshift_l(lraw[1], lraw[0], ms) << 32) | (MT)__funnelshift_l(lraw[2], lraw[1], ms);
+                } else {
+                    M = __funnelshift_l(mraw[1], mraw[0], ms);
+                    Lm = __funnelshift_l(lraw[1], lraw[0], ms);
+                }
+                const int left = (int)(len - p0);                        // positions from p0 to the window end
+                const MT in_p = top_bits<MT>(left < (int)cs ? left : (int)cs);   // this thread's positions
+                const MT bad = M | ~top_bits<MT>(left);                  // invalid character or beyond the window end
+                MT sm = bad | (bad << 1);                                // position i: any bad base among i .. i+K-1
+                sm |= sm << 2;
+                sm |= sm << (K - 4);
+                vm = ~sm & in_p;
+                const MT unres = (M | Lm) & in_p;                        // not an upper-case ATGC (F:106-118)
+                MT G = 0;                                                // bit 1 of the code: G = 2, C = 3 (invalid bases carry code 0)
+#pragma unroll
+                for (int j = 0; j < NA; ++j)
+                    if (MB - 16 - 16 * j >= 0) G |= (MT)nib_high_bits16(W[j]) << (MB - 16 - 16 * j);
+                non = popc_m(unres);
+                gc = popc_m(G & in_p & ~unres);
+                nfull = popc_m(vm);
+                // the full K-words: decode, address/value, one atomic each, no result awaited.  A chunk of PP positions
+                // without an N (nearly all of them) runs the straight-line version: no per-position test
+                auto kmer_at = [&](int i) -> uint32_t {
+                    const int wi = i >> 4, oi = (i & 15) * 2;
+                    if (oi + 2 * K <= 32) return (W[wi] << oi) >> (32 - 2 * K);
+                    return __funnelshift_l(W[wi + 1 < NA ? wi + 1 : wi], W[wi], oi) >> (32 - 2 * K);
+                };
+                if (vm == top_bits<MT>(PP)) {
+#pragma unroll
+                    for (int i = 0; i < PP; i += 2) {
+                        const uint32_t k0 = kmer_at(i), k1 = kmer_at(i + 1);
+                        atomicAdd(&nib32[k0 >> 3], 1u << ((k0 & 7u) * 4u));
+                        atomicAdd(&nib32[k1 >> 3], 1u << ((k1 & 7u) * 4u));
+                        kk[i >> 1] = k0 | (k1 << 16);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < PP; ++i) {
+                        if (vm & (MT(1) << (MB - 1 - i))) {
+                            const uint32_t kap = kmer_at(i);
+                            atomicAdd(&nib32[kap >> 3], 1u << ((kap & 7u) * 4u));
+                            kk[i >> 1] |= kap << (16 * (i & 1));
+                        }
+                    }
+                }
+                // words cut short by an N or the window end (rare): valid for v < K bases
+                MT slow = in_p & ~vm & ~bad;
+                while (slow) {
+                    const int i = clz_m(slow);
+                    slow &= ~(MT(1) << (MB - 1 - i));
+                    const int v = clz_m((MT)(bad << i));                 // 1 <= v < K
+                    const uint32_t r = r0 + (uint32_t)i;
+                    const uint32_t c32 = __funnelshift_l(__ldg(cw + (r >> 4) + 1), __ldg(cw + (r >> 4)), (r & 15u) * 2u);
+                    if (v >= A) {
+                        const uint32_t ga = lvl_off(A) + (c32 >> (32 - 2 * A));
+                        atomicAdd(&tab32[ga >> 1], 1u << ((ga & 1u) * 16u));
+                        if (v > A) {                                     // K-1 or K-2 bases: side list + flag on its bin
+                            atomicOr(&tab32[ga >> 1], 0x8000u << ((ga & 1u) * 16u));
+                            const uint32_t slot = (uint32_t)atomicAdd(&ss.cnt[par][3], 1);
+                            if (slot < kSideCap) ss.side[slot] = ((uint32_t)v << 16) | (c32 >> (32 - 2 * v));
+                        }
+                    } else {                                             // order v < A only
+                        const uint32_t g = lvl_off(v) + (c32 >> (32 - 2 * v));
+                        atomicAdd(&tab32[g >> 1], 1u << ((g & 1u) * 16u));
+                    }
+                }
+            }
+            non = __reduce_add_sync(kFull, non);
+            gc = __reduce_add_sync(kFull, gc);
+            nfull = __reduce_add_sync(kFull, nfull);
+            if (lane == 0) { atomicAdd(&ss.cnt[par][0], non); atomicAdd(&ss.cnt[par][1], gc); atomicAdd(&ss.cnt[par][2], nfull); }
+        }
+        __syncthreads();                                                   // (1)
+        const int n_non = ss.cnt[par][0], n_gc = ss.cnt[par][1], n_up = (int)len - n_non;
+        const uint32_t n_side = (uint32_t)ss.cnt[par][3];
+        if (tid < 6) ss.cnt[par ^ 1][tid] = 0;                              // next window's counters (idle until its P1)
+        const bool excluded = (double)n_non >= 0.3 * (double)len;          // F:238 / F:213
+        uint16_t* dmp = DUMP ? dump + (size_t)win * lvl_off(K + 1) : nullptr;
+        if (excluded) {
+            for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+            if (tid == 0) {
+                status[win] = FRISK_ROW_EXCLUDED;
+                for (int c = 0; c < 5; ++c) rows[(size_t)win * 5 + c] = CUDART_NAN;
+                if (redo_dst != status) redo_dst[win] = 0;
+            }
+            if (DUMP) for (uint32_t i = tid; i < lvl_off(K + 1); i += NT) dmp[i] = 0;
+            __syncthreads();
+            continue;
+        }
+        if (tid < K) {
+            const int x = tid + 1;
+            const long long d = ((long long)n_up - (long long)(x - 1)) * 2;
+            ss.q[tid] = (double)pow4(x) / (double)d;
+        }
+
+        // ---- P2a: order A = the nibble sums of four consecutive buckets (+ the short words already there).  Per word:
+        //      sum of bytes = lo-nibbles + 16 hi-nibbles, and the lo-nibbles alone -- two dp4a.  A wrapped nibble (a
+        //      K-mer seen 16+ times) loses 15 or 16 from the grand total: that is how overflow is detected, for free.
+        {
+            uint32_t tot = 0;
+            const uint32_t sw = (lane >> 2) & 1u;                          // lanes j and j+4 would share banks: swap their halves
+            for (uint32_t b5 = tid; b5 < pow4(A); b5 += NT) {
+                const uint4* src = reinterpret_cast<const uint4*>(smem) + 2u * b5;
+                const uint4 v0 = src[sw], v1 = src[sw ^ 1u];
+                uint32_t by = 0, lo = 0;
+                const uint32_t w8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { by = __dp4a(w8[j], 0x01010101u, by); lo = __dp4a(w8[j] & 0x0f0f0f0fu, 0x01010101u, lo); }
+                const uint32_t s = lo + ((by - lo) >> 4);
+                tot += s;
+                if (s) tab16[lvl_off(A) + b5] += (uint16_t)s;              // < 2^15 in total: the flag bit survives
+            }
+            tot = __reduce_add_sync(kFull, tot);
+            if (lane == 0) atomicAdd(&ss.cnt[par][4], (int)tot);
+        }
+        __syncthreads();                                                   // (1b)
+        if (ss.cnt[par][4] != ss.cnt[par][2] || n_side > kSideCap) {        // a nibble wrapped / too many cut words
+            for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+            if (tid == 0) redo_dst[win] = kRowRedo;                        // the bucketed kernel takes this window
+            __syncthreads();
+            continue;
+        }
+
+        // ---- P2: orders 4..1 by marginalisation: thread t owns order-4 bin t; orders 3 and 2 by shuffles -----
+        uint32_t c4 = 0, c3 = 0, c2 = 0, flag4 = 0;
+        if (tid < 256) {
+            if constexpr (A == 5) {
+                const uint2 ch = *reinterpret_cast<const uint2*>(tab16 + lvl_off(5) + 4 * tid);
+                c4 = (ch.x & 0x7fffu) + ((ch.x >> 16) & 0x7fffu) + (ch.y & 0x7fffu) + ((ch.y >> 16) & 0x7fffu)
+                     + tab16[lvl_off(4) + tid];                              // + the short words of order 4
+            } else {
+                const uint32_t raw = tab16[lvl_off(4) + tid];
+                c4 = raw & 0x7fffu; flag4 = raw >> 15;
+            }
+            uint32_t x = c4;
+            x += __shfl_xor_sync(kFull, x, 1);
+            x += __shfl_xor_sync(kFull, x, 2);
+            c3 = x + tab16[lvl_off(3) + (tid >> 2)];
+            uint32_t y = c3;
+            y += __shfl_xor_sync(kFull, y, 4);
+            y += __shfl_xor_sync(kFull, y, 8);
+            c2 = y + tab16[lvl_off(2) + (tid >> 4)];
+            if ((tid & 15) == 0) ss.c2[tid >> 4] = c2;
+        }
+        __syncthreads();                                                   // (2)
+        uint32_t n_at = 0, n_ta = 0, n_sub = 0, n_prod = 0;
+        if (tid < 256) {
+            const uint32_t* q2 = ss.c2 + (tid >> 6) * 4;
+            const uint32_t c1 = q2[0] + q2[1] + q2[2] + q2[3] + tab16[lvl_off(1) + (tid >> 6)];
+            const uint32_t cs4[4] = {c1, c2, c3, c4};
+            double num = 0.0;
+            uint32_t den = 0;
+#pragma unroll
+            for (int x = 1; x <= LP; ++x) {
+                if (x >= kmin) {
+                    const uint32_t c = cs4[x - 1];
+                    den += c << (2 * x);
+                    num = fma(ss.q[x - 1], u32_to_double(c * c), num);
+                }
+            }
+            pre[tid] = make_double2(num, __hiloint2double((int)flag4, (int)den));
+            if (DUMP) {
+                dmp[lvl_off(4) + tid] = (uint16_t)c4;
+                if ((tid & 3) == 0) dmp[lvl_off(3) + (tid >> 2)] = (uint16_t)c3;
+                if ((tid & 15) == 0) dmp[lvl_off(2) + (tid >> 4)] = (uint16_t)c2;
+                if ((tid & 63) == 0) dmp[lvl_off(1) + (tid >> 6)] = (uint16_t)c1;
+            }
+        }
+        if (tid == 0 && want_rip) {                                        // K >= 7 so order 2 always exists
+            n_at = ss.c2[1]; n_ta = ss.c2[4];
+            n_sub = ss.c2[3] + ss.c2[9];
+            n_prod = ss.c2[12] + ss.c2[6];
+        }
+        __syncthreads();                                                   // (3)
+        if (DUMP) {                                                        // tests only: the window's tables, all orders
+            if constexpr (A == 5)
+                for (uint32_t i = tid; i < pow4(5); i += NT) dmp[lvl_off(5) + i] = tab16[lvl_off(5) + i] & 0x7fffu;
+            for (uint32_t i = tid; i < pow4(K); i += NT) dmp[lvl_off(K) + i] = (uint16_t)((nib32[i >> 3] >> ((i & 7u) * 4u)) & 15u);
+            for (uint32_t i = tid; i < pow4(K - 1); i += NT) {
+                const uint32_t h = (nib32[i >> 1] >> ((i & 1u) * 16u)) & 0xffffu;
+                dmp[lvl_off(K - 1) + i] = (uint16_t)((h & 15u) + ((h >> 4) & 15u) + ((h >> 8) & 15u) + (h >> 12));
+            }
+            for (uint32_t i = tid; i < pow4(K - 2); i += NT) {
+                const uint2 v = nib64[i];
+                dmp[lvl_off(K - 2) + i] = (uint16_t)__dp4a(nib_pairs(v.x) + nib_pairs(v.y), 0x01010101u, 0u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (uint32_t i = 0; i < n_side; ++i) {
+                    const uint32_t e = ss.side[i], v = e >> 16, code = e & 0xffffu;
+                    if (v == (uint32_t)(K - 1)) { dmp[lvl_off(K - 1) + code] += 1; dmp[lvl_off(K - 2) + (code >> 2)] += 1; }
+                    else dmp[lvl_off(K - 2) + code] += 1;
+                }
+            }
+        }
+
+        // ---- P3: every position scores its own K-mer with weight 1 / (its count) --------------------
+        double s_w = 0.0, s_g = 0.0, s_t = 0.0;
+        const double qA = ss.q[A - 1], qK2 = ss.q[K - 3], qK1 = ss.q[K - 2], qK = ss.q[K - 1];
+        auto score_one = [&](uint32_t kap, const double2 g) {
+            const uint2 v = nib64[kap >> 4];
+            const uint32_t ws = (kap & 8u) ? v.y : v.x, wo = (kap & 8u) ? v.x : v.y;
+            const uint32_t cK = (ws >> ((kap & 7u) * 4u)) & 15u;
+            const uint32_t ps = nib_pairs(ws);
+            const uint32_t hs = ps >> ((kap & 4u) * 4u);                   // the quarter of the (K-1)-prefix: two pair sums
+            uint32_t cK1 = (hs & 0xffu) + ((hs >> 8) & 0xffu);
+            uint32_t cK2 = __dp4a(ps + nib_pairs(wo), 0x01010101u, 0u);
+            const double2 pp = pre[kap >> (2 * (K - LP))];
+            double num = pp.x;
+            uint32_t den = (uint32_t)__double2loint(pp.y);
+            uint32_t cA = 0, flag;
+            if constexpr (A > LP) {
+                const uint32_t raw = tab16[lvl_off(A) + (kap >> (2 * (K - A)))];
+                cA = raw & 0x7fffu; flag = raw >> 15;
+            } else {
+                flag = (uint32_t)__double2hiint(pp.y);
+            }
+            if (flag) {                                    // rare: a short word of K-1 / K-2 bases lies below this bin
+                for (uint32_t i = 0; i < n_side; ++i) {
+                    const uint32_t e = ss.side[i], sv = e >> 16, code = e & 0xffffu;
+                    if (sv == (uint32_t)(K - 1)) { cK1 += (code == (kap >> 2)); cK2 += ((code >> 2) == (kap >> 4)); }
+                    else cK2 += (code == (kap >> 4));
+                }
+            }
+            if constexpr (A > LP) {
+                if (A >= kmin) { den += cA << (2 * A); num = fma(qA, u32_to_double(cA * cA), num); }
+            }
+            if (K - 2 >= kmin) { den += cK2 << (2 * (K - 2)); num = fma(qK2, u32_to_double(cK2 * cK2), num); }
+            if (K - 1 >= kmin) { den += cK1 << (2 * (K - 1)); num = fma(qK1, u32_to_double(cK1 * cK1), num); }
+            den += cK << (2 * K);
+            num = fma(qK, u32_to_double(cK * cK), num);
+            // a = I_w / c_K, om = 1 / c_K from ONE reciprocal, of den * c_K (exact product, < 2^37)
+            const double dden = u32_to_double(den), dc = u32_to_double(cK);
+            const double D = dden * dc;
+            double r;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(D));
+            r = fma(r, fma(-D, r, 1.0), r);
+            r = fma(r, fma(-D, r, 1.0), r);
+            double a = num * r;
+            a = fma(fma(-D, a, num), r, a);
+            const double iw = a * dc;
+            const double om = dden * r;
+            s_w += a;
+            s_g = fma(g.x, om, s_g);                       // a NaN entry (reference: ZeroDivisionError) poisons the sum
+            s_t = fma(a, (NIB_TABLOG ? log2_pos(iw, logtab) : log2_series(iw)) - g.y, s_t);
+        };
+        {
+            const int rounds = (int)(cs >> 2);
+#pragma unroll 1
+            for (int r = 0; r < rounds; ++r) {
+                uint32_t kp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) kp[j] = (kk[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (vm & (MT(1) << (MB - 1 - j))) score_one(kp[j], __ldg(ig + kp[j]));
+                vm <<= 4;
+#pragma unroll
+                for (int i = 0; i + 2 < PP / 2; ++i) kk[i] = kk[i + 2];     // rotate: the loop body stays one round long
+            }
+        }
+#pragma unroll
+        for (int ofs = 16; ofs; ofs >>= 1) {
+            s_w += __shfl_xor_sync(kFull, s_w, ofs);
+            s_g += __shfl_xor_sync(kFull, s_g, ofs);
+            s_t += __shfl_xor_sync(kFull, s_t, ofs);
+        }
+        if (lane == 0) { ss.red[0][warp] = s_w; ss.red[1][warp] = s_g; ss.red[2][warp] = s_t; }
+        __syncthreads();                                                   // (4) everyone is done with the tables
+        for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) {
+            double a = 0, bsum = 0, c = 0;
+            for (int w = 0; w < NW; ++w) { a += ss.red[0][w]; bsum += ss.red[1][w]; c += ss.red[2][w]; }
+            uint32_t st = 0;
+            double kld = 0.0;                              // the reference returns 0 for a window without kmax-mers
+            if (!(a == 0.0)) {
+                bool zd = bsum != bsum;                    // NaN genome IVOM entry: ZeroDivisionError at F:437
+                for (int x = kmin; x <= K; ++x) zd |= ((long long)n_up - (long long)(x - 1)) == 0;
+                if (zd) { st |= FRISK_ROW_KLD_ZERODIV; kld = CUDART_NAN; }
+                else {
+                    kld = c / a + (log2(bsum) - log2(a));
+                    if (!(kld == kld) || isinf(kld)) st |= FRISK_ROW_LOG_DOMAIN;
+                }
+            }
+            double* row = rows + (size_t)win * 5;
+            row[0] = kld;
+            if (n_up == 0) { st |= FRISK_ROW_GC_ZERODIV; row[1] = CUDART_NAN; }
+            else row[1] = (double)n_gc / (double)n_up;       // F:136
+            double pi = CUDART_NAN, si = CUDART_NAN, cri = CUDART_NAN;
+            if (want_rip) {
+                if (n_at > 0) pi = (double)n_ta / (double)n_at;        // F:480-483
+                if (n_sub > 0) si = (double)n_prod / (double)n_sub;    // F:485-489
+                if (pi != 0.0 && si != 0.0) cri = pi - si;             // F:491: 0.0 falsy, NaN truthy
+            }
+            row[2] = pi; row[3] = si; row[4] = cri;
+            status[win] = st;
+            if (redo_dst != status) redo_dst[win] = 0;
+        }
+        __syncthreads();                                                   // (5) tables zeroed, ss.red consumed
+    }
+}
+
+template <int K, int PP, bool DUMP, bool ALLK>
+int launch_nibble4(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                   const uint32_t* win_len, uint64_t n_win, const double* ig, int kmin, int want_rip,
+                   double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only) {
+    using L = NibLayout<K>;
+    auto kern = score_windows_nibble_kernel<K, PP, DUMP, ALLK>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, L::TOTAL));
+    if (occ_only) { *occ_only = per_sm; return FRISK_OK; }
+    if (per_sm < 1) per_sm = 1;
+    const int sms = frisk_internal::sm_count_cached();
+    if (sms <= 0) return FRISK_E_NO_DEVICE;
+    uint64_t grid = (uint64_t)sms * (uint64_t)per_sm;
+    if (grid > n_win) grid = n_win;
+    kern<<<(unsigned)grid, kNT, L::TOTAL, st>>>(codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len,
+                                                (uint32_t)n_win, reinterpret_cast<const double2*>(ig), kmin, want_rip, rows,
+                                                status, dump, redo_dst);
+    CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+template <int K, int PP>
+int launch_nibble3(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                   const uint32_t* win_len, uint64_t n_win, const double* ig, int kmin, int want_rip,
+                   double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only) {
+    if (dump) return launch_nibble4<K, PP, true, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+    if (kmin != 1) return launch_nibble4<K, PP, false, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+    return launch_nibble4<K, PP, false, true>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+}
+
+// positions per thread: the longest window of the launch spread over the CTA (K-mer codes stay in registers between
+// the counting and the scoring pass); shorter windows of the same launch use shorter chunks
+template <int K>
+int launch_nibble(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                  const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
+                  double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only) {
+    if (max_len <= kNT * 8u)
+        return launch_nibble3<K, 8>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+    if (max_len <= kNT * 20u)
+        return launch_nibble3<K, 20>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+    if (max_len <= kNT * 32u)
+        return launch_nibble3<K, 32>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+    return FRISK_E_UNSUPPORTED;
+}
+
+}  // namespace
+
+int frisk_internal::score_nibble(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                                 const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K,
+                                 int want_rip, double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+    if (K != 7 && K != 8) return FRISK_E_UNSUPPORTED;
+    // where the hand-over marks go: `status` itself when it is device memory, device scratch when it is pinned host
+    // memory (the second launch would otherwise read its marks across PCIe, one round trip per window)
+    uint32_t* redo = status;
+    uint32_t* scratch = nullptr;
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, status) != cudaSuccess || pa.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        int rc = pool_ready();
+        if (rc) return rc;
+        CK(cudaMallocAsync((void**)&scratch, n_win * sizeof(uint32_t), st));
+        redo = scratch;
+    }
+    int rc;
+    if (K == 8) rc = launch_nibble<8>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo, st, nullptr);
+    else rc = launch_nibble<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo, st, nullptr);
+    // windows the nibble table could not hold (marked kRowRedo): exact re-run on the bucketed kernel
+    if (!rc) rc = score_bucket_redo(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, K, want_rip, rows, status, dump, redo, st);
+    if (scratch) {                                         // freed on every path (stream-ordered: behind the launches above)
+        const cudaError_t e = cudaFreeAsync(scratch, st);
+        if (!rc && e != cudaSuccess) return frisk_internal::cuda_fail(e, "cudaFreeAsync(scratch)");
+    }
+    return rc;
+}
+
+int frisk_internal::score_nibble_occupancy(int K, uint32_t max_len, int* ctas_per_sm, int* threads_per_cta) {
+    if (threads_per_cta) *threads_per_cta = kNT;
+    if (K == 8) return launch_nibble<8>(nullptr, nullptr, nullptr, nullptr, nullptr, 1, max_len, nullptr, 1, 0, nullptr, nullptr, nullptr, nullptr, 0, ctas_per_sm);
+    if (K == 7) return launch_nibble<7>(nullptr, nullptr, nullptr, nullptr, nullptr, 1, max_len, nullptr, 1, 0, nullptr, nullptr, nullptr, nullptr, 0, ctas_per_sm);
+    return FRISK_E_UNSUPPORTED;
+}

@@ -346,6 +346,16 @@ int frisk_b200_host_free(void *ptr);
  * *ms receives the kernel time; updates = blocks*1024*iters. */
 int frisk_b200_bench_smem_atomics(int blocks, int iters, int mode, float *ms, void *stream);
 
+/* Two more roofline denominators of the window kernels, measured on the GPU at hand (frisk_bench.cu):
+ * _l2_gather: `blocks` x 256 threads each issue `iters` (multiple of 4) 16-byte loads from an L2-resident table of
+ *   `table_bytes` (power of two; 1 MiB = the genome-IVOM table of kmax 8).  mode 0: every lane an independent random
+ *   entry; mode 1: a warp's lanes read increasing entries with random gaps (the sorted epilogue's pattern).
+ *   gathers = blocks*256*iters.
+ * _smem_loads: `blocks` x 256 threads each issue `iters` random loads of `elem_bytes` (4, 8 or 16) from a 32 KiB
+ *   shared-memory table (bank-conflicted reads).  loads = blocks*256*iters. */
+int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int mode, float *ms, void *stream);
+int frisk_b200_bench_smem_loads(int blocks, int iters, int elem_bytes, float *ms, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
