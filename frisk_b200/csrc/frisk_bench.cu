@@ -41,6 +41,48 @@ l2_gather_kernel(const double2* __restrict__ tab, uint32_t n_mask, int iters, in
     if (s == 1.2345e-300) sink[0] = s;
 }
 
+// mode 2: the same random gather as mode 0, but as cp.async (LDGSTS) of 16 bytes per lane into shared memory, read back
+// coalesced -- does a divergent gather cost fewer data-pipe cycles when it does not return through the register file?
+__global__ void __launch_bounds__(256, 4)
+l2_gather_async_kernel(const double2* __restrict__ tab, uint32_t n_mask, int iters, double* sink) {
+    __shared__ __align__(16) double2 stage[2][4][256];
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    double a0 = 0;
+    auto issue = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t i = lcg(x) & n_mask;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[buf][j][threadIdx.x]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(tab + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    int buf = 0;
+    for (int it = 0; it < iters; it += 4) {
+        if (it + 4 < iters) { issue(buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double2 v = stage[buf][j][threadIdx.x]; a0 += v.x + v.y; }
+        buf ^= 1;
+    }
+    if (a0 == 1.2345e-300) sink[0] = a0;
+}
+
+// mode 3: 8-byte entries (half the table bytes for the same number of entries)
+__global__ void __launch_bounds__(256, 4)
+l2_gather8_kernel(const double* __restrict__ tab, uint32_t n_mask, int iters, double* sink) {
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int it = 0; it < iters; it += 4) {
+        const uint32_t i0 = lcg(x), i1 = lcg(x), i2 = lcg(x), i3 = lcg(x);
+        a0 += __ldg(tab + (i0 & n_mask)); a1 += __ldg(tab + (i1 & n_mask));
+        a2 += __ldg(tab + (i2 & n_mask)); a3 += __ldg(tab + (i3 & n_mask));
+    }
+    const double s = a0 + a1 + a2 + a3;
+    if (s == 1.2345e-300) sink[0] = s;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256, 4)
 smem_load_kernel(int iters, T* sink) {
@@ -81,7 +123,7 @@ int time_twice(F launch, cudaStream_t st, float* ms) {
 extern "C" {
 
 int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int mode, float* ms, void* stream) {
-    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms || table_bytes < 4096 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 1)
+    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms || table_bytes < 4096 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 3)
         return FRISK_E_INVALID;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -92,7 +134,10 @@ int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int 
     CK(cudaMemsetAsync(tab, 0, table_bytes, st));
     const uint32_t n_mask = (uint32_t)(table_bytes / 16u) - 1u;
     const uint32_t gap = 14u;                            // 65,536 entries / ~4,794 distinct K-mers of a 5 kb window
-    const int rc = time_twice([&] { l2_gather_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, mode, gap, sink); }, st, ms);
+    int rc;
+    if (mode == 2) rc = time_twice([&] { l2_gather_async_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, sink); }, st, ms);
+    else if (mode == 3) rc = time_twice([&] { l2_gather8_kernel<<<blocks, 256, 0, st>>>((const double*)tab, 2u * n_mask + 1u, iters, sink); }, st, ms);
+    else rc = time_twice([&] { l2_gather_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, mode, gap, sink); }, st, ms);
     cudaFree(tab);
     cudaFree(sink);
     return rc;

@@ -1449,7 +1449,7 @@ int frisk_internal::cuda_fail(cudaError_t e, const char* what) {
 #define FRISK_DIRECT_DEFAULT(kmax, len) ((kmax) == 7 && (len) > 2042u)
 #endif
 #ifndef FRISK_NIBBLE_DEFAULT
-#define FRISK_NIBBLE_DEFAULT(kmax, len) (0 && (kmax) == 8)   // off until measured faster (tools/k8_ab.py)
+#define FRISK_NIBBLE_DEFAULT(kmax, len) ((kmax) == 8 || ((kmax) == 7 && (len) > 2042u))   // measured: tools/k8_ab.py
 #endif
 
 namespace {

@@ -16,7 +16,7 @@
 //     orders below follow by marginalisation, orders <= 4 are folded into one {numerator, denominator} pair per
 //     order-4 prefix (`pre`);
 //   * a thread's positions are fixed and so is the reduction tree -> bit-reproducible rows.
-// 40 KB of shared memory per CTA (K = 8).
+// 40-56 KB of shared memory per CTA (K = 8).
 //
 // What a nibble cannot hold is handed to the bucketed kernel (frisk_kernels.cu), exactly: a window in which some
 // K-mer occurs 16+ times (the thread whose increment wraps the nibble sees 15 in the word it got back), or with
@@ -51,6 +51,14 @@ struct NibSmem {
 #define FRISK_NIBBLE_TABLOG 0
 #endif
 constexpr bool NIB_TABLOG = FRISK_NIBBLE_TABLOG;   // 0: log2 by series, no shared-memory table read in the epilogue
+#ifndef FRISK_NIBBLE_PRE5
+#define FRISK_NIBBLE_PRE5 1
+#endif
+constexpr bool NIB_PRE5 = FRISK_NIBBLE_PRE5;       // K = 8: order 5 folded into `pre` too (one 16-byte read instead of 16 + 2)
+#ifndef FRISK_NIBBLE_PREFETCH
+#define FRISK_NIBBLE_PREFETCH 0
+#endif
+constexpr bool NIB_PREFETCH = FRISK_NIBBLE_PREFETCH;   // request the next K-mer's genome IVOM entry before scoring this one
 
 template <int K>
 struct NibLayout {
@@ -65,7 +73,10 @@ struct NibLayout {
     static constexpr uint32_t ZERO_BYTES = NIB_BYTES + LOW_BYTES;
     static constexpr uint32_t OFF_LOW = NIB_BYTES;
     static constexpr uint32_t OFF_PRE = ZERO_BYTES;
-    static constexpr uint32_t OFF_LOG = OFF_PRE + NPRE * 16u;
+    static constexpr bool FOLD_A = NIB_PRE5 && A > LP;                   // `pre` extended to order A (its own array, after the order-4 one)
+    static constexpr uint32_t NPREA = FOLD_A ? pow4(A) : 0u;
+    static constexpr uint32_t OFF_PREA = OFF_PRE + NPRE * 16u;
+    static constexpr uint32_t OFF_LOG = OFF_PREA + NPREA * 16u;
     static constexpr uint32_t OFF_SS = OFF_LOG + (NIB_TABLOG ? 128u * 16u : 0u);
     static constexpr uint32_t TOTAL = OFF_SS + (uint32_t)sizeof(NibSmem);
 };
@@ -96,6 +107,15 @@ template <typename MT> __device__ __forceinline__ MT top_bits(int n) {       // 
     return n >= MB ? ~MT(0) : ~(~MT(0) >> n);
 }
 
+#ifndef FRISK_NIBBLE_GATHER_CG
+#define FRISK_NIBBLE_GATHER_CG 1
+#endif
+#if FRISK_NIBBLE_GATHER_CG
+#define NIB_GATHER(p) __ldcg(p)                    // L2 only: the 1 MiB table never survives in a ~30 KB L1 anyway, and
+                                                   // not allocating there measured 4.7 % faster (0.703 -> 0.671 ms on C2)
+#else
+#define NIB_GATHER(p) __ldg(p)
+#endif
 #ifndef FRISK_NIBBLE_CTAS
 #define FRISK_NIBBLE_CTAS 4
 #endif
@@ -125,9 +145,10 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
     uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem + L::OFF_LOW);    // orders 1..A at lvl_off(x)
     uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem + L::OFF_LOW);
     double2* pre = reinterpret_cast<double2*>(smem + L::OFF_PRE);       // .x = num, .y = {flag, den} as two u32
+    double2* preA = reinterpret_cast<double2*>(smem + L::OFF_PREA);     // FOLD_A: the same pair through order A, per order-A prefix
     double2* logtab = reinterpret_cast<double2*>(smem + L::OFF_LOG);
     NibSmem& ss = *reinterpret_cast<NibSmem*>(smem + L::OFF_SS);
-    (void)logtab;
+    (void)logtab; (void)preA;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -320,7 +341,6 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             if ((tid & 15) == 0) ss.c2[tid >> 4] = c2;
         }
         __syncthreads();                                                   // (2)
-        uint32_t n_at = 0, n_ta = 0, n_sub = 0, n_prod = 0;
         if (tid < 256) {
             const uint32_t* q2 = ss.c2 + (tid >> 6) * 4;
             const uint32_t c1 = q2[0] + q2[1] + q2[2] + q2[3] + tab16[lvl_off(1) + (tid >> 6)];
@@ -343,12 +363,19 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 if ((tid & 63) == 0) dmp[lvl_off(1) + (tid >> 6)] = (uint16_t)c1;
             }
         }
-        if (tid == 0 && want_rip) {                                        // K >= 7 so order 2 always exists
-            n_at = ss.c2[1]; n_ta = ss.c2[4];
-            n_sub = ss.c2[3] + ss.c2[9];
-            n_prod = ss.c2[12] + ss.c2[6];
-        }
         __syncthreads();                                                   // (3)
+        if constexpr (L::FOLD_A) {                                         // order A joins the folded pair: P3 reads one entry per K-mer
+            const double qa = ss.q[A - 1];
+            for (uint32_t b = tid; b < pow4(A); b += NT) {
+                const uint32_t raw = tab16[lvl_off(A) + b], cA = raw & 0x7fffu;
+                const double2 pp = pre[b >> 2];
+                double num = pp.x;
+                uint32_t den = (uint32_t)__double2loint(pp.y);
+                if (A >= kmin) { den += cA << (2 * A); num = fma(qa, u32_to_double(cA * cA), num); }
+                preA[b] = make_double2(num, __hiloint2double((int)(raw >> 15), (int)den));
+            }
+            __syncthreads();                                               // (3b)
+        }
         if (DUMP) {                                                        // tests only: the window's tables, all orders
             if constexpr (A == 5)
                 for (uint32_t i = tid; i < pow4(5); i += NT) dmp[lvl_off(5) + i] = tab16[lvl_off(5) + i] & 0x7fffu;
@@ -382,11 +409,11 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             const uint32_t hs = ps >> ((kap & 4u) * 4u);                   // the quarter of the (K-1)-prefix: two pair sums
             uint32_t cK1 = (hs & 0xffu) + ((hs >> 8) & 0xffu);
             uint32_t cK2 = __dp4a(ps + nib_pairs(wo), 0x01010101u, 0u);
-            const double2 pp = pre[kap >> (2 * (K - LP))];
+            const double2 pp = L::FOLD_A ? preA[kap >> (2 * (K - A))] : pre[kap >> (2 * (K - LP))];
             double num = pp.x;
             uint32_t den = (uint32_t)__double2loint(pp.y);
             uint32_t cA = 0, flag;
-            if constexpr (A > LP) {
+            if constexpr (A > LP && !L::FOLD_A) {
                 const uint32_t raw = tab16[lvl_off(A) + (kap >> (2 * (K - A)))];
                 cA = raw & 0x7fffu; flag = raw >> 15;
             } else {
@@ -399,7 +426,7 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                     else cK2 += (code == (kap >> 4));
                 }
             }
-            if constexpr (A > LP) {
+            if constexpr (A > LP && !L::FOLD_A) {
                 if (A >= kmin) { den += cA << (2 * A); num = fma(qA, u32_to_double(cA * cA), num); }
             }
             if (K - 2 >= kmin) { den += cK2 << (2 * (K - 2)); num = fma(qK2, u32_to_double(cK2 * cK2), num); }
@@ -423,17 +450,28 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         };
         {
             const int rounds = (int)(cs >> 2);
+            double2 gnext = NIB_PREFETCH ? NIB_GATHER(ig + (kk[0] & 0xffffu)) : make_double2(0.0, 0.0);
 #pragma unroll 1
             for (int r = 0; r < rounds; ++r) {
-                uint32_t kp[4];
+                uint32_t kp[5];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) kp[j] = (kk[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                kp[4] = PP / 2 > 2 ? (kk[2 < PP / 2 ? 2 : 0] & 0xffffu) : 0u;   // first K-mer of the next round (0 past the end: a valid entry)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (vm & (MT(1) << (MB - 1 - j))) score_one(kp[j], __ldg(ig + kp[j]));
+                for (int j = 0; j < 4; ++j) {
+                    if constexpr (NIB_PREFETCH) {
+                        const double2 g = gnext;
+                        gnext = NIB_GATHER(ig + kp[j + 1]);                      // unconditional: an unused position holds code 0
+                        if (vm & (MT(1) << (MB - 1 - j))) score_one(kp[j], g);
+                    } else {
+                        if (vm & (MT(1) << (MB - 1 - j))) score_one(kp[j], NIB_GATHER(ig + kp[j]));
+                    }
+                }
                 vm <<= 4;
 #pragma unroll
                 for (int i = 0; i + 2 < PP / 2; ++i) kk[i] = kk[i + 2];     // rotate: the loop body stays one round long
+#pragma unroll
+                for (int i = (PP / 2 > 2 ? PP / 2 - 2 : 0); i < PP / 2; ++i) kk[i] = 0;
             }
         }
 #pragma unroll
@@ -445,33 +483,46 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         if (lane == 0) { ss.red[0][warp] = s_w; ss.red[1][warp] = s_g; ss.red[2][warp] = s_t; }
         __syncthreads();                                                   // (4) everyone is done with the tables
         for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) {
+        if (warp == 0) {
+            // the row: four IEEE divisions and two logarithms, one per LANE instead of one after the other in a single
+            // thread (the other seven warps of the CTA wait for this at the barrier below)
             double a = 0, bsum = 0, c = 0;
             for (int w = 0; w < NW; ++w) { a += ss.red[0][w]; bsum += ss.red[1][w]; c += ss.red[2][w]; }
-            uint32_t st = 0;
-            double kld = 0.0;                              // the reference returns 0 for a window without kmax-mers
-            if (!(a == 0.0)) {
-                bool zd = bsum != bsum;                    // NaN genome IVOM entry: ZeroDivisionError at F:437
-                for (int x = kmin; x <= K; ++x) zd |= ((long long)n_up - (long long)(x - 1)) == 0;
-                if (zd) { st |= FRISK_ROW_KLD_ZERODIV; kld = CUDART_NAN; }
-                else {
-                    kld = c / a + (log2(bsum) - log2(a));
-                    if (!(kld == kld) || isinf(kld)) st |= FRISK_ROW_LOG_DOMAIN;
+            double nu = 0.0, de = 1.0;
+            if (lane == 0) { nu = c; de = a; }
+            else if (lane == 1) { nu = (double)n_gc; de = (double)n_up; }                                   // F:136
+            else if (lane == 2) { nu = (double)ss.c2[4]; de = (double)ss.c2[1]; }                          // TA / AT, F:480-483
+            else if (lane == 3) { nu = (double)(ss.c2[12] + ss.c2[6]); de = (double)(ss.c2[3] + ss.c2[9]); }  // (CA+TG) / (AC+GT), F:485-489
+            const double qv = nu / de;
+            const double lgv = log2(lane == 0 ? bsum : a);
+            const double q_gc = __shfl_sync(kFull, qv, 1), q_pi = __shfl_sync(kFull, qv, 2), q_si = __shfl_sync(kFull, qv, 3);
+            const double lg_a = __shfl_sync(kFull, lgv, 1);
+            if (lane == 0) {
+                uint32_t st = 0;
+                double kld = 0.0;                          // the reference returns 0 for a window without kmax-mers
+                if (!(a == 0.0)) {
+                    bool zd = bsum != bsum;                // NaN genome IVOM entry: ZeroDivisionError at F:437
+                    for (int x = kmin; x <= K; ++x) zd |= ((long long)n_up - (long long)(x - 1)) == 0;
+                    if (zd) { st |= FRISK_ROW_KLD_ZERODIV; kld = CUDART_NAN; }
+                    else {
+                        kld = qv + (lgv - lg_a);
+                        if (!(kld == kld) || isinf(kld)) st |= FRISK_ROW_LOG_DOMAIN;
+                    }
                 }
+                double* row = rows + (size_t)win * 5;
+                row[0] = kld;
+                if (n_up == 0) { st |= FRISK_ROW_GC_ZERODIV; row[1] = CUDART_NAN; }
+                else row[1] = q_gc;
+                double pi = CUDART_NAN, si = CUDART_NAN, cri = CUDART_NAN;
+                if (want_rip) {
+                    if (ss.c2[1] > 0) pi = q_pi;
+                    if (ss.c2[3] + ss.c2[9] > 0) si = q_si;
+                    if (pi != 0.0 && si != 0.0) cri = pi - si;         // F:491: 0.0 falsy, NaN truthy
+                }
+                row[2] = pi; row[3] = si; row[4] = cri;
+                status[win] = st;
+                if (redo_dst != status) redo_dst[win] = 0;
             }
-            double* row = rows + (size_t)win * 5;
-            row[0] = kld;
-            if (n_up == 0) { st |= FRISK_ROW_GC_ZERODIV; row[1] = CUDART_NAN; }
-            else row[1] = (double)n_gc / (double)n_up;       // F:136
-            double pi = CUDART_NAN, si = CUDART_NAN, cri = CUDART_NAN;
-            if (want_rip) {
-                if (n_at > 0) pi = (double)n_ta / (double)n_at;        // F:480-483
-                if (n_sub > 0) si = (double)n_prod / (double)n_sub;    // F:485-489
-                if (pi != 0.0 && si != 0.0) cri = pi - si;             // F:491: 0.0 falsy, NaN truthy
-            }
-            row[2] = pi; row[3] = si; row[4] = cri;
-            status[win] = st;
-            if (redo_dst != status) redo_dst[win] = 0;
         }
         __syncthreads();                                                   // (5) tables zeroed, ss.red consumed
     }

@@ -254,18 +254,19 @@ def test_direct_kernel_word_ranges_against_c_oracle(eng, kw):
         win = seq[int(ref["win_off"][i]):int(ref["win_off"][i]) + int(ref["win_len"][i])]
         _, _, wt, _ = c_oracle.window_tables(win, ref["tables"], ref["meta"], full["kmin"], full["kmax"])
         assert np.array_equal(res.win_tables[i].astype(np.uint64), wt), (kw, i)
-    for opt in (b"force_bucket_kernel", b"force_direct_kernel"):
+    for opt in (b"force_bucket_kernel", b"force_direct_kernel", b"force_nibble_kernel"):
         other = _with_option(opt, 1, lambda: eng.run(g, dump=True, **full))
         assert np.array_equal(other.win_tables, res.win_tables), opt
         assert np.array_equal(other.status, res.status), opt
         assert max_rel_err(other.rows[ok, 0], res.rows[ok, 0]) < 1e-12, opt
 
 
-@pytest.mark.parametrize("opt", [None, b"force_direct_kernel"])
+@pytest.mark.parametrize("opt", [None, b"force_direct_kernel", b"force_nibble_kernel"])
 def test_direct_kernel_hands_over_what_a_byte_cannot_hold(eng, opt):
-    """Windows with a K-mer seen 256+ times (byte wrap) or with more than 64 words cut short at K-1 / K-2 bases
-    (many N boundaries) are marked for the bucketed kernel and re-done there: rows and tables still exact, and
-    no internal marker survives in the status words."""
+    """Windows with a K-mer seen 256+ times (byte wrap; the nibble kernel: 16+ times, detected through the grand
+    total of its counters) or with more than 64 words cut short at K-1 / K-2 bases (many N boundaries) are marked
+    for the bucketed kernel and re-done there: rows and tables still exact, and no internal marker survives in the
+    status words."""
     from frisk_b200 import synth
     from oracle import c_oracle
     rng = np.random.Generator(np.random.PCG64(8))
@@ -279,6 +280,10 @@ def test_direct_kernel_hands_over_what_a_byte_cannot_hold(eng, opt):
         a[p] = ord("N")
     a[40_000:40_255 + 7] = ord("T")                            # exactly 255 x TTTTTTTT
     a[45_000:45_256 + 7] = ord("G")                            # exactly 256 x GGGGGGGG
+    a[50_000:50_015 + 7] = ord("A")                            # exactly 15 x AAAAAAAA: the most a nibble holds
+    a[52_000:52_016 + 7] = ord("T")                            # exactly 16: wraps a nibble (carry into the neighbour)
+    a[54_000:54_008] = np.frombuffer(b"CCCCCCCC", dtype=np.uint8)
+    a[56_000:56_000 + 17 * 9] = np.tile(np.frombuffer(b"CCCCCCCCA", dtype=np.uint8), 17)   # 17 x the TOP nibble of its word: carry lost
     sc = [("handover", a)]
     for kw in (dict(), dict(kmax=7), dict(w=3000, step=1000, kmin=2)):
         full = dict(kmin=1, kmax=8, w=5000, step=2500, mask_host=False, scaffolds_all=False, rip=True)

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from frisk_b200 import engine as eng, dist as fdist
-from tests.test_scale_gpu import build_device_genome
+from frisk_b200.synth_device import c4_spec, build_device_genome
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -20,11 +20,7 @@ steps = int(os.environ.get("C4_STEPS", "5"))
 dev = torch.device("cuda:0")
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-rng = np.random.Generator(np.random.PCG64(4004))
-lens = rng.uniform(50e6, 250e6, 24)
-lens = (lens * (3.0e9 / lens.sum())).astype(np.int64)
-lens = np.concatenate([lens, [3_000_017, 1_234_567]])
-runs = (list(range(24)) + [24, 25], [int(lens[s] // 3) for s in range(24)] + [1_000_000, 5], [3_000_000] * 24 + [517, 2500])
+lens, runs = c4_spec()
 dg = build_device_genome(eng, lens, runs, seed=44, at_rich_block=300_000 // 16)
 g = dg.host
 wins_all = g.windows(5000, 2500, False)

@@ -39,6 +39,7 @@ out = {
     "smem_atomic_updates_per_s": {n: best(lambda m=m: atomics(m)) for m, n in [(0, "conflict_free"), (1, "random"), (2, "single_address")]},
     "smem_random_loads_per_s": {"%dB" % b: best(lambda b=b: loads(b)) for b in (4, 8, 16)},
     "l2_gather_16B_per_s": {"random_1MiB": best(lambda: gathers(0)), "sorted_1MiB": best(lambda: gathers(1)),
-                            "random_256KiB": best(lambda: gathers(0, 1 << 18)), "random_16MiB": best(lambda: gathers(0, 1 << 24))},
+                            "random_256KiB": best(lambda: gathers(0, 1 << 18)), "random_16MiB": best(lambda: gathers(0, 1 << 24)),
+                            "random_1MiB_cp_async": best(lambda: gathers(2)), "random_8B_entries_512KiB": best(lambda: gathers(3))},
 }
 print(json.dumps(out))
