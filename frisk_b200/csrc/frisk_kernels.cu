@@ -1949,6 +1949,29 @@ int frisk_b200_score_occupancy(int kmax, uint32_t max_win_len, int* ctas_per_sm,
     return FRISK_OK;
 }
 
+// Which window kernel frisk_b200_score launches for these parameters, spelled the way ncu prints it (without the
+// "<unnamed>::" prefix and the argument list): the same decisions as frisk_b200_score above, so a profile or a bench
+// line can be labelled from the launcher's own selection instead of a string constant.
+int frisk_b200_score_kernel_name(int kmin, int kmax, uint32_t max_win_len, char* buf, uint64_t cap) {
+    if (!buf || cap < 8) return FRISK_E_INVALID;
+    int rc = check_k(kmin, kmax);
+    if (rc) return rc;
+    const int allk = kmin == 1 ? 1 : 0;
+    auto chunk = [&](uint32_t a, uint32_t b, uint32_t c) { return max_win_len <= kT3 * a ? a : (max_win_len <= kT3 * b ? b : c); };
+    if (kmax > FRISK_B200_FAST_K || max_win_len > 65535u || g_force_general) snprintf(buf, cap, "gen_score_kernel");
+    else if (kmax <= 6 && !g_force_dense && !g_force_bucket) snprintf(buf, cap, "score_windows_small_kernel<%d, 0>", kmax);
+    else if (use_nibble_kernel(kmax, max_win_len))
+        snprintf(buf, cap, "score_windows_nibble_kernel<%d, %u, 0, %d>", kmax, chunk(8u, 20u, 32u), allk);
+    else if (use_direct_kernel(kmax, max_win_len)) {
+        const uint32_t r = max_win_len <= 256u * 4u * 2u - 6u ? 2u : (max_win_len <= 256u * 4u * 5u - 6u ? 5u : 8u);
+        snprintf(buf, cap, "score_windows_direct_kernel<%d, 256, %u, 0, %d>", kmax, r, allk);
+    } else if (kmax >= 4 && max_win_len <= kBuf3 - 6u && !g_force_dense) {
+        const uint32_t r = max_win_len <= kT3 * 4u * 2u - 6u ? 2u : (max_win_len <= kT3 * 4u * 5u - 6u ? 5u : 8u);
+        snprintf(buf, cap, "score_windows_bucket_kernel<%d, %u, 0, %d>", kmax, r, allk);
+    } else snprintf(buf, cap, "score_windows_kernel<%d>", kmax);
+    return FRISK_OK;
+}
+
 int frisk_b200_set_option(const char* name, int value) {
     if (!name) return FRISK_E_INVALID;
     if (strcmp(name, "force_dense_kernel") == 0) { g_force_dense = value; return FRISK_OK; }
@@ -1966,6 +1989,36 @@ int frisk_b200_kld(const double* d_genome_ivom, const double* d_window_ivom, uin
     return FRISK_OK;
 }
 
+namespace {
+// Stage marks of the last frisk_b200_run_host* / _run_resident call on a device (frisk_b200_last_run_timing): timing-enabled
+// events recorded on the call's streams; reading them back costs nothing on the data path.
+enum { kTmStart = 0, kTmUploaded, kTmCounted, kTmFinalised, kTmScored, kTmEnd, kTmCount };
+struct RunMarks {
+    cudaEvent_t ev[kTmCount] = {};
+    bool have[kTmCount] = {};
+    bool ready = false;
+};
+RunMarks g_marks[64];
+int run_marks(RunMarks** out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    RunMarks& m = g_marks[dev & 63];
+    if (!m.ready) {
+        for (auto& e : m.ev) CK(cudaEventCreate(&e));
+        m.ready = true;
+    }
+    for (auto& h : m.have) h = false;
+    *out = &m;
+    return FRISK_OK;
+}
+int mark(RunMarks* m, int which, cudaStream_t st) {
+    if (!m) return FRISK_OK;
+    CK(cudaEventRecord(m->ev[which], st));
+    m->have[which] = true;
+    return FRISK_OK;
+}
+}  // namespace
+
 // Everything after the planes are on the device: [background], finalize, genome IVOM, window
 // upload, score, download.  `copy` (nullable) already carries the uploads this run must wait for.
 // multi-GPU: where the other ranks' counters are (frisk_b200_finalize_tables_peers); world == 0: single GPU
@@ -1982,7 +2035,7 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
                     const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host,
                     int want_rip, int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
                     uint64_t* valid_kmax_out, void* dfwd, cudaStream_t st, cudaStream_t copy, cudaEvent_t copy_done,
-                    cudaEvent_t tables_ready) {
+                    cudaEvent_t tables_ready, RunMarks* tm) {
     const size_t tsz = (size_t)frisk_b200_table_size(1, kmax);
     void *dtab, *dig, *dwo = nullptr, *dwl = nullptr, *drows = nullptr, *dstat = nullptr;
     int rc;
@@ -2003,11 +2056,13 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
         // the last 32-base word is padding by construction and is only ever read as look-ahead
         rc = frisk_b200_background(dhc, dhi, dhl, 0, h_padded_len - 32, kmax, mask_host, (uint64_t*)dfwd, st);
         if (rc) return rc;
+        if ((rc = mark(tm, kTmCounted, st))) return rc;
     }
     uint64_t* dvalid = (uint64_t*)dtab + tsz;
     rc = frisk_b200_finalize_ivom((const uint64_t*)dfwd, peers.d_fwd_peers, peers.d_flag_peers, peers.rank, peers.world, peers.epoch,
                                   kmin, kmax, genome_space, (uint64_t*)dtab, dvalid, (double*)dig, st);
     if (rc) return rc;
+    if ((rc = mark(tm, kTmFinalised, st))) return rc;
     // the genome tables (0.7 MB) go back on the copy stream while the window kernel runs, not behind it
     const bool tables_aside = copy && tables_ready && (tables_out || valid_kmax_out);
     if (tables_aside) {
@@ -2030,6 +2085,7 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
         rc = frisk_b200_score(dqc, dqi, dql, (const uint64_t*)dwo, (const uint32_t*)dwl, n_win, max_win_len,
                               (const double*)dig, kmin, kmax, want_rip, k_rows, k_stat, nullptr, st);
         if (rc) return rc;
+        if ((rc = mark(tm, kTmScored, st))) return rc;
         if (!direct) {
             CK(cudaMemcpyAsync(rows_out, drows, n_win * 40, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(status_out, dstat, n_win * 4, cudaMemcpyDeviceToHost, st));
@@ -2039,6 +2095,7 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
         if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, st));
         if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, st));
     }
+    if ((rc = mark(tm, kTmEnd, st))) return rc;
     CK(cudaStreamSynchronize(st));
     if (tables_aside) CK(cudaStreamSynchronize(copy));
     return FRISK_OK;
@@ -2119,6 +2176,9 @@ static int run_host_impl(const PeerArgs& peers, const HostPlanes& h, const HostP
     cudaStream_t st = (cudaStream_t)stream;
     CopyCtx* cc = nullptr;
     if ((rc = copy_ctx(&cc))) return rc;
+    RunMarks* tm = nullptr;
+    if ((rc = run_marks(&tm))) return rc;
+    if ((rc = mark(tm, kTmStart, st))) return rc;
     const size_t tsz = (size_t)frisk_b200_table_size(1, kmax);
     void *dhc, *dhi, *dhl = nullptr, *dqc, *dqi, *dql = nullptr, *dfwd;
     if ((rc = ws_get(0, h_padded_len / 4, &dhc))) return rc;
@@ -2140,7 +2200,10 @@ static int run_host_impl(const PeerArgs& peers, const HostPlanes& h, const HostP
     // sparse invalid plane: zero fill + pairs + scatter on the COMPUTE stream, behind the first code chunk's transfer
     // (on the copy stream they would delay that chunk by four small operations); the counts on `st` follow in order
     if ((rc = upload_inv(h, dhi, 15, 16, st))) return rc;
-    uint64_t n_chunks = (h_padded_len + (8ull << 20) - 1) / (8ull << 20);
+    // (every count launch has a fixed cost -- zeroing and storing a 128 KiB table per CTA, the reduction of the partial
+    // tables -- of ~0.03 ms: 5 chunks of 8 M bases left 0.135 ms of counting behind the last upload of a 40 Mbp
+    // genome, 2 chunks of 20 M leave one chunk's count)
+    uint64_t n_chunks = (h_padded_len + (20ull << 20) - 1) / (20ull << 20);
     if (n_chunks > (uint64_t)kMaxChunks) n_chunks = kMaxChunks;
     const uint64_t chunk = ((h_padded_len + n_chunks - 1) / n_chunks + 127) & ~127ull;
     uint64_t counted = 0;
@@ -2160,6 +2223,8 @@ static int run_host_impl(const PeerArgs& peers, const HostPlanes& h, const HostP
             counted = upto;
         }
     }
+    if ((rc = mark(tm, kTmUploaded, cc->copy))) return rc;
+    if ((rc = mark(tm, kTmCounted, st))) return rc;
     if (same) { dqc = dhc; dqi = dhi; dql = dhl; }
     else {
         if ((rc = ws_get(3, q_padded_len / 4, &dqc))) return rc;
@@ -2173,7 +2238,7 @@ static int run_host_impl(const PeerArgs& peers, const HostPlanes& h, const HostP
     return run_tail(peers, (const uint32_t*)dhc, (const uint32_t*)dhi, (const uint32_t*)dhl, h_padded_len, true,
                     (const uint32_t*)dqc, (const uint32_t*)dqi, (const uint32_t*)dql, win_off, win_len, n_win, max_win_len,
                     kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out, valid_kmax_out, dfwd, st,
-                    cc->copy, cc->ev[kMaxChunks + 1], cc->ev[kMaxChunks + 2]);
+                    cc->copy, cc->ev[kMaxChunks + 1], cc->ev[kMaxChunks + 2], tm);
 }
 
 int frisk_b200_run_host(const uint32_t* h_codes, const uint32_t* h_inv, const uint32_t* h_low, uint64_t h_padded_len,
@@ -2241,9 +2306,36 @@ int frisk_b200_run_resident(const uint32_t* d_h_codes, const uint32_t* d_h_inv, 
     std::lock_guard<std::mutex> lock(g_run_mu[dev_ & 63]);
     void* dfwd;
     if ((rc = ws_get(6, ((size_t)frisk_b200_table_size(1, kmax) + 1) * 8, &dfwd))) return rc;
+    RunMarks* tm = nullptr;
+    if ((rc = run_marks(&tm))) return rc;
+    if ((rc = mark(tm, kTmStart, (cudaStream_t)stream))) return rc;
     return run_tail(PeerArgs(), d_h_codes, d_h_inv, d_h_low, h_padded_len, false, d_q_codes, d_q_inv, d_q_low, win_off, win_len, n_win,
                     max_win_len, kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out,
-                    valid_kmax_out, dfwd, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+                    valid_kmax_out, dfwd, (cudaStream_t)stream, nullptr, nullptr, nullptr, tm);
+}
+
+// Stage times (ms) of the last frisk_b200_run_host / _sparse / _peers / _run_resident call on the current device,
+// from events recorded on its streams: [0] upload of the planes finished, [1] background count finished, [2] tables
+// finalised + genome IVOM table (multi-GPU: includes the wait for the peers' counters), [3] window kernel(s) finished,
+// [4] results on the host -- each since the start of the call -- and [5] = [4].  A mark the call did not set
+// (run_resident has no upload) reads -1.
+int frisk_b200_last_run_timing(float* ms, int cap, int* n) {
+    if (!ms || cap < 1) return FRISK_E_INVALID;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    RunMarks& m = g_marks[dev & 63];
+    if (!m.ready || !m.have[kTmStart] || !m.have[kTmEnd]) return FRISK_E_INVALID;
+    CK(cudaEventSynchronize(m.ev[kTmEnd]));
+    const int order[6] = {kTmUploaded, kTmCounted, kTmFinalised, kTmScored, kTmEnd, kTmEnd};
+    int k = 0;
+    for (; k < 6 && k < cap; ++k) {
+        ms[k] = -1.0f;
+        if (!m.have[order[k]]) continue;
+        if (order[k] == kTmUploaded) CK(cudaEventSynchronize(m.ev[kTmUploaded]));
+        CK(cudaEventElapsedTime(&ms[k], m.ev[kTmStart], m.ev[order[k]]));
+    }
+    if (n) *n = k;
+    return FRISK_OK;
 }
 
 int frisk_b200_release_workspace(void) {

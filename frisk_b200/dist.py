@@ -306,32 +306,43 @@ def _find(buf: np.ndarray, pat: bytes, lo: int, hi: int) -> int:
     return -1
 
 
-def score_fasta_sharded(fasta_text, group=None, device=None, fused: bool = True, **params):
+def score_fasta_sharded(fasta_text, group=None, device=None, fused: bool = True, local_text=None, row_names: bool = True,
+                        peers=None, **params):
     """Multi-GPU hot path from FASTA text with the INGEST sharded too: rank r uploads and tokenises only
     its byte range (split_fasta_text), counts and scores its own records against the background of all
     ranks (one exchange of the counters).  Returns this rank's HotPathResult with global tables/meta;
-    ``gather_rows_in_order`` puts the rows back in file order."""
+    ``gather_rows_in_order`` puts the rows back in file order.  ``local_text``: this rank's byte range when the
+    caller has already cut the text (a rank then never sees the rest of the file); works without a process group
+    (one GPU) too."""
     import torch
     import torch.distributed as dist
     from . import engine
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    multi = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if multi else (0, 1)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    buf = np.ascontiguousarray(fasta_text, dtype=np.uint8) if not isinstance(fasta_text, (bytes, bytearray)) else np.frombuffer(fasta_text, np.uint8)
-    a, b = split_fasta_text(buf, world)[rank]
-    dq = engine.DeviceGenome.from_fasta_bytes(buf[a:b], device)
+    if local_text is not None:
+        mine = np.ascontiguousarray(local_text, dtype=np.uint8)
+        a, b = 0, int(mine.shape[0])
+    else:
+        buf = np.ascontiguousarray(fasta_text, dtype=np.uint8) if not isinstance(fasta_text, (bytes, bytearray)) else np.frombuffer(fasta_text, np.uint8)
+        a, b = split_fasta_text(buf, world)[rank]
+        mine = buf[a:b]
+    dq = engine.DeviceGenome.from_fasta_bytes(mine, device)
     g = dq.host
-    space = global_genome_space(g.genome_space, device, group)
-    peers = PeerExchange(params.get("kmax", 8), device, group) if fused else None
-    pipe = engine.Pipeline(dq, device=device, allreduce=make_allreduce(group), genome_space=space, peers=peers, **params)
+    space = global_genome_space(g.genome_space, device, group) if world > 1 else g.genome_space
+    if peers is None and fused and world > 1:          # (a caller that runs many genomes passes its PeerExchange in)
+        peers = PeerExchange(params.get("kmax", 8), device, group)
+    pipe = engine.Pipeline(dq, device=device, allreduce=make_allreduce(group) if world > 1 else None, genome_space=space, peers=peers, **params)
     pipe.enqueue()
-    res = pipe.result()
+    res = pipe.result(names=row_names)
     res.collective = "fused peer sum (NVLink)" if pipe.peers is not None else "NCCL all-reduce"
     kmax = pipe.kmax
     possible = int(np.maximum(g.scaf_len.astype(np.int64) - kmax + 1, 0).sum())
     valid_global = possible - res.meta[1]              # finalised from the summed counters: already global
     meta = torch.tensor([res.meta[0], possible, res.meta[2]], dtype=torch.int64, device=device)
-    dist.all_reduce(meta, op=dist.ReduceOp.SUM, group=group)
+    if world > 1:
+        dist.all_reduce(meta, op=dist.ReduceOp.SUM, group=group)
     tot = [int(x) for x in meta.tolist()]
     res.meta = (tot[0], tot[1] - valid_global, tot[2])
     return res, (a, b)

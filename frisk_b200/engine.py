@@ -493,10 +493,13 @@ def _slice_orders(tab: np.ndarray, kmin: int, kmax: int) -> np.ndarray:
 
 
 def assemble(query: PackedGenome, host: PackedGenome, wins: WindowList, tables_1k: np.ndarray, valid_kmax: int,
-             rows: np.ndarray, status: np.ndarray, kmin: int, kmax: int, dump: Optional[np.ndarray] = None) -> HotPathResult:
+             rows: np.ndarray, status: np.ndarray, kmin: int, kmax: int, dump: Optional[np.ndarray] = None,
+             names: bool = True) -> HotPathResult:
+    """``names=False`` leaves the per-row name list empty (``row_scaf`` + ``scaf_names`` carry the same information
+    without a Python object per row: millions of rows of a fragmented assembly)."""
     keep = (status & _lib.ROW_EXCLUDED) == 0
     idx = np.nonzero(keep)[0]
-    names = [query.names[s] for s in wins.scaf[idx]]
+    names = [query.names[s] for s in wins.scaf[idx]] if names else []
     coords = np.stack([wins.start[idx], wins.stop[idx]], axis=1) if idx.size else np.zeros((0, 2), np.int64)
     meta = (host.total_len, host.ex_max(kmax, valid_kmax), host.nn_total)
     wt = None
@@ -571,8 +574,8 @@ class Pipeline:
         with torch.cuda.device(dev):
             st = _stream_ptr(dev)
             d_fwd = self.peers.local() if self.peers is not None else self.d_fwd
+            mark()                           # a step includes zeroing its counters
             d_fwd.zero_()
-            mark()
             dh = self.dh
             _lib.check(L.frisk_b200_background(_ptr(dh.codes), _ptr(dh.inv), _ptr(dh.low), self.bg_range[0], self.bg_range[1],
                                                self.kmax, int(self.mask_host), _ptr(d_fwd), st), "frisk_b200_background")
@@ -622,7 +625,7 @@ class Pipeline:
             torch.cuda.current_stream(dev).synchronize()
         return out
 
-    def result(self) -> HotPathResult:
+    def result(self, names: bool = True) -> HotPathResult:
         import torch
         torch.cuda.synchronize(self.device)
         tables = self.d_tables.cpu().numpy().view(np.uint64)
@@ -630,7 +633,7 @@ class Pipeline:
         status = self.d_status.cpu().numpy().view(np.uint32)
         dmp = self.d_dump.cpu().numpy().view(np.uint16) if self.d_dump is not None else None
         return assemble(self.query, self.host, self.wins, tables, int(self.d_valid.item()), rows, status,
-                        self.kmin, self.kmax, dmp)
+                        self.kmin, self.kmax, dmp, names=names)
 
 
 def run(query, host=None, kmin: int = 1, kmax: int = 8, w: int = 5000,
@@ -673,6 +676,101 @@ def run_sweep(query, kmaxes: Sequence[int] = tuple(range(1, 9)), kmin: int = 1, 
         valid = int(tables[_lib.table_size(1, k - 1) if k > 1 else 0:].sum()) // 2      # both strands were added
         out[k] = assemble(g, g, wins, tables, valid, d_rows.cpu().numpy(), d_status.cpu().numpy().view(np.uint32), kmin, k)
     return out
+
+
+class Sweep:
+    """BASELINE config C3 as a resident, replayable object: scores for kmax' = kmaxes (kmin fixed) from ONE counting pass
+    (see ``run_sweep``), every buffer allocated up front so that ``enqueue`` only launches: background at max(kmaxes),
+    [all-reduce], finalise, then per k' the genome IVOM table and the window kernel.  Multi-GPU (rank / world /
+    allreduce): every rank holds the whole genome, counts its slice of the base range and scores its slice of the
+    window list for every k' (the scheme of dist.score_balanced)."""
+
+    def __init__(self, query, kmaxes: Sequence[int] = tuple(range(1, 9)), kmin: int = 1, w: int = 5000, step: int = 2500,
+                 mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True, device="cuda:0", rank: int = 0,
+                 world: int = 1, allreduce=None):
+        import torch
+        from . import dist as fdist
+        _lib.require_device()
+        self.dq = query if isinstance(query, DeviceGenome) else DeviceGenome(query, device)
+        g = self.dq.host
+        self.kmaxes = sorted(set(int(k) for k in kmaxes if int(k) >= kmin))
+        self.kmin, self.mask_host, self.rip, self.top = kmin, mask_host, rip, max(self.kmaxes)
+        self.allreduce = allreduce
+        self.wins_all = g.windows(w, step, scaffolds_all)
+        a, b = fdist.split_windows(self.wins_all.length, world)[rank]
+        self.wins = self.wins_all.slice(a, b)
+        self.bg_range = fdist.split_base_range(g.padded_len, world)[rank] if world > 1 else (0, g.padded_len - 32)
+        dev = self.dq.device
+        self.device = dev
+        n = len(self.wins)
+        tsz = _lib.table_size(1, self.top)
+        self.d_fwd = torch.zeros(tsz, dtype=torch.int64, device=dev)
+        self.d_tables = torch.empty(tsz, dtype=torch.int64, device=dev)
+        self.d_valid = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.d_ig = {k: torch.empty(2 * 4 ** k, dtype=torch.float64, device=dev) for k in self.kmaxes}
+        self.d_rows = {k: torch.empty((n, 5), dtype=torch.float64, device=dev) for k in self.kmaxes}
+        self.d_status = {k: torch.empty(n, dtype=torch.int32, device=dev) for k in self.kmaxes}
+        self.d_off = torch.from_numpy(self.wins.off.view(np.int64)).to(dev)
+        self.d_len = torch.from_numpy(self.wins.length.view(np.int32)).to(dev)
+        self.launches = 0
+
+    def enqueue(self, marks=None) -> None:
+        import torch
+        L = _lib.lib()
+        dev, g, dq = self.device, self.dq.host, self.dq
+        n = len(self.wins)
+
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream(dev))
+                marks.append(ev)
+
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            mark()
+            self.d_fwd.zero_()
+            _lib.check(L.frisk_b200_background(_ptr(dq.codes), _ptr(dq.inv), _ptr(dq.low), self.bg_range[0], self.bg_range[1], self.top,
+                                               int(self.mask_host), _ptr(self.d_fwd), st), "frisk_b200_background")
+            if self.allreduce is not None:
+                self.allreduce(self.d_fwd, g.genome_space)
+            _lib.check(L.frisk_b200_finalize_tables(_ptr(self.d_fwd), self.top, 1, _ptr(self.d_tables), _ptr(self.d_valid), st),
+                       "frisk_b200_finalize_tables")
+            mark()
+            launches = 5                                   # count, reduce, totals, low, symmetrise
+            for k in self.kmaxes:
+                _lib.check(L.frisk_b200_genome_ivom(_ptr(self.d_tables), self.kmin, k, int(g.genome_space), _ptr(self.d_ig[k]), st),
+                           "frisk_b200_genome_ivom")
+                if n:
+                    _lib.check(L.frisk_b200_score(_ptr(dq.codes), _ptr(dq.inv), _ptr(dq.low), _ptr(self.d_off), _ptr(self.d_len), n,
+                                                  self.wins.max_len, _ptr(self.d_ig[k]), self.kmin, k, int(self.rip),
+                                                  _ptr(self.d_rows[k]), _ptr(self.d_status[k]), None, st), "frisk_b200_score")
+                launches += 2 + (1 if k >= 7 else 0)       # kmax 7, 8: + the (usually empty) hand-over launch
+                mark()
+            self.launches = launches
+
+    def checksums(self):
+        """Sum of the KLD scores of this rank's rows, per k' (N-independent after a sum over ranks)."""
+        import torch
+        out = []
+        for k in self.kmaxes:
+            ok = self.d_status[k] == 0
+            kld = self.d_rows[k][:, 0]
+            out.append(torch.where(ok, kld, torch.zeros_like(kld)).sum())
+        return torch.stack(out)
+
+    def results(self):
+        """{k': HotPathResult} of this rank's rows (the order-k' tables are the prefix of the top-order tables)."""
+        import torch
+        torch.cuda.synchronize(self.device)
+        g = self.dq.host
+        out = {}
+        for k in self.kmaxes:
+            tables = self.d_tables[:_lib.table_size(1, k)].cpu().numpy().view(np.uint64)
+            valid = int(tables[_lib.table_size(1, k - 1) if k > 1 else 0:].sum()) // 2      # both strands were added
+            out[k] = assemble(g, g, self.wins, tables, valid, self.d_rows[k].cpu().numpy(),
+                              self.d_status[k].cpu().numpy().view(np.uint32), self.kmin, k)
+        return out
 
 
 def run_host(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int = 1, kmax: int = 8, w: int = 5000,

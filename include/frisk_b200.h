@@ -327,6 +327,17 @@ int frisk_b200_fasta_records(const frisk_b200_fasta *h, uint64_t *name_off, uint
 int frisk_b200_fasta_pack(frisk_b200_fasta *h, uint32_t *d_codes, uint32_t *d_inv, uint32_t *d_low, void *stream);
 int frisk_b200_fasta_close(frisk_b200_fasta *h, void *stream);
 
+/* Stage times (ms since the start of the call) of the last frisk_b200_run_host / _sparse / _peers / _run_resident call
+ * on the current device, from CUDA events recorded on the call's own streams: ms[0] planes uploaded, ms[1] background
+ * counted, ms[2] tables + genome IVOM finalised (multi-GPU: includes the wait for the peers' counters), ms[3] window
+ * kernel(s) done, ms[4] = ms[5] results on the host.  -1 for a mark the call did not set.  *n = values written. */
+int frisk_b200_last_run_timing(float *ms, int cap, int *n);
+
+/* The window kernel frisk_b200_score launches for (kmin, kmax, longest window), spelled as profilers print it
+ * (e.g. "score_windows_nibble_kernel<8, 20, 0, 1>"): labels of profiles and bench lines come from the launcher's own
+ * selection, honouring frisk_b200_set_option. */
+int frisk_b200_score_kernel_name(int kmin, int kmax, uint32_t max_win_len, char *buf, uint64_t cap);
+
 /* Free the cached device workspace of frisk_b200_run_host on the current device. */
 int frisk_b200_release_workspace(void);
 
