@@ -143,9 +143,12 @@ int frisk_b200_fasta_scan(const char* text, uint64_t n, uint64_t cap, uint64_t* 
                 cur_body = nl ? j + 1 : n; cur_len = 0;
                 have = true;                         // a non-empty name is truthy
             } else if (have) {
-                // interior whitespace stays part of the reference's string; treat it as such only for
-                // spaces/tabs inside a line, which real FASTA never has: count non-space characters
-                for (uint64_t p = a; p < b; ++p) cur_len += !is_space(t[p]);
+                // The reference strips a line only at its ends (F:149): whitespace INSIDE a sequence line stays in its
+                // string and counts towards totalLen / nnTotal / window coordinates.  Real FASTA never has it; rather
+                // than silently shifting every coordinate after it, such input is refused.
+                for (uint64_t p = a; p < b; ++p)
+                    if (is_space(t[p])) return FRISK_E_FORMAT;
+                cur_len += b - a;
             }
             // sequence lines before the first header are dropped by the reference (name is None)
         }

@@ -269,6 +269,28 @@ fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __r
                 in_hdr = h;
             }
             const uint32_t c = cls_tab[byte_of(raw, k)];
+            if (MODE == 0 && c == 9u && !in_hdr && rec >= 1u && byte_of(raw, k) != '\n') {
+                // Whitespace in a sequence line: harmless at the ends (the reference strips them, F:149 -- every '\r' of a
+                // CRLF file lands here and is cleared by its two neighbours), refused INSIDE the line, where the
+                // reference keeps it as a character of the sequence (same rule as frisk_b200_fasta_scan).
+                bool before = false, after = false;
+                uint64_t p = i0 + k;
+                int s = 0;
+                for (; s < 4096 && p > 0; ++s) {
+                    const uint32_t b = t[--p];
+                    if (b == '\n') break;
+                    if (cls_tab[b] != 9u) { before = true; break; }
+                }
+                if (s == 4096) before = true;                          // a whitespace run this long is not a line ending
+                p = i0 + k;
+                for (s = 0; s < 4096 && p + 1 < n; ++s) {
+                    const uint32_t b = t[++p];
+                    if (b == '\n') break;
+                    if (cls_tab[b] != 9u) { after = true; break; }
+                }
+                if (s == 4096) after = true;
+                if (before && after) counters[3] = 1ull;
+            }
             if (!in_hdr && c != 9u && rec >= 1u) {
                 base_mask |= 1u << k;
                 ++cnt;
@@ -398,8 +420,8 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
         FRISK_CK(cudaMallocAsync((void**)&h->d_key, T, st));
         FRISK_CK(cudaMallocAsync((void**)&h->d_carry, T, st));
         FRISK_CK(cudaMallocAsync((void**)&h->d_base_in, T * 8, st));
-        FRISK_CK(cudaMallocAsync((void**)&h->d_counters, 3 * 8, st));
-        FRISK_CK(cudaMemsetAsync(h->d_counters, 0, 3 * 8, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_counters, 4 * 8, st));
+        FRISK_CK(cudaMemsetAsync(h->d_counters, 0, 4 * 8, st));
         fasta_lines_kernel<<<(unsigned)T, kTT, 0, st>>>(h->d_text, n, h->d_nhdr, h->d_key);
         fasta_scan1_kernel<<<1, kST, 0, st>>>(h->d_nhdr, h->d_key, T, h->d_rec_base, h->d_carry, h->d_counters);
         FRISK_CK(cudaGetLastError());
@@ -418,13 +440,14 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
         FRISK_CK(cudaGetLastError());
         h->seq_len.resize(n_rec);
         h->hdr_pos.resize(n_rec);
-        unsigned long long ctr[3] = {0, 0, 0};
+        unsigned long long ctr[4] = {0, 0, 0, 0};
         if (n_rec) {
             FRISK_CK(cudaMemcpyAsync(h->seq_len.data(), h->d_len, n_rec * 8, cudaMemcpyDeviceToHost, st));
             FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data(), h->d_hdr_pos, n_rec * 8, cudaMemcpyDeviceToHost, st));
         }
-        FRISK_CK(cudaMemcpyAsync(ctr, h->d_counters, 3 * 8, cudaMemcpyDeviceToHost, st));
+        FRISK_CK(cudaMemcpyAsync(ctr, h->d_counters, 4 * 8, cudaMemcpyDeviceToHost, st));
         FRISK_CK(cudaStreamSynchronize(st));
+        if (ctr[3]) return FRISK_E_FORMAT;                             // whitespace inside a sequence line
         h->stats[1] = ctr[1];
         h->stats[2] = ctr[2];
     }

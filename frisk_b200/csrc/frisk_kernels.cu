@@ -2030,6 +2030,16 @@ struct PeerArgs {
     uint64_t epoch = 0;
 };
 
+// A window list that points outside the planes would become an illegal-address fault (and a sticky context error) in the
+// score kernel; the arrays are host memory here, so check them: O(n), ~1 ns per window.
+static int check_windows(const uint64_t* win_off, const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len, uint64_t padded_len) {
+    for (uint64_t i = 0; i < n_win; ++i) {
+        const uint64_t l = win_len[i];
+        if (l == 0 || l > max_win_len || win_off[i] > padded_len || l > padded_len - win_off[i]) return FRISK_E_INVALID;
+    }
+    return FRISK_OK;
+}
+
 static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* dhi, const uint32_t* dhl, uint64_t h_padded_len, bool bg_enqueued,
                     const uint32_t* dqc, const uint32_t* dqi, const uint32_t* dql, const uint64_t* win_off,
                     const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host,
@@ -2158,7 +2168,31 @@ static int upload_inv(const HostPlanes& hp, void* d_inv, int slot_idx, int slot_
     return FRISK_OK;
 }
 
+static int run_host_body(const PeerArgs& peers, const HostPlanes& h, const HostPlanes& q, bool same, const uint64_t* win_off, const uint32_t* win_len,
+                         uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host, int want_rip,
+                         int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
+                         uint64_t* valid_kmax_out, void* stream);
+
+// On an error the copies and kernels already queued still target the caller's (pinned) buffers: drain both streams
+// before handing control -- and with it the right to free those buffers -- back.
 static int run_host_impl(const PeerArgs& peers, const HostPlanes& h, const HostPlanes& q, bool same, const uint64_t* win_off, const uint32_t* win_len,
+                         uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host, int want_rip,
+                         int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
+                         uint64_t* valid_kmax_out, void* stream) {
+    const int rc = run_host_body(peers, h, q, same, win_off, win_len, n_win, max_win_len, kmin, kmax, mask_host, want_rip, genome_space,
+                                 rows_out, status_out, tables_out, valid_kmax_out, stream);
+    if (rc != FRISK_OK && rc != FRISK_E_INVALID && rc != FRISK_E_NO_DEVICE && rc != FRISK_E_UNSUPPORTED) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) {
+            cudaStreamSynchronize((cudaStream_t)stream);
+            if (g_copy[dev & 63].copy) cudaStreamSynchronize(g_copy[dev & 63].copy);
+        }
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int run_host_body(const PeerArgs& peers, const HostPlanes& h, const HostPlanes& q, bool same, const uint64_t* win_off, const uint32_t* win_len,
                          uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host, int want_rip,
                          int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
                          uint64_t* valid_kmax_out, void* stream) {
@@ -2169,6 +2203,7 @@ static int run_host_impl(const PeerArgs& peers, const HostPlanes& h, const HostP
     if (n_win && (!win_off || !win_len || !rows_out || !status_out)) return FRISK_E_INVALID;
     int rc = check_k(kmin, kmax);
     if (rc) return rc;
+    if ((rc = check_windows(win_off, win_len, n_win, max_win_len, q_padded_len))) return rc;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
     int dev_ = 0;
     CK(cudaGetDevice(&dev_));
@@ -2300,6 +2335,7 @@ int frisk_b200_run_resident(const uint32_t* d_h_codes, const uint32_t* d_h_inv, 
     if (n_win && (!win_off || !win_len || !rows_out || !status_out)) return FRISK_E_INVALID;
     int rc = check_k(kmin, kmax);
     if (rc) return rc;
+    if ((rc = check_windows(win_off, win_len, n_win, max_win_len, q_padded_len))) return rc;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
     int dev_ = 0;
     CK(cudaGetDevice(&dev_));
@@ -2309,9 +2345,11 @@ int frisk_b200_run_resident(const uint32_t* d_h_codes, const uint32_t* d_h_inv, 
     RunMarks* tm = nullptr;
     if ((rc = run_marks(&tm))) return rc;
     if ((rc = mark(tm, kTmStart, (cudaStream_t)stream))) return rc;
-    return run_tail(PeerArgs(), d_h_codes, d_h_inv, d_h_low, h_padded_len, false, d_q_codes, d_q_inv, d_q_low, win_off, win_len, n_win,
-                    max_win_len, kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out,
-                    valid_kmax_out, dfwd, (cudaStream_t)stream, nullptr, nullptr, nullptr, tm);
+    rc = run_tail(PeerArgs(), d_h_codes, d_h_inv, d_h_low, h_padded_len, false, d_q_codes, d_q_inv, d_q_low, win_off, win_len, n_win,
+                  max_win_len, kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out,
+                  valid_kmax_out, dfwd, (cudaStream_t)stream, nullptr, nullptr, nullptr, tm);
+    if (rc) { cudaStreamSynchronize((cudaStream_t)stream); cudaGetLastError(); }   // queued copies still target the caller's buffers
+    return rc;
 }
 
 // Stage times (ms) of the last frisk_b200_run_host / _sparse / _peers / _run_resident call on the current device,

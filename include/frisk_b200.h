@@ -68,7 +68,10 @@ uint64_t frisk_b200_table_size(int kmin, int kmax);
  * frisk_b200_fasta_scan: one pass over FASTA text, replaces iterFasta's record splitting
  * (F:148-163).  Record i has its name at text[name_off[i] .. name_off[i]+name_len[i]) (first
  * whitespace token after stripping '>' characters, F:156), its sequence lines inside
- * text[body_off[i] .. body_end[i]) and seq_len[i] bases after whitespace is stripped.
+ * text[body_off[i] .. body_end[i]) and seq_len[i] characters after the line ends are stripped.  Whitespace INSIDE a
+ * sequence line -- which the reference keeps as a character of the sequence (F:149 strips only the ends) and real
+ * FASTA never has -- is refused with FRISK_E_FORMAT, here and in frisk_b200_fasta_open, instead of silently shifting
+ * every coordinate behind it.
  * Outputs may be NULL to only count.  *n_records always receives the record count;
  * FRISK_E_CAPACITY if cap is too small.
  */

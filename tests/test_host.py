@@ -69,6 +69,35 @@ def test_pack_round_trip_and_stats():
     assert np.all(g.inv[-4:] == 0xFFFFFFFF)
 
 
+def test_window_list_outside_the_planes_is_refused():
+    """A window that reaches beyond the packed planes (or is longer than the declared maximum) would fault inside the
+    score kernel; the one-call entry points check the (host-side) list first and return FRISK_E_INVALID."""
+    g = engine.PackedGenome.from_scaffolds(synth.make("edge"))
+    wins = g.windows()
+    out = engine.HostOutputs(len(wins), 8, pinned=False)
+    for mutate in (lambda w: w.off.__setitem__(3, np.uint64(g.padded_len - 100)),      # runs past the end
+                   lambda w: w.off.__setitem__(0, np.uint64(2 ** 63)),                  # wrapped offset
+                   lambda w: w.length.__setitem__(5, np.uint32(0))):
+        bad = engine.WindowList(wins.off.copy(), wins.length.copy(), wins.scaf, wins.start, wins.stop)
+        mutate(bad)
+        P = engine._ptr
+        rc = _lib.lib().frisk_b200_run_host(P(g.codes), P(g.inv), P(g.low), g.padded_len, P(g.codes), P(g.inv), P(g.low), g.padded_len,
+                                            P(bad.off), P(bad.length), len(bad), wins.max_len, 1, 8, 0, 1, g.genome_space,
+                                            P(out.rows), P(out.status), P(out.tables), P(out.valid), None)
+        assert rc == _lib.E_INVALID                      # (checked before any device work: also without a GPU)
+
+
+def test_whitespace_inside_a_sequence_line_is_refused():
+    """F:149 strips a line only at its ends; interior whitespace would be part of the reference's sequence string.
+    The scanner refuses it (FRISK_E_FORMAT) rather than dropping it and shifting every later coordinate."""
+    for text in (b">a\nAC GT\n", b">a\nACGT\n>b\nAC\tGT\n", b">a\nAC\rGT\n"):
+        with pytest.raises(_lib.FriskError) as ei:
+            engine.PackedGenome.from_fasta_bytes(text)
+        assert ei.value.code == _lib.E_FORMAT
+    g = engine.PackedGenome.from_fasta_bytes(b"junk with spaces\n>a\n  ACGT \t \r\n\tGG\r\n   \n>b x y\nAC\n")
+    assert g.names == ["a", "b"] and list(g.scaf_len) == [6, 2]
+
+
 def test_no_lowercase_means_no_low_plane():
     g = engine.PackedGenome.from_scaffolds(synth.make("C1", 0.004))
     assert g.low is None and g.n_lower == 0 and g.nn_total == 0

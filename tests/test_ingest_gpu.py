@@ -46,7 +46,7 @@ def test_reference_scanning_rules():
             b">>seq1 description words\nACGT\n  \nacgtNN\r\n"
             b">seq2\tother\n\nAC\nGT\n"
             b">empty_record\n"
-            b"  >indented_header x\n AC GT \n"
+            b"  >indented_header x\n ACGT \t\n"
             b">last\nTT>TT")
     g = assert_same_genome(text)
     assert g.names == ["seq1", "seq2", "empty_record", "indented_header", "last"]
@@ -95,6 +95,22 @@ def test_fuzzed_texts():
         if trial % 4 == 1:
             text = text.rstrip(b"\r\n")
         assert_same_genome(text)
+
+
+@pytest.mark.parametrize("text", [b">a\nAC GT\n", b">a\nACGT\n>b\nAC\tGT\nAA\n", b">a\n" + b"ACGT" * 2000 + b"\rA\n",
+                                  b">a\n" + b"A" * 4090 + b"  \t  C\n", b">a\nAC" + b" " * 6000 + b"GT\n"])
+def test_whitespace_inside_a_sequence_line_is_refused(text):
+    """The reference strips a line only at its ends (F:149): whitespace INSIDE a sequence line would be a character of
+    its sequence (counted in totalLen, nnTotal and every coordinate after it).  Host scanner and device ingest both
+    refuse such text instead of silently deviating; whitespace at the ends of lines (CRLF, indentation) is fine."""
+    from frisk_b200 import engine
+    with pytest.raises(_lib.FriskError) as ei:
+        engine.DeviceGenome.from_fasta_bytes(text)
+    assert ei.value.code == _lib.E_FORMAT
+    with pytest.raises(_lib.FriskError) as ei:
+        engine.PackedGenome.from_fasta_bytes(text)
+    assert ei.value.code == _lib.E_FORMAT
+    assert_same_genome(b">a\n  ACGT \t \r\n\tGG\r\n" + b" " * 5000 + b"\n>b x y\nAC\n")
 
 
 def test_empty_and_malformed_inputs():
