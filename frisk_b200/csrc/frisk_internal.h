@@ -53,6 +53,11 @@ int score_nibble(const uint32_t* codes, const uint32_t* inv, const uint32_t* low
                  const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
                  double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st);
 int score_nibble_occupancy(int K, uint32_t max_len, int* ctas_per_sm, int* threads_per_cta);
+// the k sweep (BASELINE config C3): rows of kmax' = 1..8, kmin 1, from one pass over every window; ig / rows / status are
+// HOST arrays of 8 device pointers
+int score_sweep(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off, const uint32_t* win_len,
+                uint64_t n_win, uint32_t max_len, const double* const* ig, int want_rip, double* const* rows,
+                uint32_t* const* status, cudaStream_t st);
 
 }  // namespace frisk_internal
 

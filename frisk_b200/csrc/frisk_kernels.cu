@@ -1202,7 +1202,8 @@ __global__ void __launch_bounds__(kT3, 6)
 score_windows_small_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                            const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
                            const double2* __restrict__ ig, int kmin, int want_rip,
-                           double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
+                           double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump,
+                           const uint32_t* __restrict__ redo_src) {
     using L = SmallLayout<K>;
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem);
@@ -1224,6 +1225,8 @@ score_windows_small_kernel(const uint32_t* __restrict__ codes, const uint32_t* _
     __syncthreads();
 
     for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x) {
+        // second launch behind the k sweep (frisk_nibble.cu): only the windows it handed over
+        if (redo_src && !(redo_src[win] & frisk_internal::kRowRedo)) continue;
         const uint64_t o = win_off[win];
         const uint32_t len = win_len[win];
         const uint32_t o_lo = (uint32_t)(o & 31);
@@ -1640,7 +1643,7 @@ int launch_score_bucket_redo(const uint32_t* codes, const uint32_t* inv, const u
 template <int K>
 int launch_score_small(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                        const uint32_t* win_len, uint64_t n_win, const double* ig, int kmin, int want_rip,
-                       double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+                       double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, const uint32_t* redo_src = nullptr) {
     using L = SmallLayout<K>;
     auto launch = [&](auto kern) -> int {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
@@ -1653,7 +1656,7 @@ int launch_score_small(const uint32_t* codes, const uint32_t* inv, const uint32_
         if (grid > n_win) grid = n_win;
         kern<<<(unsigned)grid, kT3, L::TOTAL, st>>>(codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len,
                                                     (uint32_t)n_win, reinterpret_cast<const double2*>(ig), kmin, want_rip, rows,
-                                                    status, dump);
+                                                    status, dump, redo_src);
         CK(cudaGetLastError());
         return FRISK_OK;
     };
@@ -1714,6 +1717,13 @@ int frisk_internal::score_bucket_redo(const uint32_t* codes, const uint32_t* inv
     if (max_len > kBuf3 - 6u || !redo_src) return FRISK_E_UNSUPPORTED;
     if (K == 8) return launch_score_bucket_redo<8>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo_src, st);
     if (K == 7) return launch_score_bucket_redo<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo_src, st);
+    // the k sweep hands a window over for EVERY kmax': 4..6 on the bucketed kernel too, 1..3 on the small-K kernel
+    if (K == 6) return launch_score_bucket_redo<6>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo_src, st);
+    if (K == 5) return launch_score_bucket_redo<5>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo_src, st);
+    if (K == 4) return launch_score_bucket_redo<4>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo_src, st);
+    if (K == 3) return launch_score_small<3>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, st, redo_src);
+    if (K == 2) return launch_score_small<2>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, st, redo_src);
+    if (K == 1) return launch_score_small<1>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, st, redo_src);
     return FRISK_E_UNSUPPORTED;
 }
 
@@ -1901,6 +1911,16 @@ int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint3
     }
     DISPATCH_K(kmax, launch_score<K>(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, rip,
                                      d_rows, d_status, d_dump, st));
+}
+
+int frisk_b200_score_sweep(const uint32_t* d_codes, const uint32_t* d_inv, const uint32_t* d_low, const uint64_t* d_win_off,
+                           const uint32_t* d_win_len, uint64_t n_win, uint32_t max_win_len, const double* const* d_ig, int kmax,
+                           int want_rip, double* const* d_rows, uint32_t* const* d_status, void* stream) {
+    if (n_win == 0) return FRISK_OK;
+    if (!d_codes || !d_inv || !d_win_off || !d_win_len || !d_ig || !d_rows || !d_status) return FRISK_E_INVALID;
+    if (kmax != 8 || max_win_len > kBuf3 - 6u || n_win > 0xffffffffull) return FRISK_E_UNSUPPORTED;
+    return frisk_internal::score_sweep(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, want_rip, d_rows, d_status,
+                                       (cudaStream_t)stream);
 }
 
 int frisk_b200_score_occupancy(int kmax, uint32_t max_win_len, int* ctas_per_sm, int* threads_per_cta) {

@@ -44,6 +44,7 @@ struct NibSmem {
     double red[3][kNT / 32];
     int cnt[2][6];                    // [window parity][n_non, n_gc, full K-words counted, n_side, sum of all nibbles, -]
     uint32_t c2[16];                  // final dinucleotide counts (RIP, and the way up to order 1)
+    uint32_t c1[4];                   // sweep: final base counts
     uint32_t side[kSideCap];          // v << 16 | code of a word valid for v = K-1 or K-2 bases only
 };
 
@@ -120,16 +121,27 @@ template <typename MT> __device__ __forceinline__ MT top_bits(int n) {       // 
 #define FRISK_NIBBLE_CTAS 4
 #endif
 
+// The k sweep of BASELINE config C3 (scores for kmax' = 1..K with kmin = 1, i.e. K reference runs `-m 1 -k k'`, F:1197-1206)
+// from ONE pass over the window: the counts of every order are there after the marginalisation, so the SWEEP
+// instantiation evaluates all K scores -- kmax' <= K-2 by walking that order's bins (coalesced genome-IVOM reads),
+// K-1 and K per position with weights 1/c -- and writes K rows per window.
+struct NibSweep {
+    const double2* ig[8];             // genome IVOM table of kmax' = i + 1
+    double* rows[8];
+    uint32_t* status[8];
+};
+
 // PP = positions per thread: a thread owns ONE chunk of cs <= PP consecutive positions of the window
 // (cs = the window length spread over the CTA, a multiple of 4), reads the three or four code words and two or three
 // mask words that cover it once, and issues the atomics of its full K-words back to back from registers.
-template <int K, int PP, bool DUMP, bool ALLK>
+template <int K, int PP, bool DUMP, bool ALLK, bool SWEEP = false>
 __global__ void __launch_bounds__(kNT, FRISK_NIBBLE_CTAS)
 score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                             const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
                             const double2* __restrict__ ig, int kmin_arg, int want_rip,
                             double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump,
-                            uint32_t* redo_dst) {
+                            uint32_t* redo_dst, const NibSweep sw) {
+    static_assert(!SWEEP || (K == 8 && ALLK && !DUMP && NIB_PRE5), "the sweep instantiation: K = 8, kmin = 1");
     using L = NibLayout<K>;
     static_assert(PP % 4 == 0 && PP >= 4 && PP + K - 1 <= 64, "chunk size");
     constexpr int A = L::A, LP = L::LP, NT = kNT, NW = NT / 32;
@@ -276,7 +288,13 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         uint16_t* dmp = DUMP ? dump + (size_t)win * lvl_off(K + 1) : nullptr;
         if (excluded) {
             for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-            if (tid == 0) {
+            if (SWEEP) {
+                if (tid < K) {
+                    sw.status[tid][win] = FRISK_ROW_EXCLUDED;
+                    for (int c = 0; c < 5; ++c) sw.rows[tid][(size_t)win * 5 + c] = CUDART_NAN;
+                }
+                if (tid == 0) redo_dst[win] = 0;
+            } else if (tid == 0) {
                 status[win] = FRISK_ROW_EXCLUDED;
                 for (int c = 0; c < 5; ++c) rows[(size_t)win * 5 + c] = CUDART_NAN;
                 if (redo_dst != status) redo_dst[win] = 0;
@@ -314,7 +332,7 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
         __syncthreads();                                                   // (1b)
         if (ss.cnt[par][4] != ss.cnt[par][2] || n_side > kSideCap) {        // a nibble wrapped / too many cut words
             for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-            if (tid == 0) redo_dst[win] = kRowRedo;                        // the bucketed kernel takes this window
+            if (tid == 0) redo_dst[win] = kRowRedo;                        // the bucketed kernel takes this window (sweep: per kmax')
             __syncthreads();
             continue;
         }
@@ -356,6 +374,12 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                 }
             }
             pre[tid] = make_double2(num, __hiloint2double((int)flag4, (int)den));
+            if (SWEEP) {                                                   // the bin walks of kmax' <= 4 read the TOTALS
+                tab16[lvl_off(4) + tid] = (uint16_t)c4;
+                if ((tid & 3) == 0) tab16[lvl_off(3) + (tid >> 2)] = (uint16_t)c3;
+                if ((tid & 15) == 0) tab16[lvl_off(2) + (tid >> 4)] = (uint16_t)c2;
+                if ((tid & 63) == 0) ss.c1[tid >> 6] = c1;                 // (its table entry is still being read by the others)
+            }
             if (DUMP) {
                 dmp[lvl_off(4) + tid] = (uint16_t)c4;
                 if ((tid & 3) == 0) dmp[lvl_off(3) + (tid >> 2)] = (uint16_t)c3;
@@ -396,6 +420,178 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                     else dmp[lvl_off(K - 2) + code] += 1;
                 }
             }
+        }
+
+        if constexpr (SWEEP) {
+            // ======== all K scores of this window (kmax' = 1..K, kmin = 1) ========
+            double (*sred)[3][NW] = reinterpret_cast<double (*)[3][NW]>(pre);   // [kmax' - 1][sum][warp]; `pre` is dead after the kmax' = 4 walk
+            auto warp_store = [&](int ks, double a, double b, double c) {
+#pragma unroll
+                for (int ofs = 16; ofs; ofs >>= 1) {
+                    a += __shfl_xor_sync(kFull, a, ofs); b += __shfl_xor_sync(kFull, b, ofs); c += __shfl_xor_sync(kFull, c, ofs);
+                }
+                if (lane == 0) { sred[ks][0][warp] = a; sred[ks][1][warp] = b; sred[ks][2][warp] = c; }
+            };
+            auto accum = [&](double num, uint32_t den, const double2 g, double& a, double& b, double& c) {
+                const double iw = div_pos(num, u32_to_double(den));
+                a += iw; b += g.x; c = fma(iw, log2_series(iw) - g.y, c);
+            };
+            // kmax' = 4: one bin per thread, straight from `pre`; its sums wait in registers for the barrier that retires `pre`
+            double w4 = 0.0, g4 = 0.0, t4 = 0.0;
+            if (tab16[lvl_off(4) + tid]) {
+                const double2 pp = pre[tid];
+                accum(pp.x, (uint32_t)__double2loint(pp.y), __ldg(sw.ig[3] + tid), w4, g4, t4);
+            }
+            __syncthreads();                                               // (3c)
+            warp_store(3, w4, g4, t4);
+            // kmax' = 1..3: from the totals
+#pragma unroll
+            for (int kq = 1; kq <= 3; ++kq) {
+                double a = 0.0, b = 0.0, c = 0.0;
+                if ((uint32_t)tid < pow4(kq)) {
+                    double num = 0.0;
+                    uint32_t den = 0, ck = 0;
+#pragma unroll
+                    for (int x = 1; x <= kq; ++x) {
+                        const uint32_t idx = (uint32_t)tid >> (2 * (kq - x));
+                        ck = x == 1 ? ss.c1[idx] : (uint32_t)tab16[lvl_off(x) + idx];
+                        den += ck << (2 * x);
+                        num = fma(ss.q[x - 1], u32_to_double(ck * ck), num);
+                    }
+                    if (ck) accum(num, den, __ldg(sw.ig[kq - 1] + tid), a, b, c);
+                }
+                warp_store(kq - 1, a, b, c);
+            }
+            // kmax' = 5: the folded pair of every occupied order-5 bin
+            {
+                double a = 0.0, b = 0.0, c = 0.0;
+                for (uint32_t bin = tid; bin < pow4(5); bin += NT) {
+                    if (tab16[lvl_off(5) + bin] & 0x7fffu) {
+                        const double2 pp = preA[bin];
+                        accum(pp.x, (uint32_t)__double2loint(pp.y), __ldg(sw.ig[4] + bin), a, b, c);
+                    }
+                }
+                warp_store(4, a, b, c);
+            }
+            const double q6 = ss.q[5], q7 = ss.q[6], q8 = ss.q[7];
+            // the words cut at 7 / 6 bases (side list) that fall below a bucket / a quarter
+            auto side_counts = [&](uint32_t bucket, uint32_t code7, uint32_t& c6, uint32_t& c7) {
+                for (uint32_t i = 0; i < n_side; ++i) {
+                    const uint32_t e = ss.side[i], sv = e >> 16, code = e & 0xffffu;
+                    if (sv == 7u) { c7 += (code == code7); c6 += ((code >> 2) == bucket); }
+                    else c6 += (code == bucket);
+                }
+            };
+            // kmax' = 6: one bucket = one 6-mer
+            {
+                double a = 0.0, b = 0.0, c = 0.0;
+                for (uint32_t bk = tid; bk < L::NBK; bk += NT) {
+                    const uint2 v = nib64[bk];
+                    uint32_t c6 = __dp4a(nib_pairs(v.x) + nib_pairs(v.y), 0x01010101u, 0u), c7 = 0;
+                    const double2 pp = preA[bk >> 2];
+                    if (__double2hiint(pp.y)) side_counts(bk, 0xffffffffu, c6, c7);
+                    if (c6) accum(fma(q6, u32_to_double(c6 * c6), pp.x), (uint32_t)__double2loint(pp.y) + (c6 << 12), __ldg(sw.ig[5] + bk), a, b, c);
+                }
+                warp_store(5, a, b, c);
+            }
+            // kmax' = 7 and 8: every position, weights 1 / c7 and 1 / c8
+            double w7 = 0.0, g7 = 0.0, t7 = 0.0, w8 = 0.0, g8 = 0.0, t8 = 0.0;
+            auto weighted = [&](double num, uint32_t den, uint32_t cnt, const double2 g, double& a, double& b, double& c) {
+                const double dden = u32_to_double(den), dc = u32_to_double(cnt);
+                const double D = dden * dc;
+                double r;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(D));
+                r = fma(r, fma(-D, r, 1.0), r);
+                r = fma(r, fma(-D, r, 1.0), r);
+                double x = num * r;
+                x = fma(fma(-D, x, num), r, x);                            // I_w / cnt
+                a += x;
+                b = fma(g.x, dden * r, b);                                 // I_g / cnt
+                c = fma(x, log2_series(x * dc) - g.y, c);
+            };
+            auto eval7 = [&](uint32_t code7, const uint2 v, const double2 pp, uint32_t c6, uint32_t c7) {
+                weighted(fma(q7, u32_to_double(c7 * c7), fma(q6, u32_to_double(c6 * c6), pp.x)),
+                         (uint32_t)__double2loint(pp.y) + (c6 << 12) + (c7 << 14), c7, NIB_GATHER(sw.ig[6] + code7), w7, g7, t7);
+                (void)v;
+            };
+            {
+                const int rounds = (int)(cs >> 2);
+#pragma unroll 1
+                for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (vm & (MT(1) << (MB - 1 - j))) {
+                            const uint32_t kap = (kk[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                            const double2 gg8 = NIB_GATHER(sw.ig[7] + kap);
+                            const uint2 v = nib64[kap >> 4];
+                            const uint32_t ws = (kap & 8u) ? v.y : v.x, wo = (kap & 8u) ? v.x : v.y;
+                            const uint32_t c8 = (ws >> ((kap & 7u) * 4u)) & 15u;
+                            const uint32_t ps = nib_pairs(ws);
+                            const uint32_t hs = ps >> ((kap & 4u) * 4u);
+                            uint32_t c7 = (hs & 0xffu) + ((hs >> 8) & 0xffu);
+                            uint32_t c6 = __dp4a(ps + nib_pairs(wo), 0x01010101u, 0u);
+                            const double2 pp = preA[kap >> 6];
+                            if (__double2hiint(pp.y)) side_counts(kap >> 4, kap >> 2, c6, c7);
+                            eval7(kap >> 2, v, pp, c6, c7);
+                            const double n7 = fma(q7, u32_to_double(c7 * c7), fma(q6, u32_to_double(c6 * c6), pp.x));
+                            weighted(fma(q8, u32_to_double(c8 * c8), n7), (uint32_t)__double2loint(pp.y) + (c6 << 12) + (c7 << 14) + (c8 << 16), c8, gg8,
+                                     w8, g8, t8);
+                        }
+                    }
+                    vm <<= 4;
+#pragma unroll
+                    for (int i = 0; i + 2 < PP / 2; ++i) kk[i] = kk[i + 2];
+                }
+            }
+            if ((uint32_t)tid < n_side) {                                  // a word of exactly 7 bases is an occurrence of its 7-mer too
+                const uint32_t e = ss.side[tid];
+                if ((e >> 16) == 7u) {
+                    const uint32_t code7 = e & 0xffffu, bk = code7 >> 2;
+                    const uint2 v = nib64[bk];
+                    const uint32_t h = ((code7 & 2u) ? v.y : v.x) >> ((code7 & 1u) * 16u);
+                    uint32_t c7 = (h & 15u) + ((h >> 4) & 15u) + ((h >> 8) & 15u) + ((h >> 12) & 15u);
+                    uint32_t c6 = __dp4a(nib_pairs(v.x) + nib_pairs(v.y), 0x01010101u, 0u);
+                    side_counts(bk, code7, c6, c7);
+                    eval7(code7, v, preA[bk >> 2], c6, c7);
+                }
+            }
+            warp_store(6, w7, g7, t7);
+            warp_store(7, w8, g8, t8);
+            __syncthreads();                                               // (4) everyone is done with the tables
+            for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+            if (warp == 0) {                                               // lane i finalises the row of kmax' = i + 1
+                const int kq = lane < K ? lane + 1 : K;
+                double a = 0, bsum = 0, c = 0;
+                for (int w = 0; w < NW; ++w) { a += sred[kq - 1][0][w]; bsum += sred[kq - 1][1][w]; c += sred[kq - 1][2][w]; }
+                uint32_t st = 0;
+                double kld = 0.0;
+                if (!(a == 0.0)) {
+                    bool zd = bsum != bsum;
+                    for (int x = 1; x <= kq; ++x) zd |= ((long long)n_up - (long long)(x - 1)) == 0;
+                    if (zd) { st |= FRISK_ROW_KLD_ZERODIV; kld = CUDART_NAN; }
+                    else {
+                        kld = c / a + (log2(bsum) - log2(a));
+                        if (!(kld == kld) || isinf(kld)) st |= FRISK_ROW_LOG_DOMAIN;
+                    }
+                }
+                double gcv = CUDART_NAN;
+                if (n_up == 0) st |= FRISK_ROW_GC_ZERODIV; else gcv = (double)n_gc / (double)n_up;
+                double pi = CUDART_NAN, si = CUDART_NAN, cri = CUDART_NAN;
+                if (want_rip && kq >= 2) {
+                    const uint32_t n_at = ss.c2[1], n_ta = ss.c2[4], n_sub = ss.c2[3] + ss.c2[9], n_prod = ss.c2[12] + ss.c2[6];
+                    if (n_at > 0) pi = (double)n_ta / (double)n_at;
+                    if (n_sub > 0) si = (double)n_prod / (double)n_sub;
+                    if (pi != 0.0 && si != 0.0) cri = pi - si;
+                }
+                if (lane < K) {
+                    double* row = sw.rows[lane] + (size_t)win * 5;
+                    row[0] = kld; row[1] = gcv; row[2] = pi; row[3] = si; row[4] = cri;
+                    sw.status[lane][win] = st;
+                }
+                if (lane == 0) redo_dst[win] = 0;
+            }
+            __syncthreads();                                               // (5)
+            continue;
         }
 
         // ---- P3: every position scores its own K-mer with weight 1 / (its count) --------------------
@@ -546,7 +742,27 @@ int launch_nibble4(const uint32_t* codes, const uint32_t* inv, const uint32_t* l
     if (grid > n_win) grid = n_win;
     kern<<<(unsigned)grid, kNT, L::TOTAL, st>>>(codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len,
                                                 (uint32_t)n_win, reinterpret_cast<const double2*>(ig), kmin, want_rip, rows,
-                                                status, dump, redo_dst);
+                                                status, dump, redo_dst, NibSweep());
+    CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+template <int PP>
+int launch_sweep(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off, const uint32_t* win_len,
+                 uint64_t n_win, const NibSweep& sw, int want_rip, uint32_t* redo_dst, cudaStream_t st) {
+    using L = NibLayout<8>;
+    auto kern = score_windows_nibble_kernel<8, PP, false, true, true>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, L::TOTAL));
+    if (per_sm < 1) per_sm = 1;
+    const int sms = frisk_internal::sm_count_cached();
+    if (sms <= 0) return FRISK_E_NO_DEVICE;
+    uint64_t grid = (uint64_t)sms * (uint64_t)per_sm;
+    if (grid > n_win) grid = n_win;
+    kern<<<(unsigned)grid, kNT, L::TOTAL, st>>>(codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len,
+                                                (uint32_t)n_win, nullptr, 1, want_rip, nullptr, nullptr, nullptr, redo_dst, sw);
     CK(cudaGetLastError());
     return FRISK_OK;
 }
@@ -610,4 +826,30 @@ int frisk_internal::score_nibble_occupancy(int K, uint32_t max_len, int* ctas_pe
     if (K == 8) return launch_nibble<8>(nullptr, nullptr, nullptr, nullptr, nullptr, 1, max_len, nullptr, 1, 0, nullptr, nullptr, nullptr, nullptr, 0, ctas_per_sm);
     if (K == 7) return launch_nibble<7>(nullptr, nullptr, nullptr, nullptr, nullptr, 1, max_len, nullptr, 1, 0, nullptr, nullptr, nullptr, nullptr, 0, ctas_per_sm);
     return FRISK_E_UNSUPPORTED;
+}
+
+// The k sweep: rows of kmax' = 1..8 (kmin 1) for every window from one pass (see NibSweep).  A window the 4-bit counters
+// cannot hold is handed, for every kmax', to the kernel that serves that kmax' on its own.
+int frisk_internal::score_sweep(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                                const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* const* ig, int want_rip,
+                                double* const* rows, uint32_t* const* status, cudaStream_t st) {
+    if (max_len > kNT * 32u || max_len > 8186u) return FRISK_E_UNSUPPORTED;
+    NibSweep sw;
+    for (int k = 0; k < 8; ++k) {
+        if (!ig[k] || !rows[k] || !status[k]) return FRISK_E_INVALID;
+        sw.ig[k] = reinterpret_cast<const double2*>(ig[k]); sw.rows[k] = rows[k]; sw.status[k] = status[k];
+    }
+    int rc = pool_ready();
+    if (rc) return rc;
+    uint32_t* redo = nullptr;
+    CK(cudaMallocAsync((void**)&redo, n_win * sizeof(uint32_t), st));
+    if (max_len <= kNT * 8u) rc = launch_sweep<8>(codes, inv, low, win_off, win_len, n_win, sw, want_rip, redo, st);
+    else if (max_len <= kNT * 20u) rc = launch_sweep<20>(codes, inv, low, win_off, win_len, n_win, sw, want_rip, redo, st);
+    else rc = launch_sweep<32>(codes, inv, low, win_off, win_len, n_win, sw, want_rip, redo, st);
+    for (int k = 1; k <= 8 && !rc; ++k)
+        rc = score_bucket_redo(codes, inv, low, win_off, win_len, n_win, max_len, ig[k - 1], 1, k, want_rip && k >= 2, rows[k - 1],
+                               status[k - 1], nullptr, redo, st);
+    const cudaError_t e = cudaFreeAsync(redo, st);
+    if (!rc && e != cudaSuccess) return frisk_internal::cuda_fail(e, "cudaFreeAsync(redo)");
+    return rc;
 }

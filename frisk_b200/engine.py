@@ -651,13 +651,19 @@ def run(query, host=None, kmin: int = 1, kmax: int = 8, w: int = 5000,
 
 
 def run_sweep(query, kmaxes: Sequence[int] = tuple(range(1, 9)), kmin: int = 1, w: int = 5000, step: int = 2500,
-              mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True, device="cuda:0"):
+              mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True, device="cuda:0", fused: bool = True):
     """Scores for several --maxWordSize values in one go (BASELINE config C3: the k sweep 1..8, i.e. eight
     reference runs ``-m kmin -k k'``).  The count of x-words does not depend on kmax (F:338-351 counts every
     order independently), so ONE background pass at max(kmaxes) serves every k'; per k' only the genome
     IVOM table and the window kernel run.  Returns {k': HotPathResult}."""
     import torch
     _lib.require_device()
+    if fused:                                   # kmax' = 1..8, kmin 1: one window kernel for all of them
+        sw = Sweep(query, kmaxes, kmin, w, step, mask_host, scaffolds_all, rip, device)
+        if sw.fused:
+            sw.enqueue()
+            return sw.results()
+        query = sw.dq
     dq = query if isinstance(query, DeviceGenome) else DeviceGenome(query, device)
     g = dq.host
     top = max(kmaxes)
@@ -687,7 +693,7 @@ class Sweep:
 
     def __init__(self, query, kmaxes: Sequence[int] = tuple(range(1, 9)), kmin: int = 1, w: int = 5000, step: int = 2500,
                  mask_host: bool = False, scaffolds_all: bool = False, rip: bool = True, device="cuda:0", rank: int = 0,
-                 world: int = 1, allreduce=None):
+                 world: int = 1, allreduce=None, fused: bool = True):
         import torch
         from . import dist as fdist
         _lib.require_device()
@@ -713,6 +719,11 @@ class Sweep:
         self.d_off = torch.from_numpy(self.wins.off.view(np.int64)).to(dev)
         self.d_len = torch.from_numpy(self.wins.length.view(np.int32)).to(dev)
         self.launches = 0
+        # kmax' = 1..8 with kmin 1 and windows the shared-memory kernels hold: one fused launch (frisk_b200_score_sweep)
+        self.fused = bool(fused) and self.kmaxes == list(range(1, 9)) and kmin == 1 and 0 < self.wins.max_len <= 8186
+        if self.fused:
+            mk = lambda ts: (C.c_void_p * 8)(*[C.c_void_p(int(ts[k].data_ptr())) for k in range(1, 9)])
+            self._ig_ptrs, self._row_ptrs, self._st_ptrs = mk(self.d_ig), mk(self.d_rows), mk(self.d_status)
 
     def enqueue(self, marks=None) -> None:
         import torch
@@ -738,14 +749,24 @@ class Sweep:
                        "frisk_b200_finalize_tables")
             mark()
             launches = 5                                   # count, reduce, totals, low, symmetrise
+            fused = self.fused and n > 0
             for k in self.kmaxes:
                 _lib.check(L.frisk_b200_genome_ivom(_ptr(self.d_tables), self.kmin, k, int(g.genome_space), _ptr(self.d_ig[k]), st),
                            "frisk_b200_genome_ivom")
+                if fused:
+                    launches += 1
+                    continue
                 if n:
                     _lib.check(L.frisk_b200_score(_ptr(dq.codes), _ptr(dq.inv), _ptr(dq.low), _ptr(self.d_off), _ptr(self.d_len), n,
                                                   self.wins.max_len, _ptr(self.d_ig[k]), self.kmin, k, int(self.rip),
                                                   _ptr(self.d_rows[k]), _ptr(self.d_status[k]), None, st), "frisk_b200_score")
                 launches += 2 + (1 if k >= 7 else 0)       # kmax 7, 8: + the (usually empty) hand-over launch
+                mark()
+            if fused:                                      # ONE window kernel for all eight kmax' (+ eight empty hand-over launches)
+                _lib.check(L.frisk_b200_score_sweep(_ptr(dq.codes), _ptr(dq.inv), _ptr(dq.low), _ptr(self.d_off), _ptr(self.d_len), n,
+                                                    self.wins.max_len, self._ig_ptrs, 8, int(self.rip), self._row_ptrs, self._st_ptrs, st),
+                           "frisk_b200_score_sweep")
+                launches += 9
                 mark()
             self.launches = launches
 

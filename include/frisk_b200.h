@@ -336,6 +336,15 @@ int frisk_b200_fasta_close(frisk_b200_fasta *h, void *stream);
  * kernel(s) done, ms[4] = ms[5] results on the host.  -1 for a mark the call did not set.  *n = values written. */
 int frisk_b200_last_run_timing(float *ms, int cap, int *n);
 
+/* The k sweep of BASELINE config C3 in ONE launch: rows for kmax' = 1..8 (kmin 1: eight reference runs `-m 1 -k k'`,
+ * F:1197-1206 / F:1478-1494) of every window from one pass over it.  d_ig / d_rows / d_status are HOST arrays of 8
+ * device pointers: the genome IVOM table (frisk_b200_genome_ivom with kmin 1, kmax k'), the rows [n_win][5] and the
+ * status words of kmax' = index + 1.  kmax must be 8 and windows at most 8,186 bases (FRISK_E_UNSUPPORTED otherwise:
+ * call frisk_b200_score per kmax').  PI / SI / CRI are NaN for kmax' = 1, as in the reference (F:1467). */
+int frisk_b200_score_sweep(const uint32_t *d_codes, const uint32_t *d_inv, const uint32_t *d_low, const uint64_t *d_win_off,
+                           const uint32_t *d_win_len, uint64_t n_win, uint32_t max_win_len, const double *const *d_ig,
+                           int kmax, int want_rip, double *const *d_rows, uint32_t *const *d_status, void *stream);
+
 /* The window kernel frisk_b200_score launches for (kmin, kmax, longest window), spelled as profilers print it
  * (e.g. "score_windows_nibble_kernel<8, 20, 0, 1>"): labels of profiles and bench lines come from the launcher's own
  * selection, honouring frisk_b200_set_option. */

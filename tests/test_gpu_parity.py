@@ -602,3 +602,36 @@ def test_no_silent_fallback_symbols_loaded(eng):
     assert _lib.device_count() >= 1
     with open("/proc/self/maps") as fh:
         assert "libfrisk_b200.so" in fh.read()
+
+
+def test_fused_k_sweep_matches_the_per_kmax_launches(eng):
+    """frisk_b200_score_sweep (kmax' = 1..8 from one pass over every window, BASELINE config C3) == eight separate
+    launches, on the edge genome (lower case, IUPAC, N runs, low-complexity stretches that overflow the 4-bit counters
+    and are handed over per kmax') and a C3 slice; and == the oracle for every kmax'."""
+    from frisk_b200 import synth
+    from oracle import c_oracle
+    rng = np.random.Generator(np.random.PCG64(21))
+    extra = synth.iid_bases(rng, 30_000, 0.4)
+    extra[5_000:5_040] = ord("A")                                   # 33 x AAAAAAAA: nibble overflow -> hand-over
+    extra[9_000:9_006] = ord("N")
+    for p in range(15_000, 19_000, 37):                              # > 64 cut words in one window -> hand-over
+        extra[p] = ord("N")
+    sc = synth.make("edge") + synth.make("C3", 0.002) + [("extra", extra)]
+    g = eng.PackedGenome.from_scaffolds(sc)
+    for kw in (dict(), dict(w=2000, step=500, scaffolds_all=True), dict(w=8000, step=4000)):
+        fused = eng.run_sweep(g, fused=True, **kw)
+        plain = eng.run_sweep(g, fused=False, **kw)
+        assert sorted(fused) == sorted(plain) == list(range(1, 9))
+        for k in range(1, 9):
+            a, b = fused[k], plain[k]
+            assert np.array_equal(a.tables, b.tables) and a.meta == b.meta and a.names == b.names
+            assert np.array_equal(a.coords, b.coords) and np.array_equal(a.status, b.status), (kw, k)
+            ok = b.status == 0
+            assert max_rel_err(a.rows[ok, 0], b.rows[ok, 0]) < 1e-12, (kw, k)
+            assert np.array_equal(a.rows[:, 1:], b.rows[:, 1:], equal_nan=True), (kw, k)
+            ref = c_oracle.run(sc, threads=4, kmin=1, kmax=k, w=kw.get("w", 5000), step=kw.get("step", 2500),
+                               scaffolds_all=kw.get("scaffolds_all", False))
+            assert np.array_equal(a.coords, ref["coords"]) and np.array_equal(a.status & 7, ref["status"] & 7)
+            okr = ref["status"] == 0
+            assert_rows_close(a.rows[okr], ref["rows"][okr], rtol_kld=1e-6, rtol_other=1e-15, what="sweep k=%d" % k)
+            assert max_rel_err(a.rows[okr, 0], ref["rows"][okr, 0]) < 1e-10
