@@ -69,6 +69,40 @@ l2_gather_async_kernel(const double2* __restrict__ tab, uint32_t n_mask, int ite
     if (a0 == 1.2345e-300) sink[0] = a0;
 }
 
+// mode 4: the gather as 16-byte BULK async copies (cp.async.bulk, the TMA engine) into shared memory, completion on an
+// mbarrier, read back coalesced -- does the copy engine take small random pieces off the LSU data pipe, and how fast?
+__global__ void __launch_bounds__(256, 4)
+l2_gather_bulk_kernel(const double2* __restrict__ tab, uint32_t n_mask, int iters, double* sink) {
+    __shared__ __align__(16) double2 stage[4][256];
+    __shared__ __align__(8) unsigned long long bar;
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    double a0 = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < iters; it += 4) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 64;" ::"r"(bar_a) : "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t i = lcg(x) & n_mask;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[j][threadIdx.x]);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];"
+                         ::"r"(dst), "l"(tab + i), "r"(bar_a) : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+        phase ^= 1u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double2 v = stage[j][threadIdx.x]; a0 += v.x + v.y; }
+        __syncthreads();                                   // the stage is rewritten by the next round's copies
+    }
+    if (a0 == 1.2345e-300) sink[0] = a0;
+}
+
 // mode 3: 8-byte entries (half the table bytes for the same number of entries)
 __global__ void __launch_bounds__(256, 4)
 l2_gather8_kernel(const double* __restrict__ tab, uint32_t n_mask, int iters, double* sink) {
@@ -123,7 +157,7 @@ int time_twice(F launch, cudaStream_t st, float* ms) {
 extern "C" {
 
 int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int mode, float* ms, void* stream) {
-    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms || table_bytes < 4096 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 3)
+    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms || table_bytes < 4096 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 4)
         return FRISK_E_INVALID;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -136,6 +170,7 @@ int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int 
     const uint32_t gap = 14u;                            // 65,536 entries / ~4,794 distinct K-mers of a 5 kb window
     int rc;
     if (mode == 2) rc = time_twice([&] { l2_gather_async_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, sink); }, st, ms);
+    else if (mode == 4) rc = time_twice([&] { l2_gather_bulk_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, sink); }, st, ms);
     else if (mode == 3) rc = time_twice([&] { l2_gather8_kernel<<<blocks, 256, 0, st>>>((const double*)tab, 2u * n_mask + 1u, iters, sink); }, st, ms);
     else rc = time_twice([&] { l2_gather_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, mode, gap, sink); }, st, ms);
     cudaFree(tab);

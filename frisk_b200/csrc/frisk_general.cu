@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kGT, 1)
 gen_score_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                  const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ win_len, uint32_t n_win,
                  const double2* __restrict__ ig, int kmin, int K, int want_rip, uint32_t* __restrict__ slab, uint64_t slab_words,
-                 double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump) {
+                 double* __restrict__ rows, uint32_t* __restrict__ status, uint16_t* __restrict__ dump,
+                 const uint32_t* __restrict__ redo_list, const uint32_t* __restrict__ redo_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GenSmem& ss = *reinterpret_cast<GenSmem*>(smem_raw);
     uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(GenSmem) + 15) & ~(size_t)15));   // orders 1..min(K,6)
@@ -150,7 +151,21 @@ gen_score_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict_
     if (tid == 0) { ss.n_non = 0; ss.n_gc = 0; ss.flags = 0; }
     __syncthreads();
 
-    for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x) {
+    // Second launch behind the kmax 9..12 kernel (frisk_nibble_ext.cu): only the windows it handed over, as a compacted
+    // list.  A CTA without work leaves at once; one with work initialises its own slab (the host skipped that: the slab
+    // of a launch that usually has nothing to do is not worth 100+ MB of memset per CTA).
+    const uint32_t n_todo = redo_list ? *redo_count : n_win;
+    if (redo_list) {
+        if (blockIdx.x >= n_todo) return;
+        if (K > kSmemOrders) {
+            const uint64_t count_words = loff(K + 1) - loff(kSmemOrders + 1);
+            for (uint64_t i = tid; i < count_words; i += kGT) gtab[i] = 0u;
+            for (uint64_t i = tid; i < (uint64_t)p4(K); i += kGT) gtab[count_words + i] = kFullMask;
+        }
+        __syncthreads();
+    }
+    for (uint32_t todo = blockIdx.x; todo < n_todo; todo += gridDim.x) {
+        const uint32_t win = redo_list ? redo_list[todo] : todo;
         const uint64_t o = win_off[win];
         const uint32_t len = win_len[win];
         // one position: 16 bases of codes from it, unresolved mask of the 32 bases from it, v = longest valid word (<= K)
@@ -296,6 +311,13 @@ int sms() {
     return n;
 }
 
+// indices of the windows marked kRowRedo, in any order
+__global__ void __launch_bounds__(256)
+gen_compact_kernel(const uint32_t* __restrict__ marks, uint32_t n, uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n && (marks[i] & frisk_internal::kRowRedo)) list[atomicAdd(count, 1u)] = i;
+}
+
 }  // namespace
 
 namespace frisk_internal {
@@ -334,11 +356,12 @@ int general_genome_ivom(const uint64_t* tables, int kmin, int K, int64_t space, 
 
 int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                   const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
-                  double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+                  double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, const uint32_t* redo_src, int grid_cap) {
     if (dump && max_len > 65535u) return FRISK_E_UNSUPPORTED;          // the test dump is 16-bit
     const int n = sms();
     if (n <= 0) return FRISK_E_NO_DEVICE;
     uint64_t grid = (uint64_t)n;
+    if (grid_cap > 0 && grid > (uint64_t)grid_cap) grid = (uint64_t)grid_cap;   // a hand-over launch: few windows, small slab
     if (grid > n_win) grid = n_win;
     // per-CTA slab: orders 7..K (u32 counts) + first-occurrence position per K-mer
     const uint64_t slab_words = K > kSmemOrders ? (loff(K + 1) - loff(kSmemOrders + 1)) + p4(K) : 0;
@@ -348,10 +371,21 @@ int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* lo
         { const int rc = pool_ready(); if (rc) return rc; }
         // stream-ordered: up to 156 MB per CTA at K = 12, handed back as soon as the kernel is done
         FRISK_CK(cudaMallocAsync((void**)&slab, (size_t)(grid * slab_words * 4), st));
-        for (uint64_t c = 0; c < grid; ++c) {                          // counts = 0, first = "none"
+        for (uint64_t c = 0; c < grid && !redo_src; ++c) {             // counts = 0, first = "none" (hand-over launch: in the kernel)
             FRISK_CK(cudaMemsetAsync(slab + c * slab_words, 0, count_words * 4, st));
             FRISK_CK(cudaMemsetAsync(slab + c * slab_words + count_words, 0xff, p4(K) * 4, st));
         }
+    }
+    // hand-over launch: compact the marked windows into a list first (a CTA scanning the marks one by one would spend a
+    // global-memory round trip per window)
+    uint32_t* redo_list = nullptr;
+    uint32_t* redo_count = nullptr;
+    if (redo_src) {
+        { const int rc = pool_ready(); if (rc) return rc; }
+        FRISK_CK(cudaMallocAsync((void**)&redo_list, (size_t)(n_win + 1) * 4, st));
+        redo_count = redo_list + n_win;
+        FRISK_CK(cudaMemsetAsync(redo_count, 0, 4, st));
+        gen_compact_kernel<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(redo_src, (uint32_t)n_win, redo_list, redo_count);
     }
     const int KS = K < kSmemOrders ? K : kSmemOrders;
     const size_t smem = ((sizeof(GenSmem) + 15) & ~(size_t)15) + (size_t)loff(KS + 1) * 4 + (K <= kSmemOrders ? (size_t)p4(K) * 4 : 0);
@@ -359,8 +393,9 @@ int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* lo
     if (dump) gen_zero_dump_kernel<<<1024, 256, 0, st>>>(dump, n_win * loff(K + 1));
     gen_score_kernel<<<(unsigned)grid, kGT, smem, st>>>(codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off),
                                                        win_len, (uint32_t)n_win, reinterpret_cast<const double2*>(ig), kmin, K,
-                                                       want_rip, slab, slab_words, rows, status, dump);
+                                                       want_rip, slab, slab_words, rows, status, dump, redo_list, redo_count);
     FRISK_CK(cudaGetLastError());
+    if (redo_list) FRISK_CK(cudaFreeAsync(redo_list, st));
     if (slab) FRISK_CK(cudaFreeAsync(slab, st));
     return FRISK_OK;
 }

@@ -28,7 +28,15 @@ int general_finalize(const uint64_t* fwd, int K, int symmetric, uint64_t* tables
 int general_genome_ivom(const uint64_t* tables, int kmin, int K, int64_t space, double* ig, cudaStream_t st);
 int general_score(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                   const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
-                  double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st);
+                  double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, const uint32_t* redo_src = nullptr,
+                  int grid_cap = 0);
+
+// kmax 9..12, windows <= 8,186 bases (frisk_nibble_ext.cu): orders 1..8 as in the kmax-8 nibble kernel, orders 9..K from the
+// observation that an 8-mer seen once has only unique extensions (the few repeated ones go through a shared-memory hash
+// table).  What it cannot hold is marked kRowRedo and re-done by general_score behind it.
+int score_nibble_ext(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
+                     const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
+                     double* rows, uint32_t* status, cudaStream_t st);
 
 
 // direct score kernel (frisk_direct.cu): kmax 7, 8 and windows <= 8,186 bases.  Windows it cannot finish exactly

@@ -1875,6 +1875,11 @@ int frisk_b200_score(const uint32_t* d_codes, const uint32_t* d_inv, const uint3
     if (max_win_len > FRISK_B200_MAX_WINDOW || n_win > 0xffffffffull) return FRISK_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int rip = want_rip && kmin <= 2 && kmax >= 2;
+    // kmax 9..12 on windows the shared-memory kernels hold: the extension kernel (orders 1..8 as at kmax 8, 9..K from the few
+    // repeated 8-mers); the test-only table dump stays on the general kernel
+    if (kmax > FRISK_B200_FAST_K && kmax <= 12 && max_win_len <= kBuf3 - 6u && !d_dump && !g_force_general)
+        return frisk_internal::score_nibble_ext(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, kmax,
+                                                rip, d_rows, d_status, st);
     if (kmax > FRISK_B200_FAST_K || max_win_len > 65535u || g_force_general)
         return frisk_internal::general_score(d_codes, d_inv, d_low, d_win_off, d_win_len, n_win, max_win_len, d_ig, kmin, kmax,
                                              rip, d_rows, d_status, d_dump, st);
@@ -1978,7 +1983,9 @@ int frisk_b200_score_kernel_name(int kmin, int kmax, uint32_t max_win_len, char*
     if (rc) return rc;
     const int allk = kmin == 1 ? 1 : 0;
     auto chunk = [&](uint32_t a, uint32_t b, uint32_t c) { return max_win_len <= kT3 * a ? a : (max_win_len <= kT3 * b ? b : c); };
-    if (kmax > FRISK_B200_FAST_K || max_win_len > 65535u || g_force_general) snprintf(buf, cap, "gen_score_kernel");
+    if (kmax > FRISK_B200_FAST_K && kmax <= 12 && max_win_len <= kBuf3 - 6u && !g_force_general)
+        snprintf(buf, cap, "score_windows_nibble_ext_kernel<%u, %d>", chunk(8u, 20u, 32u), allk);
+    else if (kmax > FRISK_B200_FAST_K || max_win_len > 65535u || g_force_general) snprintf(buf, cap, "gen_score_kernel");
     else if (kmax <= 6 && !g_force_dense && !g_force_bucket) snprintf(buf, cap, "score_windows_small_kernel<%d, 0>", kmax);
     else if (use_nibble_kernel(kmax, max_win_len))
         snprintf(buf, cap, "score_windows_nibble_kernel<%d, %u, 0, %d>", kmax, chunk(8u, 20u, 32u), allk);

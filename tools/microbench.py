@@ -40,6 +40,6 @@ out = {
     "smem_random_loads_per_s": {"%dB" % b: best(lambda b=b: loads(b)) for b in (4, 8, 16)},
     "l2_gather_16B_per_s": {"random_1MiB": best(lambda: gathers(0)), "sorted_1MiB": best(lambda: gathers(1)),
                             "random_256KiB": best(lambda: gathers(0, 1 << 18)), "random_16MiB": best(lambda: gathers(0, 1 << 24)),
-                            "random_1MiB_cp_async": best(lambda: gathers(2)), "random_8B_entries_512KiB": best(lambda: gathers(3))},
+                            "random_1MiB_cp_async": best(lambda: gathers(2)), "random_8B_entries_512KiB": best(lambda: gathers(3)), "random_1MiB_cp_async_bulk": best(lambda: gathers(4))},
 }
 print(json.dumps(out))
