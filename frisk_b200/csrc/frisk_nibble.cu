@@ -108,6 +108,11 @@ template <typename MT> __device__ __forceinline__ MT top_bits(int n) {       // 
     return n >= MB ? ~MT(0) : ~(~MT(0) >> n);
 }
 
+#ifndef FRISK_NIBBLE_WALK
+#define FRISK_NIBBLE_WALK 0
+#endif
+constexpr bool NIB_WALK = FRISK_NIBBLE_WALK;       // scoring pass re-reads the thread's code words and walks them with a 2-bit
+                                                   // shift register instead of keeping PP K-mer codes in registers
 #ifndef FRISK_NIBBLE_GATHER_CG
 #define FRISK_NIBBLE_GATHER_CG 1
 #endif
@@ -241,7 +246,7 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                         const uint32_t k0 = kmer_at(i), k1 = kmer_at(i + 1);
                         atomicAdd(&nib32[k0 >> 3], 1u << ((k0 & 7u) * 4u));
                         atomicAdd(&nib32[k1 >> 3], 1u << ((k1 & 7u) * 4u));
-                        kk[i >> 1] = k0 | (k1 << 16);
+                        if (!NIB_WALK || SWEEP) kk[i >> 1] = k0 | (k1 << 16);
                     }
                 } else {
 #pragma unroll
@@ -249,7 +254,7 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
                         if (vm & (MT(1) << (MB - 1 - i))) {
                             const uint32_t kap = kmer_at(i);
                             atomicAdd(&nib32[kap >> 3], 1u << ((kap & 7u) * 4u));
-                            kk[i >> 1] |= kap << (16 * (i & 1));
+                            if (!NIB_WALK || SWEEP) kk[i >> 1] |= kap << (16 * (i & 1));
                         }
                     }
                 }
@@ -644,7 +649,26 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
             s_g = fma(g.x, om, s_g);                       // a NaN entry (reference: ZeroDivisionError) poisons the sum
             s_t = fma(a, (NIB_TABLOG ? log2_pos(iw, logtab) : log2_series(iw)) - g.y, s_t);
         };
-        {
+        if constexpr (NIB_WALK && !SWEEP) {
+            if (p0 < len) {
+                constexpr int NWK = (PP + K - 1 + 15 + 15) / 16;               // aligned words: the chunk, K-1 bases of look-ahead, 16 for the walk
+                const uint32_t r0 = o_lo + p0;
+                uint32_t rw[NWK + 1];
+#pragma unroll
+                for (int j = 0; j <= NWK; ++j) rw[j] = __ldg(cw + (r0 >> 4) + j);
+                const uint32_t sc = (r0 & 15u) * 2u;
+                uint32_t Wa = __funnelshift_l(rw[1], rw[0], sc), Wb = __funnelshift_l(rw[2], rw[1], sc);
+                uint32_t Wc = NWK > 2 ? __funnelshift_l(rw[NWK > 2 ? 3 : 0], rw[2], sc) : 0u;
+                uint32_t Wd = NWK > 3 ? __funnelshift_l(rw[NWK > 3 ? 4 : 0], rw[NWK > 3 ? 3 : 0], sc) : 0u;
+                const int n_pos = (int)(len - p0) < (int)cs ? (int)(len - p0) : (int)cs;
+#pragma unroll 1
+                for (int i = 0; i < n_pos; ++i) {
+                    if (vm & (MT(1) << (MB - 1))) score_one(Wa >> (32 - 2 * K), NIB_GATHER(ig + (Wa >> (32 - 2 * K))));
+                    vm <<= 1;
+                    Wa = __funnelshift_l(Wb, Wa, 2); Wb = __funnelshift_l(Wc, Wb, 2); Wc = __funnelshift_l(Wd, Wc, 2); Wd <<= 2;
+                }
+            }
+        } else {
             const int rounds = (int)(cs >> 2);
             double2 gnext = NIB_PREFETCH ? NIB_GATHER(ig + (kk[0] & 0xffffu)) : make_double2(0.0, 0.0);
 #pragma unroll 1
@@ -751,7 +775,8 @@ template <int PP>
 int launch_sweep(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off, const uint32_t* win_len,
                  uint64_t n_win, const NibSweep& sw, int want_rip, uint32_t* redo_dst, cudaStream_t st) {
     using L = NibLayout<8>;
-    auto kern = score_windows_nibble_kernel<8, PP, false, true, true>;
+    if constexpr (!NIB_PRE5) return FRISK_E_UNSUPPORTED;               // (an A/B build without the order-5 fold has no sweep kernel)
+    auto kern = score_windows_nibble_kernel<8, PP, false, true, NIB_PRE5>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;

@@ -528,8 +528,7 @@ int frisk_internal::score_nibble_ext(const uint32_t* codes, const uint32_t* inv,
     else if (max_len <= kNT * 20u) rc = launch_ext<20>(codes, inv, low, win_off, win_len, n_win, ig, kmin, K, want_rip, rows, status, redo, st);
     else rc = launch_ext<32>(codes, inv, low, win_off, win_len, n_win, ig, kmin, K, want_rip, rows, status, redo, st);
     // the windows this kernel could not hold: exact re-run on the general kernel (a few CTAs: its per-CTA slab is large)
-    // (its stream-ordered slab must stay below what the memory pool keeps cached -- 1 GiB -- or every call pays a real
-    // allocation: 39 ms at kmax 12 with 8 CTAs x 156 MB)
+    // (few CTAs: the slab is 156 MB per CTA at kmax 12, and a hand-over launch usually has nothing to do)
     if (!rc) rc = general_score(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, K, want_rip, rows, status, nullptr, st, redo,
                                 K <= 10 ? 8 : 2);
     if (scratch) {

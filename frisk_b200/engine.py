@@ -113,6 +113,37 @@ def _decode_names(buf: np.ndarray, name_off: np.ndarray, name_len: np.ndarray) -
     return [flat[a:b] for a, b in zip(starts.tolist(), ends.tolist())]
 
 
+class LazyNames:
+    """The scaffold names of a FASTA text, decoded from the header positions on first use: a fragmented assembly has a
+    million of them, and a caller that only wants rows (``row_scaf`` indexes the scaffolds) never pays for the strings."""
+
+    def __init__(self, buf: np.ndarray, name_off: np.ndarray, name_len: np.ndarray):
+        self._src = (buf, name_off, name_len)
+        self._n = int(len(name_off))
+        self._names: Optional[List[str]] = None
+
+    def _all(self) -> List[str]:
+        if self._names is None:
+            self._names = _decode_names(*self._src)
+            self._src = None
+        return self._names
+
+    def __len__(self) -> int:
+        return self._n
+
+    def __getitem__(self, i):
+        return self._all()[i]
+
+    def __iter__(self):
+        return iter(self._all())
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self):
+        return "LazyNames(%d)" % self._n
+
+
 @dataclass
 class WindowList:
     """Candidate windows in crawlGenome order (F:194-251), before the 30 % unresolved filter."""
@@ -326,7 +357,7 @@ class DeviceGenome:
                 _lib.check(L.frisk_b200_fasta_pack(h, _ptr(codes), _ptr(inv), _ptr(low), st), "frisk_b200_fasta_pack")
             finally:
                 L.frisk_b200_fasta_close(h, st)
-        names = _decode_names(buf, name_off, name_len)
+        names = LazyNames(buf, name_off, name_len)
         g = PackedGenome(names, seq_len, scaf_off, P, None, None, None, int(stats[0]), int(stats[1]), int(stats[2]), False)
         return cls(g, dev, planes=(codes, inv, low))
 
@@ -499,7 +530,8 @@ def assemble(query: PackedGenome, host: PackedGenome, wins: WindowList, tables_1
     without a Python object per row: millions of rows of a fragmented assembly)."""
     keep = (status & _lib.ROW_EXCLUDED) == 0
     idx = np.nonzero(keep)[0]
-    names = [query.names[s] for s in wins.scaf[idx]] if names else []
+    want_names = bool(names)
+    names = [query.names[s] for s in wins.scaf[idx]] if want_names else []
     coords = np.stack([wins.start[idx], wins.stop[idx]], axis=1) if idx.size else np.zeros((0, 2), np.int64)
     meta = (host.total_len, host.ex_max(kmax, valid_kmax), host.nn_total)
     wt = None
@@ -507,7 +539,7 @@ def assemble(query: PackedGenome, host: PackedGenome, wins: WindowList, tables_1
         wt = _slice_orders(dump[idx], kmin, kmax)
     return HotPathResult(kmin, kmax, _slice_orders(tables_1k, kmin, kmax).copy(), meta, names, coords,
                          rows[idx], status[idx].astype(np.uint32), len(wins), idx, wins.scaf[idx].astype(np.int64), wt,
-                         scaf_names=list(query.names))
+                         scaf_names=list(query.names) if want_names else query.names)
 
 
 class Pipeline:
@@ -629,8 +661,17 @@ class Pipeline:
         import torch
         torch.cuda.synchronize(self.device)
         tables = self.d_tables.cpu().numpy().view(np.uint64)
-        rows = self.d_rows.cpu().numpy()
-        status = self.d_status.cpu().numpy().view(np.uint32)
+        n = len(self.wins)
+        if n >= (1 << 16):                      # large row sets come back through page-locked memory (pageable: ~3 GB/s)
+            h_rows = _alloc((n, 5), np.float64, True)
+            h_stat = _alloc((n,), np.int32, True)
+            torch.from_numpy(h_rows).copy_(self.d_rows, non_blocking=True)
+            torch.from_numpy(h_stat).copy_(self.d_status, non_blocking=True)
+            torch.cuda.synchronize(self.device)
+            rows, status = h_rows, h_stat.view(np.uint32)
+        else:
+            rows = self.d_rows.cpu().numpy()
+            status = self.d_status.cpu().numpy().view(np.uint32)
         dmp = self.d_dump.cpu().numpy().view(np.uint16) if self.d_dump is not None else None
         return assemble(self.query, self.host, self.wins, tables, int(self.d_valid.item()), rows, status,
                         self.kmin, self.kmax, dmp, names=names)
