@@ -819,6 +819,14 @@ score_windows_bucket_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
     const uint16_t* tabB = tab16 + lvl_off(B);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (redo_src) {
+        // hand-over launch: nearly always there is nothing to do.  All threads look at this CTA's marks at once and the CTA
+        // leaves if none is set (walking them one window at a time cost 26 us per step: a global round trip per window)
+        bool any = false;
+        for (uint32_t w = blockIdx.x + (uint32_t)tid * gridDim.x; w < n_win; w += gridDim.x * (uint32_t)kT3)
+            any |= (redo_src[w] & frisk_internal::kRowRedo) != 0u;
+        if (!__syncthreads_or(any)) return;
+    }
     for (uint32_t i = tid; i < L::ZERO_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid < 8) { ss.cnt[tid >> 2][tid & 3] = 0; ss.flags[tid & 1] = 0; }
     if (tid < 128) {
@@ -1214,6 +1222,12 @@ score_windows_small_kernel(const uint32_t* __restrict__ codes, const uint32_t* _
     constexpr int P = L::P;
     (void)pre;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (redo_src) {                                                        // hand-over launch: leave at once when no window of this CTA is marked
+        bool any = false;
+        for (uint32_t w = blockIdx.x + (uint32_t)tid * gridDim.x; w < n_win; w += gridDim.x * (uint32_t)kT3)
+            any |= (redo_src[w] & frisk_internal::kRowRedo) != 0u;
+        if (!__syncthreads_or(any)) return;
+    }
 
     for (uint32_t i = tid; i < L::TAB_BYTES / 16u; i += kT3) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) { ss.n_non = 0; ss.n_gc = 0; ss.flags = 0; }
@@ -1991,7 +2005,7 @@ int frisk_b200_score_kernel_name(int kmin, int kmax, uint32_t max_win_len, char*
     else if (kmax > FRISK_B200_FAST_K || max_win_len > 65535u || g_force_general) snprintf(buf, cap, "gen_score_kernel");
     else if (kmax <= 6 && !g_force_dense && !g_force_bucket) snprintf(buf, cap, "score_windows_small_kernel<%d, 0>", kmax);
     else if (use_nibble_kernel(kmax, max_win_len))
-        snprintf(buf, cap, "score_windows_nibble_kernel<%d, %u, 0, %d>", kmax, chunk(8u, 20u, 32u), allk);
+        snprintf(buf, cap, "score_windows_nibble_kernel<%d, %u, 0, %d, 0>", kmax, chunk(8u, 20u, 32u), allk);
     else if (use_direct_kernel(kmax, max_win_len)) {
         const uint32_t r = max_win_len <= 256u * 4u * 2u - 6u ? 2u : (max_win_len <= 256u * 4u * 5u - 6u ? 5u : 8u);
         snprintf(buf, cap, "score_windows_direct_kernel<%d, 256, %u, 0, %d>", kmax, r, allk);
