@@ -691,15 +691,29 @@ def run_gpu(args):
 
     # ---- the other blocks (each rank takes part; rank 0 reports)
     extra = {}
+
+    def guarded(name, fn, *a):
+        """An extra block must never cost the headline line: a failure is reported in its place."""
+        try:
+            extra[name] = fn(*a)
+        except Exception as e:                      # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            try:
+                torch.cuda.empty_cache()
+            except Exception:
+                pass
+
     if not args.profile and not args.quick:
         if world > 1:
-            extra["parity"] = parity_block(rank, world, dev, scaffolds, genome, pipe, allreduce, space)
+            guarded("parity", parity_block, rank, world, dev, scaffolds, genome, pipe, allreduce, space)
         del flush
         torch.cuda.empty_cache()
-        extra["strong"] = strong_block(rank, world, dev, peers_ok)
+        guarded("strong", strong_block, rank, world, dev, peers_ok)
         if world > 1 or args.c5:
-            extra["c5"] = c5_block(rank, world, dev, peers_ok)
-        extra["c3_sweep"] = c3_sweep_block(rank, world, dev)
+            guarded("c5", c5_block, rank, world, dev, peers_ok)
+        guarded("c3_sweep", c3_sweep_block, rank, world, dev)
 
     occ = None
     try:

@@ -5,6 +5,7 @@
 //   frisk_b200_bench_smem_loads  random 4/8/16-byte loads from a 32 KiB shared-memory table (bank-conflicted reads:
 //                                what a position-ordered epilogue does to its count tables)
 // (the shared-memory ATOMIC rate is frisk_b200_bench_smem_atomics in frisk_kernels.cu)
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -103,6 +104,51 @@ l2_gather_bulk_kernel(const double2* __restrict__ tab, uint32_t n_mask, int iter
     if (a0 == 1.2345e-300) sink[0] = a0;
 }
 
+// mode 5: the gather as TMA tile::gather4 loads (four rows of a 2-D tensor per instruction; tensor map with a box of one
+// row), completion on an mbarrier, read back.  The table holds {i, -i} in entry i so that the kernel can
+// check what arrived; a poll budget turns a descriptor the hardware does not like into an error instead of a hang.
+__global__ void __launch_bounds__(256, 4)
+l2_gather4_kernel(const __grid_constant__ CUtensorMap map, uint32_t n_mask, int iters, double* sink, unsigned int* bad) {
+    __shared__ __align__(128) double2 stage[256][8];      // 128 bytes per thread: every destination 128-byte aligned
+    __shared__ __align__(8) unsigned long long bar;
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    double a0 = 0;
+    uint32_t phase = 0;
+    bool dead = false;
+    for (int it = 0; it < iters && !dead; it += 4) {
+        const int32_t r0 = (int32_t)(lcg(x) & n_mask), r1 = (int32_t)(lcg(x) & n_mask), r2 = (int32_t)(lcg(x) & n_mask), r3 = (int32_t)(lcg(x) & n_mask);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 64;" ::"r"(bar_a) : "memory");
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[threadIdx.x][0]);
+        asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                     ::"r"(dst), "l"(&map), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar_a) : "memory");
+        uint32_t done = 0;
+        for (int poll = 0; !done && poll < 4000000; ++poll)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+        if (!done) { atomicAdd(bad, 1000000u); dead = true; break; }
+        phase ^= 1u;
+        const int32_t rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 v = stage[threadIdx.x][j];
+            if (v.x != (double)rr[j] || v.y != -(double)rr[j]) atomicAdd(bad, 1u);
+            a0 += v.x + v.y;
+        }
+        __syncthreads();
+    }
+    if (a0 == 1.2345e-300) sink[0] = a0;
+}
+
+__global__ void fill_pattern_kernel(double2* tab, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tab[i] = make_double2((double)i, -(double)i);
+}
+
 // mode 3: 8-byte entries (half the table bytes for the same number of entries)
 __global__ void __launch_bounds__(256, 4)
 l2_gather8_kernel(const double* __restrict__ tab, uint32_t n_mask, int iters, double* sink) {
@@ -157,7 +203,7 @@ int time_twice(F launch, cudaStream_t st, float* ms) {
 extern "C" {
 
 int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int mode, float* ms, void* stream) {
-    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms || table_bytes < 4096 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 4)
+    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms || table_bytes < 4096 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 5)
         return FRISK_E_INVALID;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -169,7 +215,35 @@ int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int 
     const uint32_t n_mask = (uint32_t)(table_bytes / 16u) - 1u;
     const uint32_t gap = 14u;                            // 65,536 entries / ~4,794 distinct K-mers of a 5 kb window
     int rc;
-    if (mode == 2) rc = time_twice([&] { l2_gather_async_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, sink); }, st, ms);
+    if (mode >= 5) {
+        // tensor map of the table as a [rows][2 doubles] tensor; the driver entry point comes through the runtime
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { cudaFree(tab); cudaFree(sink); return FRISK_E_UNSUPPORTED; }
+        CUtensorMap map;
+        const cuuint64_t gdim[2] = {2, (cuuint64_t)n_mask + 1};
+        const cuuint64_t gstride[1] = {16};
+        const cuuint32_t box[2] = {2, 1};                  // (a box of 4 rows is rejected; destinations must be 128-byte aligned:
+                                                           //  64- and 80-byte slot strides fault with cudaErrorMisalignedAddress)
+        const cuuint32_t estride[2] = {1, 1};
+        const CUresult cr = ((EncodeFn)fn)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, tab, gdim, gstride, box, estride,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { cudaFree(tab); cudaFree(sink); return FRISK_E_UNSUPPORTED; }
+        unsigned int* bad = nullptr;
+        CK(cudaMalloc(&bad, 4));
+        CK(cudaMemsetAsync(bad, 0, 4, st));
+        fill_pattern_kernel<<<(n_mask + 256) / 256, 256, 0, st>>>(tab, n_mask + 1);
+        rc = time_twice([&] { l2_gather4_kernel<<<blocks, 256, 0, st>>>(map, n_mask, iters, sink, bad); }, st, ms);
+        unsigned int h_bad = 0;
+        if (cudaMemcpy(&h_bad, bad, 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = FRISK_E_CUDA;
+        cudaFree(bad);
+        if (!rc && h_bad) rc = h_bad >= 1000000u ? FRISK_E_UNSUPPORTED : FRISK_E_FORMAT;   // never completed / wrong data
+    } else if (mode == 2) rc = time_twice([&] { l2_gather_async_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, sink); }, st, ms);
     else if (mode == 4) rc = time_twice([&] { l2_gather_bulk_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, sink); }, st, ms);
     else if (mode == 3) rc = time_twice([&] { l2_gather8_kernel<<<blocks, 256, 0, st>>>((const double*)tab, 2u * n_mask + 1u, iters, sink); }, st, ms);
     else rc = time_twice([&] { l2_gather_kernel<<<blocks, 256, 0, st>>>(tab, n_mask, iters, mode, gap, sink); }, st, ms);

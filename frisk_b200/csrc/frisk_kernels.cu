@@ -1463,10 +1463,10 @@ int frisk_internal::cuda_fail(cudaError_t e, const char* what) {
 }
 
 #ifndef FRISK_DIRECT_DEFAULT
-#define FRISK_DIRECT_DEFAULT(kmax, len) ((kmax) == 7 && (len) > 2042u)
+#define FRISK_DIRECT_DEFAULT(kmax, len) ((kmax) == 7)   // (reached for short windows only: w = 1000 / 500: 1.00 / 1.59 ms vs 1.05 / 1.76 nibble, 1.14 / 1.85 bucketed)
 #endif
 #ifndef FRISK_NIBBLE_DEFAULT
-#define FRISK_NIBBLE_DEFAULT(kmax, len) ((kmax) == 8 || ((kmax) == 7 && (len) > 2042u))   // measured: tools/k8_ab.py
+#define FRISK_NIBBLE_DEFAULT(kmax, len) ((kmax) == 8 || ((kmax) == 7 && (len) > 1500u))   // measured: tools/k8_ab.py
 #endif
 
 namespace {

@@ -15,6 +15,8 @@ d_tables, _ = engine.finalize(engine.background(dq, 8), 8)
 KERNELS = (("nibble", b"force_nibble_kernel"), ("bucket", b"force_bucket_kernel"), ("direct", b"force_direct_kernel"))
 only = os.environ.get("FRISK_AB_ONLY", "").split(",") if os.environ.get("FRISK_AB_ONLY") else None
 shapes = ((5000, 2500), (2000, 1000), (8000, 4000)) if not os.environ.get("FRISK_AB_QUICK") else ((5000, 2500),)
+if os.environ.get("FRISK_AB_SHAPES"):                      # e.g. "1000:500,500:250"
+    shapes = tuple(tuple(int(x) for x in item.split(":")) for item in os.environ["FRISK_AB_SHAPES"].split(","))
 out = []
 for (w, step) in shapes:
     wins = g.windows(w, step, False)

@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from frisk_b200 import _lib
 
 L = _lib.lib()
+L.frisk_b200_last_cuda_error.restype = C.c_char_p
 _lib.require_device()
 
 
@@ -34,6 +35,20 @@ def loads(nbytes):
     _lib.check(L.frisk_b200_bench_smem_loads(blocks, iters, nbytes, C.byref(ms), None), "bench_smem_loads")
     return blocks * 256 * iters / (ms.value * 1e-3)
 
+
+def gather4(mode):
+    ms = C.c_float(0)
+    blocks, iters = 148 * 4, 2048
+    rc = L.frisk_b200_bench_l2_gather(blocks, iters, 1 << 20, mode, C.byref(ms), None)
+    return blocks * 256 * iters / (ms.value * 1e-3) if rc == 0 else "rc=%d (%s)" % (rc, L.frisk_b200_strerror(rc).decode())
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "gather4":
+    # (probed and removed: a tensor-map box of 4 rows is rejected, and destinations that are only 64- or 80-byte aligned
+    # fault with cudaErrorMisalignedAddress: every gather4 needs a 128-byte aligned 64-byte landing slot)
+    r = {"box_rows_1": gather4(5)}
+    print(json.dumps({"tma_gather4_rows_per_s": r}))
+    sys.exit(0)
 
 out = {
     "smem_atomic_updates_per_s": {n: best(lambda m=m: atomics(m)) for m, n in [(0, "conflict_free"), (1, "random"), (2, "single_address")]},
