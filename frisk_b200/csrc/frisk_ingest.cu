@@ -23,11 +23,19 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <new>
 #include <vector>
 
 #include "../../include/frisk_b200.h"
 #include "frisk_internal.h"
+
+namespace frisk_internal {
+int g_ingest_exact = 0;          // tests: always take the one-copy, count-first open
+int g_ingest_chunk_tiles = 0;    // tests: tiles per upload chunk at least this (0 = default), so small texts are chunked too
+}  // namespace frisk_internal
 
 namespace {
 
@@ -35,6 +43,9 @@ constexpr int kTT = 256;                    // threads per tile
 constexpr uint32_t kTile = kTT * 16u;       // text bytes per tile
 constexpr int kST = 1024;                   // threads of the (single-CTA) tile scans
 constexpr uint32_t kFullMask = 0xffffffffu;
+// device counters of one open(): records, countN statistics (2), interior whitespace seen, and the state of a chunked open
+enum { kCtrRecords = 0, kCtrNonUpper = 1, kCtrLower = 2, kCtrWhitespace = 3, kCtrAmbig = 4, kCtrOverflow = 5, kCtrKeyCarry = 6,
+       kCtrBaseCarry = 7, kCtrCount = 8 };
 
 // class of a byte: 0..3 = A,T,G,C (F:70 order); 4..7 = a,t,g,c; 8 = anything else; 9 = whitespace
 // removed by the reference's line.strip() (F:149)
@@ -54,8 +65,11 @@ __device__ __forceinline__ uint32_t byte_of(const uint4& v, int k) {
 
 // Is the line starting at byte i a header?  Its first non-blank character decides (the reference
 // strips the line before looking at it, F:149-153).
-__device__ bool line_is_header(const uint8_t* __restrict__ t, uint64_t i, uint64_t n) {
+// `avail` (<= n): bytes already on the device (chunked upload).  A decision that would need a byte beyond it is reported
+// through *ambig (the caller then falls back to the one-shot path); with avail == n it cannot happen.
+__device__ bool line_is_header(const uint8_t* __restrict__ t, uint64_t i, uint64_t n, uint64_t avail, uint32_t* ambig) {
     while (i < n) {
+        if (i >= avail) { *ambig = 1u; return false; }
         const uint32_t c = t[i];
         if (c == '\n') return false;                 // blank line
         if (class_of(c) != 9u) return c == '>';
@@ -66,14 +80,14 @@ __device__ bool line_is_header(const uint8_t* __restrict__ t, uint64_t i, uint64
 
 // bit k of start_mask: a line starts at byte i0 + k; of hdr_mask: ... and it is a header line
 __device__ __forceinline__ void find_starts(const uint8_t* __restrict__ t, uint64_t n, uint64_t i0, const uint4& raw,
-                                            uint32_t& start_mask, uint32_t& hdr_mask) {
+                                            uint32_t& start_mask, uint32_t& hdr_mask, uint64_t avail, uint32_t* ambig) {
     start_mask = 0; hdr_mask = 0;
     uint32_t prev = i0 ? (uint32_t)t[i0 - 1] : (uint32_t)'\n';
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         if (prev == '\n') {
             start_mask |= 1u << k;
-            if (line_is_header(t, i0 + k, n)) hdr_mask |= 1u << k;
+            if (line_is_header(t, i0 + k, n, avail, ambig)) hdr_mask |= 1u << k;
         }
         prev = byte_of(raw, k);
     }
@@ -160,13 +174,14 @@ __device__ __forceinline__ T block_excl_seg(bool f, T v, T* smv, uint32_t* smf, 
 
 // ---- pass 1: line starts ------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTT)
-fasta_lines_kernel(const uint8_t* __restrict__ t, uint64_t n, uint32_t* __restrict__ tile_nhdr, uint8_t* __restrict__ tile_key) {
+fasta_lines_kernel(const uint8_t* __restrict__ t, uint64_t n, uint32_t* __restrict__ tile_nhdr, uint8_t* __restrict__ tile_key,
+                   uint64_t tile0, uint64_t avail, uint32_t* __restrict__ ambig) {
     __shared__ uint32_t sm[64];
-    const uint64_t tile = blockIdx.x;
+    const uint64_t tile = tile0 + blockIdx.x;
     const uint64_t i0 = tile * kTile + threadIdx.x * 16u;
     const uint4 raw = *reinterpret_cast<const uint4*>(t + i0);
     uint32_t sm_, hm_;
-    find_starts(t, n, i0, raw, sm_, hm_);
+    find_starts(t, n, i0, raw, sm_, hm_, avail, ambig);
     uint32_t total, last;
     block_excl_sum<uint32_t>(__popc(hm_), sm, &total);
     block_excl_last(last_key(sm_, hm_), sm, &last);
@@ -175,12 +190,17 @@ fasta_lines_kernel(const uint8_t* __restrict__ t, uint64_t n, uint32_t* __restri
 
 // ---- scan 1 over tiles: records before each tile, header state carried into it -----------------
 __global__ void __launch_bounds__(kST)
-fasta_scan1_kernel(const uint32_t* __restrict__ tile_nhdr, const uint8_t* __restrict__ tile_key, uint64_t n_tiles,
+fasta_scan1_kernel(const uint32_t* __restrict__ tile_nhdr, const uint8_t* __restrict__ tile_key, uint64_t tile_lo, uint64_t tile_hi,
                    uint32_t* __restrict__ tile_rec_base, uint8_t* __restrict__ tile_carry_hdr,
-                   unsigned long long* __restrict__ counters) {
+                   unsigned long long* __restrict__ counters, uint32_t* __restrict__ key_carry) {
+    // tiles [tile_lo, tile_hi): one chunk of a chunked upload (or everything); counters[0] = records before tile_lo on entry,
+    // records before tile_hi on exit; *key_carry = state of the last line start before the range (0 none, 1 sequence, 2 header)
     __shared__ uint32_t sm[64];
+    const uint64_t n_tiles = tile_hi - tile_lo;
     const uint64_t per = (n_tiles + kST - 1) / kST;
-    const uint64_t lo = min((uint64_t)threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
+    const uint64_t lo = tile_lo + min((uint64_t)threadIdx.x * per, n_tiles), hi = min(lo + per, tile_hi);
+    const uint32_t rec_in = (uint32_t)counters[0], key_in = *key_carry;
+    __syncthreads();
     uint32_t sum = 0, key = 0;
     for (uint64_t i = lo; i < hi; ++i) {
         sum += tile_nhdr[i];
@@ -188,8 +208,9 @@ fasta_scan1_kernel(const uint32_t* __restrict__ tile_nhdr, const uint8_t* __rest
         if (k) key = k;
     }
     uint32_t total, last;
-    uint32_t run = block_excl_sum<uint32_t>(sum, sm, &total);
+    uint32_t run = rec_in + block_excl_sum<uint32_t>(sum, sm, &total);
     uint32_t rk = block_excl_last(key, sm, &last);
+    if (!rk) rk = key_in;
     for (uint64_t i = lo; i < hi; ++i) {
         tile_rec_base[i] = run;
         tile_carry_hdr[i] = (uint8_t)(rk == 2u);
@@ -197,17 +218,22 @@ fasta_scan1_kernel(const uint32_t* __restrict__ tile_nhdr, const uint8_t* __rest
         const uint32_t k = tile_key[i];
         if (k) rk = k;
     }
-    if (threadIdx.x == 0) counters[0] = total;
+    if (threadIdx.x == 0) { counters[0] = (unsigned long long)rec_in + total; if (last) *key_carry = last; }
 }
 
 // ---- scan 2 over tiles (segmented by headers): bases of the open record before each tile ------------
 __global__ void __launch_bounds__(kST)
 fasta_scan2_kernel(const uint32_t* __restrict__ tile_nhdr, const uint32_t* __restrict__ tile_pre,
-                   const uint32_t* __restrict__ tile_post, uint64_t n_tiles, unsigned long long* __restrict__ tile_base_in) {
+                   const uint32_t* __restrict__ tile_post, uint64_t tile_lo, uint64_t tile_hi,
+                   unsigned long long* __restrict__ tile_base_in, unsigned long long* __restrict__ base_carry) {
+    // tiles [tile_lo, tile_hi); *base_carry = bases of the open record before tile_lo on entry, before tile_hi on exit
     __shared__ unsigned long long smv[32];
     __shared__ uint32_t smf[32];
+    const uint64_t n_tiles = tile_hi - tile_lo;
     const uint64_t per = (n_tiles + kST - 1) / kST;
-    const uint64_t lo = min((uint64_t)threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
+    const uint64_t lo = tile_lo + min((uint64_t)threadIdx.x * per, n_tiles), hi = min(lo + per, tile_hi);
+    const unsigned long long carry_in = *base_carry;
+    __syncthreads();
     bool f = false;
     unsigned long long v = 0;
     for (uint64_t i = lo; i < hi; ++i) {
@@ -215,10 +241,12 @@ fasta_scan2_kernel(const uint32_t* __restrict__ tile_nhdr, const uint32_t* __res
     }
     bool rb;
     unsigned long long run = block_excl_seg<unsigned long long>(f, v, smv, smf, &rb);
+    if (!rb) run += carry_in;                                   // no header yet in this range: the open record continues
     for (uint64_t i = lo; i < hi; ++i) {
         tile_base_in[i] = run;
         if (tile_nhdr[i]) run = tile_post[i]; else run += tile_pre[i];
     }
+    if (threadIdx.x == kST - 1) *base_carry = run;              // (an empty last range leaves `run` = the prefix of everything)
 }
 
 // ---- passes 2 and 3: classify every byte of a tile -------------------------------------------------
@@ -231,23 +259,29 @@ fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __r
                   unsigned long long* __restrict__ rec_hdr_pos, unsigned long long* __restrict__ rec_len,
                   uint32_t* __restrict__ tile_pre, uint32_t* __restrict__ tile_post, unsigned long long* __restrict__ counters,
                   const unsigned long long* __restrict__ tile_base_in, const unsigned long long* __restrict__ scaf_off,
-                  uint32_t* __restrict__ codes, uint32_t* __restrict__ inv, uint32_t* __restrict__ low) {
+                  uint32_t* __restrict__ codes, uint32_t* __restrict__ inv, uint32_t* __restrict__ low,
+                  uint64_t tile0, uint64_t avail, uint64_t rec_cap) {
+    // tiles tile0 .. of a chunked upload whose first `avail` bytes are on the device (MODE 0; avail == n otherwise);
+    // rec_cap: entries of rec_hdr_pos / rec_len (MODE 0) -- a record beyond it raises counters[kCtrOverflow]
     __shared__ uint32_t sm[64];
     __shared__ uint32_t smf[32];
     __shared__ uint8_t cls_tab[256];
     const int tid = threadIdx.x;
     cls_tab[tid] = (uint8_t)class_of((uint32_t)tid);
-    const uint64_t tile = blockIdx.x;
+    const uint64_t tile = tile0 + blockIdx.x;
     const uint64_t i0 = tile * kTile + (uint64_t)tid * 16u;
     const uint4 raw = *reinterpret_cast<const uint4*>(t + i0);
     uint32_t start_mask, hdr_mask;
-    find_starts(t, n, i0, raw, start_mask, hdr_mask);
+    uint32_t* const ambig = reinterpret_cast<uint32_t*>(counters + kCtrAmbig);
+    find_starts(t, n, i0, raw, start_mask, hdr_mask, avail, ambig);
     const uint32_t n_hdr_t = __popc(hdr_mask);
     uint32_t tile_hdrs, last;
     const uint32_t hdr_before = block_excl_sum<uint32_t>(n_hdr_t, sm, &tile_hdrs);     // (also orders cls_tab)
     const uint32_t key_before = block_excl_last(last_key(start_mask, hdr_mask), sm, &last);
     bool in_hdr = key_before ? key_before == 2u : tile_carry_hdr[tile] != 0;
     const uint32_t rec_start = tile_rec_base[tile] + hdr_before;       // headers before this thread; open record = rec_start - 1
+    const bool fits = MODE != 0 || (uint64_t)rec_start + n_hdr_t <= rec_cap;   // every record this thread writes to exists
+    if (MODE == 0 && !fits) counters[kCtrOverflow] = 1ull;
 
     // walk the 16 bytes: which are bases, how many before the first / after the last header
     uint32_t base_mask = 0, cnt = 0, pre = 0, non_upper = 0, lower = 0;
@@ -261,10 +295,10 @@ fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __r
                 const bool h = (hdr_mask >> k) & 1u;
                 if (h) {
                     if (!seen_hdr) { pre = cnt; seen_hdr = true; }
-                    else if (MODE == 0 && cnt && rec >= 1u) atomicAdd(&rec_len[rec - 1u], (unsigned long long)cnt);
+                    else if (MODE == 0 && fits && cnt && rec >= 1u) atomicAdd(&rec_len[rec - 1u], (unsigned long long)cnt);
                     cnt = 0;
                     ++rec;
-                    if (MODE == 0) rec_hdr_pos[rec - 1u] = i0 + k;
+                    if (MODE == 0 && fits) rec_hdr_pos[rec - 1u] = i0 + k;
                 }
                 in_hdr = h;
             }
@@ -284,12 +318,13 @@ fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __r
                 if (s == 4096) before = true;                          // a whitespace run this long is not a line ending
                 p = i0 + k;
                 for (s = 0; s < 4096 && p + 1 < n; ++s) {
+                    if (p + 1 >= avail) { *ambig = 1u; break; }         // the rest of the line is not on the device yet
                     const uint32_t b = t[++p];
                     if (b == '\n') break;
                     if (cls_tab[b] != 9u) { after = true; break; }
                 }
                 if (s == 4096) after = true;
-                if (before && after) counters[3] = 1ull;
+                if (before && after) counters[kCtrWhitespace] = 1ull;
             }
             if (!in_hdr && c != 9u && rec >= 1u) {
                 base_mask |= 1u << k;
@@ -306,13 +341,13 @@ fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __r
     if (MODE == 0) {
         if (seen_hdr) {
             const uint32_t amount = carry + pre;                        // this tile's share of the record the header closes
-            if (rec_start >= 1u && amount) atomicAdd(&rec_len[rec_start - 1u], (unsigned long long)amount);
+            if (fits && rec_start >= 1u && amount) atomicAdd(&rec_len[rec_start - 1u], (unsigned long long)amount);
             if (!reset_before) tile_pre[tile] = amount;
         }
         if (tid == kTT - 1) {
             const uint32_t s = seen_hdr ? cnt : carry + cnt;            // bases after the tile's last header (all, if none)
             const uint32_t rec_end = rec_start + n_hdr_t;
-            if (rec_end >= 1u && s) atomicAdd(&rec_len[rec_end - 1u], (unsigned long long)s);
+            if (fits && rec_end >= 1u && s) atomicAdd(&rec_len[rec_end - 1u], (unsigned long long)s);
             tile_post[tile] = s;
             if (!reset_before && !seen_hdr) tile_pre[tile] = s;
         }
@@ -320,8 +355,8 @@ fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __r
         block_excl_sum<uint32_t>(non_upper, sm, &tot_non);
         block_excl_sum<uint32_t>(lower, sm, &tot_low);
         if (tid == 0) {
-            if (tot_non) atomicAdd(&counters[1], (unsigned long long)tot_non);
-            if (tot_low) atomicAdd(&counters[2], (unsigned long long)tot_low);
+            if (tot_non) atomicAdd(&counters[kCtrNonUpper], (unsigned long long)tot_non);
+            if (tot_low) atomicAdd(&counters[kCtrLower], (unsigned long long)tot_low);
         }
     } else {
         // A thread's bases land on consecutive packed positions (per record), i.e. in at most two
@@ -401,7 +436,40 @@ int free_all(frisk_b200_fasta* h, cudaStream_t st) {
     return FRISK_OK;
 }
 
-int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st) {
+// ---- the upload lane: text chunks travel on a second stream while the tile passes of the previous chunk run -------------
+constexpr int kMaxChunks = 8;
+constexpr uint64_t kMinChunkTiles = 512;            // 2 MiB of text: below that a chunk's copy is shorter than its launches
+constexpr int kRetryExact = -1000;                  // internal: the chunked / speculative open could not decide, open again
+constexpr uint64_t kFirstFetch = 4096;              // records read back with the counters (one synchronisation when R <= this)
+
+struct UploadLane {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ready = nullptr, done[kMaxChunks] = {};
+};
+std::mutex g_lane_mu;
+std::atomic<uint64_t> g_open_stats[2];
+UploadLane g_lane[64];
+
+int upload_lane(UploadLane** out) {
+    int dev = 0;
+    FRISK_CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return FRISK_E_UNSUPPORTED;
+    std::lock_guard<std::mutex> lk(g_lane_mu);
+    UploadLane& l = g_lane[dev];
+    if (!l.copy) {
+        FRISK_CK(cudaStreamCreateWithFlags(&l.copy, cudaStreamNonBlocking));
+        FRISK_CK(cudaEventCreateWithFlags(&l.ready, cudaEventDisableTiming));
+        for (auto& e : l.done) FRISK_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    *out = &l;
+    return FRISK_OK;
+}
+
+// exact = false: the text goes up in chunks and every chunk is tokenised while the next one is on the bus; the record table is
+//   sized by a guess (one record per 64 bytes of text + 4096).  A line decision that needs a byte of a later chunk, or more
+//   records than the guess, returns kRetryExact.
+// exact = true: one copy, records counted (one more synchronisation) before the record table is allocated.  Cannot fail that way.
+int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st, bool exact) {
     int rc = frisk_internal::pool_ready();
     if (rc) return rc;
     h->n = n;
@@ -412,7 +480,6 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
         const uint64_t padded_text = T * kTile + 16;
         FRISK_CK(cudaMallocAsync((void**)&h->d_text, padded_text, st));
         FRISK_CK(cudaMemsetAsync(h->d_text + n, '\n', padded_text - n, st));
-        FRISK_CK(cudaMemcpyAsync(h->d_text, text, n, cudaMemcpyHostToDevice, st));
         FRISK_CK(cudaMallocAsync((void**)&h->d_nhdr, T * 4, st));
         FRISK_CK(cudaMallocAsync((void**)&h->d_rec_base, T * 4, st));
         FRISK_CK(cudaMallocAsync((void**)&h->d_pre, T * 4, st));
@@ -420,36 +487,81 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
         FRISK_CK(cudaMallocAsync((void**)&h->d_key, T, st));
         FRISK_CK(cudaMallocAsync((void**)&h->d_carry, T, st));
         FRISK_CK(cudaMallocAsync((void**)&h->d_base_in, T * 8, st));
-        FRISK_CK(cudaMallocAsync((void**)&h->d_counters, 4 * 8, st));
-        FRISK_CK(cudaMemsetAsync(h->d_counters, 0, 4 * 8, st));
-        fasta_lines_kernel<<<(unsigned)T, kTT, 0, st>>>(h->d_text, n, h->d_nhdr, h->d_key);
-        fasta_scan1_kernel<<<1, kST, 0, st>>>(h->d_nhdr, h->d_key, T, h->d_rec_base, h->d_carry, h->d_counters);
+        FRISK_CK(cudaMallocAsync((void**)&h->d_counters, kCtrCount * 8, st));
+        FRISK_CK(cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, st));
+        uint32_t* const d_ambig = reinterpret_cast<uint32_t*>(h->d_counters + kCtrAmbig);
+        uint32_t* const d_key_carry = reinterpret_cast<uint32_t*>(h->d_counters + kCtrKeyCarry);
+
+        uint64_t cap = 0;
+        auto alloc_records = [&](uint64_t R) -> int {
+            cap = R;
+            FRISK_CK(cudaMallocAsync((void**)&h->d_hdr_pos, R * 8, st));
+            FRISK_CK(cudaMallocAsync((void**)&h->d_len, R * 8, st));
+            FRISK_CK(cudaMallocAsync((void**)&h->d_scaf_off, R * 8, st));
+            FRISK_CK(cudaMemsetAsync(h->d_len, 0, R * 8, st));
+            return FRISK_OK;
+        };
+        auto tile_passes = [&](uint64_t t0, uint64_t t1, uint64_t avail) {
+            fasta_tile_kernel<0><<<(unsigned)(t1 - t0), kTT, 0, st>>>(h->d_text, n, h->d_rec_base, h->d_carry, h->d_hdr_pos, h->d_len,
+                                                                      h->d_pre, h->d_post, h->d_counters, nullptr, nullptr, nullptr,
+                                                                      nullptr, nullptr, t0, avail, cap);
+            fasta_scan2_kernel<<<1, kST, 0, st>>>(h->d_nhdr, h->d_pre, h->d_post, t0, t1, h->d_base_in,
+                                                  h->d_counters + kCtrBaseCarry);
+        };
+        const uint64_t min_chunk_tiles = frisk_internal::g_ingest_chunk_tiles > 0 ? (uint64_t)frisk_internal::g_ingest_chunk_tiles : kMinChunkTiles;
+        const int n_chunks = exact ? 1 : (int)std::max<uint64_t>(1, std::min<uint64_t>(kMaxChunks, T / min_chunk_tiles));
+        if (!exact && (rc = alloc_records(n / 64 + 4096))) return rc;
+        UploadLane* lane = nullptr;
+        if (n_chunks > 1) {
+            if ((rc = upload_lane(&lane))) return rc;
+            FRISK_CK(cudaEventRecord(lane->ready, st));                 // the text buffer exists (stream-ordered allocation)
+            FRISK_CK(cudaStreamWaitEvent(lane->copy, lane->ready, 0));
+        }
+        const uint64_t per = (T + n_chunks - 1) / n_chunks;
+        for (int c = 0; c < n_chunks; ++c) {
+            const uint64_t t0 = std::min<uint64_t>((uint64_t)c * per, T), t1 = std::min<uint64_t>(t0 + per, T);
+            if (t0 == t1) continue;
+            const uint64_t b0 = t0 * kTile, b1 = std::min<uint64_t>(t1 * kTile, n);
+            if (lane) {
+                FRISK_CK(cudaMemcpyAsync(h->d_text + b0, text + b0, b1 - b0, cudaMemcpyHostToDevice, lane->copy));
+                FRISK_CK(cudaEventRecord(lane->done[c], lane->copy));
+                FRISK_CK(cudaStreamWaitEvent(st, lane->done[c], 0));
+            } else {
+                FRISK_CK(cudaMemcpyAsync(h->d_text + b0, text + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+            }
+            fasta_lines_kernel<<<(unsigned)(t1 - t0), kTT, 0, st>>>(h->d_text, n, h->d_nhdr, h->d_key, t0, b1, d_ambig);
+            fasta_scan1_kernel<<<1, kST, 0, st>>>(h->d_nhdr, h->d_key, t0, t1, h->d_rec_base, h->d_carry, h->d_counters, d_key_carry);
+            if (!exact) tile_passes(t0, t1, b1);
+        }
         FRISK_CK(cudaGetLastError());
-        unsigned long long n_rec = 0;
-        FRISK_CK(cudaMemcpyAsync(&n_rec, h->d_counters, 8, cudaMemcpyDeviceToHost, st));
+        unsigned long long ctr[kCtrCount] = {};
+        if (exact) {
+            FRISK_CK(cudaMemcpyAsync(ctr, h->d_counters, 8, cudaMemcpyDeviceToHost, st));
+            FRISK_CK(cudaStreamSynchronize(st));
+            if ((rc = alloc_records(ctr[kCtrRecords] ? ctr[kCtrRecords] : 1))) return rc;
+            tile_passes(0, T, n);
+            FRISK_CK(cudaGetLastError());
+        }
+        const uint64_t first = std::min<uint64_t>(cap, kFirstFetch);
+        h->seq_len.resize(first);
+        h->hdr_pos.resize(first);
+        FRISK_CK(cudaMemcpyAsync(h->seq_len.data(), h->d_len, first * 8, cudaMemcpyDeviceToHost, st));
+        FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data(), h->d_hdr_pos, first * 8, cudaMemcpyDeviceToHost, st));
+        FRISK_CK(cudaMemcpyAsync(ctr, h->d_counters, kCtrCount * 8, cudaMemcpyDeviceToHost, st));
         FRISK_CK(cudaStreamSynchronize(st));
+        if (!exact && (ctr[kCtrAmbig] || ctr[kCtrOverflow])) return kRetryExact;
+        if (ctr[kCtrWhitespace]) return FRISK_E_FORMAT;                // whitespace inside a sequence line
+        const uint64_t n_rec = ctr[kCtrRecords];
         h->n_rec = n_rec;
-        const uint64_t R = n_rec ? n_rec : 1;
-        FRISK_CK(cudaMallocAsync((void**)&h->d_hdr_pos, R * 8, st));
-        FRISK_CK(cudaMallocAsync((void**)&h->d_len, R * 8, st));
-        FRISK_CK(cudaMallocAsync((void**)&h->d_scaf_off, R * 8, st));
-        FRISK_CK(cudaMemsetAsync(h->d_len, 0, R * 8, st));
-        fasta_tile_kernel<0><<<(unsigned)T, kTT, 0, st>>>(h->d_text, n, h->d_rec_base, h->d_carry, h->d_hdr_pos, h->d_len,
-                                                          h->d_pre, h->d_post, h->d_counters, nullptr, nullptr, nullptr, nullptr, nullptr);
-        fasta_scan2_kernel<<<1, kST, 0, st>>>(h->d_nhdr, h->d_pre, h->d_post, T, h->d_base_in);
-        FRISK_CK(cudaGetLastError());
         h->seq_len.resize(n_rec);
         h->hdr_pos.resize(n_rec);
-        unsigned long long ctr[4] = {0, 0, 0, 0};
-        if (n_rec) {
-            FRISK_CK(cudaMemcpyAsync(h->seq_len.data(), h->d_len, n_rec * 8, cudaMemcpyDeviceToHost, st));
-            FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data(), h->d_hdr_pos, n_rec * 8, cudaMemcpyDeviceToHost, st));
+        if (n_rec > first) {
+            FRISK_CK(cudaMemcpyAsync(h->seq_len.data() + first, h->d_len + first, (n_rec - first) * 8, cudaMemcpyDeviceToHost, st));
+            FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data() + first, h->d_hdr_pos + first, (n_rec - first) * 8, cudaMemcpyDeviceToHost, st));
+            FRISK_CK(cudaStreamSynchronize(st));
         }
-        FRISK_CK(cudaMemcpyAsync(ctr, h->d_counters, 4 * 8, cudaMemcpyDeviceToHost, st));
-        FRISK_CK(cudaStreamSynchronize(st));
-        if (ctr[3]) return FRISK_E_FORMAT;                             // whitespace inside a sequence line
-        h->stats[1] = ctr[1];
-        h->stats[2] = ctr[2];
+        h->stats[1] = ctr[kCtrNonUpper];
+        h->stats[2] = ctr[kCtrLower];
     }
     // names (F:156) and the 128-base aligned layout
     const uint64_t R = h->n_rec;
@@ -480,7 +592,16 @@ int frisk_b200_fasta_open(const char* text, uint64_t n, void* stream, frisk_b200
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     try {
-        rc = open_impl(h, text, n, st);
+        const bool exact = frisk_internal::g_ingest_exact != 0;
+        rc = open_impl(h, text, n, st, exact);
+        if (rc == FRISK_OK && !exact) g_open_stats[0].fetch_add(1);
+        if (rc == kRetryExact) {
+            g_open_stats[1].fetch_add(1);
+            if ((rc = free_all(h, st)) == FRISK_OK) {
+                *h = frisk_b200_fasta();
+                rc = open_impl(h, text, n, st, true);
+            }
+        }
     } catch (...) {                                   // std::bad_alloc of the record table: nothing crosses the ABI
         rc = FRISK_E_CAPACITY;
     }
@@ -516,11 +637,18 @@ int frisk_b200_fasta_pack(frisk_b200_fasta* h, uint32_t* d_codes, uint32_t* d_in
     if (d_low) FRISK_CK(cudaMemsetAsync(d_low, 0, P / 8, st));
     if (h->n_tiles && h->n_rec)
         fasta_tile_kernel<1><<<(unsigned)h->n_tiles, kTT, 0, st>>>(h->d_text, h->n, h->d_rec_base, h->d_carry, nullptr, nullptr,
-                                                                   nullptr, nullptr, nullptr, h->d_base_in, h->d_scaf_off,
-                                                                   d_codes, d_inv, d_low);
+                                                                   nullptr, nullptr, h->d_counters, h->d_base_in, h->d_scaf_off,
+                                                                   d_codes, d_inv, d_low, 0, h->n, 0);
     const uint64_t R = h->n_rec ? h->n_rec : 1;
     fasta_padding_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(h->d_scaf_off, h->d_len, h->n_rec, P, d_inv);
     FRISK_CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+int frisk_b200_fasta_open_stats(uint64_t out[2]) {
+    if (!out) return FRISK_E_INVALID;
+    out[0] = g_open_stats[0].load();
+    out[1] = g_open_stats[1].load();
     return FRISK_OK;
 }
 

@@ -16,6 +16,7 @@ int ws_get(int slot, size_t bytes, void** out);
 
 // once per device: let the default memory pool keep up to 1 GiB of freed cudaMallocAsync scratch
 int pool_ready();
+extern int g_ingest_exact, g_ingest_chunk_tiles;   // frisk_ingest.cu; set through frisk_b200_set_option
 
 // FASTA header rule of the reference (F:156): name = line.strip().strip('>').split()[0].
 // The line starts at `line_start`; returns false for an empty name (the reference raises IndexError).

@@ -2023,6 +2023,8 @@ int frisk_b200_set_option(const char* name, int value) {
     if (strcmp(name, "force_bucket_kernel") == 0) { g_force_bucket = value; return FRISK_OK; }
     if (strcmp(name, "force_direct_kernel") == 0) { g_force_direct = value; return FRISK_OK; }
     if (strcmp(name, "force_nibble_kernel") == 0) { g_force_nibble = value; return FRISK_OK; }
+    if (strcmp(name, "ingest_exact_open") == 0) { frisk_internal::g_ingest_exact = value; return FRISK_OK; }
+    if (strcmp(name, "ingest_chunk_tiles") == 0) { frisk_internal::g_ingest_chunk_tiles = value; return FRISK_OK; }
     return FRISK_E_INVALID;
 }
 
@@ -2283,12 +2285,19 @@ static int run_host_body(const PeerArgs& peers, const HostPlanes& h, const HostP
     // tables -- of ~0.03 ms: 5 chunks of 8 M bases left 0.135 ms of counting behind the last upload of a 40 Mbp
     // genome, 2 chunks of 20 M leave one chunk's count)
     uint64_t n_chunks = (h_padded_len + (20ull << 20) - 1) / (20ull << 20);
-    if (n_chunks > (uint64_t)kMaxChunks) n_chunks = kMaxChunks;
-    const uint64_t chunk = ((h_padded_len + n_chunks - 1) / n_chunks + 127) & ~127ull;
+    if (n_chunks > (uint64_t)kMaxChunks - 1) n_chunks = kMaxChunks - 1;
+    // ... plus a SHORT last chunk (1/16 of the planes): the count of the last chunk is the only one not hidden behind
+    // an upload, so it should cover little (the fixed cost of a count launch remains)
+    const uint64_t tail = h_padded_len >= (1ull << 22) ? ((h_padded_len / 16) + 127) & ~127ull : 0;
+    const uint64_t body = h_padded_len - tail;
+    const uint64_t chunk = ((body + n_chunks - 1) / n_chunks + 127) & ~127ull;
+    if (tail) ++n_chunks;
     uint64_t counted = 0;
     for (uint64_t c = 0; c < n_chunks; ++c) {
-        const uint64_t b0 = c * chunk, b1 = (b0 + chunk < h_padded_len) ? b0 + chunk : h_padded_len;
-        if (b0 >= b1) break;
+        const uint64_t b0 = (tail && c == n_chunks - 1) ? body : c * chunk;
+        const uint64_t lim = (tail && c < n_chunks - 1) ? body : h_padded_len;
+        const uint64_t b1 = (tail && c == n_chunks - 1) ? h_padded_len : ((b0 + chunk < lim) ? b0 + chunk : lim);
+        if (b0 >= b1) continue;
         CK(cudaMemcpyAsync((char*)dhc + b0 / 4, (const char*)h.codes + b0 / 4, (b1 - b0) / 4, cudaMemcpyHostToDevice, cc->copy));
         if (h.inv) CK(cudaMemcpyAsync((char*)dhi + b0 / 8, (const char*)h.inv + b0 / 8, (b1 - b0) / 8, cudaMemcpyHostToDevice, cc->copy));
         if (h.low) CK(cudaMemcpyAsync((char*)dhl + b0 / 8, (const char*)h.low + b0 / 8, (b1 - b0) / 8, cudaMemcpyHostToDevice, cc->copy));

@@ -237,7 +237,11 @@ int frisk_b200_score_occupancy(int kmax, uint32_t max_win_len, int *ctas_per_sm,
  * dense-table kernel (the path for windows of 8,187..65,535 bases) for every input; "force_bucket_kernel" = 1 keeps
  * kmax 4..8 on the bucketed kernel (default for kmax 8); "force_direct_kernel" = 1 runs kmax 7 and 8 on the direct
  * kernel (default for kmax 7) wherever windows are <= 8,186 bases; "force_general_kernel" = 1 selects the general
- * (global-memory, run-time K) path.  All of them produce the same rows (tests/test_gpu_parity.py). */
+ * (global-memory, run-time K) path.  All of them produce the same rows (tests/test_gpu_parity.py).
+ * "ingest_exact_open" = 1 makes frisk_b200_fasta_open copy the text in one piece and count the records before it
+ * allocates the record table (the fallback of the default chunked open); "ingest_chunk_tiles" = t lets texts of
+ * 2t or more 4096-byte tiles be uploaded in chunks (default 512: 2 MiB per chunk, at most 8 chunks).  Same genome
+ * either way (tests/test_ingest_gpu.py). */
 int frisk_b200_set_option(const char *name, int value);
 
 /*
@@ -313,8 +317,13 @@ int frisk_b200_run_resident(const uint32_t *d_h_codes, const uint32_t *d_h_inv, 
  * are bit-identical to those of frisk_b200_fasta_scan + frisk_b200_pack_layout + frisk_b200_pack.
  *
  * frisk_b200_fasta_open: H2D of text[0..n) (asynchronous when `text` is pinned), record detection
- * and per-record lengths on the device, names (F:156) and the packed layout on the host.  Blocks
- * until the record table is known.  *n_records, *padded_len and stats[3] (totalLen, nnTotal,
+ * and per-record lengths on the device, names (F:156) and the packed layout on the host.  Texts of
+ * 4 MiB and more go up in <= 8 chunks on a second stream, each chunk tokenised while the next is on
+ * the bus; the record table is sized by a guess (n/64 + 4096 records) so that the call synchronises
+ * once.  A text the chunked pass cannot decide (a blank run across a chunk boundary, more records than
+ * the guess) is opened again in one piece with the records counted first -- same result, reported by
+ * frisk_b200_fasta_open_stats (out[0] opens that completed chunked/speculative, out[1] opens that were
+ * redone exactly; process-wide).  Blocks until the record table is known.  *n_records, *padded_len and stats[3] (totalLen, nnTotal,
  * number of lower-case acgt -- as frisk_b200_pack) describe the result; the caller then allocates
  * the planes (padded_len/16 and padded_len/32 uint32 words) and calls frisk_b200_fasta_pack, which
  * only enqueues work on `stream`.  frisk_b200_fasta_records copies the record table (any pointer
@@ -329,6 +338,7 @@ int frisk_b200_fasta_records(const frisk_b200_fasta *h, uint64_t *name_off, uint
                              uint64_t *scaf_off);
 int frisk_b200_fasta_pack(frisk_b200_fasta *h, uint32_t *d_codes, uint32_t *d_inv, uint32_t *d_low, void *stream);
 int frisk_b200_fasta_close(frisk_b200_fasta *h, void *stream);
+int frisk_b200_fasta_open_stats(uint64_t out[2]);
 
 /* Stage times (ms since the start of the call) of the last frisk_b200_run_host / _sparse / _peers / _run_resident call
  * on the current device, from CUDA events recorded on the call's own streams: ms[0] planes uploaded, ms[1] background

@@ -25,9 +25,40 @@ def fasta_text(scaffolds, width=60, eol=b"\n", trailing_newline=True):
     return text
 
 
-def assert_same_genome(text):
+def open_stats():
+    out = np.zeros(2, dtype=np.uint64)
+    _lib.check(_lib.lib().frisk_b200_fasta_open_stats(out.ctypes.data), "fasta_open_stats")
+    return int(out[0]), int(out[1])
+
+
+class ingest_options:
+    """frisk_b200_fasta_open modes: default (chunks of >= 2 MiB), chunks of one or a few 4096-byte tiles (so that
+    test-sized texts cross chunk boundaries everywhere), and the one-piece exact open."""
+    MODES = {"default": {}, "chunk1": {"ingest_chunk_tiles": 1}, "chunk3": {"ingest_chunk_tiles": 3},
+             "exact": {"ingest_exact_open": 1}}
+
+    def __init__(self, mode):
+        self.opts = self.MODES[mode]
+
+    def __enter__(self):
+        for k, v in self.opts.items():
+            _lib.check(_lib.lib().frisk_b200_set_option(k.encode(), v), "set_option")
+
+    def __exit__(self, *exc):
+        for k in self.opts:
+            _lib.lib().frisk_b200_set_option(k.encode(), 0)
+
+
+def assert_same_genome(text, modes=("default", "chunk1", "chunk3", "exact")):
     host = engine.PackedGenome.from_fasta_bytes(text)
-    dev = engine.DeviceGenome.from_fasta_bytes(text).to_host()
+    for mode in modes:
+        with ingest_options(mode):
+            dev = engine.DeviceGenome.from_fasta_bytes(text).to_host()
+        _assert_same(dev, host)
+    return host
+
+
+def _assert_same(dev, host):
     assert dev.names == host.names
     assert np.array_equal(dev.scaf_len, host.scaf_len)
     assert np.array_equal(dev.scaf_off, host.scaf_off)
@@ -38,7 +69,6 @@ def assert_same_genome(text):
     assert (dev.low is None) == (host.low is None)
     if host.low is not None:
         assert np.array_equal(dev.low, host.low)
-    return host
 
 
 def test_reference_scanning_rules():
@@ -147,6 +177,39 @@ def test_large_single_line_record_and_many_small_records():
     tiny = [("t%d" % i, np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(rng.integers(0, 40)))])
             for i in range(5000)]                              # ... and 5,000 records shorter than a line
     assert_same_genome(fasta_text(small + tiny, width=60))
+
+
+def test_chunked_open_carries_state_across_chunks_and_falls_back_when_it_cannot_decide():
+    """The chunked open (text uploaded in pieces, each tokenised while the next is on the bus) carries the record count,
+    the header/sequence state of the open line and the bases of the open record from chunk to chunk; what it cannot
+    decide without a later chunk, or more records than its guess, is redone by the exact open.  Same genome always."""
+    rng = np.random.default_rng(5)
+    sc = synth.make("C2", 0.02, seed=9)                         # ~0.8 MB of text: 8 chunks of ~25 tiles with chunk1
+    text = fasta_text(sc, 60)
+    done0, redo0 = open_stats()
+    assert_same_genome(text, modes=("chunk1",))
+    done1, redo1 = open_stats()
+    assert (done1 - done0, redo1 - redo0) == (1, 0), "an ordinary FASTA file completes on the chunked path"
+    # one record spanning every chunk, on a single line and on many
+    one = [("solo", np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 300_000)])]
+    for width in (0, 61):
+        assert_same_genome(fasta_text(one, width), modes=("chunk1", "chunk3"))
+    assert open_stats()[1] == redo1
+    # a header line and a blank run lying across chunk boundaries (8 chunks of 2 tiles = 8192 bytes each)
+    for shift in (8180, 8190, 8191, 8192, 8193):
+        body = b">a\n" + b"A" * (shift - 4) + b"\n"
+        for sep in (b">b description\n", b"   \t  \n", b"  >c\n"):
+            assert_same_genome(body + sep + b"ACGT" * 14000 + b"\n>z\nGG\n", modes=("chunk1",))
+    assert open_stats()[1] > redo1, "blank bytes before a chunk boundary need the next chunk: redone exactly"
+    # more records than the guess (n/64 + 4096)
+    done2, redo2 = open_stats()
+    many = b"".join(b">r%d\nA\n" % i for i in range(60_000))
+    g = assert_same_genome(many, modes=("default",))
+    assert len(g.names) == 60_000 and open_stats()[1] == redo2 + 1
+    with ingest_options("exact"):
+        d, r = open_stats()
+        engine.DeviceGenome.from_fasta_bytes(text)
+        assert open_stats() == (d, r), "the exact open is neither chunked nor a retry"
 
 
 def test_multi_gigabyte_text_beyond_2_pow_32_bytes():
