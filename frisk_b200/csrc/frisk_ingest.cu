@@ -45,7 +45,11 @@ constexpr int kST = 1024;                   // threads of the (single-CTA) tile 
 constexpr uint32_t kFullMask = 0xffffffffu;
 // device counters of one open(): records, countN statistics (2), interior whitespace seen, and the state of a chunked open
 enum { kCtrRecords = 0, kCtrNonUpper = 1, kCtrLower = 2, kCtrWhitespace = 3, kCtrAmbig = 4, kCtrOverflow = 5, kCtrKeyCarry = 6,
-       kCtrBaseCarry = 7, kCtrCount = 8 };
+       kCtrBaseCarry = 7,
+       // streamed planes (fasta_layout_kernel): records that have their offset, plane words handed to the count hook,
+       // records whose padding is flagged, padded length of the finished layout
+       kLayAssigned = 8, kLayCounted = 9, kLayPadded = 10, kLayPaddedLen = 11, kCtrCount = 12,
+       kRangeSlots = 4 };                 // per chunk, behind the counters: {word_lo, word_hi, rec_lo, rec_hi}
 
 // class of a byte: 0..3 = A,T,G,C (F:70 order); 4..7 = a,t,g,c; 8 = anything else; 9 = whitespace
 // removed by the reference's line.strip() (F:149)
@@ -267,6 +271,7 @@ fasta_tile_kernel(const uint8_t* __restrict__ t, uint64_t n, const uint32_t* __r
     __shared__ uint32_t smf[32];
     __shared__ uint8_t cls_tab[256];
     const int tid = threadIdx.x;
+    if (MODE == 1 && counters[kCtrOverflow]) return;                   // streamed planes: no layout to write to (whole grid)
     cls_tab[tid] = (uint8_t)class_of((uint32_t)tid);
     const uint64_t tile = tile0 + blockIdx.x;
     const uint64_t i0 = tile * kTile + (uint64_t)tid * 16u;
@@ -412,6 +417,84 @@ fasta_padding_kernel(const unsigned long long* __restrict__ scaf_off, const unsi
     for (; a < b; a += 32) inv[a >> 5] = 0xffffffffu;
 }
 
+// ---- streamed planes: the layout of the records seen so far, on the device ---------------------------------------
+// Runs behind the tile passes of every chunk.  Records [lay[kLayAssigned], n_rec) get their offset (frisk_b200_pack_layout's
+// rule: next = align_up(off + len + 1, 128) -- the length of every record but the open one is final); out[0..1] = the plane
+// words that are final now and not yet counted (the count kernel looks one word ahead), out[2..3] = the records whose padding
+// can be flagged now.  final: the text is complete, the open record closes and the trailing padding is part of the ranges.
+__device__ __forceinline__ unsigned long long align128(unsigned long long v) { return (v + 127ull) & ~127ull; }
+
+__global__ void __launch_bounds__(kST)
+fasta_layout_kernel(const unsigned long long* __restrict__ rec_len, unsigned long long* __restrict__ scaf_off,
+                    unsigned long long* __restrict__ counters, unsigned long long* __restrict__ out, uint64_t rec_cap,
+                    uint64_t plane_cap, int count_now, int final) {
+    __shared__ unsigned long long sm[64];
+    const unsigned long long n_rec = counters[kCtrRecords];
+    if (counters[kCtrOverflow] != 0ull || n_rec > rec_cap) {           // (uniform: nothing below is touched)
+        if (threadIdx.x == 0) {
+            counters[kCtrOverflow] = 1ull;
+            out[0] = out[1] = counters[kLayCounted];
+            out[2] = out[3] = counters[kLayPadded];
+        }
+        return;
+    }
+    const unsigned long long r0 = counters[kLayAssigned];
+    const unsigned long long base = r0 ? scaf_off[r0 - 1] : 0ull;
+    const unsigned long long cnt = n_rec - r0;
+    const unsigned long long per = (cnt + kST - 1) / kST;
+    const unsigned long long lo = r0 + min((unsigned long long)threadIdx.x * per, cnt), hi = min(lo + per, n_rec);
+    unsigned long long sum = 0;
+    for (unsigned long long e = lo; e < hi; ++e) sum += e ? align128(rec_len[e - 1] + 1ull) : 0ull;
+    unsigned long long total;
+    unsigned long long run = base + block_excl_sum<unsigned long long>(sum, sm, &total);
+    for (unsigned long long e = lo; e < hi; ++e) {
+        run += e ? align128(rec_len[e - 1] + 1ull) : 0ull;
+        scaf_off[e] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long pos_hi = n_rec ? scaf_off[n_rec - 1] + counters[kCtrBaseCarry] : 0ull;   // first unwritten base
+        const unsigned long long padded = (n_rec ? align128(pos_hi + 1ull) : 0ull) + 128ull;
+        const unsigned long long w_lo = counters[kLayCounted], p_lo = counters[kLayPadded];
+        if (padded > plane_cap) {
+            counters[kCtrOverflow] = 1ull;
+            out[0] = out[1] = w_lo; out[2] = out[3] = p_lo;
+            return;
+        }
+        counters[kLayAssigned] = n_rec;
+        unsigned long long w_hi = w_lo, p_hi = final ? n_rec : max(p_lo, n_rec ? n_rec - 1ull : 0ull);
+        if (final) w_hi = padded / 32ull - 1ull;
+        else if (count_now && (pos_hi >> 5) >= 1ull) w_hi = max(w_lo, (pos_hi >> 5) - 1ull);
+        if (!count_now) w_hi = w_lo;
+        out[0] = w_lo; out[1] = w_hi; counters[kLayCounted] = w_hi;
+        out[2] = p_lo; out[3] = p_hi; counters[kLayPadded] = p_hi;
+        if (final) counters[kLayPaddedLen] = padded;
+    }
+}
+
+// padding of records [range[0], range[1]) (device-side range of fasta_layout_kernel); the last record of a finished text is
+// padded up to the layout's padded length
+__global__ void __launch_bounds__(256)
+fasta_padding_range_kernel(const unsigned long long* __restrict__ scaf_off, const unsigned long long* __restrict__ rec_len,
+                           const unsigned long long* __restrict__ range, const unsigned long long* __restrict__ counters, int final,
+                           uint32_t* __restrict__ inv) {
+    const unsigned long long n_rec = counters[kCtrRecords];
+    if (final && n_rec == 0ull && counters[kCtrOverflow] == 0ull) {     // no record at all: 128 invalid bases
+        if (blockIdx.x == 0 && threadIdx.x < 4) inv[threadIdx.x] = 0xffffffffu;
+        return;
+    }
+    for (unsigned long long r = range[0] + (unsigned long long)blockIdx.x * 256u + threadIdx.x; r < range[1];
+         r += (unsigned long long)gridDim.x * 256u) {
+        unsigned long long a = scaf_off[r] + rec_len[r];
+        const unsigned long long b = (r + 1 < n_rec) ? scaf_off[r + 1] : counters[kLayPaddedLen];
+        if (a & 31u) {
+            atomicOr(&inv[a >> 5], 0xffffffffu >> (uint32_t)(a & 31u));
+            a = (a | 31u) + 1u;
+        }
+        for (; a < b; a += 32) inv[a >> 5] = 0xffffffffu;
+    }
+}
+
 }  // namespace
 
 struct frisk_b200_fasta {
@@ -421,6 +504,8 @@ struct frisk_b200_fasta {
     uint32_t *d_nhdr = nullptr, *d_rec_base = nullptr, *d_pre = nullptr, *d_post = nullptr;
     uint8_t *d_key = nullptr, *d_carry = nullptr;
     unsigned long long *d_base_in = nullptr, *d_hdr_pos = nullptr, *d_len = nullptr, *d_scaf_off = nullptr, *d_counters = nullptr;
+    uint32_t *d_codes = nullptr, *d_inv = nullptr, *d_low = nullptr;     // planes built by the open itself (streamed planes)
+    bool planes_ready = false;
     std::vector<uint64_t> name_off, seq_len, scaf_off, hdr_pos;
     std::vector<uint32_t> name_len;
 };
@@ -428,11 +513,13 @@ struct frisk_b200_fasta {
 namespace {
 int free_all(frisk_b200_fasta* h, cudaStream_t st) {
     void* ptrs[] = {h->d_text, h->d_nhdr, h->d_rec_base, h->d_pre, h->d_post, h->d_key, h->d_carry,
-                    h->d_base_in, h->d_hdr_pos, h->d_len, h->d_scaf_off, h->d_counters};
+                    h->d_base_in, h->d_hdr_pos, h->d_len, h->d_scaf_off, h->d_counters, h->d_codes, h->d_inv, h->d_low};
     for (void* p : ptrs)
         if (p) FRISK_CK(cudaFreeAsync(p, st));
     h->d_text = nullptr; h->d_nhdr = h->d_rec_base = h->d_pre = h->d_post = nullptr; h->d_key = h->d_carry = nullptr;
     h->d_base_in = h->d_hdr_pos = h->d_len = h->d_scaf_off = h->d_counters = nullptr;
+    h->d_codes = h->d_inv = h->d_low = nullptr;
+    h->planes_ready = false;
     return FRISK_OK;
 }
 
@@ -469,13 +556,18 @@ int upload_lane(UploadLane** out) {
 //   sized by a guess (one record per 64 bytes of text + 4096).  A line decision that needs a byte of a later chunk, or more
 //   records than the guess, returns kRetryExact.
 // exact = true: one copy, records counted (one more synchronisation) before the record table is allocated.  Cannot fail that way.
-int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st, bool exact) {
+// sink (nullable, !exact only): the PLANES are built during the open as well -- allocated by the handle for an upper bound of
+//   the layout (text bytes + 128 per guessed record), each chunk laid out (fasta_layout_kernel), packed and padded behind its
+//   tile passes, and the plane words that became final handed to sink->on_range while the next chunk is still on the bus.
+int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st, bool exact, frisk_internal::IngestSink* sink) {
     int rc = frisk_internal::pool_ready();
     if (rc) return rc;
+    if (exact) sink = nullptr;
     h->n = n;
     h->n_tiles = n ? (n + kTile - 1) / kTile : 0;
     if (h->n_tiles > 0x7fffffffull) return FRISK_E_UNSUPPORTED;         // 8 TB of text per call
     const uint64_t T = h->n_tiles;
+    if (!T && sink) return kRetryExact;                                 // (empty text: nothing to stream)
     if (T) {
         const uint64_t padded_text = T * kTile + 16;
         FRISK_CK(cudaMallocAsync((void**)&h->d_text, padded_text, st));
@@ -487,12 +579,13 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
         FRISK_CK(cudaMallocAsync((void**)&h->d_key, T, st));
         FRISK_CK(cudaMallocAsync((void**)&h->d_carry, T, st));
         FRISK_CK(cudaMallocAsync((void**)&h->d_base_in, T * 8, st));
-        FRISK_CK(cudaMallocAsync((void**)&h->d_counters, kCtrCount * 8, st));
-        FRISK_CK(cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, st));
+        constexpr size_t kCtrWords = kCtrCount + (size_t)kRangeSlots * kMaxChunks;
+        FRISK_CK(cudaMallocAsync((void**)&h->d_counters, kCtrWords * 8, st));
+        FRISK_CK(cudaMemsetAsync(h->d_counters, 0, kCtrWords * 8, st));
         uint32_t* const d_ambig = reinterpret_cast<uint32_t*>(h->d_counters + kCtrAmbig);
         uint32_t* const d_key_carry = reinterpret_cast<uint32_t*>(h->d_counters + kCtrKeyCarry);
 
-        uint64_t cap = 0;
+        uint64_t cap = 0, plane_cap = 0;
         auto alloc_records = [&](uint64_t R) -> int {
             cap = R;
             FRISK_CK(cudaMallocAsync((void**)&h->d_hdr_pos, R * 8, st));
@@ -511,20 +604,35 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
         const uint64_t min_chunk_tiles = frisk_internal::g_ingest_chunk_tiles > 0 ? (uint64_t)frisk_internal::g_ingest_chunk_tiles : kMinChunkTiles;
         const int n_chunks = exact ? 1 : (int)std::max<uint64_t>(1, std::min<uint64_t>(kMaxChunks, T / min_chunk_tiles));
         if (!exact && (rc = alloc_records(n / 64 + 4096))) return rc;
+        if (sink) {
+            // every base is a byte of the text; every record adds < 128 + 128 bases of padding: room for one record per KiB
+            plane_cap = ((n + 127) & ~127ull) + 256ull * (n / 1024 + 4096) + 256;
+            FRISK_CK(cudaMallocAsync((void**)&h->d_codes, plane_cap / 4, st));
+            FRISK_CK(cudaMallocAsync((void**)&h->d_inv, plane_cap / 8, st));
+            FRISK_CK(cudaMallocAsync((void**)&h->d_low, plane_cap / 8, st));
+            FRISK_CK(cudaMemsetAsync(h->d_codes, 0, plane_cap / 4, st));
+            FRISK_CK(cudaMemsetAsync(h->d_inv, 0, plane_cap / 8, st));
+            FRISK_CK(cudaMemsetAsync(h->d_low, 0, plane_cap / 8, st));
+        }
         UploadLane* lane = nullptr;
-        if (n_chunks > 1) {
+        if (n_chunks > 1 || sink) {
             if ((rc = upload_lane(&lane))) return rc;
             FRISK_CK(cudaEventRecord(lane->ready, st));                 // the text buffer exists (stream-ordered allocation)
             FRISK_CK(cudaStreamWaitEvent(lane->copy, lane->ready, 0));
         }
         const uint64_t per = (T + n_chunks - 1) / n_chunks;
-        for (int c = 0; c < n_chunks; ++c) {
-            const uint64_t t0 = std::min<uint64_t>((uint64_t)c * per, T), t1 = std::min<uint64_t>(t0 + per, T);
-            if (t0 == t1) continue;
+        const int count_every = n_chunks > 4 ? 2 : 1;                   // (a count launch has a fixed cost: fewer, larger ranges)
+        int last_chunk = 0;
+        for (int c = 0; c < n_chunks; ++c)
+            if (std::min<uint64_t>((uint64_t)c * per, T) < T) last_chunk = c;
+        for (int c = 0; c <= last_chunk; ++c) {
+            const uint64_t t0 = (uint64_t)c * per, t1 = std::min<uint64_t>(t0 + per, T);
             const uint64_t b0 = t0 * kTile, b1 = std::min<uint64_t>(t1 * kTile, n);
+            const bool final = c == last_chunk;
             if (lane) {
                 FRISK_CK(cudaMemcpyAsync(h->d_text + b0, text + b0, b1 - b0, cudaMemcpyHostToDevice, lane->copy));
                 FRISK_CK(cudaEventRecord(lane->done[c], lane->copy));
+                if (final && sink && sink->uploaded_mark) FRISK_CK(cudaEventRecord(sink->uploaded_mark, lane->copy));
                 FRISK_CK(cudaStreamWaitEvent(st, lane->done[c], 0));
             } else {
                 FRISK_CK(cudaMemcpyAsync(h->d_text + b0, text + b0, b1 - b0, cudaMemcpyHostToDevice, st));
@@ -532,6 +640,26 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
             fasta_lines_kernel<<<(unsigned)(t1 - t0), kTT, 0, st>>>(h->d_text, n, h->d_nhdr, h->d_key, t0, b1, d_ambig);
             fasta_scan1_kernel<<<1, kST, 0, st>>>(h->d_nhdr, h->d_key, t0, t1, h->d_rec_base, h->d_carry, h->d_counters, d_key_carry);
             if (!exact) tile_passes(t0, t1, b1);
+            if (sink) {
+                unsigned long long* const d_range = h->d_counters + kCtrCount + (size_t)kRangeSlots * c;
+                const bool count_now = final || (c % count_every) == count_every - 1;
+                fasta_layout_kernel<<<1, kST, 0, st>>>(h->d_len, h->d_scaf_off, h->d_counters, d_range, cap, plane_cap,
+                                                       (int)(count_now && (bool)sink->on_range), (int)final);
+                if (final) {                                            // the record table is final: the host can have it now,
+                    FRISK_CK(cudaEventRecord(lane->ready, st));         // while the last chunk is still being packed and counted
+                    FRISK_CK(cudaStreamWaitEvent(lane->copy, lane->ready, 0));
+                }
+                fasta_tile_kernel<1><<<(unsigned)(t1 - t0), kTT, 0, st>>>(h->d_text, n, h->d_rec_base, h->d_carry, nullptr, nullptr,
+                                                                          nullptr, nullptr, h->d_counters, h->d_base_in, h->d_scaf_off,
+                                                                          h->d_codes, h->d_inv, h->d_low, t0, b1, 0);
+                fasta_padding_range_kernel<<<final ? 32 : 8, 256, 0, st>>>(h->d_scaf_off, h->d_len, d_range + 2, h->d_counters, (int)final,
+                                                                           h->d_inv);
+                FRISK_CK(cudaGetLastError());
+                if (count_now && sink->on_range) {
+                    const uint64_t words_hint = ((b1 - (uint64_t)(c / count_every) * count_every * per * kTile) >> 5) + 8;
+                    if ((rc = sink->on_range(h->d_codes, h->d_inv, h->d_low, d_range, words_hint, st))) return rc;
+                }
+            }
         }
         FRISK_CK(cudaGetLastError());
         unsigned long long ctr[kCtrCount] = {};
@@ -542,13 +670,14 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
             tile_passes(0, T, n);
             FRISK_CK(cudaGetLastError());
         }
+        cudaStream_t back = sink ? lane->copy : st;                     // the stream the record table comes back on
         const uint64_t first = std::min<uint64_t>(cap, kFirstFetch);
         h->seq_len.resize(first);
         h->hdr_pos.resize(first);
-        FRISK_CK(cudaMemcpyAsync(h->seq_len.data(), h->d_len, first * 8, cudaMemcpyDeviceToHost, st));
-        FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data(), h->d_hdr_pos, first * 8, cudaMemcpyDeviceToHost, st));
-        FRISK_CK(cudaMemcpyAsync(ctr, h->d_counters, kCtrCount * 8, cudaMemcpyDeviceToHost, st));
-        FRISK_CK(cudaStreamSynchronize(st));
+        FRISK_CK(cudaMemcpyAsync(h->seq_len.data(), h->d_len, first * 8, cudaMemcpyDeviceToHost, back));
+        FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data(), h->d_hdr_pos, first * 8, cudaMemcpyDeviceToHost, back));
+        FRISK_CK(cudaMemcpyAsync(ctr, h->d_counters, kCtrCount * 8, cudaMemcpyDeviceToHost, back));
+        FRISK_CK(cudaStreamSynchronize(back));
         if (!exact && (ctr[kCtrAmbig] || ctr[kCtrOverflow])) return kRetryExact;
         if (ctr[kCtrWhitespace]) return FRISK_E_FORMAT;                // whitespace inside a sequence line
         const uint64_t n_rec = ctr[kCtrRecords];
@@ -556,12 +685,13 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
         h->seq_len.resize(n_rec);
         h->hdr_pos.resize(n_rec);
         if (n_rec > first) {
-            FRISK_CK(cudaMemcpyAsync(h->seq_len.data() + first, h->d_len + first, (n_rec - first) * 8, cudaMemcpyDeviceToHost, st));
-            FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data() + first, h->d_hdr_pos + first, (n_rec - first) * 8, cudaMemcpyDeviceToHost, st));
-            FRISK_CK(cudaStreamSynchronize(st));
+            FRISK_CK(cudaMemcpyAsync(h->seq_len.data() + first, h->d_len + first, (n_rec - first) * 8, cudaMemcpyDeviceToHost, back));
+            FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data() + first, h->d_hdr_pos + first, (n_rec - first) * 8, cudaMemcpyDeviceToHost, back));
+            FRISK_CK(cudaStreamSynchronize(back));
         }
         h->stats[1] = ctr[kCtrNonUpper];
         h->stats[2] = ctr[kCtrLower];
+        if (sink) h->padded_len = ctr[kLayPaddedLen];                  // (checked against the host's layout below)
     }
     // names (F:156) and the 128-base aligned layout
     const uint64_t R = h->n_rec;
@@ -573,14 +703,90 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
         total += h->seq_len[r];
     }
     h->stats[0] = total;
+    const uint64_t device_padded = h->padded_len;
     rc = frisk_b200_pack_layout(h->seq_len.data(), R, h->scaf_off.data(), &h->padded_len);
     if (rc) return rc;
-    if (R) FRISK_CK(cudaMemcpyAsync(h->d_scaf_off, h->scaf_off.data(), R * 8, cudaMemcpyHostToDevice, st));
+    if (sink) {
+        if (device_padded != h->padded_len) return kRetryExact;         // (cannot happen: both sides apply the same rule)
+        h->planes_ready = true;
+        sink->counted = (bool)sink->on_range;
+    } else if (R) {
+        FRISK_CK(cudaMemcpyAsync(h->d_scaf_off, h->scaf_off.data(), R * 8, cudaMemcpyHostToDevice, st));
+    }
     return FRISK_OK;
+}
+
+int pack_impl(frisk_b200_fasta* h, uint32_t* d_codes, uint32_t* d_inv, uint32_t* d_low, cudaStream_t st) {
+    const uint64_t P = h->padded_len;
+    FRISK_CK(cudaMemsetAsync(d_codes, 0, P / 4, st));
+    FRISK_CK(cudaMemsetAsync(d_inv, 0, P / 8, st));
+    if (d_low) FRISK_CK(cudaMemsetAsync(d_low, 0, P / 8, st));
+    if (h->n_tiles && h->n_rec)
+        fasta_tile_kernel<1><<<(unsigned)h->n_tiles, kTT, 0, st>>>(h->d_text, h->n, h->d_rec_base, h->d_carry, nullptr, nullptr,
+                                                                   nullptr, nullptr, h->d_counters, h->d_base_in, h->d_scaf_off,
+                                                                   d_codes, d_inv, d_low, 0, h->n, 0);
+    const uint64_t R = h->n_rec ? h->n_rec : 1;
+    fasta_padding_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(h->d_scaf_off, h->d_len, h->n_rec, P, d_inv);
+    FRISK_CK(cudaGetLastError());
+    return FRISK_OK;
+}
+
+// open with retry; sink (nullable): planes built by the open and owned by the handle (streamed, or -- after a retry --
+// packed in one piece behind the exact open; sink->counted tells which)
+int open_any(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st, frisk_internal::IngestSink* sink) {
+    const bool exact = frisk_internal::g_ingest_exact != 0;
+    if (sink) sink->counted = false;
+    int rc = open_impl(h, text, n, st, exact, sink);
+    if (rc == FRISK_OK && !exact) g_open_stats[0].fetch_add(1);
+    if (rc == kRetryExact) {
+        if (n) g_open_stats[1].fetch_add(1);
+        if (sink && sink->abandon && (rc = sink->abandon(st))) return rc;
+        if ((rc = free_all(h, st))) return rc;
+        *h = frisk_b200_fasta();
+        rc = open_impl(h, text, n, st, true, nullptr);
+    }
+    if (rc == FRISK_OK && sink && !h->planes_ready) {
+        const uint64_t P = h->padded_len;
+        FRISK_CK(cudaMallocAsync((void**)&h->d_codes, P / 4, st));
+        FRISK_CK(cudaMallocAsync((void**)&h->d_inv, P / 8, st));
+        if (h->stats[2]) FRISK_CK(cudaMallocAsync((void**)&h->d_low, P / 8, st));
+        if ((rc = pack_impl(h, h->d_codes, h->d_inv, h->d_low, st))) return rc;
+        h->planes_ready = true;
+        sink->counted = false;
+    }
+    return rc;
 }
 }  // namespace
 
+int frisk_internal::fasta_open_planes(const char* text, uint64_t n, cudaStream_t st, IngestSink* sink, frisk_b200_fasta** out) {
+    if (!out || !sink || (!text && n)) return FRISK_E_INVALID;
+    *out = nullptr;
+    frisk_b200_fasta* h = new (std::nothrow) frisk_b200_fasta();
+    if (!h) return FRISK_E_INVALID;
+    int rc;
+    try {
+        rc = open_any(h, text, n, st, sink);
+    } catch (...) {
+        rc = FRISK_E_CAPACITY;
+    }
+    if (rc) {
+        free_all(h, st);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return FRISK_OK;
+}
+
 extern "C" {
+
+int frisk_b200_fasta_info(const frisk_b200_fasta* h, uint64_t* n_records, uint64_t* padded_len, uint64_t stats[3]) {
+    if (!h) return FRISK_E_INVALID;
+    if (n_records) *n_records = h->n_rec;
+    if (padded_len) *padded_len = h->padded_len;
+    if (stats) { stats[0] = h->stats[0]; stats[1] = h->stats[1]; stats[2] = h->stats[2]; }
+    return FRISK_OK;
+}
 
 int frisk_b200_fasta_open(const char* text, uint64_t n, void* stream, frisk_b200_fasta** out, uint64_t* n_records,
                           uint64_t* padded_len, uint64_t stats[3]) {
@@ -592,16 +798,7 @@ int frisk_b200_fasta_open(const char* text, uint64_t n, void* stream, frisk_b200
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     try {
-        const bool exact = frisk_internal::g_ingest_exact != 0;
-        rc = open_impl(h, text, n, st, exact);
-        if (rc == FRISK_OK && !exact) g_open_stats[0].fetch_add(1);
-        if (rc == kRetryExact) {
-            g_open_stats[1].fetch_add(1);
-            if ((rc = free_all(h, st)) == FRISK_OK) {
-                *h = frisk_b200_fasta();
-                rc = open_impl(h, text, n, st, true);
-            }
-        }
+        rc = open_any(h, text, n, st, nullptr);
     } catch (...) {                                   // std::bad_alloc of the record table: nothing crosses the ABI
         rc = FRISK_E_CAPACITY;
     }
@@ -630,18 +827,14 @@ int frisk_b200_fasta_records(const frisk_b200_fasta* h, uint64_t* name_off, uint
 
 int frisk_b200_fasta_pack(frisk_b200_fasta* h, uint32_t* d_codes, uint32_t* d_inv, uint32_t* d_low, void* stream) {
     if (!h || !d_codes || !d_inv) return FRISK_E_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    const uint64_t P = h->padded_len;
-    FRISK_CK(cudaMemsetAsync(d_codes, 0, P / 4, st));
-    FRISK_CK(cudaMemsetAsync(d_inv, 0, P / 8, st));
-    if (d_low) FRISK_CK(cudaMemsetAsync(d_low, 0, P / 8, st));
-    if (h->n_tiles && h->n_rec)
-        fasta_tile_kernel<1><<<(unsigned)h->n_tiles, kTT, 0, st>>>(h->d_text, h->n, h->d_rec_base, h->d_carry, nullptr, nullptr,
-                                                                   nullptr, nullptr, h->d_counters, h->d_base_in, h->d_scaf_off,
-                                                                   d_codes, d_inv, d_low, 0, h->n, 0);
-    const uint64_t R = h->n_rec ? h->n_rec : 1;
-    fasta_padding_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(h->d_scaf_off, h->d_len, h->n_rec, P, d_inv);
-    FRISK_CK(cudaGetLastError());
+    return pack_impl(h, d_codes, d_inv, d_low, (cudaStream_t)stream);
+}
+
+int frisk_b200_fasta_planes(const frisk_b200_fasta* h, const uint32_t** d_codes, const uint32_t** d_inv, const uint32_t** d_low) {
+    if (!h || !h->planes_ready) return FRISK_E_INVALID;
+    if (d_codes) *d_codes = h->d_codes;
+    if (d_inv) *d_inv = h->d_inv;
+    if (d_low) *d_low = h->stats[2] ? h->d_low : nullptr;            // no lower-case base: no plane (as frisk_b200_pack reports it)
     return FRISK_OK;
 }
 

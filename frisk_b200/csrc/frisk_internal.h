@@ -6,6 +6,10 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <functional>
+
+struct frisk_b200_fasta;
+
 namespace frisk_internal {
 
 // records the CUDA error text for frisk_b200_last_cuda_error() and returns FRISK_E_CUDA
@@ -17,6 +21,22 @@ int ws_get(int slot, size_t bytes, void** out);
 // once per device: let the default memory pool keep up to 1 GiB of freed cudaMallocAsync scratch
 int pool_ready();
 extern int g_ingest_exact, g_ingest_chunk_tiles;   // frisk_ingest.cu; set through frisk_b200_set_option
+
+// Streamed FASTA open that also builds the planes (frisk_ingest.cu; used by frisk_b200_run_fasta).  While the text is
+// still arriving, on_range (optional) is handed the plane words [d_word_range[0], d_word_range[1]) -- a DEVICE-side range --
+// that became final: the caller counts them.  If the streamed attempt has to be abandoned (see frisk_b200_fasta_open),
+// abandon() undoes what on_range accumulated, the text is opened and packed in one piece, and counted stays false.
+struct IngestSink {
+    std::function<int(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const unsigned long long* d_word_range,
+                      uint64_t words_hint, cudaStream_t st)> on_range;
+    std::function<int(cudaStream_t st)> abandon;
+    cudaEvent_t uploaded_mark = nullptr;     // recorded behind the last text chunk's copy
+    bool counted = false;                    // out: on_range saw every word of [0, padded_len / 32 - 1)
+};
+int fasta_open_planes(const char* text, uint64_t n, cudaStream_t st, IngestSink* sink, frisk_b200_fasta** out);
+// background count of a word range that lives in device memory (frisk_kernels.cu); kmax <= FRISK_B200_FAST_K
+int background_device_range(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const unsigned long long* d_word_range,
+                            uint64_t words_hint, int kmax, int mask_host, uint64_t* fwd, cudaStream_t st);
 
 // FASTA header rule of the reference (F:156): name = line.strip().strip('>').split()[0].
 // The line starts at `line_start`; returns false for an empty name (the reference raises IndexError).

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "../../include/frisk_b200.h"
 #include "frisk_internal.h"
@@ -84,10 +85,11 @@ template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
 bg_count_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ low,
                 uint64_t word_lo, uint64_t word_hi, int mask_host, unsigned long long* __restrict__ fwd,
-                uint32_t* __restrict__ partial) {
+                uint32_t* __restrict__ partial, const unsigned long long* __restrict__ d_range) {
     constexpr uint32_t NB = pow4(K);
     constexpr uint32_t NW = NB / 2u;                       // shared words: two u16 bins each
     extern __shared__ __align__(16) uint32_t tab[];
+    if (d_range) { word_lo = d_range[0]; word_hi = d_range[1]; }     // range produced on the device (streamed FASTA ingest)
     const uint64_t n_words = word_hi - word_lo;
     const uint64_t per = (n_words + gridDim.x - 1) / gridDim.x;
     const uint64_t w0 = word_lo + per * blockIdx.x;
@@ -1482,7 +1484,8 @@ int sm_count() {
 
 template <int K>
 int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, uint64_t w_lo, uint64_t w_hi,
-                      int mask_host, uint64_t* fwd, cudaStream_t st) {
+                      int mask_host, uint64_t* fwd, cudaStream_t st, const unsigned long long* d_range = nullptr) {
+    // d_range: the kernel reads its range from device memory; [w_lo, w_hi) then only sizes the grid
     constexpr uint32_t NB = pow4(K);
     constexpr uint32_t NW = NB / 2u;
     const size_t smem = (size_t)NW * 4;
@@ -1503,7 +1506,7 @@ int launch_background(const uint32_t* codes, const uint32_t* inv, const uint32_t
         CK(cudaMallocAsync((void**)&partial, (size_t)grid * NW * sizeof(uint32_t), st));
     }
     bg_count_kernel<K><<<grid, kThreads, smem, st>>>(codes, inv, low, w_lo, w_hi, mask_host,
-                                                      reinterpret_cast<unsigned long long*>(fwd), partial);
+                                                      reinterpret_cast<unsigned long long*>(fwd), partial, d_range);
     if (partial) {
         bg_reduce_kernel<K><<<(NW + 31) / 32, 256, 0, st>>>(partial, grid, reinterpret_cast<unsigned long long*>(fwd));
         CK(cudaFreeAsync(partial, st));
@@ -1809,6 +1812,20 @@ int frisk_b200_background(const uint32_t* d_codes, const uint32_t* d_inv, const 
         return frisk_internal::general_background(d_codes, d_inv, d_low, first_base >> 5, last_base >> 5, kmax, mask_host, d_fwd, st);
     DISPATCH_K(kmax, launch_background<K>(d_codes, d_inv, d_low, first_base >> 5, last_base >> 5, mask_host, d_fwd, st));
 }
+
+}  // extern "C"
+
+int frisk_internal::background_device_range(const uint32_t* codes, const uint32_t* inv, const uint32_t* low,
+                                            const unsigned long long* d_word_range, uint64_t words_hint, int kmax, int mask_host,
+                                            uint64_t* fwd, cudaStream_t st) {
+    if (!codes || !inv || !fwd || !d_word_range) return FRISK_E_INVALID;
+    int rc = check_k(1, kmax);
+    if (rc) return rc;
+    if (kmax > FRISK_B200_FAST_K) return FRISK_E_UNSUPPORTED;
+    DISPATCH_K(kmax, launch_background<K>(codes, inv, low, 0, words_hint ? words_hint : 1, mask_host, fwd, st, d_word_range));
+}
+
+extern "C" {
 
 int frisk_b200_finalize_tables(const uint64_t* d_fwd, int kmax, int symmetric, uint64_t* d_tables, uint64_t* d_valid_kmax,
                                void* stream) {
@@ -2402,6 +2419,137 @@ int frisk_b200_run_resident(const uint32_t* d_h_codes, const uint32_t* d_h_inv, 
                   max_win_len, kmin, kmax, mask_host, want_rip, genome_space, rows_out, status_out, tables_out,
                   valid_kmax_out, dfwd, (cudaStream_t)stream, nullptr, nullptr, nullptr, tm);
     if (rc) { cudaStreamSynchronize((cudaStream_t)stream); cudaGetLastError(); }   // queued copies still target the caller's buffers
+    return rc;
+}
+
+// ---- FASTA text in, rows out, one call -------------------------------------------------------------------------------
+// The text goes up in chunks; each chunk is tokenised, laid out, packed and (kmax <= 8) counted on the device while the
+// next one is on the bus (frisk_ingest.cu).  The host sees the record table as soon as the last chunk is tokenised, derives
+// names and windows while that chunk is still being packed and counted, and queues tables -> IVOM -> window kernel behind it.
+namespace {
+struct HostStage { void* p = nullptr; size_t cap = 0; };
+HostStage g_stage[64][2];        // pinned staging of the window list (off, len), grown on demand
+
+int stage_get(int dev, int slot, size_t bytes, void** out) {
+    HostStage& s = g_stage[dev & 63][slot];
+    if (s.cap < bytes) {
+        if (s.p) CK(cudaFreeHost(s.p));
+        s.p = nullptr; s.cap = 0;
+        const size_t want = bytes + bytes / 2 + 4096;
+        CK(cudaHostAlloc(&s.p, want, cudaHostAllocDefault));
+        s.cap = want;
+    }
+    *out = s.p;
+    return FRISK_OK;
+}
+
+int run_fasta_body(const char* h_text, uint64_t h_n, const char* q_text, uint64_t q_n, int w, int step, int scaffolds_all,
+                   int kmin, int kmax, int mask_host, int want_rip, uint64_t rows_cap, double* rows_out, uint32_t* status_out,
+                   uint64_t* tables_out, uint64_t* valid_kmax_out, uint64_t* n_win_out, frisk_b200_fasta** host_out,
+                   frisk_b200_fasta** query_out, cudaStream_t st, int dev) {
+    int rc;
+    CopyCtx* cc = nullptr;
+    if ((rc = copy_ctx(&cc))) return rc;
+    RunMarks* tm = nullptr;
+    if ((rc = run_marks(&tm))) return rc;
+    if ((rc = mark(tm, kTmStart, st))) return rc;
+    const size_t tsz = (size_t)frisk_b200_table_size(1, kmax);
+    void* dfwd;
+    if ((rc = ws_get(6, (tsz + 1) * 8, &dfwd))) return rc;
+    CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, st));
+
+    frisk_internal::IngestSink sink;
+    if (kmax <= FRISK_B200_FAST_K)
+        sink.on_range = [&](const uint32_t* c, const uint32_t* i, const uint32_t* l, const unsigned long long* d_range,
+                            uint64_t hint, cudaStream_t s2) {
+            return frisk_internal::background_device_range(c, i, l, d_range, hint, kmax, mask_host, (uint64_t*)dfwd, s2);
+        };
+    sink.abandon = [&](cudaStream_t s2) {
+        CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, s2));
+        return (int)FRISK_OK;
+    };
+    sink.uploaded_mark = tm->ev[kTmUploaded];
+    if ((rc = frisk_internal::fasta_open_planes(h_text, h_n, st, &sink, host_out))) return rc;
+    tm->have[kTmUploaded] = h_n > 0;                                // (recorded behind the last text chunk)
+    const bool counted = sink.counted;
+    if (counted && (rc = mark(tm, kTmCounted, st))) return rc;
+    frisk_b200_fasta* hh = *host_out;
+    frisk_b200_fasta* qh = hh;
+    const bool same = !q_text || (q_text == h_text && q_n == h_n);
+    if (!same) {
+        frisk_internal::IngestSink qsink;                            // planes only: nothing of the query is counted
+        if ((rc = frisk_internal::fasta_open_planes(q_text, q_n, st, &qsink, query_out))) return rc;
+        qh = *query_out;
+    }
+    uint64_t h_rec = 0, h_padded = 0, h_stats[3], q_rec = 0, q_padded = 0, q_stats[3];
+    if ((rc = frisk_b200_fasta_info(hh, &h_rec, &h_padded, h_stats))) return rc;
+    if ((rc = frisk_b200_fasta_info(qh, &q_rec, &q_padded, q_stats))) return rc;
+    const uint32_t *dhc, *dhi, *dhl, *dqc, *dqi, *dql;
+    if ((rc = frisk_b200_fasta_planes(hh, &dhc, &dhi, &dhl))) return rc;
+    if ((rc = frisk_b200_fasta_planes(qh, &dqc, &dqi, &dql))) return rc;
+
+    // windows of the query (F:194-251), into pinned staging
+    std::vector<uint64_t> seq_len((size_t)q_rec), scaf_off((size_t)q_rec);
+    if ((rc = frisk_b200_fasta_records(qh, nullptr, nullptr, seq_len.data(), scaf_off.data()))) return rc;
+    uint64_t n_win = 0;
+    if ((rc = frisk_b200_windows(seq_len.data(), scaf_off.data(), q_rec, w, step, scaffolds_all, 0, nullptr, nullptr, nullptr,
+                                 nullptr, nullptr, &n_win)))
+        return rc;
+    if (n_win_out) *n_win_out = n_win;
+    if (n_win > rows_cap) return FRISK_E_CAPACITY;
+    void *win_off = nullptr, *win_len = nullptr;
+    uint32_t max_len = 0;
+    if (n_win) {
+        if ((rc = stage_get(dev, 0, n_win * 8, &win_off))) return rc;
+        if ((rc = stage_get(dev, 1, n_win * 4, &win_len))) return rc;
+        if ((rc = frisk_b200_windows(seq_len.data(), scaf_off.data(), q_rec, w, step, scaffolds_all, n_win, (uint64_t*)win_off,
+                                     (uint32_t*)win_len, nullptr, nullptr, nullptr, &n_win)))
+            return rc;
+        const uint32_t* wl = (const uint32_t*)win_len;
+        for (uint64_t i = 0; i < n_win; ++i) max_len = wl[i] > max_len ? wl[i] : max_len;
+    }
+    CK(cudaEventRecord(cc->ev[kMaxChunks], st));                    // the copy stream joins behind the ingest
+    CK(cudaStreamWaitEvent(cc->copy, cc->ev[kMaxChunks], 0));
+    return run_tail(PeerArgs(), dhc, dhi, dhl, h_padded, counted, dqc, dqi, dql, (const uint64_t*)win_off, (const uint32_t*)win_len,
+                    n_win, max_len, kmin, kmax, mask_host, want_rip, (int64_t)h_stats[0] - (int64_t)h_stats[1], rows_out, status_out,
+                    tables_out, valid_kmax_out, dfwd, st, cc->copy, cc->ev[kMaxChunks + 1], cc->ev[kMaxChunks + 2], tm);
+}
+}  // namespace
+
+int frisk_b200_run_fasta(const char* h_text, uint64_t h_n, const char* q_text, uint64_t q_n, int w, int step, int scaffolds_all,
+                         int kmin, int kmax, int mask_host, int want_rip, uint64_t rows_cap, double* rows_out,
+                         uint32_t* status_out, uint64_t* tables_out, uint64_t* valid_kmax_out, uint64_t* n_win_out,
+                         frisk_b200_fasta** host_out, frisk_b200_fasta** query_out, void* stream) {
+    if (!host_out || !query_out || (!h_text && h_n) || (!q_text && q_n) || (rows_cap && (!rows_out || !status_out)))
+        return FRISK_E_INVALID;
+    *host_out = *query_out = nullptr;
+    if (n_win_out) *n_win_out = 0;
+    int rc = check_k(kmin, kmax);
+    if (rc) return rc;
+    if (w < 1 || step < 1) return FRISK_E_INVALID;
+    if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_run_mu[dev & 63]);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool threw = false;
+    try {
+        rc = run_fasta_body(h_text, h_n, q_text, q_n, w, step, scaffolds_all, kmin, kmax, mask_host, want_rip, rows_cap, rows_out,
+                            status_out, tables_out, valid_kmax_out, n_win_out, host_out, query_out, st, dev);
+    } catch (...) {
+        rc = FRISK_E_CAPACITY;
+        threw = true;
+    }
+    if (rc != FRISK_OK) {                                           // queued work still targets the caller's buffers
+        cudaStreamSynchronize(st);
+        if (g_copy[dev & 63].copy) cudaStreamSynchronize(g_copy[dev & 63].copy);
+        cudaGetLastError();
+        if (rc != FRISK_E_CAPACITY || threw) {                      // (too few rows: the handles stay, with their planes)
+            if (*query_out) frisk_b200_fasta_close(*query_out, st);
+            if (*host_out) frisk_b200_fasta_close(*host_out, st);
+            *host_out = *query_out = nullptr;
+        }
+    }
     return rc;
 }
 

@@ -910,13 +910,82 @@ def run_resident(dq: DeviceGenome, dh: Optional[DeviceGenome] = None, kmin: int 
     return assemble(query, host, wins, out.tables, int(out.valid[0]), out.rows[:n], out.status[:n], kmin, kmax)
 
 
-def run_fasta(query_text, host_text=None, device="cuda:0", out=None, assemble_result: bool = True, **params):
-    """FASTA text (bytes / uint8 array) in, rows out: device-side ingest + frisk_b200_run_resident.
-    This is the whole of the reference's stages 2+3 (F:1442, F:1478-1494) including its three
-    passes over the file (F:170, F:203, F:297) with the host doing nothing but one copy."""
-    dq = DeviceGenome.from_fasta_bytes(query_text, device)
-    dh = DeviceGenome.from_fasta_bytes(host_text, device) if host_text is not None else None
-    return run_resident(dq, dh, out=out, assemble_result=assemble_result, **params)
+class _HandlePlane:
+    """A plane that belongs to a frisk_b200_fasta handle (frisk_b200_fasta_planes): just its device address."""
+
+    def __init__(self, ptr):
+        self._p = int(ptr or 0)
+
+    def data_ptr(self) -> int:
+        return self._p
+
+
+def _genome_from_handle(L, h, buf) -> PackedGenome:
+    nrec, padded = C.c_uint64(0), C.c_uint64(0)
+    stats = np.zeros(3, np.uint64)
+    _lib.check(L.frisk_b200_fasta_info(h, C.byref(nrec), C.byref(padded), _ptr(stats)), "frisk_b200_fasta_info")
+    R = int(nrec.value)
+    name_off = np.zeros(R, np.uint64); name_len = np.zeros(R, np.uint32)
+    seq_len = np.zeros(R, np.uint64); scaf_off = np.zeros(R, np.uint64)
+    _lib.check(L.frisk_b200_fasta_records(h, _ptr(name_off), _ptr(name_len), _ptr(seq_len), _ptr(scaf_off)),
+               "frisk_b200_fasta_records")
+    return PackedGenome(LazyNames(buf, name_off, name_len), seq_len, scaf_off, int(padded.value), None, None, None,
+                        int(stats[0]), int(stats[1]), int(stats[2]), False)
+
+
+def run_fasta(query_text, host_text=None, device="cuda:0", out=None, assemble_result: bool = True, kmin: int = 1,
+              kmax: int = 8, w: int = 5000, step: int = 2500, mask_host: bool = False, scaffolds_all: bool = False,
+              rip: bool = True):
+    """FASTA text (bytes / uint8 array, ideally page-locked) in, rows out, through ONE C call (frisk_b200_run_fasta): the
+    text is uploaded in chunks and tokenised, packed and counted on the device while it arrives; names and windows are
+    derived on the host while the last chunk is still being counted; then tables, IVOM, window kernel, rows.  This is the
+    whole of the reference's stages 2+3 (F:1442, F:1478-1494) including its three passes over the file (F:170, F:203,
+    F:297).  ``out``: reusable HostOutputs (its row capacity is used; ``out.n_win`` is set)."""
+    import torch
+    _lib.require_device()
+    L = _lib.lib()
+    qbuf = _as_u8(query_text)
+    hbuf = _as_u8(host_text) if host_text is not None else qbuf
+    dev = torch.device(device)
+    if out is None:
+        out = HostOutputs(qbuf.shape[0] // step + qbuf.shape[0] // 512 + 64, kmax)
+    hh, qh = C.c_void_p(), C.c_void_p()
+    n_win = C.c_uint64(0)
+    with torch.cuda.device(dev):
+        st = _stream_ptr(dev)
+        rc = L.frisk_b200_run_fasta(_ptr(hbuf), hbuf.shape[0], _ptr(qbuf) if host_text is not None else None,
+                                    qbuf.shape[0] if host_text is not None else 0, w, step, int(scaffolds_all), kmin, kmax,
+                                    int(mask_host), int(rip), out.rows.shape[0], _ptr(out.rows), _ptr(out.status),
+                                    _ptr(out.tables), _ptr(out.valid), C.byref(n_win), C.byref(hh), C.byref(qh), st)
+        try:
+            if rc not in (_lib.OK, _lib.E_CAPACITY):
+                _lib.check(rc, "frisk_b200_run_fasta")
+            n = int(n_win.value)
+            need_genomes = assemble_result or rc == _lib.E_CAPACITY
+            host = _genome_from_handle(L, hh, hbuf) if need_genomes else None
+            query = (_genome_from_handle(L, qh, qbuf) if qh else host) if need_genomes else None
+            if rc == _lib.E_CAPACITY:
+                # more windows than the guessed row capacity: the planes are on the device, score them into enough rows
+                def planes(h):
+                    c, i, l = C.c_void_p(), C.c_void_p(), C.c_void_p()
+                    _lib.check(L.frisk_b200_fasta_planes(h, C.byref(c), C.byref(i), C.byref(l)), "frisk_b200_fasta_planes")
+                    return (_HandlePlane(c.value), _HandlePlane(i.value), _HandlePlane(l.value) if l.value else None)
+                dh = DeviceGenome(host, dev, planes=planes(hh))
+                dq = DeviceGenome(query, dev, planes=planes(qh)) if qh else dh
+                out = HostOutputs(n, kmax)
+                out = run_resident(dq, dh, kmin=kmin, kmax=kmax, w=w, step=step, mask_host=mask_host,
+                                   scaffolds_all=scaffolds_all, rip=rip, out=out, assemble_result=False)
+        finally:
+            if qh:
+                L.frisk_b200_fasta_close(qh, st)
+            if hh:
+                L.frisk_b200_fasta_close(hh, st)
+    out.n_win = n
+    if not assemble_result:
+        return out
+    wins = query.windows(w, step, scaffolds_all)
+    assert len(wins) == n
+    return assemble(query, host, wins, out.tables, int(out.valid[0]), out.rows[:n], out.status[:n], kmin, kmax)
 
 
 class HostOutputs:

@@ -340,6 +340,28 @@ int frisk_b200_fasta_pack(frisk_b200_fasta *h, uint32_t *d_codes, uint32_t *d_in
 int frisk_b200_fasta_close(frisk_b200_fasta *h, void *stream);
 int frisk_b200_fasta_open_stats(uint64_t out[2]);
 
+/* frisk_b200_run_fasta: FASTA text in, rows out, ONE call -- the reference's stages 2+3 (F:1442, F:1478-1494) including
+ * its three passes over the file (F:170, F:203, F:297).  h_text is the genome the background is counted on (--hostSeq,
+ * or the query itself), q_text the genome whose windows are scored (NULL, or the same pointer and size: the same genome).
+ * The text goes up in chunks; each chunk is tokenised, laid out, packed and (kmax <= 8) counted on the device while the next
+ * chunk is on the bus; the record table comes back once, as soon as the last chunk is tokenised, and names, windows
+ * (frisk_b200_windows with w, step, scaffolds_all) and the launch of tables -> IVOM -> window kernel happen on the host while
+ * that chunk is still being packed and counted.  rows_out / status_out have room for rows_cap windows (pinned buffers are
+ * written by the kernel directly); *n_win_out always receives the number of windows.
+ * *host_out / *query_out (query_out: NULL when the genomes are the same) are handles as of frisk_b200_fasta_open whose PLANES
+ * exist and belong to the handle (frisk_b200_fasta_planes; padded_len etc. from frisk_b200_fasta_info, the record table
+ * from frisk_b200_fasta_records) until frisk_b200_fasta_close.
+ * FRISK_E_CAPACITY: more windows than rows_cap -- nothing was scored, but the handles are valid: allocate *n_win_out rows and
+ * call frisk_b200_run_resident on their planes.  Any other error: no handle is returned.  Blocks until the rows are on the
+ * host.  Stage times: frisk_b200_last_run_timing (ms[0] = text uploaded, ms[1] = tokenised + packed + counted). */
+int frisk_b200_run_fasta(const char *h_text, uint64_t h_n, const char *q_text, uint64_t q_n, int w, int step,
+                         int scaffolds_all, int kmin, int kmax, int mask_host, int want_rip, uint64_t rows_cap,
+                         double *rows_out, uint32_t *status_out, uint64_t *tables_out, uint64_t *valid_kmax_out,
+                         uint64_t *n_win_out, frisk_b200_fasta **host_out, frisk_b200_fasta **query_out, void *stream);
+int frisk_b200_fasta_info(const frisk_b200_fasta *h, uint64_t *n_records, uint64_t *padded_len, uint64_t stats[3]);
+int frisk_b200_fasta_planes(const frisk_b200_fasta *h, const uint32_t **d_codes, const uint32_t **d_inv,
+                            const uint32_t **d_low);
+
 /* Stage times (ms since the start of the call) of the last frisk_b200_run_host / _sparse / _peers / _run_resident call
  * on the current device, from CUDA events recorded on the call's own streams: ms[0] planes uploaded, ms[1] background
  * counted, ms[2] tables + genome IVOM finalised (multi-GPU: includes the wait for the peers' counters), ms[3] window

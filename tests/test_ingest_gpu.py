@@ -160,8 +160,18 @@ def test_fasta_text_to_rows_matches_reference_golden(case):
     from tests.test_gpu_parity import _check_against_golden
     gold = Golden(case)
     host = gold.host()
-    res = engine.run_fasta(fasta_text(gold.scaffolds()), fasta_text(host) if host is not None else None, **gold.kwargs())
+    qtext, htext = fasta_text(gold.scaffolds()), fasta_text(host) if host is not None else None
+    res = engine.run_fasta(qtext, htext, **gold.kwargs())
     _check_against_golden(res, gold, case + "[run_fasta]")
+    # the streamed call with test-sized chunks (planes laid out, packed and counted chunk by chunk), the exact open behind
+    # it, and a row buffer that is too small (second stage through frisk_b200_run_resident on the handles' planes)
+    for mode in ("chunk1", "chunk3", "exact"):
+        with ingest_options(mode):
+            alt = engine.run_fasta(qtext, htext, **gold.kwargs())
+        assert np.array_equal(alt.rows, res.rows, equal_nan=True) and np.array_equal(alt.tables, res.tables), mode
+    small = engine.HostOutputs(1, gold.kwargs().get("kmax", 8))
+    alt = engine.run_fasta(qtext, htext, out=small, **gold.kwargs())
+    assert np.array_equal(alt.rows, res.rows, equal_nan=True) and np.array_equal(alt.tables, res.tables)
     # same kernels as the packed-plane entry point -> identical bits
     q = engine.PackedGenome.from_scaffolds(gold.scaffolds())
     h = engine.PackedGenome.from_scaffolds(host) if host is not None else None
