@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <functional>
 #include <mutex>
 #include <vector>
 
@@ -2103,27 +2104,36 @@ static int check_windows(const uint64_t* win_off, const uint32_t* win_len, uint6
     return FRISK_OK;
 }
 
+typedef std::function<int(const uint64_t** win_off, const uint32_t** win_len, uint64_t* n_win, uint32_t* max_win_len)> LateWindows;
+
 static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* dhi, const uint32_t* dhl, uint64_t h_padded_len, bool bg_enqueued,
                     const uint32_t* dqc, const uint32_t* dqi, const uint32_t* dql, const uint64_t* win_off,
                     const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host,
                     int want_rip, int64_t genome_space, double* rows_out, uint32_t* status_out, uint64_t* tables_out,
                     uint64_t* valid_kmax_out, void* dfwd, cudaStream_t st, cudaStream_t copy, cudaEvent_t copy_done,
-                    cudaEvent_t tables_ready, RunMarks* tm) {
+                    cudaEvent_t tables_ready, RunMarks* tm, const LateWindows* late = nullptr) {
+    // late: the window list is produced by the caller AFTER the tables' finalisation has been queued (frisk_b200_run_fasta:
+    // the host derives the windows while the device is still counting)
     const size_t tsz = (size_t)frisk_b200_table_size(1, kmax);
     void *dtab, *dig, *dwo = nullptr, *dwl = nullptr, *drows = nullptr, *dstat = nullptr;
     int rc;
     if ((rc = ws_get(7, (tsz + 1) * 8, &dtab))) return rc;
     if ((rc = ws_get(8, (size_t)pow4(kmax) * 16, &dig))) return rc;
-    if (n_win) {
-        if ((rc = ws_get(9, n_win * 8, &dwo))) return rc;
-        if ((rc = ws_get(10, n_win * 4, &dwl))) return rc;
-        if ((rc = ws_get(11, n_win * 40, &drows))) return rc;
-        if ((rc = ws_get(12, n_win * 4, &dstat))) return rc;
-        cudaStream_t up = copy ? copy : st;             // the window list rides behind the planes
-        CK(cudaMemcpyAsync(dwo, win_off, n_win * 8, cudaMemcpyHostToDevice, up));
-        CK(cudaMemcpyAsync(dwl, win_len, n_win * 4, cudaMemcpyHostToDevice, up));
-    }
-    if (copy) CK(cudaEventRecord(copy_done, copy));
+    auto upload_windows = [&]() -> int {
+        if (n_win) {
+            int rc2;
+            if ((rc2 = ws_get(9, n_win * 8, &dwo))) return rc2;
+            if ((rc2 = ws_get(10, n_win * 4, &dwl))) return rc2;
+            if ((rc2 = ws_get(11, n_win * 40, &drows))) return rc2;
+            if ((rc2 = ws_get(12, n_win * 4, &dstat))) return rc2;
+            cudaStream_t up = copy ? copy : st;         // the window list rides behind the planes
+            CK(cudaMemcpyAsync(dwo, win_off, n_win * 8, cudaMemcpyHostToDevice, up));
+            CK(cudaMemcpyAsync(dwl, win_len, n_win * 4, cudaMemcpyHostToDevice, up));
+        }
+        if (copy) CK(cudaEventRecord(copy_done, copy));
+        return FRISK_OK;
+    };
+    if (!late && (rc = upload_windows())) return rc;
     if (!bg_enqueued) {
         CK(cudaMemsetAsync(dfwd, 0, (tsz + 1) * 8, st));
         // the last 32-base word is padding by construction and is only ever read as look-ahead
@@ -2143,6 +2153,10 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
         CK(cudaStreamWaitEvent(copy, tables_ready, 0));
         if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, copy));
         if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, copy));
+    }
+    if (late) {
+        if ((rc = (*late)(&win_off, &win_len, &n_win, &max_win_len))) return rc;
+        if ((rc = upload_windows())) return rc;
     }
     if (copy) CK(cudaStreamWaitEvent(st, copy_done, 0));
     if (n_win) {
@@ -2488,31 +2502,29 @@ int run_fasta_body(const char* h_text, uint64_t h_n, const char* q_text, uint64_
     if ((rc = frisk_b200_fasta_planes(hh, &dhc, &dhi, &dhl))) return rc;
     if ((rc = frisk_b200_fasta_planes(qh, &dqc, &dqi, &dql))) return rc;
 
-    // windows of the query (F:194-251), into pinned staging
-    std::vector<uint64_t> seq_len((size_t)q_rec), scaf_off((size_t)q_rec);
-    if ((rc = frisk_b200_fasta_records(qh, nullptr, nullptr, seq_len.data(), scaf_off.data()))) return rc;
-    uint64_t n_win = 0;
-    if ((rc = frisk_b200_windows(seq_len.data(), scaf_off.data(), q_rec, w, step, scaffolds_all, 0, nullptr, nullptr, nullptr,
-                                 nullptr, nullptr, &n_win)))
-        return rc;
-    if (n_win_out) *n_win_out = n_win;
-    if (n_win > rows_cap) return FRISK_E_CAPACITY;
-    void *win_off = nullptr, *win_len = nullptr;
-    uint32_t max_len = 0;
-    if (n_win) {
-        if ((rc = stage_get(dev, 0, n_win * 8, &win_off))) return rc;
-        if ((rc = stage_get(dev, 1, n_win * 4, &win_len))) return rc;
-        if ((rc = frisk_b200_windows(seq_len.data(), scaf_off.data(), q_rec, w, step, scaffolds_all, n_win, (uint64_t*)win_off,
-                                     (uint32_t*)win_len, nullptr, nullptr, nullptr, &n_win)))
-            return rc;
-        const uint32_t* wl = (const uint32_t*)win_len;
-        for (uint64_t i = 0; i < n_win; ++i) max_len = wl[i] > max_len ? wl[i] : max_len;
-    }
+    // windows of the query (F:194-251), into pinned staging -- produced once the tables' finalisation is queued
+    const LateWindows late = [&](const uint64_t** win_off, const uint32_t** win_len, uint64_t* n_win, uint32_t* max_len) -> int {
+        int rc2;
+        std::vector<uint64_t> seq_len((size_t)q_rec), scaf_off((size_t)q_rec);
+        if ((rc2 = frisk_b200_fasta_records(qh, nullptr, nullptr, seq_len.data(), scaf_off.data()))) return rc2;
+        void *wo = nullptr, *wl = nullptr;
+        if ((rc2 = stage_get(dev, 0, (rows_cap + 1) * 8, &wo))) return rc2;
+        if ((rc2 = stage_get(dev, 1, (rows_cap + 1) * 4, &wl))) return rc2;
+        uint64_t nw = 0;
+        rc2 = frisk_b200_windows(seq_len.data(), scaf_off.data(), q_rec, w, step, scaffolds_all, rows_cap, (uint64_t*)wo, (uint32_t*)wl,
+                                 nullptr, nullptr, nullptr, &nw);
+        if (n_win_out) *n_win_out = nw;
+        if (rc2) return rc2;                                         // (FRISK_E_CAPACITY: more windows than rows_cap)
+        uint32_t mx = 0;
+        for (uint64_t i = 0; i < nw; ++i) mx = ((const uint32_t*)wl)[i] > mx ? ((const uint32_t*)wl)[i] : mx;
+        *win_off = (const uint64_t*)wo; *win_len = (const uint32_t*)wl; *n_win = nw; *max_len = mx;
+        return FRISK_OK;
+    };
     CK(cudaEventRecord(cc->ev[kMaxChunks], st));                    // the copy stream joins behind the ingest
     CK(cudaStreamWaitEvent(cc->copy, cc->ev[kMaxChunks], 0));
-    return run_tail(PeerArgs(), dhc, dhi, dhl, h_padded, counted, dqc, dqi, dql, (const uint64_t*)win_off, (const uint32_t*)win_len,
-                    n_win, max_len, kmin, kmax, mask_host, want_rip, (int64_t)h_stats[0] - (int64_t)h_stats[1], rows_out, status_out,
-                    tables_out, valid_kmax_out, dfwd, st, cc->copy, cc->ev[kMaxChunks + 1], cc->ev[kMaxChunks + 2], tm);
+    return run_tail(PeerArgs(), dhc, dhi, dhl, h_padded, counted, dqc, dqi, dql, nullptr, nullptr, 0, 0, kmin, kmax, mask_host, want_rip,
+                    (int64_t)h_stats[0] - (int64_t)h_stats[1], rows_out, status_out, tables_out, valid_kmax_out, dfwd, st, cc->copy,
+                    cc->ev[kMaxChunks + 1], cc->ev[kMaxChunks + 2], tm, &late);
 }
 }  // namespace
 

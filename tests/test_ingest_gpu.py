@@ -205,8 +205,8 @@ def test_chunked_open_carries_state_across_chunks_and_falls_back_when_it_cannot_
     for width in (0, 61):
         assert_same_genome(fasta_text(one, width), modes=("chunk1", "chunk3"))
     assert open_stats()[1] == redo1
-    # a header line and a blank run lying across chunk boundaries (8 chunks of 2 tiles = 8192 bytes each)
-    for shift in (8180, 8190, 8191, 8192, 8193):
+    # a header line and a blank run lying across chunk boundaries (chunks of 4 tiles = 16,384 bytes each)
+    for shift in (16372, 16382, 16383, 16384, 16385):
         body = b">a\n" + b"A" * (shift - 4) + b"\n"
         for sep in (b">b description\n", b"   \t  \n", b"  >c\n"):
             assert_same_genome(body + sep + b"ACGT" * 14000 + b"\n>z\nGG\n", modes=("chunk1",))
