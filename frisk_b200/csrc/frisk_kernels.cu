@@ -15,6 +15,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -2312,22 +2313,42 @@ static int run_host_body(const PeerArgs& peers, const HostPlanes& h, const HostP
     // sparse invalid plane: zero fill + pairs + scatter on the COMPUTE stream, behind the first code chunk's transfer
     // (on the copy stream they would delay that chunk by four small operations); the counts on `st` follow in order
     if ((rc = upload_inv(h, dhi, 15, 16, st))) return rc;
-    // (every count launch has a fixed cost -- zeroing and storing a 128 KiB table per CTA, the reduction of the partial
-    // tables -- of ~0.03 ms: 5 chunks of 8 M bases left 0.135 ms of counting behind the last upload of a 40 Mbp
-    // genome, 2 chunks of 20 M leave one chunk's count)
-    uint64_t n_chunks = (h_padded_len + (20ull << 20) - 1) / (20ull << 20);
-    if (n_chunks > (uint64_t)kMaxChunks - 1) n_chunks = kMaxChunks - 1;
-    // ... plus a SHORT last chunk (1/16 of the planes): the count of the last chunk is the only one not hidden behind
-    // an upload, so it should cover little (the fixed cost of a count launch remains)
-    const uint64_t tail = h_padded_len >= (1ull << 22) ? ((h_padded_len / 16) + 127) & ~127ull : 0;
-    const uint64_t body = h_padded_len - tail;
-    const uint64_t chunk = ((body + n_chunks - 1) / n_chunks + 127) & ~127ull;
-    if (tail) ++n_chunks;
+    // Chunk plan: equal chunks of <= 64 M bases.  Measured on C2 (40 Mbp, profiles/r02_upload_plans.txt): one chunk -- upload,
+    // then one count of 0.07 ms -- beats every split (2 chunks +0.02 ms, 3 chunks +0.04..0.1 ms): a count that runs beside
+    // the copy takes about twice as long, every extra copy and count launch has a fixed cost, and the whole count is short
+    // next to the upload.  Genomes of hundreds of Mbp and more keep the split: there the last chunk's count is what shows.
+    // FRISK_UPLOAD_PLAN="f0,f1,..." (relative chunk sizes) overrides the plan (tools/upload_plans.sh).
+    uint64_t bounds[kMaxChunks + 1];
+    uint64_t n_chunks = 0;
+    bounds[0] = 0;
+    {
+        int parts[kMaxChunks];
+        int n_parts = (int)((h_padded_len + (64ull << 20) - 1) / (64ull << 20));
+        if (n_parts > kMaxChunks - 1) n_parts = kMaxChunks - 1;
+        if (n_parts < 1) n_parts = 1;
+        for (int i = 0; i < n_parts; ++i) parts[i] = 1;
+        if (const char* e = getenv("FRISK_UPLOAD_PLAN")) {
+            n_parts = 0;
+            for (const char* p = e; *p && n_parts < kMaxChunks - 1;) {
+                parts[n_parts++] = atoi(p);
+                while (*p && *p != ',') ++p;
+                if (*p == ',') ++p;
+            }
+        }
+        int total = 0, acc = 0;
+        for (int i = 0; i < n_parts; ++i) total += parts[i] > 0 ? parts[i] : 0;
+        for (int i = 0; i < n_parts && total > 0; ++i) {
+            if (parts[i] <= 0) continue;
+            acc += parts[i];
+            uint64_t b = i == n_parts - 1 ? h_padded_len : ((h_padded_len / (uint64_t)total) * (uint64_t)acc + 127) & ~127ull;
+            if (b > h_padded_len) b = h_padded_len;
+            if (b > bounds[n_chunks]) bounds[++n_chunks] = b;
+        }
+        if (n_chunks == 0 || bounds[n_chunks] != h_padded_len) bounds[++n_chunks] = h_padded_len;
+    }
     uint64_t counted = 0;
     for (uint64_t c = 0; c < n_chunks; ++c) {
-        const uint64_t b0 = (tail && c == n_chunks - 1) ? body : c * chunk;
-        const uint64_t lim = (tail && c < n_chunks - 1) ? body : h_padded_len;
-        const uint64_t b1 = (tail && c == n_chunks - 1) ? h_padded_len : ((b0 + chunk < lim) ? b0 + chunk : lim);
+        const uint64_t b0 = bounds[c], b1 = bounds[c + 1];
         if (b0 >= b1) continue;
         CK(cudaMemcpyAsync((char*)dhc + b0 / 4, (const char*)h.codes + b0 / 4, (b1 - b0) / 4, cudaMemcpyHostToDevice, cc->copy));
         if (h.inv) CK(cudaMemcpyAsync((char*)dhi + b0 / 8, (const char*)h.inv + b0 / 8, (b1 - b0) / 8, cudaMemcpyHostToDevice, cc->copy));
