@@ -91,6 +91,8 @@ __device__ __forceinline__ uint32_t last_key(uint32_t start_mask, uint32_t hdr_m
 }
 
 // ---- block-wide scans (blockDim.x a multiple of 32, <= 1024); sm: >= 64 words of shared memory ----------
+// Two levels: a shuffle scan inside every warp, the warp totals through shared memory, and -- instead of every thread walking
+// the totals one by one -- the same shuffle scan over the (<= 32) totals, done by every warp for itself.
 template <typename T>
 __device__ __forceinline__ T block_excl_sum(T v, T* sm, T* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -102,15 +104,16 @@ __device__ __forceinline__ T block_excl_sum(T v, T* sm, T* total) {
     }
     if (lane == 31) sm[warp] = incl;
     __syncthreads();
-    T before = 0, tot = 0;
-    for (int w = 0; w < nw; ++w) {
-        const T x = sm[w];
-        if (w < warp) before += x;
-        tot += x;
+    T w = lane < nw ? sm[lane] : T(0);
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        const T y = __shfl_up_sync(kFullMask, w, ofs);
+        if (lane >= ofs) w += y;
     }
+    const T before = __shfl_sync(kFullMask, w, warp ? warp - 1 : 0);
+    *total = __shfl_sync(kFullMask, w, nw - 1);
     __syncthreads();
-    *total = tot;
-    return before + incl - v;
+    return (warp ? before : T(0)) + incl - v;
 }
 
 // "last writer wins": the last non-zero key among the threads before this one (0 if none);
@@ -124,13 +127,14 @@ __device__ __forceinline__ uint32_t block_excl_last(uint32_t key, uint32_t* sm, 
     const uint32_t wl = __shfl_sync(kFullMask, key, ball ? 31 - __clz(ball) : 0);
     if (lane == 0) sm[warp] = ball ? wl : 0u;
     __syncthreads();
-    uint32_t carry = 0, tot = 0;
-    for (int w = 0; w < nw; ++w) {
-        const uint32_t x = sm[w];
-        if (x) { tot = x; if (w < warp) carry = x; }
-    }
+    const uint32_t x = lane < nw ? sm[lane] : 0u;
+    const uint32_t wb = __ballot_sync(kFullMask, x != 0u);
+    const uint32_t wprior = wb & ((1u << warp) - 1u);
+    uint32_t carry = __shfl_sync(kFullMask, x, wprior ? 31 - __clz(wprior) : 0);
+    if (!wprior) carry = 0;
+    const uint32_t tot = __shfl_sync(kFullMask, x, wb ? 31 - __clz(wb) : 0);
     __syncthreads();
-    *last = tot;
+    *last = wb ? tot : 0u;
     return v ? v : carry;
 }
 
@@ -139,7 +143,7 @@ __device__ __forceinline__ uint32_t block_excl_last(uint32_t key, uint32_t* sm, 
 // before this thread; *reset_before = some earlier thread has a reset.
 template <typename T>
 __device__ __forceinline__ T block_excl_seg(bool f, T v, T* smv, uint32_t* smf, bool* reset_before) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     T iv = v;
     uint32_t fl = f ? 1u : 0u;
 #pragma unroll
@@ -153,11 +157,17 @@ __device__ __forceinline__ T block_excl_seg(bool f, T v, T* smv, uint32_t* smf, 
     if (lane == 0) { ev = 0; ef = 0; }
     if (lane == 31) { smv[warp] = iv; smf[warp] = fl; }
     __syncthreads();
-    T c = 0;
-    uint32_t cf = 0;
-    for (int w = 0; w < warp; ++w) {
-        if (smf[w]) { c = smv[w]; cf = 1; } else c += smv[w];
+    T wv = lane < nw ? smv[lane] : T(0);                     // the same segmented scan over the warp totals
+    uint32_t wf = lane < nw ? smf[lane] : 0u;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        const T uv = __shfl_up_sync(kFullMask, wv, ofs);
+        const uint32_t uf = __shfl_up_sync(kFullMask, wf, ofs);
+        if (lane >= ofs) { if (!wf) wv += uv; wf |= uf; }
     }
+    T c = __shfl_sync(kFullMask, wv, warp ? warp - 1 : 0);
+    uint32_t cf = __shfl_sync(kFullMask, wf, warp ? warp - 1 : 0);
+    if (!warp) { c = 0; cf = 0; }
     __syncthreads();
     if (!ef) ev += c;
     *reset_before = (ef | cf) != 0u;
