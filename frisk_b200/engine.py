@@ -86,6 +86,21 @@ def _alloc(shape, dtype, pinned: bool) -> np.ndarray:
     return np.empty(shape, dtype=dtype)
 
 
+_STAGING = {}
+
+
+def _staging(tag: str, shape, dtype) -> np.ndarray:
+    """A page-locked staging array that is reused from call to call (grown when too small): page-locking tens of MB
+    costs milliseconds.  The contents are only valid until the next call with the same tag -- copy out of it."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    buf = _STAGING.get(tag)
+    if buf is None or buf.nbytes < n:
+        buf = _alloc(n + n // 4 + 4096, np.uint8, True)
+        _STAGING[tag] = buf
+    return buf[:n].view(dtype).reshape(shape)
+
+
 def _alloc_u32(n: int, pinned: bool) -> np.ndarray:
     return _alloc(n, np.uint32, pinned)
 
@@ -663,8 +678,8 @@ class Pipeline:
         tables = self.d_tables.cpu().numpy().view(np.uint64)
         n = len(self.wins)
         if n >= (1 << 16):                      # large row sets come back through page-locked memory (pageable: ~3 GB/s)
-            h_rows = _alloc((n, 5), np.float64, True)
-            h_stat = _alloc((n,), np.int32, True)
+            h_rows = _staging("rows", (n, 5), np.float64)       # (assemble copies what it keeps)
+            h_stat = _staging("status", (n,), np.int32)
             torch.from_numpy(h_rows).copy_(self.d_rows, non_blocking=True)
             torch.from_numpy(h_stat).copy_(self.d_status, non_blocking=True)
             torch.cuda.synchronize(self.device)
