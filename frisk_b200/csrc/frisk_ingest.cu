@@ -667,6 +667,7 @@ constexpr uint64_t kFirstFetch = 4096;              // records read back with th
 struct UploadLane {
     cudaStream_t copy = nullptr;
     cudaEvent_t ready = nullptr, done[kMaxChunks] = {};
+    std::mutex mu;                                   // one open at a time per device: the events above are shared
 };
 std::mutex g_lane_mu;
 std::atomic<uint64_t> g_open_stats[2];
@@ -706,6 +707,7 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
     const uint64_t T = h->n_tiles;
     UploadLane* lane = nullptr;
     if ((rc = upload_lane(&lane))) return rc;
+    std::lock_guard<std::mutex> one_open(lane->mu);
     constexpr size_t kCtrWords = kCtrCount + (size_t)kRangeSlots * kMaxChunks;
     const uint64_t Tp = (T + kSP - 1) / kSP * kSP;                      // the tile scan loads vectors of kSP tiles
     auto alloc_scan = [&]() -> int {   // one allocation for the counters and everything per tile

@@ -251,5 +251,29 @@ def test_argument_checks_answer_before_any_device_work():
     assert b"unsupported" in L.frisk_b200_strerror(_lib.E_UNSUPPORTED) and L.frisk_b200_strerror(-99) == b"unknown error"
     assert L.frisk_b200_set_option(b"no_such_option", 1) == _lib.E_INVALID
     assert L.frisk_b200_set_option(None, 1) == _lib.E_INVALID
-    for opt in (b"force_dense_kernel", b"force_general_kernel", b"force_bucket_kernel", b"force_direct_kernel"):
+    # frisk_b200_run_fasta: argument checks come before anything touches a device; without a GPU it says so
+    hh, qh = C.c_void_p(), C.c_void_p()
+    txt = np.frombuffer(b">a\nACGT\n", dtype=np.uint8)
+    tp = C.c_void_p(txt.ctypes.data)
+    assert L.frisk_b200_run_fasta(tp, 8, null, 0, 5000, 2500, 0, 1, 8, 0, 1, 0, null, null, null, null, C.byref(n), None,
+                                  C.byref(qh), null) == _lib.E_INVALID                               # no place for the handle
+    assert L.frisk_b200_run_fasta(null, 8, null, 0, 5000, 2500, 0, 1, 8, 0, 1, 0, null, null, null, null, C.byref(n),
+                                  C.byref(hh), C.byref(qh), null) == _lib.E_INVALID                  # text missing
+    assert L.frisk_b200_run_fasta(tp, 8, null, 0, 5000, 2500, 0, 1, 8, 0, 1, 4, null, null, null, null, C.byref(n),
+                                  C.byref(hh), C.byref(qh), null) == _lib.E_INVALID                  # rows_cap without rows
+    assert L.frisk_b200_run_fasta(tp, 8, null, 0, 5000, 2500, 0, 3, 2, 0, 1, 0, null, null, null, null, C.byref(n),
+                                  C.byref(hh), C.byref(qh), null) == _lib.E_INVALID                  # kmin > kmax
+    assert L.frisk_b200_run_fasta(tp, 8, null, 0, 0, 2500, 0, 1, 8, 0, 1, 0, null, null, null, null, C.byref(n),
+                                  C.byref(hh), C.byref(qh), null) == _lib.E_INVALID                  # window length 0
+    if L.frisk_b200_device_count() <= 0:
+        assert L.frisk_b200_run_fasta(tp, 8, null, 0, 5000, 2500, 0, 1, 8, 0, 1, 0, null, null, null, null, C.byref(n),
+                                      C.byref(hh), C.byref(qh), null) == _lib.E_NO_DEVICE
+        assert not hh.value and not qh.value
+    stats2 = np.zeros(2, np.uint64)
+    assert L.frisk_b200_fasta_open_stats(C.c_void_p(stats2.ctypes.data)) == _lib.OK
+    assert L.frisk_b200_fasta_open_stats(null) == _lib.E_INVALID
+    assert L.frisk_b200_fasta_info(null, None, None, null) == _lib.E_INVALID
+    assert L.frisk_b200_fasta_planes(null, None, None, None) == _lib.E_INVALID
+    for opt in (b"force_dense_kernel", b"force_general_kernel", b"force_bucket_kernel", b"force_direct_kernel",
+                b"force_nibble_kernel", b"ingest_exact_open", b"ingest_chunk_tiles"):
         assert L.frisk_b200_set_option(opt, 1) == 0 and L.frisk_b200_set_option(opt, 0) == 0, opt   # the switches in the header
