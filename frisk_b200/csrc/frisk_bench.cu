@@ -42,6 +42,25 @@ l2_gather_kernel(const double2* __restrict__ tab, uint32_t n_mask, int iters, in
     if (s == 1.2345e-300) sink[0] = s;
 }
 
+// mode 6: the random gather of mode 0 through the TEXTURE path (tex1Dfetch of 16-byte texels from linear memory): does the
+// texture unit look up more than one cache line per clock?
+__global__ void __launch_bounds__(256, 4)
+l2_gather_tex_kernel(cudaTextureObject_t tex, uint32_t n_mask, int iters, double* sink) {
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int it = 0; it < iters; it += 4) {
+        const uint32_t i0 = lcg(x), i1 = lcg(x), i2 = lcg(x), i3 = lcg(x);
+        const uint4 v0 = tex1Dfetch<uint4>(tex, (int)(i0 & n_mask)), v1 = tex1Dfetch<uint4>(tex, (int)(i1 & n_mask));
+        const uint4 v2 = tex1Dfetch<uint4>(tex, (int)(i2 & n_mask)), v3 = tex1Dfetch<uint4>(tex, (int)(i3 & n_mask));
+        a0 += __hiloint2double(v0.y, v0.x) + __hiloint2double(v0.w, v0.z);
+        a1 += __hiloint2double(v1.y, v1.x) + __hiloint2double(v1.w, v1.z);
+        a2 += __hiloint2double(v2.y, v2.x) + __hiloint2double(v2.w, v2.z);
+        a3 += __hiloint2double(v3.y, v3.x) + __hiloint2double(v3.w, v3.z);
+    }
+    const double s = a0 + a1 + a2 + a3;
+    if (s == 1.2345e-300) sink[0] = s;
+}
+
 // mode 2: the same random gather as mode 0, but as cp.async (LDGSTS) of 16 bytes per lane into shared memory, read back
 // coalesced -- does a divergent gather cost fewer data-pipe cycles when it does not return through the register file?
 __global__ void __launch_bounds__(256, 4)
@@ -203,7 +222,7 @@ int time_twice(F launch, cudaStream_t st, float* ms) {
 extern "C" {
 
 int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int mode, float* ms, void* stream) {
-    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms || table_bytes < 4096 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 5)
+    if (blocks <= 0 || iters <= 0 || (iters & 3) || !ms || table_bytes < 4096 || (table_bytes & (table_bytes - 1)) || mode < 0 || mode > 6)
         return FRISK_E_INVALID;
     if (frisk_b200_device_count() <= 0) return FRISK_E_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -215,7 +234,19 @@ int frisk_b200_bench_l2_gather(int blocks, int iters, uint64_t table_bytes, int 
     const uint32_t n_mask = (uint32_t)(table_bytes / 16u) - 1u;
     const uint32_t gap = 14u;                            // 65,536 entries / ~4,794 distinct K-mers of a 5 kb window
     int rc;
-    if (mode >= 5) {
+    if (mode == 6) {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = tab;
+        rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+        rd.res.linear.sizeInBytes = table_bytes;
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t tex = 0;
+        CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        rc = time_twice([&] { l2_gather_tex_kernel<<<blocks, 256, 0, st>>>(tex, n_mask, iters, sink); }, st, ms);
+        cudaDestroyTextureObject(tex);
+    } else if (mode == 5) {
         // tensor map of the table as a [rows][2 doubles] tensor; the driver entry point comes through the runtime
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -6,19 +6,21 @@
 // (frisk_b200_fasta_scan + frisk_b200_pack), whose outputs it reproduces bit for bit.  The host
 // only copies the raw text to the device and reads back one small record table.
 //
-// The text is cut into tiles of 4096 bytes (256 threads x 16 bytes).  What a byte means depends on
-// the line it is in (header or sequence) and on the record it belongs to, i.e. on everything before
-// it, so the work is three tile passes separated by two scans over per-tile summaries:
-//   fasta_lines_kernel     per tile: number of header lines starting in it, and whether the last
-//                          line starting in it is a header
-//   fasta_scan1_kernel     over tiles: records before the tile, header state carried into the tile
-//   fasta_tile_kernel<0>   per tile: classify every byte; per record: header position and length
-//                          (one atomic per record piece, not per base); per tile: bases before the
-//                          first / after the last header; countN statistics
-//   fasta_scan2_kernel     over tiles (segmented): bases of the open record before the tile
-//   [host: names from the header positions, 128-base aligned layout -> scaf_off]
-//   fasta_tile_kernel<1>   per tile: every thread ORs the <= 16 bases of its 16 bytes into the planes
-//   fasta_padding_kernel   per record: the padding up to the next 128-base boundary is flagged invalid
+// The text is cut into tiles of 4096 bytes (256 threads x 16 bytes).  What a byte means depends on the line it is in (header
+// or sequence), on the record it belongs to and on where that record starts in the packed planes, i.e. on everything before
+// it.  Two passes over the text with one scan over per-tile summaries between them:
+//   fasta_summary_kernel   per tile: header lines, state of the last line start, bases before the first line start / before
+//                          the first header / after the last header, packed space of the records inside the tile
+//   fasta_tilescan_kernel  over tiles (one CTA, batches of 4096 tiles in registers): records before every tile, the line state
+//                          it starts in, bases and packed offset of the record open there -- frisk_b200_pack_layout's layout
+//                          computed on the device -- and which plane words are final (what the caller may count already)
+//   fasta_pack_kernel      per tile: planes (a word-wide path for plain ACGT lines, byte by byte for anything else), record
+//                          table (header position, length, offset: written once, by the thread that sees the next header),
+//                          padding flags, countN statistics
+// The text travels in chunks on a second stream; the three kernels of a chunk run while the next chunk is on the bus, with
+// the state between chunks in device memory.  Record table and planes are sized by a guess so that the host synchronises
+// once; a text that does not fit the guesses, or a line decision that needs a byte of a later chunk, is redone in one piece
+// with exact sizes (open_any).  The planes belong to the handle.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

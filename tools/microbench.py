@@ -43,6 +43,11 @@ def gather4(mode):
     return blocks * 256 * iters / (ms.value * 1e-3) if rc == 0 else "rc=%d (%s)" % (rc, L.frisk_b200_strerror(rc).decode())
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "tex":
+    print(json.dumps({"l2_gather_16B_per_s": {"ldg_random_1MiB": best(lambda: gathers(0)), "tex1Dfetch_random_1MiB": best(lambda: gathers(6)),
+                                              "ldg_random_64KiB": best(lambda: gathers(0, 1 << 16)),
+                                              "tex1Dfetch_random_64KiB": best(lambda: gathers(6, 1 << 16))}}))
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "gather4":
     # (probed and removed: a tensor-map box of 4 rows is rejected, and destinations that are only 64- or 80-byte aligned
     # fault with cudaErrorMisalignedAddress: every gather4 needs a 128-byte aligned 64-byte landing slot)
