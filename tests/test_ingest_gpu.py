@@ -169,6 +169,18 @@ def test_fasta_text_to_rows_matches_reference_golden(case):
         with ingest_options(mode):
             alt = engine.run_fasta(qtext, htext, **gold.kwargs())
         assert np.array_equal(alt.rows, res.rows, equal_nan=True) and np.array_equal(alt.tables, res.tables), mode
+    # page-locked text: every chunk's copy is queued before anything else is set up (a different order of the same work)
+    pq = engine._alloc(len(qtext), np.uint8, True)
+    pq[:] = np.frombuffer(qtext, dtype=np.uint8)
+    ph = None
+    if htext is not None:
+        ph = engine._alloc(len(htext), np.uint8, True)
+        ph[:] = np.frombuffer(htext, dtype=np.uint8)
+    for mode in ("default", "chunk1"):
+        with ingest_options(mode):
+            alt = engine.run_fasta(pq, ph, **gold.kwargs())
+        assert np.array_equal(alt.rows, res.rows, equal_nan=True) and np.array_equal(alt.tables, res.tables), "pinned " + mode
+        assert alt.names == res.names
     small = engine.HostOutputs(1, gold.kwargs().get("kmax", 8))
     alt = engine.run_fasta(qtext, htext, out=small, **gold.kwargs())
     assert np.array_equal(alt.rows, res.rows, equal_nan=True) and np.array_equal(alt.tables, res.tables)
