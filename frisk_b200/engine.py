@@ -249,10 +249,10 @@ class PackedGenome:
         L = _lib.lib()
         n = C.c_uint64(0)
         nsc = len(self.names)
-        rc = L.frisk_b200_windows(_ptr(self.scaf_len), _ptr(self.scaf_off), nsc, w, step, int(scaffolds_all), 0,
-                                  None, None, None, None, None, C.byref(n))
-        _lib.check(rc, "frisk_b200_windows")
-        cap = int(n.value)
+        if w < 1 or step < 1:
+            _lib.check(_lib.E_INVALID, "frisk_b200_windows")
+        # one pass: a scaffold yields at most len // step + 2 windows (the grid, the tail jump-back, the --scaffoldsAll rescue)
+        cap = int((self.scaf_len.astype(np.int64) // step + 2).sum()) if nsc else 0
         pinned = self.pinned
         off = _alloc(cap, np.uint64, pinned); ln = _alloc(cap, np.uint32, pinned)     # these two go to the device
         sc = np.zeros(cap, np.uint32)
@@ -260,7 +260,8 @@ class PackedGenome:
         _lib.check(L.frisk_b200_windows(_ptr(self.scaf_len), _ptr(self.scaf_off), nsc, w, step, int(scaffolds_all), cap,
                                         _ptr(off), _ptr(ln), _ptr(sc), _ptr(st), _ptr(sp), C.byref(n)),
                    "frisk_b200_windows")
-        return WindowList(off, ln, sc, st, sp)
+        k = int(n.value)
+        return WindowList(off[:k], ln[:k], sc[:k], st[:k], sp[:k])
 
     def inv_sparse(self) -> Tuple[np.ndarray, np.ndarray]:
         """The invalid plane's non-zero words as (word index, word) arrays (frisk_b200_plane_sparse),
@@ -544,16 +545,30 @@ def assemble(query: PackedGenome, host: PackedGenome, wins: WindowList, tables_1
     """``names=False`` leaves the per-row name list empty (``row_scaf`` + ``scaf_names`` carry the same information
     without a Python object per row: millions of rows of a fragmented assembly)."""
     keep = (status & _lib.ROW_EXCLUDED) == 0
-    idx = np.nonzero(keep)[0]
+    n_all = len(status)
+    if bool(keep.all()):
+        # nothing excluded (the usual case for a genome without long N runs): plain copies instead of gathers -- this is
+        # tens of MB per million windows, and host time counts in the ingest-inclusive figures
+        idx = np.arange(n_all, dtype=np.int64)
+        take = lambda a: np.array(a[:n_all], copy=True)
+    else:
+        idx = np.nonzero(keep)[0]
+        take = lambda a: a[idx]
     want_names = bool(names)
-    names = [query.names[s] for s in wins.scaf[idx]] if want_names else []
-    coords = np.stack([wins.start[idx], wins.stop[idx]], axis=1) if idx.size else np.zeros((0, 2), np.int64)
+    scaf = take(wins.scaf)
+    names = [query.names[s] for s in scaf] if want_names else []
+    if idx.size:
+        coords = np.empty((idx.size, 2), np.int64)
+        coords[:, 0] = take(wins.start)
+        coords[:, 1] = take(wins.stop)
+    else:
+        coords = np.zeros((0, 2), np.int64)
     meta = (host.total_len, host.ex_max(kmax, valid_kmax), host.nn_total)
     wt = None
     if dump is not None:
-        wt = _slice_orders(dump[idx], kmin, kmax)
+        wt = _slice_orders(take(dump), kmin, kmax)
     return HotPathResult(kmin, kmax, _slice_orders(tables_1k, kmin, kmax).copy(), meta, names, coords,
-                         rows[idx], status[idx].astype(np.uint32), len(wins), idx, wins.scaf[idx].astype(np.int64), wt,
+                         take(rows), take(status).astype(np.uint32, copy=False), len(wins), idx, scaf.astype(np.int64), wt,
                          scaf_names=list(query.names) if want_names else query.names)
 
 
