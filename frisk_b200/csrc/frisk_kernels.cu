@@ -2326,9 +2326,8 @@ static int run_host_body(const PeerArgs& peers, const HostPlanes& h, const HostP
         int n_parts = (int)((h_padded_len + (64ull << 20) - 1) / (64ull << 20));
         if (n_parts > kMaxChunks - 1) n_parts = kMaxChunks - 1;
         if (n_parts < 1) n_parts = 1;
-        // several ranks copying at once share the host's H2D bandwidth (8 GPUs: 24-36 GB/s each instead of 54,
-        // profiles/r02_pcie_contention_8gpu.json): the upload is then long enough to hide the first half's count behind it
-        if (n_parts < 2 && peers.world >= 4 && h_padded_len >= (1ull << 24)) n_parts = 2;
+        // (also when eight ranks share the host's H2D bandwidth and the upload takes twice as long, profiles/
+        // r02_pcie_contention_8gpu.json: two chunks measured 0.50 ms to the end of the count against 0.48 for one)
         for (int i = 0; i < n_parts; ++i) parts[i] = 1;
         if (const char* e = getenv("FRISK_UPLOAD_PLAN")) {
             n_parts = 0;
