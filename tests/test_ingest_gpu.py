@@ -97,6 +97,12 @@ def test_headers_around_tile_boundaries():
         first = letters[rng.integers(0, len(letters), shift)].tobytes()
         text = b">a\n" + first + b"\n>b\n" + b"ACGT" * 3000 + b"\n>c\n\n>d\nA\n"
         assert_same_genome(text)
+    # a header line longer than two tiles (and, with test-sized chunks, longer than a chunk), one that ends exactly at a tile
+    # boundary, and a '>' inside a sequence line right after such a header
+    for hdr_len in (4093, 4094, 9000, 20000):
+        text = b">a\nACGT\n>" + b"h" * hdr_len + b" d\n" + b"AC>GT" * 500 + b"\n>c\nTTTT\n"
+        g = assert_same_genome(text)
+        assert list(g.scaf_len) == [4, 2500, 4]
     # a tile made of headers only, and one made of blank lines only
     text = b"".join(b">r%05d\n" % i for i in range(2000)) + b"\n" * 9000 + b">z\nACGT\n" + b" " * 5000 + b"\nGG\n"
     g = assert_same_genome(text)
