@@ -468,7 +468,23 @@ int frisk_b200_windows(const uint64_t* scaf_len, const uint64_t* scaf_off, uint6
         }
         // Once j + w overshoots it does so for every later j too, so the reference's never-cleared
         // `jumpback` flag (F:232) just means: every remaining j re-emits the last w bases (F:243).
-        for (uint64_t j = 0; j + (uint64_t)step <= size; j += (uint64_t)step) {  // xrange(0, size - i + 1, i)
+        // the regular part of the grid -- j + w <= size -- without a call per window: plain array fills
+        uint64_t j0 = 0;
+        if (size >= (uint64_t)w && (uint64_t)w <= FRISK_B200_MAX_WINDOW) {
+            // j = 0, step, ... while j + step <= size (the xrange) and j + w <= size (no jump-back yet); none if size < step
+            const uint64_t n_reg = size >= (uint64_t)step ? std::min(size - (uint64_t)w, size - (uint64_t)step) / (uint64_t)step + 1 : 0;
+            if (n + n_reg <= cap) {
+                const uint64_t base = scaf_off[s];
+                if (win_off) for (uint64_t k = 0; k < n_reg; ++k) win_off[n + k] = base + k * (uint64_t)step;
+                if (win_len) for (uint64_t k = 0; k < n_reg; ++k) win_len[n + k] = (uint32_t)w;
+                if (win_scaf) for (uint64_t k = 0; k < n_reg; ++k) win_scaf[n + k] = (uint32_t)s;
+                if (win_start) for (uint64_t k = 0; k < n_reg; ++k) win_start[n + k] = (int64_t)(k * (uint64_t)step) + 1;
+                if (win_stop) for (uint64_t k = 0; k < n_reg; ++k) win_stop[n + k] = (int64_t)(k * (uint64_t)step + (uint64_t)w);
+                n += n_reg;
+                j0 = n_reg * (uint64_t)step;
+            }
+        }
+        for (uint64_t j = j0; j + (uint64_t)step <= size; j += (uint64_t)step) {  // xrange(0, size - i + 1, i)
             if (j + (uint64_t)w > size) {                                                          // F:230-232, F:243
                 // size < w (possible when 0.75 w < step): seq[size - w : size] has a NEGATIVE start, which Python
                 // counts from the end -- the slice is the last min(w - size, size) bases; the coordinates stay

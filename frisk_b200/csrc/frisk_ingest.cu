@@ -670,6 +670,7 @@ struct UploadLane {
     cudaStream_t copy = nullptr;
     cudaEvent_t ready = nullptr, done[kMaxChunks] = {};
     std::mutex mu;                                   // one open at a time per device: the events above are shared
+    unsigned long long* stage = nullptr;             // page-locked landing zone of the counters + the first kFirstFetch records
 };
 std::mutex g_lane_mu;
 std::atomic<uint64_t> g_open_stats[2];
@@ -685,6 +686,7 @@ int upload_lane(UploadLane** out) {
         FRISK_CK(cudaStreamCreateWithFlags(&l.copy, cudaStreamNonBlocking));
         FRISK_CK(cudaEventCreateWithFlags(&l.ready, cudaEventDisableTiming));
         for (auto& e : l.done) FRISK_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        FRISK_CK(cudaHostAlloc((void**)&l.stage, (2 * kFirstFetch + kCtrCount) * 8, cudaHostAllocDefault));
     }
     *out = &l;
     return FRISK_OK;
@@ -848,19 +850,23 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
             FRISK_CK(cudaGetLastError());
             back = st;
         }
+        // counters and the first records land in page-locked memory (a pageable destination makes every copy a blocking,
+        // staged one): three copies queued, one synchronisation
         const uint64_t first = std::min<uint64_t>(rec_cap, kFirstFetch);
-        h->seq_len.resize(first);
-        h->hdr_pos.resize(first);
-        FRISK_CK(cudaMemcpyAsync(h->seq_len.data(), h->d_len, first * 8, cudaMemcpyDeviceToHost, back));
-        FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data(), h->d_hdr_pos, first * 8, cudaMemcpyDeviceToHost, back));
-        FRISK_CK(cudaMemcpyAsync(ctr, h->d_counters, kCtrCount * 8, cudaMemcpyDeviceToHost, back));
+        unsigned long long* const sg = lane->stage;
+        FRISK_CK(cudaMemcpyAsync(sg, h->d_len, first * 8, cudaMemcpyDeviceToHost, back));
+        FRISK_CK(cudaMemcpyAsync(sg + kFirstFetch, h->d_hdr_pos, first * 8, cudaMemcpyDeviceToHost, back));
+        FRISK_CK(cudaMemcpyAsync(sg + 2 * kFirstFetch, h->d_counters, kCtrCount * 8, cudaMemcpyDeviceToHost, back));
         FRISK_CK(cudaStreamSynchronize(back));
+        memcpy(ctr, sg + 2 * kFirstFetch, kCtrCount * 8);
         if (!exact && (ctr[kCtrAmbig] || ctr[kCtrOverflow])) return kRetryExact;
         if (ctr[kCtrWhitespace]) return FRISK_E_FORMAT;                // whitespace inside a sequence line
         const uint64_t n_rec = ctr[kCtrRecords];
         h->n_rec = n_rec;
         h->seq_len.resize(n_rec);
         h->hdr_pos.resize(n_rec);
+        memcpy(h->seq_len.data(), sg, std::min<uint64_t>(first, n_rec) * 8);
+        memcpy(h->hdr_pos.data(), sg + kFirstFetch, std::min<uint64_t>(first, n_rec) * 8);
         if (n_rec > first) {
             FRISK_CK(cudaMemcpyAsync(h->seq_len.data() + first, h->d_len + first, (n_rec - first) * 8, cudaMemcpyDeviceToHost, back));
             FRISK_CK(cudaMemcpyAsync(h->hdr_pos.data() + first, h->d_hdr_pos + first, (n_rec - first) * 8, cudaMemcpyDeviceToHost, back));

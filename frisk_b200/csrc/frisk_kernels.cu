@@ -18,6 +18,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
 #include <functional>
 #include <mutex>
 #include <vector>
@@ -1532,8 +1534,14 @@ int launch_finalize(const Fwd f, int symmetric, uint64_t* tables, uint64_t* vali
 template <int K, typename Fwd>
 int launch_finalize_ivom(Fwd f, int kmin, int64_t space, uint64_t* tables, uint64_t* valid, double* ig, cudaStream_t st) {
     auto kern = finalize_ivom_kernel<K, Fwd>;
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+    static std::atomic<int> cached[64];                                  // occupancy once per device and instantiation
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    int per_sm = cached[dev & 63].load(std::memory_order_acquire);
+    if (per_sm == 0) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+        if (per_sm > 0) cached[dev & 63].store(per_sm, std::memory_order_release);
+    }
     const int sms = sm_count();
     if (sms <= 0) return FRISK_E_NO_DEVICE;
     if (per_sm < 1) return FRISK_E_UNSUPPORTED;
@@ -2057,7 +2065,7 @@ int frisk_b200_kld(const double* d_genome_ivom, const double* d_window_ivom, uin
 namespace {
 // Stage marks of the last frisk_b200_run_host* / _run_resident call on a device (frisk_b200_last_run_timing): timing-enabled
 // events recorded on the call's streams; reading them back costs nothing on the data path.
-enum { kTmStart = 0, kTmUploaded, kTmCounted, kTmFinalised, kTmScored, kTmEnd, kTmCount };
+enum { kTmStart = 0, kTmUploaded, kTmCounted, kTmFinalised, kTmScored, kTmEnd, kTmScoreStart, kTmCount };
 struct RunMarks {
     cudaEvent_t ev[kTmCount] = {};
     bool have[kTmCount] = {};
@@ -2107,6 +2115,21 @@ static int check_windows(const uint64_t* win_off, const uint32_t* win_len, uint6
 
 typedef std::function<int(const uint64_t** win_off, const uint32_t** win_len, uint64_t* n_win, uint32_t* max_win_len)> LateWindows;
 
+// FRISK_RUN_TRACE=1: host-side timeline of a one-call run on stderr (microseconds since the first stamp)
+struct HostTrace {
+    bool on = getenv("FRISK_RUN_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0;
+    char buf[512]; int len = 0; bool started = false;
+    void stamp(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        if (!started) { t0 = now; started = true; }
+        len += snprintf(buf + len, sizeof(buf) - (size_t)len, " %s=%.1f", what, std::chrono::duration<double, std::micro>(now - t0).count());
+    }
+    void flush() { if (on && len) fprintf(stderr, "host trace (us):%s\n", buf); len = 0; started = false; }
+};
+static thread_local HostTrace g_trace;
+
 static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* dhi, const uint32_t* dhl, uint64_t h_padded_len, bool bg_enqueued,
                     const uint32_t* dqc, const uint32_t* dqi, const uint32_t* dql, const uint64_t* win_off,
                     const uint32_t* win_len, uint64_t n_win, uint32_t max_win_len, int kmin, int kmax, int mask_host,
@@ -2123,13 +2146,21 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
     auto upload_windows = [&]() -> int {
         if (n_win) {
             int rc2;
-            if ((rc2 = ws_get(9, n_win * 8, &dwo))) return rc2;
-            if ((rc2 = ws_get(10, n_win * 4, &dwl))) return rc2;
+            // (offsets and lengths in one host block -- frisk_b200_run_fasta's staging -- travel as one copy)
+            const bool one_block = (const void*)win_len == (const void*)(win_off + n_win);
+            if ((rc2 = ws_get(9, one_block ? n_win * 12 : n_win * 8, &dwo))) return rc2;
+            if (one_block) dwl = (char*)dwo + n_win * 8;
+            else if ((rc2 = ws_get(10, n_win * 4, &dwl))) return rc2;
             if ((rc2 = ws_get(11, n_win * 40, &drows))) return rc2;
             if ((rc2 = ws_get(12, n_win * 4, &dstat))) return rc2;
-            cudaStream_t up = copy ? copy : st;         // the window list rides behind the planes
-            CK(cudaMemcpyAsync(dwo, win_off, n_win * 8, cudaMemcpyHostToDevice, up));
-            CK(cudaMemcpyAsync(dwl, win_len, n_win * 4, cudaMemcpyHostToDevice, up));
+            // the window list rides behind the planes -- but a late one goes on the compute stream: the copy stream is busy
+            // bringing the tables back by then, and the window kernel would wait 0.03 ms for its 190 KB behind them
+            cudaStream_t up = (copy && !late) ? copy : st;
+            if (one_block) CK(cudaMemcpyAsync(dwo, win_off, n_win * 12, cudaMemcpyHostToDevice, up));
+            else {
+                CK(cudaMemcpyAsync(dwo, win_off, n_win * 8, cudaMemcpyHostToDevice, up));
+                CK(cudaMemcpyAsync(dwl, win_len, n_win * 4, cudaMemcpyHostToDevice, up));
+            }
         }
         if (copy) CK(cudaEventRecord(copy_done, copy));
         return FRISK_OK;
@@ -2155,9 +2186,12 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
         if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, copy));
         if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, copy));
     }
+    g_trace.stamp("finalize_queued");
     if (late) {
         if ((rc = (*late)(&win_off, &win_len, &n_win, &max_win_len))) return rc;
+        g_trace.stamp("windows");
         if ((rc = upload_windows())) return rc;
+        g_trace.stamp("windows_queued");
     }
     if (copy) CK(cudaStreamWaitEvent(st, copy_done, 0));
     if (n_win) {
@@ -2170,9 +2204,11 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
         cudaGetLastError();                             // a pageable pointer makes the query itself report an error
         double* k_rows = direct ? (double*)pa_rows.devicePointer : (double*)drows;
         uint32_t* k_stat = direct ? (uint32_t*)pa_stat.devicePointer : (uint32_t*)dstat;
+        if ((rc = mark(tm, kTmScoreStart, st))) return rc;
         rc = frisk_b200_score(dqc, dqi, dql, (const uint64_t*)dwo, (const uint32_t*)dwl, n_win, max_win_len,
                               (const double*)dig, kmin, kmax, want_rip, k_rows, k_stat, nullptr, st);
         if (rc) return rc;
+        g_trace.stamp("score_queued");
         if ((rc = mark(tm, kTmScored, st))) return rc;
         if (!direct) {
             CK(cudaMemcpyAsync(rows_out, drows, n_win * 40, cudaMemcpyDeviceToHost, st));
@@ -2185,6 +2221,8 @@ static int run_tail(const PeerArgs& peers, const uint32_t* dhc, const uint32_t* 
     }
     if ((rc = mark(tm, kTmEnd, st))) return rc;
     CK(cudaStreamSynchronize(st));
+    g_trace.stamp("done");
+    g_trace.flush();
     if (tables_aside) CK(cudaStreamSynchronize(copy));
     return FRISK_OK;
 }
@@ -2506,7 +2544,9 @@ int run_fasta_body(const char* h_text, uint64_t h_n, const char* q_text, uint64_
         return (int)FRISK_OK;
     };
     sink.uploaded_mark = tm->ev[kTmUploaded];
+    g_trace.stamp("call");
     if ((rc = frisk_internal::fasta_open_planes(h_text, h_n, st, &sink, host_out))) return rc;
+    g_trace.stamp("open_returned");
     tm->have[kTmUploaded] = h_n > 0;                                // (recorded behind the last text chunk)
     const bool counted = sink.counted;
     if (counted && (rc = mark(tm, kTmCounted, st))) return rc;
@@ -2531,7 +2571,7 @@ int run_fasta_body(const char* h_text, uint64_t h_n, const char* q_text, uint64_
         std::vector<uint64_t> seq_len((size_t)q_rec), scaf_off((size_t)q_rec);
         if ((rc2 = frisk_b200_fasta_records(qh, nullptr, nullptr, seq_len.data(), scaf_off.data()))) return rc2;
         void *wo = nullptr, *wl = nullptr;
-        if ((rc2 = stage_get(dev, 0, (rows_cap + 1) * 8, &wo))) return rc2;
+        if ((rc2 = stage_get(dev, 0, (rows_cap + 1) * 12, &wo))) return rc2;
         if ((rc2 = stage_get(dev, 1, (rows_cap + 1) * 4, &wl))) return rc2;
         uint64_t nw = 0;
         rc2 = frisk_b200_windows(seq_len.data(), scaf_off.data(), q_rec, w, step, scaffolds_all, rows_cap, (uint64_t*)wo, (uint32_t*)wl,
@@ -2539,8 +2579,13 @@ int run_fasta_body(const char* h_text, uint64_t h_n, const char* q_text, uint64_
         if (n_win_out) *n_win_out = nw;
         if (rc2) return rc2;                                         // (FRISK_E_CAPACITY: more windows than rows_cap)
         uint32_t mx = 0;
-        for (uint64_t i = 0; i < nw; ++i) mx = ((const uint32_t*)wl)[i] > mx ? ((const uint32_t*)wl)[i] : mx;
-        *win_off = (const uint64_t*)wo; *win_len = (const uint32_t*)wl; *n_win = nw; *max_len = mx;
+        uint32_t* const packed = (uint32_t*)((uint64_t*)wo + nw);    // the lengths move right behind the offsets: one H2D copy
+        for (uint64_t i = 0; i < nw; ++i) {
+            const uint32_t l = ((const uint32_t*)wl)[i];
+            packed[i] = l;
+            mx = l > mx ? l : mx;
+        }
+        *win_off = (const uint64_t*)wo; *win_len = packed; *n_win = nw; *max_len = mx;
         return FRISK_OK;
     };
     CK(cudaEventRecord(cc->ev[kMaxChunks], st));                    // the copy stream joins behind the ingest
@@ -2591,7 +2636,8 @@ int frisk_b200_run_fasta(const char* h_text, uint64_t h_n, const char* q_text, u
 // Stage times (ms) of the last frisk_b200_run_host / _sparse / _peers / _run_resident call on the current device,
 // from events recorded on its streams: [0] upload of the planes finished, [1] background count finished, [2] tables
 // finalised + genome IVOM table (multi-GPU: includes the wait for the peers' counters), [3] window kernel(s) finished,
-// [4] results on the host -- each since the start of the call -- and [5] = [4].  A mark the call did not set
+// [4] results on the host -- each since the start of the call -- and [5] the moment the window kernel could start
+// (everything it waits for is done and its launch has reached the device).  A mark the call did not set
 // (run_resident has no upload) reads -1.
 int frisk_b200_last_run_timing(float* ms, int cap, int* n) {
     if (!ms || cap < 1) return FRISK_E_INVALID;
@@ -2600,7 +2646,7 @@ int frisk_b200_last_run_timing(float* ms, int cap, int* n) {
     RunMarks& m = g_marks[dev & 63];
     if (!m.ready || !m.have[kTmStart] || !m.have[kTmEnd]) return FRISK_E_INVALID;
     CK(cudaEventSynchronize(m.ev[kTmEnd]));
-    const int order[6] = {kTmUploaded, kTmCounted, kTmFinalised, kTmScored, kTmEnd, kTmEnd};
+    const int order[6] = {kTmUploaded, kTmCounted, kTmFinalised, kTmScored, kTmEnd, kTmScoreStart};
     int k = 0;
     for (; k < 6 && k < cap; ++k) {
         ms[k] = -1.0f;

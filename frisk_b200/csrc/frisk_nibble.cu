@@ -28,6 +28,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/frisk_b200.h"
 #include "frisk_internal.h"
 #include "frisk_device.cuh"
@@ -771,10 +773,17 @@ int launch_nibble4(const uint32_t* codes, const uint32_t* inv, const uint32_t* l
                    double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only) {
     using L = NibLayout<K>;
     auto kern = score_windows_nibble_kernel<K, PP, DUMP, ALLK>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, L::TOTAL));
+    // attributes and occupancy once per device and instantiation: three runtime calls less in front of every launch
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    int per_sm = cached[dev & 63].load(std::memory_order_acquire);
+    if (per_sm == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, L::TOTAL));
+        if (per_sm > 0) cached[dev & 63].store(per_sm, std::memory_order_release);
+    }
     if (occ_only) { *occ_only = per_sm; return FRISK_OK; }
     if (per_sm < 1) per_sm = 1;
     const int sms = frisk_internal::sm_count_cached();

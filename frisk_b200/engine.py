@@ -389,6 +389,26 @@ class DeviceGenome:
                             self.inv.cpu().numpy().view(np.uint32), low, g.total_len, g.nn_total, g.n_lower, False)
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
+def _device_ctx(device):
+    """``torch.cuda.device(device)`` -- or nothing when that device is current already (entering and leaving the context
+    costs ~10 us of cudaSetDevice calls, which shows in a 1 ms call)."""
+    import torch
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return _NULL_CTX if torch.cuda.current_device() == idx else torch.cuda.device(dev)
+
+
 def _stream_ptr(device) -> C.c_void_p:
     if not _torch_loaded():
         return C.c_void_p(0)                 # no torch in the process: the default stream
@@ -931,8 +951,7 @@ def run_resident(dq: DeviceGenome, dh: Optional[DeviceGenome] = None, kmin: int 
         _lib.check(_lib.lib().frisk_b200_set_device(_device_index(dq.device)), "frisk_b200_set_device")
         rc = call()
     else:
-        import torch
-        with torch.cuda.device(dq.device):
+        with _device_ctx(dq.device):
             rc = call()
     _lib.check(rc, "frisk_b200_run_resident")
     if not assemble_result:
@@ -981,7 +1000,7 @@ def run_fasta(query_text, host_text=None, device="cuda:0", out=None, assemble_re
         out = HostOutputs(qbuf.shape[0] // step + qbuf.shape[0] // 512 + 64, kmax)
     hh, qh = C.c_void_p(), C.c_void_p()
     n_win = C.c_uint64(0)
-    with torch.cuda.device(dev):
+    with _device_ctx(dev):
         st = _stream_ptr(dev)
         rc = L.frisk_b200_run_fasta(_ptr(hbuf), hbuf.shape[0], _ptr(qbuf) if host_text is not None else None,
                                     qbuf.shape[0] if host_text is not None else 0, w, step, int(scaffolds_all), kmin, kmax,

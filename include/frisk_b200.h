@@ -365,7 +365,7 @@ int frisk_b200_fasta_planes(const frisk_b200_fasta *h, const uint32_t **d_codes,
 /* Stage times (ms since the start of the call) of the last frisk_b200_run_host / _sparse / _peers / _run_resident call
  * on the current device, from CUDA events recorded on the call's own streams: ms[0] planes uploaded, ms[1] background
  * counted, ms[2] tables + genome IVOM finalised (multi-GPU: includes the wait for the peers' counters), ms[3] window
- * kernel(s) done, ms[4] = ms[5] results on the host.  -1 for a mark the call did not set.  *n = values written. */
+ * kernel(s) done, ms[4] results on the host, ms[5] the moment the window kernel could start (its inputs done, its launch on the device).  -1 for a mark the call did not set.  *n = values written. */
 int frisk_b200_last_run_timing(float *ms, int cap, int *n);
 
 /* The k sweep of BASELINE config C3 in ONE launch: rows for kmax' = 1..8 (kmin 1: eight reference runs `-m 1 -k k'`,

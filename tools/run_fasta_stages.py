@@ -27,9 +27,9 @@ for opt in [None] + [a for a in sys.argv[1:]]:
         wall = (time.perf_counter() - t0) * 1e3
         ms = (C.c_float * 8)(); nn = C.c_int(0)
         L.frisk_b200_last_run_timing(ms, 8, C.byref(nn))
-        reps.append([round(float(x), 3) for x in ms[:5]] + [round(wall, 3)])
-    med = [float(np.median([r[i] for r in reps[3:]])) for i in range(6)]
-    rows.append({"option": opt, "uploaded/counted/finalised/scored/end/wall_ms": med})
+        reps.append([round(float(x), 3) for x in ms[:5]] + [round(wall, 3), round(float(ms[5]), 3)])
+    med = [float(np.median([r[i] for r in reps[3:]])) for i in range(7)]
+    rows.append({"option": opt, "uploaded/counted/finalised/scored/end/wall/score_start_ms": med})
     if opt:
         L.frisk_b200_set_option(k.encode(), 0)
 print(json.dumps({"text_bytes": int(text.shape[0]), "n_win": out.n_win, "open_stats": None, "rows": rows}, indent=1))
