@@ -63,6 +63,7 @@ PROTOTYPES = {
     "frisk_b200_fasta_open_stats": (_i, [_p]),
     "frisk_b200_run_fasta": (_i, [_p, _u64, _p, _u64, _i, _i, _i, _i, _i, _i, _i, _u64, _p, _p, _p, _p, C.POINTER(_u64),
                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _p]),
+    "frisk_b200_windows_device": (_i, [_p, _p, _u64, _i, _i, _i, _u64, _p, _p, _p, _p, _p]),
     "frisk_b200_fasta_info": (_i, [_p, C.POINTER(_u64), C.POINTER(_u64), _p]),
     "frisk_b200_fasta_planes": (_i, [_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "frisk_b200_last_run_timing": (_i, [C.POINTER(C.c_float), _i, C.POINTER(_i)]),

@@ -38,6 +38,13 @@ int fasta_open_planes(const char* text, uint64_t n, cudaStream_t st, IngestSink*
 int background_device_range(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const unsigned long long* d_word_range,
                             uint64_t words_hint, int kmax, int mask_host, uint64_t* fwd, cudaStream_t st);
 
+// frisk_b200_windows on the device (frisk_windows.cu): window list, window count and genome space from a record table in
+// device memory; d_n_rec / d_bad / d_non_upper point into the ingest's counters.  d_win_off == nullptr: count / space only.
+int windows_device(const unsigned long long* d_len, const unsigned long long* d_scaf_off, const unsigned long long* d_n_rec,
+                   const unsigned long long* d_bad, const unsigned long long* d_non_upper, uint64_t rec_cap, int w, int step,
+                   int scaffolds_all, uint64_t cap, unsigned long long* d_first, unsigned long long* d_win_off, uint32_t* d_win_len,
+                   unsigned long long* d_n_win, long long* d_space, cudaStream_t st);
+
 // FASTA header rule of the reference (F:156): name = line.strip().strip('>').split()[0].
 // The line starts at `line_start`; returns false for an empty name (the reference raises IndexError).
 bool parse_header_name(const unsigned char* t, uint64_t n, uint64_t line_start, uint64_t* name_off, uint32_t* name_len);

@@ -358,6 +358,13 @@ int frisk_b200_run_fasta(const char *h_text, uint64_t h_n, const char *q_text, u
                          int scaffolds_all, int kmin, int kmax, int mask_host, int want_rip, uint64_t rows_cap,
                          double *rows_out, uint32_t *status_out, uint64_t *tables_out, uint64_t *valid_kmax_out,
                          uint64_t *n_win_out, frisk_b200_fasta **host_out, frisk_b200_fasta **query_out, void *stream);
+/* frisk_b200_windows_device: the window list of frisk_b200_windows (same windows, same order) from a record table that
+ * lives in DEVICE memory, written to device memory; *d_n_windows receives the count (windows beyond `cap` are not
+ * written), *d_genome_space (nullable) the sum of the lengths.  What frisk_b200_run_fasta does between the ingest and the
+ * window kernel, exposed for tests. */
+int frisk_b200_windows_device(const uint64_t *d_scaf_len, const uint64_t *d_scaf_off, uint64_t n_scaf, int w, int step,
+                              int scaffolds_all, uint64_t cap, uint64_t *d_win_off, uint32_t *d_win_len,
+                              uint64_t *d_n_windows, int64_t *d_genome_space, void *stream);
 int frisk_b200_fasta_info(const frisk_b200_fasta *h, uint64_t *n_records, uint64_t *padded_len, uint64_t stats[3]);
 int frisk_b200_fasta_planes(const frisk_b200_fasta *h, const uint32_t **d_codes, const uint32_t **d_inv,
                             const uint32_t **d_low);

@@ -1,6 +1,8 @@
 """Device-side FASTA ingest (frisk_ingest.cu) against the host packer, which tests/test_host.py holds
 to the reference's iterFasta/countN rules (F:139-164, F:106-118): same records, same layout, and
 bit-identical planes; then the whole FASTA-text-in, rows-out path against the golden fixtures."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -238,6 +240,45 @@ def test_chunked_open_carries_state_across_chunks_and_falls_back_when_it_cannot_
         d, r = open_stats()
         engine.DeviceGenome.from_fasta_bytes(text)
         assert open_stats() == (d, r), "the exact open is neither chunked nor a retry"
+
+
+@pytest.mark.parametrize("w,step,all_", [(5000, 2500, False), (5000, 2500, True), (1000, 800, False), (1000, 800, True),
+                                        (700, 1000, True), (64, 1, False), (3000, 3000, True)])
+def test_device_window_list_is_the_host_window_list(w, step, all_):
+    """frisk_b200_run_fasta builds its window list on the device (frisk_windows.cu) so that nothing between the last byte of the
+    text and the window kernel waits for the host: same windows, same order as frisk_b200_windows (crawlGenome, F:194-251) --
+    size rule, grid, jump-back tail, --scaffoldsAll rescue, scaffolds shorter than a window or a step."""
+    import torch
+    rng = np.random.default_rng(w + step)
+    lens = np.concatenate([rng.integers(0, 4 * w, 300), rng.integers(0, 40, 50), np.array([w, w - 1, w + 1, step, step - 1, 2 * w,
+                           int(1.75 * w - step), int(1.75 * w - step) + 1, 0, 1, 250_000])]).astype(np.uint64)
+    rng.shuffle(lens)
+    off = np.zeros(len(lens), np.uint64)
+    padded = C.c_uint64(0)
+    L = _lib.lib()
+    _lib.check(L.frisk_b200_pack_layout(engine._ptr(lens), len(lens), engine._ptr(off), C.byref(padded)), "pack_layout")
+    n = C.c_uint64(0)
+    _lib.check(L.frisk_b200_windows(engine._ptr(lens), engine._ptr(off), len(lens), w, step, int(all_), 0, None, None, None, None,
+                                    None, C.byref(n)), "windows")
+    cap = int(n.value)
+    h_off, h_len = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+    _lib.check(L.frisk_b200_windows(engine._ptr(lens), engine._ptr(off), len(lens), w, step, int(all_), cap, engine._ptr(h_off),
+                                    engine._ptr(h_len), None, None, None, C.byref(n)), "windows")
+    dev = torch.device("cuda:0")
+    d_lens, d_off = torch.from_numpy(lens.view(np.int64)).to(dev), torch.from_numpy(off.view(np.int64)).to(dev)
+    for dcap in (cap + 7, max(cap - 5, 0)):
+        d_wo = torch.full((dcap + 1,), -1, dtype=torch.int64, device=dev)
+        d_wl = torch.full((dcap + 1,), -1, dtype=torch.int32, device=dev)
+        d_n = torch.zeros(2, dtype=torch.int64, device=dev)
+        _lib.check(L.frisk_b200_windows_device(engine._ptr(d_lens), engine._ptr(d_off), len(lens), w, step, int(all_), dcap,
+                                               engine._ptr(d_wo), engine._ptr(d_wl), C.c_void_p(d_n.data_ptr()),
+                                               C.c_void_p(d_n.data_ptr() + 8), engine._stream_ptr(dev)), "windows_device")
+        torch.cuda.synchronize()
+        assert int(d_n[0]) == cap and int(d_n[1]) == int(lens.sum())
+        k = min(cap, dcap)
+        assert np.array_equal(d_wo.cpu().numpy()[:k].view(np.uint64), h_off[:k])
+        assert np.array_equal(d_wl.cpu().numpy()[:k].view(np.uint32), h_len[:k])
+        assert int(d_wo[dcap]) == -1 and int(d_wl[dcap]) == -1, "nothing is written beyond the capacity"
 
 
 def test_multi_gigabyte_text_beyond_2_pow_32_bytes():
