@@ -56,6 +56,9 @@ enum { kCtrRecords = 0, kCtrNonUpper = 1, kCtrLower = 2, kCtrWhitespace = 3, kCt
        kCtrCount = 12,
        kRangeSlots = 2 };      // per chunk, behind the counters: {word_lo, word_hi}
 
+static_assert((int)kCtrRecords == (int)frisk_internal::kIngestRecords && (int)kCtrNonUpper == (int)frisk_internal::kIngestNonUpper &&
+              (int)kCtrOverflow == (int)frisk_internal::kIngestOverflow, "frisk_internal.h names these counters");
+
 // class of a byte: 0..3 = A,T,G,C (F:70 order); 4..7 = a,t,g,c; 8 = anything else; 9 = whitespace
 // removed by the reference's line.strip() (F:149)
 __device__ __forceinline__ uint32_t class_of(uint32_t c) {
@@ -636,6 +639,8 @@ struct frisk_b200_fasta {
                        *d_counters = nullptr;
     uint32_t *d_codes = nullptr, *d_inv = nullptr, *d_low = nullptr;     // the planes, built by the open and owned by the handle
     void *d_scan_slab = nullptr, *d_out_slab = nullptr;                  // what the pointers above (but d_text) are carved from
+    uint64_t rec_cap = 0;                                                // entries of the device record table
+    bool streamed = false;                                               // opened on the chunked, speculatively sized path
     std::vector<uint64_t> name_off, seq_len, scaf_off, hdr_pos;
     std::vector<uint32_t> name_len;
 };
@@ -729,6 +734,7 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
     uint64_t rec_cap = 0, plane_cap = 0;
     auto alloc_out = [&](uint64_t R, uint64_t P) -> int {              // record table of R entries, planes of P bases (zeroed)
         rec_cap = R; plane_cap = P;
+        h->rec_cap = R;
         FRISK_CK(cudaMallocAsync(&h->d_out_slab, 3 * (R * 8 + 256) + P / 2 + 3 * 256, st));
         char* cur = (char*)h->d_out_slab;
         carve(cur, h->d_codes, P / 4); carve(cur, h->d_inv, P / 8); carve(cur, h->d_low, P / 8);
@@ -829,6 +835,7 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
                 if ((rc = sink->on_range(h->d_codes, h->d_inv, h->d_low, d_range, ((b1 - counted_from) >> 5) + 8, st))) return rc;
                 counted_from = b1;
             }
+            if (final && sink && sink->on_complete && (rc = sink->on_complete(h, st))) return rc;
             tmark(st);
         }
         if (trace) {
@@ -891,6 +898,7 @@ int open_impl(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st
     if (rc) return rc;
     if (device_padded != h->padded_len) return exact ? FRISK_E_CUDA : kRetryExact;   // (cannot happen: both sides apply one rule)
     if (sink) sink->counted = (bool)sink->on_range;
+    h->streamed = !exact;
     return FRISK_OK;
 }
 
@@ -912,6 +920,17 @@ int open_any(frisk_b200_fasta* h, const char* text, uint64_t n, cudaStream_t st,
     return rc;
 }
 }  // namespace
+
+bool frisk_internal::fasta_open_was_streamed(const frisk_b200_fasta* h) { return h && h->streamed; }
+
+int frisk_internal::fasta_device_table(const frisk_b200_fasta* h, const unsigned long long** d_len, const unsigned long long** d_scaf_off,
+                                       const unsigned long long** d_counters, uint64_t* rec_cap, const uint32_t** d_codes,
+                                       const uint32_t** d_inv, const uint32_t** d_low) {
+    if (!h || !h->d_counters || !h->d_len || !h->d_codes) return FRISK_E_INVALID;
+    *d_len = h->d_len; *d_scaf_off = h->d_scaf_off; *d_counters = h->d_counters; *rec_cap = h->rec_cap;
+    *d_codes = h->d_codes; *d_inv = h->d_inv; *d_low = h->d_low;
+    return FRISK_OK;
+}
 
 int frisk_internal::fasta_open_planes(const char* text, uint64_t n, cudaStream_t st, IngestSink* sink, frisk_b200_fasta** out) {
     if (!out || !sink || (!text && n)) return FRISK_E_INVALID;

@@ -30,9 +30,19 @@ struct IngestSink {
     std::function<int(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const unsigned long long* d_word_range,
                       uint64_t words_hint, cudaStream_t st)> on_range;
     std::function<int(cudaStream_t st)> abandon;
+    // called once the last chunk's passes (and its on_range) are queued: the record table and the planes are complete in
+    // stream order, the host has not seen anything yet -- whatever only needs DEVICE-side results can be queued here
+    std::function<int(frisk_b200_fasta* h, cudaStream_t st)> on_complete;
     cudaEvent_t uploaded_mark = nullptr;     // recorded behind the last text chunk's copy
     bool counted = false;                    // out: on_range saw every word of [0, padded_len / 32 - 1)
 };
+// the device side of a handle's record table, for on_complete: lengths, offsets, capacity, and the ingest's counters
+// (records at [kIngestRecords], non-upper-case bases at [kIngestNonUpper], "capacities exceeded" at [kIngestOverflow])
+enum { kIngestRecords = 0, kIngestNonUpper = 1, kIngestOverflow = 5 };
+bool fasta_open_was_streamed(const frisk_b200_fasta* h);     // false: the handle comes from the exact re-open
+int fasta_device_table(const frisk_b200_fasta* h, const unsigned long long** d_len, const unsigned long long** d_scaf_off,
+                       const unsigned long long** d_counters, uint64_t* rec_cap, const uint32_t** d_codes, const uint32_t** d_inv,
+                       const uint32_t** d_low);
 int fasta_open_planes(const char* text, uint64_t n, cudaStream_t st, IngestSink* sink, frisk_b200_fasta** out);
 // background count of a word range that lives in device memory (frisk_kernels.cu); kmax <= FRISK_B200_FAST_K
 int background_device_range(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const unsigned long long* d_word_range,
@@ -87,7 +97,7 @@ int sm_count_cached();
 // words) are marked kRowRedo and re-done by the bucketed kernel, exactly like the direct kernel's hand-over.
 int score_nibble(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                  const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K, int want_rip,
-                 double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st);
+                 double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st, const unsigned long long* n_win_dev = nullptr);
 int score_nibble_occupancy(int K, uint32_t max_len, int* ctas_per_sm, int* threads_per_cta);
 // the k sweep (BASELINE config C3): rows of kmax' = 1..8, kmin 1, from one pass over every window; ig / rows / status are
 // HOST arrays of 8 device pointers

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <functional>
@@ -199,8 +200,10 @@ bg_reduce_kernel(const uint32_t* __restrict__ partial, int n_parts, unsigned lon
 // staging copy: the reduction happens in the registers of the kernel that needs the sums).
 struct LocalFwd {
     const unsigned long long* p;
+    const long long* space_dev = nullptr;     // genome space in device memory (frisk_b200_run_fasta: the host does not know it yet)
     __device__ __forceinline__ unsigned long long operator()(uint32_t i) const { return p[i]; }
     __device__ __forceinline__ void arrive_and_wait() const {}
+    __device__ __forceinline__ long long space(long long by_value) const { return space_dev ? *space_dev : by_value; }
 };
 constexpr int kMaxPeers = 16;
 struct PeerFwd {
@@ -208,6 +211,7 @@ struct PeerFwd {
     unsigned long long* flags[kMaxPeers];     // flags[q][r]: "rank r's counters of epoch >= value are complete", in rank q's memory
     int n, rank;
     unsigned long long epoch;                 // 0: the caller already synchronised the GPUs
+    __device__ __forceinline__ long long space(long long by_value) const { return by_value; }
     __device__ __forceinline__ unsigned long long operator()(uint32_t i) const {
         unsigned long long s = 0;
         for (int q = 0; q < n; ++q) s += __ldcv(p[q] + i);       // written before the peers' arrival below
@@ -402,7 +406,8 @@ finalize_ivom_kernel(const Fwd fwd, unsigned long long* __restrict__ tables, uns
     const uint32_t gtid = blockIdx.x * 256 + threadIdx.x, gstride = gridDim.x * 256;
     for (uint32_t i = gtid; i < lvl_off(K + 1); i += gstride) symmetrise_entry<K>(tables, i);
     grid.sync();
-    for (uint32_t kappa = gtid; kappa < pow4(K); kappa += gstride) genome_ivom_entry<K>(tables, kmin, space, ig, kappa);
+    const long long sp = fwd.space(space);
+    for (uint32_t kappa = gtid; kappa < pow4(K); kappa += gstride) genome_ivom_entry<K>(tables, kmin, sp, ig, kappa);
 }
 
 // ============================================================================================
@@ -2544,19 +2549,128 @@ int run_fasta_body(const char* h_text, uint64_t h_n, const char* q_text, uint64_
         return (int)FRISK_OK;
     };
     sink.uploaded_mark = tm->ev[kTmUploaded];
+    const bool same = !q_text || (q_text == h_text && q_n == h_n);
+
+    // ---- the device-only tail: with the nibble kernel (kmax 7, 8; windows <= 8,186 bases) everything behind the ingest is queued
+    // from inside the open, before the host has seen the record table -- genome space and window list by frisk_windows.cu,
+    // the window count read by the window kernel from device memory -- so that no launch waits for the host.  If the
+    // streamed open has to be redone (sink.counted comes back false), what was queued here ran on provisional data into
+    // the caller's row buffers (inside their capacity) and is simply done again by the host-driven tail below.
+    const double min_size = (double)w + (((double)w * 0.75) - (double)step);
+    const uint32_t len_bound = (uint32_t)std::min<double>(4.0e9, std::max<double>((double)w, scaffolds_all ? min_size : 0.0));
+    const bool dev_tail = kmax <= FRISK_B200_FAST_K && rows_cap > 0 && rows_cap <= 0xffffffffull && (uint64_t)w <= FRISK_B200_MAX_WINDOW &&
+                          len_bound <= 8186u && use_nibble_kernel(kmax, len_bound) && !getenv("FRISK_RUN_FASTA_HOST_TAIL");
+    void *dtab = nullptr, *dig = nullptr, *dwin = nullptr, *dfirst = nullptr, *dscal = nullptr;
+    bool tail_queued = false;
+    double* k_rows = rows_out;
+    uint32_t* k_stat = status_out;
+    bool rows_direct = false;
+    if (dev_tail) {
+        if ((rc = ws_get(7, (tsz + 1) * 8, &dtab))) return rc;
+        if ((rc = ws_get(8, (size_t)pow4(kmax) * 16, &dig))) return rc;
+        if ((rc = ws_get(9, rows_cap * 12, &dwin))) return rc;
+        if ((rc = ws_get(20, 64, &dscal))) return rc;              // [0] number of windows, [1] genome space
+        cudaPointerAttributes pa_rows{}, pa_stat{};
+        const bool direct = cudaPointerGetAttributes(&pa_rows, rows_out) == cudaSuccess && pa_rows.type == cudaMemoryTypeHost &&
+                            cudaPointerGetAttributes(&pa_stat, status_out) == cudaSuccess && pa_stat.type == cudaMemoryTypeHost &&
+                            pa_rows.devicePointer && pa_stat.devicePointer;
+        cudaGetLastError();
+        rows_direct = direct;
+        if (direct) { k_rows = (double*)pa_rows.devicePointer; k_stat = (uint32_t*)pa_stat.devicePointer; }
+        else {
+            void *drows, *dstat;
+            if ((rc = ws_get(11, rows_cap * 40, &drows))) return rc;
+            if ((rc = ws_get(12, rows_cap * 4, &dstat))) return rc;
+            k_rows = (double*)drows; k_stat = (uint32_t*)dstat;
+        }
+    }
+    const uint32_t* win_codes[3] = {nullptr, nullptr, nullptr};      // planes of the genome whose windows are scored
+    auto queue_windows_and_score = [&](frisk_b200_fasta* h, bool with_space, cudaStream_t s2) -> int {
+        const unsigned long long *d_len, *d_off, *d_ctr;
+        uint64_t rec_cap = 0;
+        int rc2;
+        if ((rc2 = frisk_internal::fasta_device_table(h, &d_len, &d_off, &d_ctr, &rec_cap, &win_codes[0], &win_codes[1], &win_codes[2])))
+            return rc2;
+        if ((rc2 = ws_get(19, (rec_cap + 2) * 8, &dfirst))) return rc2;
+        unsigned long long* const scal = (unsigned long long*)dscal;
+        if ((rc2 = frisk_internal::windows_device(d_len, d_off, d_ctr + frisk_internal::kIngestRecords, d_ctr + frisk_internal::kIngestOverflow,
+                                                  d_ctr + frisk_internal::kIngestNonUpper, rec_cap, w, step, scaffolds_all, rows_cap,
+                                                  (unsigned long long*)dfirst, (unsigned long long*)dwin,
+                                                  (uint32_t*)((unsigned long long*)dwin + rows_cap), scal,
+                                                  with_space ? (long long*)(scal + 1) : nullptr, s2)))
+            return rc2;
+        return FRISK_OK;
+    };
+    auto queue_finalize = [&](cudaStream_t s2) -> int {
+        const LocalFwd f{reinterpret_cast<const unsigned long long*>(dfwd), (const long long*)((unsigned long long*)dscal + 1)};
+        uint64_t* dvalid = (uint64_t*)dtab + tsz;
+        int rc2 = FRISK_E_UNSUPPORTED;
+        switch (kmax) {
+            case 1: rc2 = launch_finalize_ivom<1, LocalFwd>(f, kmin, 0, (uint64_t*)dtab, dvalid, (double*)dig, s2); break;
+            case 2: rc2 = launch_finalize_ivom<2, LocalFwd>(f, kmin, 0, (uint64_t*)dtab, dvalid, (double*)dig, s2); break;
+            case 3: rc2 = launch_finalize_ivom<3, LocalFwd>(f, kmin, 0, (uint64_t*)dtab, dvalid, (double*)dig, s2); break;
+            case 4: rc2 = launch_finalize_ivom<4, LocalFwd>(f, kmin, 0, (uint64_t*)dtab, dvalid, (double*)dig, s2); break;
+            case 5: rc2 = launch_finalize_ivom<5, LocalFwd>(f, kmin, 0, (uint64_t*)dtab, dvalid, (double*)dig, s2); break;
+            case 6: rc2 = launch_finalize_ivom<6, LocalFwd>(f, kmin, 0, (uint64_t*)dtab, dvalid, (double*)dig, s2); break;
+            case 7: rc2 = launch_finalize_ivom<7, LocalFwd>(f, kmin, 0, (uint64_t*)dtab, dvalid, (double*)dig, s2); break;
+            case 8: rc2 = launch_finalize_ivom<8, LocalFwd>(f, kmin, 0, (uint64_t*)dtab, dvalid, (double*)dig, s2); break;
+            default: break;
+        }
+        if (rc2) return rc2;
+        if ((rc2 = mark(tm, kTmFinalised, s2))) return rc2;
+        // the genome tables (0.7 MB) go back on the copy stream while the window kernel runs
+        CK(cudaEventRecord(cc->ev[kMaxChunks + 2], s2));
+        CK(cudaStreamWaitEvent(cc->copy, cc->ev[kMaxChunks + 2], 0));
+        if (tables_out) CK(cudaMemcpyAsync(tables_out, dtab, tsz * 8, cudaMemcpyDeviceToHost, cc->copy));
+        if (valid_kmax_out) CK(cudaMemcpyAsync(valid_kmax_out, dvalid, 8, cudaMemcpyDeviceToHost, cc->copy));
+        return FRISK_OK;
+    };
+    auto queue_score = [&](cudaStream_t s2) -> int {
+        int rc2;
+        if ((rc2 = mark(tm, kTmScoreStart, s2))) return rc2;
+        rc2 = frisk_internal::score_nibble(win_codes[0], win_codes[1], win_codes[2], (const uint64_t*)dwin,
+                                           (const uint32_t*)((unsigned long long*)dwin + rows_cap), rows_cap, len_bound, (const double*)dig,
+                                           kmin, kmax, want_rip, k_rows, k_stat, nullptr, s2, (const unsigned long long*)dscal);
+        if (rc2) return rc2;
+        tail_queued = true;
+        return mark(tm, kTmScored, s2);
+    };
+    if (dev_tail)
+        sink.on_complete = [&](frisk_b200_fasta* h, cudaStream_t s2) -> int {
+            int rc2;
+            if ((rc2 = mark(tm, kTmCounted, s2))) return rc2;
+            // genome space of the host genome (and, when it is the scored genome too, its window list), tables, IVOM, score
+            if ((rc2 = queue_windows_and_score(h, true, s2))) return rc2;
+            if ((rc2 = queue_finalize(s2))) return rc2;
+            return same ? queue_score(s2) : FRISK_OK;
+        };
     g_trace.stamp("call");
     if ((rc = frisk_internal::fasta_open_planes(h_text, h_n, st, &sink, host_out))) return rc;
     g_trace.stamp("open_returned");
     tm->have[kTmUploaded] = h_n > 0;                                // (recorded behind the last text chunk)
     const bool counted = sink.counted;
-    if (counted && (rc = mark(tm, kTmCounted, st))) return rc;
+    bool tail_ok = dev_tail && counted && (tail_queued || !same);   // (an exact re-open leaves counted == false)
+    if (!tail_ok) tm->have[kTmFinalised] = tm->have[kTmScoreStart] = tm->have[kTmScored] = false;
+    if (counted && !dev_tail && (rc = mark(tm, kTmCounted, st))) return rc;
     frisk_b200_fasta* hh = *host_out;
     frisk_b200_fasta* qh = hh;
-    const bool same = !q_text || (q_text == h_text && q_n == h_n);
     if (!same) {
         frisk_internal::IngestSink qsink;                            // planes only: nothing of the query is counted
+        bool q_queued = false;
+        if (tail_ok)
+            qsink.on_complete = [&](frisk_b200_fasta* h, cudaStream_t s2) -> int {
+                int rc2;
+                if ((rc2 = queue_windows_and_score(h, false, s2))) return rc2;
+                if ((rc2 = queue_score(s2))) return rc2;
+                q_queued = true;
+                return FRISK_OK;
+            };
+        qsink.counted = false;
         if ((rc = frisk_internal::fasta_open_planes(q_text, q_n, st, &qsink, query_out))) return rc;
         qh = *query_out;
+        // (qsink has no on_range, so `counted` says nothing: a query that was re-opened exactly has a handle without the
+        // speculative table the hook used -- detect it by the hook not having run or the open statistics)
+        tail_ok = tail_ok && q_queued && frisk_internal::fasta_open_was_streamed(qh);
     }
     uint64_t h_rec = 0, h_padded = 0, h_stats[3], q_rec = 0, q_padded = 0, q_stats[3];
     if ((rc = frisk_b200_fasta_info(hh, &h_rec, &h_padded, h_stats))) return rc;
@@ -2588,6 +2702,25 @@ int run_fasta_body(const char* h_text, uint64_t h_n, const char* q_text, uint64_
         *win_off = (const uint64_t*)wo; *win_len = packed; *n_win = nw; *max_len = mx;
         return FRISK_OK;
     };
+    if (tail_ok) {
+        // everything is queued: bring the tables and the window count back, wait, check the capacity
+        void* h_scal = nullptr;
+        if ((rc = stage_get(dev, 1, 64, &h_scal))) return rc;
+        if (!rows_direct) {                                          // pageable result buffers: the rows come back by copy
+            CK(cudaMemcpyAsync(rows_out, k_rows, rows_cap * 40, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(status_out, k_stat, rows_cap * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaMemcpyAsync(h_scal, dscal, 16, cudaMemcpyDeviceToHost, st));
+        if ((rc = mark(tm, kTmEnd, st))) return rc;
+        CK(cudaStreamSynchronize(st));
+        CK(cudaStreamSynchronize(cc->copy));                         // the tables came back beside the window kernel
+        g_trace.stamp("done");
+        g_trace.flush();
+        const uint64_t n_win = ((const uint64_t*)h_scal)[0];
+        if (n_win_out) *n_win_out = n_win;
+        if ((int64_t)((const uint64_t*)h_scal)[1] != (int64_t)h_stats[0] - (int64_t)h_stats[1]) return FRISK_E_CUDA;   // (cannot happen)
+        return n_win > rows_cap ? FRISK_E_CAPACITY : FRISK_OK;
+    }
     CK(cudaEventRecord(cc->ev[kMaxChunks], st));                    // the copy stream joins behind the ingest
     CK(cudaStreamWaitEvent(cc->copy, cc->ev[kMaxChunks], 0));
     return run_tail(PeerArgs(), dhc, dhi, dhl, h_padded, counted, dqc, dqi, dql, nullptr, nullptr, 0, 0, kmin, kmax, mask_host, want_rip,

@@ -138,6 +138,8 @@ constexpr bool NIB_WALK = FRISK_NIBBLE_WALK;       // scoring pass re-reads the 
 // instantiation evaluates all K scores -- kmax' <= K-2 by walking that order's bins (coalesced genome-IVOM reads),
 // K-1 and K per position with weights 1/c -- and writes K rows per window.
 struct NibSweep {
+    const unsigned long long* n_win_dev;   // nullable: the number of windows lives in device memory (frisk_b200_run_fasta builds
+                                           // its window list on the device); the n_win argument is then the capacity
     const double2* ig[8];             // genome IVOM table of kmax' = i + 1
     double* rows[8];
     uint32_t* status[8];
@@ -184,6 +186,7 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
     }
     __syncthreads();
 
+    if (sw.n_win_dev) n_win = (uint32_t)min((unsigned long long)n_win, *sw.n_win_dev);
     int par = 1;
     for (uint32_t win = blockIdx.x; win < n_win; win += gridDim.x) {
         const uint64_t o = win_off[win];
@@ -770,7 +773,8 @@ score_windows_nibble_kernel(const uint32_t* __restrict__ codes, const uint32_t* 
 template <int K, int PP, bool DUMP, bool ALLK>
 int launch_nibble4(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                    const uint32_t* win_len, uint64_t n_win, const double* ig, int kmin, int want_rip,
-                   double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only) {
+                   double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only,
+                   const unsigned long long* n_win_dev = nullptr) {
     using L = NibLayout<K>;
     auto kern = score_windows_nibble_kernel<K, PP, DUMP, ALLK>;
     // attributes and occupancy once per device and instantiation: three runtime calls less in front of every launch
@@ -790,9 +794,11 @@ int launch_nibble4(const uint32_t* codes, const uint32_t* inv, const uint32_t* l
     if (sms <= 0) return FRISK_E_NO_DEVICE;
     uint64_t grid = (uint64_t)sms * (uint64_t)per_sm;
     if (grid > n_win) grid = n_win;
+    NibSweep sw{};
+    sw.n_win_dev = n_win_dev;
     kern<<<(unsigned)grid, kNT, L::TOTAL, st>>>(codes, inv, low, reinterpret_cast<const unsigned long long*>(win_off), win_len,
                                                 (uint32_t)n_win, reinterpret_cast<const double2*>(ig), kmin, want_rip, rows,
-                                                status, dump, redo_dst, NibSweep());
+                                                status, dump, redo_dst, sw);
     CK(cudaGetLastError());
     return FRISK_OK;
 }
@@ -821,10 +827,11 @@ int launch_sweep(const uint32_t* codes, const uint32_t* inv, const uint32_t* low
 template <int K, int PP>
 int launch_nibble3(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                    const uint32_t* win_len, uint64_t n_win, const double* ig, int kmin, int want_rip,
-                   double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only) {
-    if (dump) return launch_nibble4<K, PP, true, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
-    if (kmin != 1) return launch_nibble4<K, PP, false, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
-    return launch_nibble4<K, PP, false, true>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+                   double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only,
+                   const unsigned long long* n_win_dev = nullptr) {
+    if (dump) return launch_nibble4<K, PP, true, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only, n_win_dev);
+    if (kmin != 1) return launch_nibble4<K, PP, false, false>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only, n_win_dev);
+    return launch_nibble4<K, PP, false, true>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only, n_win_dev);
 }
 
 // positions per thread: the longest window of the launch spread over the CTA (K-mer codes stay in registers between
@@ -832,13 +839,14 @@ int launch_nibble3(const uint32_t* codes, const uint32_t* inv, const uint32_t* l
 template <int K>
 int launch_nibble(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                   const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int want_rip,
-                  double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only) {
+                  double* rows, uint32_t* status, uint16_t* dump, uint32_t* redo_dst, cudaStream_t st, int* occ_only,
+                  const unsigned long long* n_win_dev = nullptr) {
     if (max_len <= kNT * 8u)
-        return launch_nibble3<K, 8>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+        return launch_nibble3<K, 8>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only, n_win_dev);
     if (max_len <= kNT * 20u)
-        return launch_nibble3<K, 20>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+        return launch_nibble3<K, 20>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only, n_win_dev);
     if (max_len <= kNT * 32u)
-        return launch_nibble3<K, 32>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only);
+        return launch_nibble3<K, 32>(codes, inv, low, win_off, win_len, n_win, ig, kmin, want_rip, rows, status, dump, redo_dst, st, occ_only, n_win_dev);
     return FRISK_E_UNSUPPORTED;
 }
 
@@ -846,23 +854,28 @@ int launch_nibble(const uint32_t* codes, const uint32_t* inv, const uint32_t* lo
 
 int frisk_internal::score_nibble(const uint32_t* codes, const uint32_t* inv, const uint32_t* low, const uint64_t* win_off,
                                  const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* ig, int kmin, int K,
-                                 int want_rip, double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st) {
+                                 int want_rip, double* rows, uint32_t* status, uint16_t* dump, cudaStream_t st,
+                                 const unsigned long long* n_win_dev) {
     if (K != 7 && K != 8) return FRISK_E_UNSUPPORTED;
+    if (max_len > 8186u) return FRISK_E_UNSUPPORTED;
     // where the hand-over marks go: `status` itself when it is device memory, device scratch when it is pinned host
     // memory (the second launch would otherwise read its marks across PCIe, one round trip per window)
     uint32_t* redo = status;
     uint32_t* scratch = nullptr;
     cudaPointerAttributes pa{};
-    if (cudaPointerGetAttributes(&pa, status) != cudaSuccess || pa.type != cudaMemoryTypeDevice) {
+    if (n_win_dev || cudaPointerGetAttributes(&pa, status) != cudaSuccess || pa.type != cudaMemoryTypeDevice) {
         cudaGetLastError();
         int rc = pool_ready();
         if (rc) return rc;
         CK(cudaMallocAsync((void**)&scratch, n_win * sizeof(uint32_t), st));
+        // window count in device memory: n_win is only the capacity, and the hand-over launch below walks all of it --
+        // marks beyond the real count must read "nothing to redo"
+        if (n_win_dev) CK(cudaMemsetAsync(scratch, 0, n_win * sizeof(uint32_t), st));
         redo = scratch;
     }
     int rc;
-    if (K == 8) rc = launch_nibble<8>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo, st, nullptr);
-    else rc = launch_nibble<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo, st, nullptr);
+    if (K == 8) rc = launch_nibble<8>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo, st, nullptr, n_win_dev);
+    else rc = launch_nibble<7>(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, want_rip, rows, status, dump, redo, st, nullptr, n_win_dev);
     // windows the nibble table could not hold (marked kRowRedo): exact re-run on the bucketed kernel
     if (!rc) rc = score_bucket_redo(codes, inv, low, win_off, win_len, n_win, max_len, ig, kmin, K, want_rip, rows, status, dump, redo, st);
     if (scratch) {                                         // freed on every path (stream-ordered: behind the launches above)
