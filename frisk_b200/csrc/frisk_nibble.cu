@@ -898,7 +898,7 @@ int frisk_internal::score_sweep(const uint32_t* codes, const uint32_t* inv, cons
                                 const uint32_t* win_len, uint64_t n_win, uint32_t max_len, const double* const* ig, int want_rip,
                                 double* const* rows, uint32_t* const* status, cudaStream_t st) {
     if (max_len > kNT * 32u || max_len > 8186u) return FRISK_E_UNSUPPORTED;
-    NibSweep sw;
+    NibSweep sw{};
     for (int k = 0; k < 8; ++k) {
         if (!ig[k] || !rows[k] || !status[k]) return FRISK_E_INVALID;
         sw.ig[k] = reinterpret_cast<const double2*>(ig[k]); sw.rows[k] = rows[k]; sw.status[k] = status[k];
