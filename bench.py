@@ -793,7 +793,8 @@ def run_gpu(args):
             "e2e_fasta": ({"value": all_bases / (fasta_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": fasta_ms,
                            "h2d_bytes_per_step": fasta_bytes_n + wins.off.nbytes + wins.length.nbytes, "d2h_bytes_per_step": d2h,
                            "api": "frisk_b200_run_fasta (C ABI, one call: chunked upload of pinned FASTA text, device-side tokenise + "
-                                  "layout + pack + count per chunk while the next is on the bus, then tables, IVOM, window kernel, rows)",
+                                  "layout + pack + count per chunk while the next is on the bus; genome space and window list built on the device, so tables, "
+                                  "IVOM and window kernel are queued before the host has seen the record table; rows)",
                            "stages": fasta_stages}
                           if fasta_ms else None),
             "gpu_launches": pipe.launches_per_step * args.steps,

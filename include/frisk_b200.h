@@ -344,9 +344,11 @@ int frisk_b200_fasta_open_stats(uint64_t out[2]);
  * its three passes over the file (F:170, F:203, F:297).  h_text is the genome the background is counted on (--hostSeq,
  * or the query itself), q_text the genome whose windows are scored (NULL, or the same pointer and size: the same genome).
  * The text goes up in chunks; each chunk is tokenised, laid out, packed and (kmax <= 8) counted on the device while the next
- * chunk is on the bus; the record table comes back once, as soon as the last chunk is tokenised, and names, windows
- * (frisk_b200_windows with w, step, scaffolds_all) and the launch of tables -> IVOM -> window kernel happen on the host while
- * that chunk is still being packed and counted.  rows_out / status_out have room for rows_cap windows (pinned buffers are
+ * chunk is on the bus.  With kmax 7 or 8 and windows of <= 8,186 bases nothing behind the last chunk waits for the host:
+ * genome space, window list (frisk_b200_windows' windows for w, step, scaffolds_all) and window count are produced on the
+ * device, and tables -> IVOM -> window kernel are queued before the host has seen the record table, which it reads (names,
+ * FRISK_E_FORMAT) while the window kernel runs.  Otherwise the record table comes back once, as soon as the last chunk is
+ * packed, and windows and launches happen on the host while that chunk is still being counted.  rows_out / status_out have room for rows_cap windows (pinned buffers are
  * written by the kernel directly); *n_win_out always receives the number of windows.
  * *host_out / *query_out (query_out: NULL when the genomes are the same) are handles as of frisk_b200_fasta_open whose PLANES
  * exist and belong to the handle (frisk_b200_fasta_planes; padded_len etc. from frisk_b200_fasta_info, the record table
