@@ -667,6 +667,7 @@ def run_gpu(args):
         if fasta_stage_rows:
             m = np.mean(np.array(fasta_stage_rows), axis=0)
             fasta_stages = {"text_uploaded": float(m[0]), "tokenised+packed+counted": float(m[1]), "tables+ivom": float(m[2]),
+                            "window_kernel_started": float(m[5]) if len(m) > 5 else None,
                             "scored": float(m[3]), "rows_on_host": float(m[4]),
                             "note": "ms since the start of the one C call (device-side events on the call's streams), mean over the "
                                     "timed steps; tokenise, pack and count of a chunk run while the next chunk is on the bus"}
@@ -688,7 +689,7 @@ def run_gpu(args):
     # per-rank stage breakdown of the e2e call: max and min over ranks of each stage's mean
     breakdown = None
     if stage_rows:
-        mean = np.array(stage_rows).mean(0)                      # [uploaded, counted, finalised, scored, end, end] since call start
+        mean = np.array(stage_rows).mean(0)                      # [uploaded, counted, finalised, scored, end, window kernel started] since call start
         per = np.array([mean[0], mean[1], mean[2] - mean[1], mean[3] - mean[2], mean[4] - mean[3], mean[4]])
         tmax = torch.tensor(per, dtype=torch.float64, device=dev); tmin = tmax.clone()
         if world > 1:
