@@ -173,7 +173,11 @@ class WindowList:
 
     @property
     def max_len(self) -> int:
-        return int(self.length.max()) if len(self) else 0
+        m = self.__dict__.get("_max_len")
+        if m is None:                                  # (a pass over the list: computed once, the one-call paths ask every call)
+            m = int(self.length.max()) if len(self) else 0
+            self.__dict__["_max_len"] = m
+        return m
 
     def slice(self, a: int, b: int) -> "WindowList":
         return WindowList(self.off[a:b], self.length[a:b], self.scaf[a:b], self.start[a:b], self.stop[a:b])
@@ -278,6 +282,14 @@ class PackedGenome:
                        "frisk_b200_plane_sparse")
             self._inv_sparse = (idx[:cap], val[:cap])
         return self._inv_sparse
+
+    def prefers_sparse(self) -> bool:
+        """Upload the invalid plane as its non-zero words?  (when that is at most a quarter of the dense plane; cached)"""
+        v = getattr(self, "_prefers_sparse", None)
+        if v is None:
+            v = 8 * len(self.inv_sparse()[0]) <= self.inv.nbytes // 4 and self.padded_len // 32 < 2 ** 32
+            self._prefers_sparse = v
+        return v
 
     def ex_max(self, kmax: int, valid_kmax: int) -> int:
         """exMax (F:344): kmax-words that contain an invalid character."""
@@ -903,7 +915,7 @@ def run_host(query: PackedGenome, host: Optional[PackedGenome] = None, kmin: int
     # ``sparse``: upload the (nearly empty) invalid planes as their non-zero words
     # (frisk_b200_run_host_sparse); None = whenever that is at most a quarter of the dense plane
     if sparse is None:
-        sparse = all(8 * len(g.inv_sparse()[0]) <= g.inv.nbytes // 4 and g.padded_len // 32 < 2 ** 32 for g in {id(host): host, id(query): query}.values())
+        sparse = host.prefers_sparse() and (query is host or query.prefers_sparse())
     if sparse:
         (hi, hv), (qi, qv) = host.inv_sparse(), query.inv_sparse()
         rc = _lib.lib().frisk_b200_run_host_sparse(
