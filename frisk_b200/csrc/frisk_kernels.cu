@@ -2630,7 +2630,8 @@ int run_fasta_body(const char* h_text, uint64_t h_n, const char* q_text, uint64_
         if ((rc2 = mark(tm, kTmScoreStart, s2))) return rc2;
         rc2 = frisk_internal::score_nibble(win_codes[0], win_codes[1], win_codes[2], (const uint64_t*)dwin,
                                            (const uint32_t*)((unsigned long long*)dwin + rows_cap), rows_cap, len_bound, (const double*)dig,
-                                           kmin, kmax, want_rip, k_rows, k_stat, nullptr, s2, (const unsigned long long*)dscal);
+                                           kmin, kmax, want_rip && kmin <= 2 && kmax >= 2 /* as frisk_b200_score: RIP needs orders 1 and 2 */,
+                                           k_rows, k_stat, nullptr, s2, (const unsigned long long*)dscal);
         if (rc2) return rc2;
         tail_queued = true;
         return mark(tm, kTmScored, s2);

@@ -163,7 +163,11 @@ def test_empty_and_malformed_inputs():
 
 
 @pytest.mark.parametrize("case", ["edge_default", "edge_scaffoldsAll", "edge_maskHost", "c1_small", "c2_small",
-                                  "c2_small_query_vs_c1_host"])
+                                  "c2_small_query_vs_c1_host",
+                                  # other word sizes / window shapes: kmin > 1 (device tail, kmin template), kmax 9 and
+                                  # kmax <= 5 (host-driven tail), windows shorter than a step's complement, scaffoldsAll rescue
+                                  "edge_k4_8", "edge_k1_9", "edge_k2_5_w1000_i250", "edge_k1_3_w3000_i1000",
+                                  "short_w1000_i800", "short_w1000_i800_all"])
 def test_fasta_text_to_rows_matches_reference_golden(case):
     from tests.test_gpu_parity import _check_against_golden
     gold = Golden(case)
