@@ -235,6 +235,17 @@ def test_chunked_open_carries_state_across_chunks_and_falls_back_when_it_cannot_
         for sep in (b">b description\n", b"   \t  \n", b"  >c\n"):
             assert_same_genome(body + sep + b"ACGT" * 14000 + b"\n>z\nGG\n", modes=("chunk1",))
     assert open_stats()[1] > redo1, "blank bytes before a chunk boundary need the next chunk: redone exactly"
+    # the one-call path queues tables, IVOM and the window kernel from inside the streamed open; when that open is redone,
+    # what was queued on the provisional data is discarded and the host-driven tail produces the same rows
+    amb = b">a\n" + b"A" * (16384 - 8) + b"\n" + b"   \t  \n" + b"ACGT" * 14000 + b"\n>z\n" + b"GATTACA" * 700 + b"\n"
+    with ingest_options("exact"):
+        want = engine.run_fasta(amb, w=1000, step=500)
+    d, r = open_stats()
+    with ingest_options("chunk1"):
+        got = engine.run_fasta(amb, w=1000, step=500)
+    assert open_stats()[1] == r + 1, "this text cannot be decided chunk by chunk"
+    assert np.array_equal(got.rows, want.rows, equal_nan=True) and np.array_equal(got.tables, want.tables) and len(got.rows) > 50
+    assert got.names == want.names and np.array_equal(got.coords, want.coords)
     # more records than the guess (n/64 + 4096)
     done2, redo2 = open_stats()
     many = b"".join(b">r%d\nA\n" % i for i in range(60_000))
