@@ -193,6 +193,9 @@ def test_fasta_text_to_rows_matches_reference_golden(case):
             alt = engine.run_fasta(pq, ph, **gold.kwargs())
         assert np.array_equal(alt.rows, res.rows, equal_nan=True) and np.array_equal(alt.tables, res.tables), "pinned " + mode
         assert alt.names == res.names
+    pageable = engine.HostOutputs(res.n_candidates + 3, gold.kwargs().get("kmax", 8), pinned=False)   # rows come back by copy
+    alt = engine.run_fasta(qtext, htext, out=pageable, **gold.kwargs())
+    assert np.array_equal(alt.rows, res.rows, equal_nan=True) and np.array_equal(alt.tables, res.tables)
     small = engine.HostOutputs(1, gold.kwargs().get("kmax", 8))
     alt = engine.run_fasta(qtext, htext, out=small, **gold.kwargs())
     assert np.array_equal(alt.rows, res.rows, equal_nan=True) and np.array_equal(alt.tables, res.tables)
