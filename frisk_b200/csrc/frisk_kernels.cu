@@ -213,8 +213,14 @@ struct PeerFwd {
     unsigned long long epoch;                 // 0: the caller already synchronised the GPUs
     __device__ __forceinline__ long long space(long long by_value) const { return by_value; }
     __device__ __forceinline__ unsigned long long operator()(uint32_t i) const {
+        // every peer's load is issued before any of them is consumed: a loop over the run-time `n` with the running sum in
+        // it makes each NVLink round trip wait for the one before (8 ranks: 8 exposed latencies per counter instead of 1)
+        unsigned long long v[kMaxPeers];
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q) v[q] = q < n ? __ldcv(p[q] + i) : 0ull;   // written before the peers' arrival below
         unsigned long long s = 0;
-        for (int q = 0; q < n; ++q) s += __ldcv(p[q] + i);       // written before the peers' arrival below
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q) s += v[q];
         return s;
     }
     // Cross-GPU barrier folded into the first kernel that needs the peers' counters: this rank's count
