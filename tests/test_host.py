@@ -277,3 +277,27 @@ def test_argument_checks_answer_before_any_device_work():
     for opt in (b"force_dense_kernel", b"force_general_kernel", b"force_bucket_kernel", b"force_direct_kernel",
                 b"force_nibble_kernel", b"ingest_exact_open", b"ingest_chunk_tiles"):
         assert L.frisk_b200_set_option(opt, 1) == 0 and L.frisk_b200_set_option(opt, 0) == 0, opt   # the switches in the header
+
+
+def test_assemble_copies_or_gathers_the_same_rows():
+    """engine.assemble takes plain copies when no window is excluded and gathers otherwise: same fields either way, and the
+    result never aliases the (reused, page-locked) buffers it was built from."""
+    rng = np.random.default_rng(4)
+    sc = [("s%d" % i, np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(n))]) for i, n in enumerate((9000, 30000, 700, 12000))]
+    g = engine.PackedGenome.from_scaffolds(sc)
+    wins = g.windows(1000, 500, True)
+    n = len(wins)
+    assert n > 50 and wins.max_len == 1000 and wins.max_len == int(wins.length.max())
+    rows = rng.random((n, 5))
+    tables = np.arange(_lib.table_size(1, 3), dtype=np.uint64)
+    for excluded in ([], [0, 7, n - 1]):
+        status = np.zeros(n, np.uint32)
+        status[excluded] = _lib.ROW_EXCLUDED
+        res = engine.assemble(g, g, wins, tables, 123, rows, status, 1, 3)
+        keep = np.setdiff1d(np.arange(n), excluded)
+        assert np.array_equal(res.rows, rows[keep]) and np.array_equal(res.win_index, keep)
+        assert np.array_equal(res.coords[:, 0], wins.start[keep]) and np.array_equal(res.coords[:, 1], wins.stop[keep])
+        assert res.names == [g.names[s] for s in wins.scaf[keep]] and np.array_equal(res.row_scaf, wins.scaf[keep])
+        assert res.n_candidates == n and not np.shares_memory(res.rows, rows)
+        lean = engine.assemble(g, g, wins, tables, 123, rows, status, 1, 3, names=False)
+        assert lean.names == [] and np.array_equal(lean.rows, res.rows)
