@@ -1009,7 +1009,10 @@ def run_fasta(query_text, host_text=None, device="cuda:0", out=None, assemble_re
     hbuf = _as_u8(host_text) if host_text is not None else qbuf
     dev = torch.device(device)
     if out is None:
-        out = HostOutputs(qbuf.shape[0] // step + qbuf.shape[0] // 512 + 64, kmax)
+        # rows: a guess (one window per step of text, one more per 4 KiB for short scaffolds); a text with more windows comes
+        # back with FRISK_E_CAPACITY and is scored in a second stage below -- page-locking a far larger buffer "to be safe"
+        # would cost more than the run (~0.3 ms per MB)
+        out = HostOutputs(qbuf.shape[0] // step + qbuf.shape[0] // 4096 + 64, kmax)
     hh, qh = C.c_void_p(), C.c_void_p()
     n_win = C.c_uint64(0)
     with _device_ctx(dev):
