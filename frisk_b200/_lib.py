@@ -111,7 +111,7 @@ def lib():
             fn = getattr(L, name)          # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.frisk_b200_abi_version() != 1:
+        if L.frisk_b200_abi_version() != 2:
             raise RuntimeError("libfrisk_b200.so ABI version mismatch")
         _LIB = L
     return _LIB

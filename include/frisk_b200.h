@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FRISK_B200_ABI_VERSION 1
+#define FRISK_B200_ABI_VERSION 2              /* 2: round 2 -- run_fasta, fasta handles own their planes, score sweep, timing mark 5 */
 #define FRISK_B200_MAX_K 12              /* largest supported --maxWordSize (K <= 8: shared-memory kernels; 9..12: general path) */
 #define FRISK_B200_FAST_K 8              /* ... served by the tuned shared-memory kernels */
 #define FRISK_B200_MAX_WINDOW 0x7fffffff /* largest window length (<= 65,535: shared-memory kernels; longer: general path) */

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.frisk_b200_abi_version() == 1
+    assert L.frisk_b200_abi_version() == 2
     assert _lib.table_size(1, 8) == 87380 and _lib.table_size(4, 8) == 87380 - 84
 
 
