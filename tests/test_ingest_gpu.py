@@ -206,6 +206,18 @@ def test_fasta_text_to_rows_matches_reference_golden(case):
     assert np.array_equal(res.rows, ref.rows, equal_nan=True) and np.array_equal(res.tables, ref.tables)
 
 
+@pytest.mark.parametrize("kmax,w,step", [(7, 5000, 2500), (7, 1200, 600), (6, 5000, 2500), (8, 8000, 4000), (8, 9000, 4500)])
+def test_fasta_text_path_equals_the_packed_plane_path(kmax, w, step):
+    """Whichever tail frisk_b200_run_fasta takes -- device-built window list with the nibble kernel (kmax 7 and 8, windows up to
+    8,186 bases), host-built list otherwise -- its rows are bit for bit those of the packed-plane entry point."""
+    sc = synth.make("edge") + synth.make("C2", 0.004, seed=3)
+    text = fasta_text(sc)
+    ref = engine.run(engine.PackedGenome.from_scaffolds(sc), kmax=kmax, w=w, step=step, scaffolds_all=True)
+    got = engine.run_fasta(text, kmax=kmax, w=w, step=step, scaffolds_all=True)
+    assert np.array_equal(got.rows, ref.rows, equal_nan=True) and np.array_equal(got.tables, ref.tables)
+    assert got.names == ref.names and np.array_equal(got.coords, ref.coords) and np.array_equal(got.status, ref.status)
+
+
 def test_large_single_line_record_and_many_small_records():
     big = synth.make("C1", 0.2)                                # one 1 Mbp scaffold on a single line
     assert_same_genome(fasta_text(big, width=0))
