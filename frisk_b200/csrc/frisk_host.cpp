@@ -41,6 +41,37 @@ int pack_one(const unsigned char* s, const unsigned char* e, uint64_t expect, ui
     uint32_t cw = 0, iw = 0, lw = 0;
     uint64_t pos = base;
     for (const unsigned char* p = s; p < e; ++p) {
+        // eight plain upper-case bases at once (a 60-column line is 7 such groups + 4 bytes + the newline): is every byte one of
+        // A, C, G, T?  then 2 bits each straight from the ASCII codes -- bits 2..1 of A/C/T/G are 00/01/10/11, the F:70 order
+        // A,T,G,C is (b0, b1^b0) -- gathered by one multiply per four characters.  No mask bits to set.
+        while (p + 8 <= e && n + 8 <= expect) {
+            uint64_t x;
+            memcpy(&x, p, 8);
+            const uint64_t m = 0x7F7F7F7F7F7F7F7Full;
+            const uint64_t xa = x ^ 0x4141414141414141ull, xc = x ^ 0x4343434343434343ull, xg = x ^ 0x4747474747474747ull,
+                           xt = x ^ 0x5454545454545454ull;
+            if ((((xa & m) + m) | xa) & (((xc & m) + m) | xc) & (((xg & m) + m) | xg) & (((xt & m) + m) | xt) & 0x8080808080808080ull) break;
+            const uint64_t y = x >> 1;
+            const uint64_t c2 = ((y & 0x0101010101010101ull) << 1) | ((y ^ (y >> 1)) & 0x0101010101010101ull);
+            const uint32_t bits16 = ((((uint32_t)c2 * 0x40100401u) >> 24) << 8) | (((uint32_t)(c2 >> 32) * 0x40100401u) >> 24);
+            const uint32_t j = (uint32_t)(pos & 15);
+            if (j <= 8) {
+                cw |= bits16 << (16 - 2 * j);
+                if (j == 8) { codes[pos >> 4] = cw; cw = 0; }
+            } else {
+                cw |= bits16 >> (2 * (j - 8));
+                codes[pos >> 4] = cw;
+                cw = bits16 << (32 - 2 * (j - 8));
+            }
+            const uint64_t np = pos + 8;
+            if ((np ^ pos) >> 5) {                       // a mask word was completed (the eight bases add no mask bits)
+                inv[pos >> 5] = iw; iw = 0;
+                if (low) low[pos >> 5] = lw;
+                lw = 0;
+            }
+            pos = np; n += 8; p += 8;
+        }
+        if (p >= e) break;
         const uint8_t c = kClass.t[*p];
         if (c == 9) continue;
         if (n == expect) return FRISK_E_FORMAT;
@@ -146,7 +177,16 @@ int frisk_b200_fasta_scan(const char* text, uint64_t n, uint64_t cap, uint64_t* 
                 // The reference strips a line only at its ends (F:149): whitespace INSIDE a sequence line stays in its
                 // string and counts towards totalLen / nnTotal / window coordinates.  Real FASTA never has it; rather
                 // than silently shifting every coordinate after it, such input is refused.
-                for (uint64_t p = a; p < b; ++p)
+                uint64_t p = a;
+                for (; p + 8 <= b; p += 8) {             // eight bytes at a time: is any of them < 0x21 ?  (exact test below)
+                    uint64_t x;
+                    memcpy(&x, t + p, 8);
+                    if (~(((x | 0x8080808080808080ull) - 0x2121212121212121ull) | x) & 0x8080808080808080ull) {
+                        for (uint64_t q = p; q < p + 8; ++q)
+                            if (is_space(t[q])) return FRISK_E_FORMAT;
+                    }
+                }
+                for (; p < b; ++p)
                     if (is_space(t[p])) return FRISK_E_FORMAT;
                 cur_len += b - a;
             }

@@ -214,14 +214,22 @@ class PackedGenome:
         L = _lib.lib()
         buf = _as_u8(text)
         n = C.c_uint64(0)
-        _lib.check(L.frisk_b200_fasta_scan(_ptr(buf), buf.shape[0], 0, None, None, None, None, None, C.byref(n)),
-                   "frisk_b200_fasta_scan")
-        cap = int(n.value)
-        name_off = np.zeros(cap, np.uint64); name_len = np.zeros(cap, np.uint32)
-        body_off = np.zeros(cap, np.uint64); body_end = np.zeros(cap, np.uint64); seq_len = np.zeros(cap, np.uint64)
-        _lib.check(L.frisk_b200_fasta_scan(_ptr(buf), buf.shape[0], cap, _ptr(name_off), _ptr(name_len), _ptr(body_off),
-                                           _ptr(body_end), _ptr(seq_len), C.byref(n)), "frisk_b200_fasta_scan")
-        return cls._pack(_decode_names(buf, name_off, name_len), buf, body_off, body_end, seq_len, pinned, threads)
+        # one pass over the text with a guessed record capacity (one record per 2 KiB + 1024); a second one with the exact
+        # count only when the guess was too small (the scan reports the count either way)
+        cap = buf.shape[0] // 2048 + 1024
+        while True:
+            name_off = np.zeros(cap, np.uint64); name_len = np.zeros(cap, np.uint32)
+            body_off = np.zeros(cap, np.uint64); body_end = np.zeros(cap, np.uint64); seq_len = np.zeros(cap, np.uint64)
+            rc = L.frisk_b200_fasta_scan(_ptr(buf), buf.shape[0], cap, _ptr(name_off), _ptr(name_len), _ptr(body_off),
+                                         _ptr(body_end), _ptr(seq_len), C.byref(n))
+            if rc == _lib.E_CAPACITY and int(n.value) > cap:
+                cap = int(n.value)
+                continue
+            _lib.check(rc, "frisk_b200_fasta_scan")
+            break
+        k = int(n.value)
+        return cls._pack(_decode_names(buf, name_off[:k], name_len[:k]), buf, body_off[:k], body_end[:k], seq_len[:k], pinned,
+                         threads)
 
     @classmethod
     def from_fasta(cls, path: str, pinned: bool = False, threads: int = 0) -> "PackedGenome":
